@@ -1,0 +1,550 @@
+// libbsc_b200/csrc/api.cu -- the C-ABI boundary (include/libbsc_b200.h).
+//
+// Host glue only: parameter validation, the 28-byte block header, error codes, H2D/D2H copies and
+// the per-device context pool.  Every byte-touching stage (BWT / ST / QLFC / Adler-32) runs as
+// CUDA kernels on the current device; there is NO CPU implementation of those stages in this
+// library -- if CUDA is unavailable every entry point returns LIBBSC_GPU_NOT_SUPPORTED.
+//
+// Mirrors libbsc/libbsc/libbsc.cpp (bsc_store 68-81, bsc_compress 213-338, bsc_block_info 340-418,
+// bsc_decompress 522-617) and the stage entry points libbsc.cpp calls:
+// bsc_bwt_encode/decode (bwt.h:56,68), bsc_st_encode (st.h:57), bsc_coder_compress/decompress
+// (coder.h:56,66), bsc_adler32 (adler32.h).
+#include "common.cuh"
+#include "stages.cuh"
+#include "../../include/libbsc_b200.h"
+
+#include <mutex>
+#include <vector>
+#include <sys/mman.h>
+#include <unistd.h>
+
+// ---------------------------------------------------------------------------------------------
+// context pool
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int MAX_DEVICES = 16;
+std::mutex g_pool_mutex;
+std::vector<Ctx *> g_pool[MAX_DEVICES];
+bool g_initialised = false;
+int g_features = 0;
+void *(*g_malloc)(size_t) = nullptr;
+void *(*g_zero_malloc)(size_t) = nullptr;
+void (*g_free)(void *) = nullptr;
+unsigned long long g_launches_retired = 0;
+
+Ctx *ctx_new(int device, cudaStream_t stream, bool own)
+{
+    Ctx *c = new Ctx();
+    c->device = device;
+    try {
+        CUDA_TRY(cudaSetDevice(device));
+        if (own) { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->owns_stream = true; }
+        else c->stream = stream;
+        CUDA_TRY(cudaMallocHost((void **)&c->h_mail, 1024));
+        CUDA_TRY(cudaMalloc((void **)&c->d_mail, 1024));
+        CUDA_TRY(cudaMemsetAsync(c->d_mail, 0, 1024, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    } catch (...) { delete c; throw; }
+    return c;
+}
+
+void ctx_delete(Ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->arena.destroy();
+    if (c->h_mail) cudaFreeHost(c->h_mail);
+    if (c->d_mail) cudaFree(c->d_mail);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->qlfc_tables) cudaFree(c->qlfc_tables);
+    if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+Ctx *ctx_acquire()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        if (!g_pool[dev].empty()) { Ctx *c = g_pool[dev].back(); g_pool[dev].pop_back(); return c; }
+    }
+    try { return ctx_new(dev, nullptr, true); } catch (...) { cudaGetLastError(); return nullptr; }
+}
+
+void ctx_release(Ctx *c)
+{
+    if (!c) return;
+    c->arena.reset();
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    g_pool[c->device].push_back(c);
+}
+
+int map_failure(const CudaFail &f)
+{
+    cudaGetLastError();
+    return f.err == cudaErrorMemoryAllocation ? LIBBSC_GPU_NOT_ENOUGH_MEMORY : LIBBSC_GPU_ERROR;
+}
+
+// run `body(ctx)` on a pooled context, translating CUDA failures into libbsc error codes
+template <class F> int with_ctx(F body)
+{
+    Ctx *c = ctx_acquire();
+    if (!c) return LIBBSC_GPU_NOT_SUPPORTED;
+    int r;
+    try { r = body(c); }
+    catch (const CudaFail &f) { r = map_failure(f); cudaStreamSynchronize(c->stream); cudaGetLastError(); }
+    ctx_release(c);
+    return r;
+}
+template <class F> int guarded(Ctx *c, F body)
+{
+    try { return body(); }
+    catch (const CudaFail &f) { int r = map_failure(f); cudaStreamSynchronize(c->stream); cudaGetLastError(); c->arena.reset(); return r; }
+}
+
+// arena sizes (bytes) generous enough for each stage at block length n
+size_t need_bwt_encode(size_t n) { return 58 * n + (64u << 20); }
+size_t need_bwt_decode(size_t n) { return 8 * n + (16u << 20); }
+size_t need_st_encode(size_t n)  { return 30 * n + (16u << 20); }
+size_t need_coder(size_t n)      { return 12 * n + (64u << 20); }
+
+unsigned int host_adler32(const unsigned char *p, size_t n)
+{
+    unsigned int a = 1, b = 0;
+    while (n) { size_t k = n < 5552 ? n : 5552; n -= k; while (k--) { a += *p++; b += a; } a %= 65521u; b %= 65521u; }
+    return (b << 16) | a;
+}
+void put32(unsigned char *p, unsigned int v) { memcpy(p, &v, 4); }
+unsigned int get32(const unsigned char *p) { unsigned int v; memcpy(&v, p, 4); return v; }
+
+// number of bytes starting at p (up to `want`) that lie in mapped pages
+size_t readable_prefix(const void *p, size_t want)
+{
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    size_t addr = (size_t)p, first = addr & ~(page - 1), ok = 0;
+    unsigned char vec;
+    for (size_t pg = first; pg < addr + want; pg += page) {
+        if (mincore((void *)pg, page, &vec) != 0) break;
+        ok = pg + page - addr;
+    }
+    return ok < want ? ok : want;
+}
+
+bool sorter_valid(int s) { return s == 1 || (s >= 3 && s <= 8); }
+
+// ---------------------------------------------------------------------------------------------
+// device-resident block compress / decompress
+// ---------------------------------------------------------------------------------------------
+// Stored block (libbsc.cpp:68-81) built on the device: header on host, data D2D.
+int store_dev(Ctx *ctx, const u8 *d_in, int n, u8 *d_out, u32 adler_data)
+{
+    unsigned char h[LIBBSC_HEADER_SIZE];
+    put32(h, (u32)(n + LIBBSC_HEADER_SIZE)); put32(h + 4, (u32)n); put32(h + 8, 0); put32(h + 12, 0);
+    put32(h + 16, adler_data); put32(h + 20, adler_data); put32(h + 24, host_adler32(h, 24));
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(d_out + LIBBSC_HEADER_SIZE, d_in, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    memcpy(ctx->h_mail + 64, h, LIBBSC_HEADER_SIZE);
+    CUDA_TRY(cudaMemcpyAsync(d_out, ctx->h_mail + 64, LIBBSC_HEADER_SIZE, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+    return n + LIBBSC_HEADER_SIZE;
+}
+
+// bsc_compress with LZP disabled, everything in HBM.  d_out must hold n + 28 bytes.
+int compress_dev(Ctx *ctx, const u8 *d_in, int n, u8 *d_out, int blockSorter, int coder, int features, bool inplace_rules)
+{
+    if (!sorter_valid(blockSorter)) return LIBBSC_BAD_PARAMETER;
+    if (coder < 1 || coder > 3) return LIBBSC_BAD_PARAMETER;
+    if (n < 0 || n > 1073741824) return LIBBSC_BAD_PARAMETER;
+    int mode = blockSorter | (coder << 5);
+    const u32 adler_data = stage_adler32(ctx, d_in, n);
+    if (n <= LIBBSC_HEADER_SIZE) return store_dev(ctx, d_in, n, d_out, adler_data);
+
+    Arena &A = ctx->arena;
+    const size_t mark = A.mark();
+    u8 *work = A.get<u8>((size_t)n + 64);
+    CUDA_TRY(cudaMemcpyAsync(work, d_in, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+
+    int indexes[256]; unsigned char num_indexes = 0; int index;
+    if (blockSorter == 1) index = stage_bwt_encode(ctx, work, n, &num_indexes, indexes);
+    else index = stage_st_encode(ctx, work, n, blockSorter);
+    if (n < 64 * 1024) num_indexes = 0;                   // libbsc.cpp:303
+    if (index < 0) { A.release(mark); return index; }
+
+    int result = stage_coder_compress(ctx, work, d_out + LIBBSC_HEADER_SIZE, n, coder, features);
+    A.release(mark);
+    if (result == LIBBSC_NOT_SUPPORTED) return result;
+    if (result < 0 || result + 1 + 4 * num_indexes >= n) {
+        if (inplace_rules) return LIBBSC_NOT_COMPRESSIBLE;               // libbsc.cpp:188-191
+        return store_dev(ctx, d_in, n, d_out, adler_data);               // libbsc.cpp:315-318
+    }
+    unsigned char *tail = (unsigned char *)(ctx->h_mail + 96);            // pinned, <= 4*255+1 bytes needs care: num_indexes <= 15 here
+    memcpy(tail, indexes, 4 * (size_t)num_indexes);
+    tail[4 * num_indexes] = num_indexes;
+    CUDA_TRY(cudaMemcpyAsync(d_out + LIBBSC_HEADER_SIZE + result, tail, 4 * (size_t)num_indexes + 1, cudaMemcpyHostToDevice, ctx->stream));
+    result += 1 + 4 * num_indexes;
+    const u32 adler_payload = stage_adler32(ctx, d_out + LIBBSC_HEADER_SIZE, result);
+    unsigned char *h = (unsigned char *)(ctx->h_mail + 64);
+    put32(h, (u32)(result + LIBBSC_HEADER_SIZE)); put32(h + 4, (u32)n); put32(h + 8, (u32)mode); put32(h + 12, (u32)index);
+    put32(h + 16, adler_data); put32(h + 20, adler_payload); put32(h + 24, host_adler32(h, 24));
+    CUDA_TRY(cudaMemcpyAsync(d_out, h, LIBBSC_HEADER_SIZE, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+    return result + LIBBSC_HEADER_SIZE;
+}
+
+int block_info_host(const unsigned char *h, int headerSize, int *pBlockSize, int *pDataSize)
+{
+    if (headerSize < LIBBSC_HEADER_SIZE) return LIBBSC_UNEXPECTED_EOB;
+    if (get32(h + 24) != host_adler32(h, 24)) return LIBBSC_DATA_CORRUPT;
+    int blockSize = (int)get32(h), dataSize = (int)get32(h + 4), mode = (int)get32(h + 8), index = (int)get32(h + 12);
+    int lzpHash = (mode >> 16) & 0xff, lzpMin = (mode >> 8) & 0xff, coder = (mode >> 5) & 7, sorter = mode & 0x1f;
+    int rebuilt = 0;
+    if (sorter_valid(sorter)) rebuilt = sorter; else if (sorter > 0) return LIBBSC_DATA_CORRUPT;
+    if (coder >= 1 && coder <= 3) rebuilt += coder << 5; else if (coder > 0) return LIBBSC_DATA_CORRUPT;
+    if (lzpMin != 0 || lzpHash != 0) {
+        if (lzpMin < 4 || lzpMin > 255) return LIBBSC_DATA_CORRUPT;
+        if (lzpHash < 10 || lzpHash > 28) return LIBBSC_DATA_CORRUPT;
+        rebuilt += (lzpMin << 8) + (lzpHash << 16);
+    }
+    if (rebuilt != mode) return LIBBSC_DATA_CORRUPT;
+    if (blockSize < LIBBSC_HEADER_SIZE || blockSize > LIBBSC_HEADER_SIZE + dataSize) return LIBBSC_DATA_CORRUPT;
+    if (index < 0 || index > dataSize) return LIBBSC_DATA_CORRUPT;
+    if (pBlockSize) *pBlockSize = blockSize;
+    if (pDataSize) *pDataSize = dataSize;
+    return LIBBSC_NO_ERROR;
+}
+
+// bsc_decompress body once the 28-byte header `h` is on the host and the block is in HBM.
+int decompress_dev(Ctx *ctx, const unsigned char *h, const u8 *d_block, int inputSize, u8 *d_out, int outputSize, int features)
+{
+    int blockSize = 0, dataSize = 0;
+    int info = block_info_host(h, inputSize, &blockSize, &dataSize);
+    if (info != LIBBSC_NO_ERROR) return info;
+    if (inputSize < blockSize || outputSize < dataSize) return LIBBSC_UNEXPECTED_EOB;
+    const int payload = blockSize - LIBBSC_HEADER_SIZE;
+    if (get32(h + 20) != stage_adler32(ctx, d_block + LIBBSC_HEADER_SIZE, payload)) return LIBBSC_DATA_CORRUPT;
+    const int mode = (int)get32(h + 8);
+    if (mode == 0) {
+        if (dataSize > 0) CUDA_TRY(cudaMemcpyAsync(d_out, d_block + LIBBSC_HEADER_SIZE, (size_t)dataSize, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->sync();
+        return LIBBSC_NO_ERROR;
+    }
+    if (mode != (mode & 0xff)) return LIBBSC_NOT_SUPPORTED;              // LZP stays on the host side of the boundary
+    const int index = (int)get32(h + 12); const u32 adler_data = get32(h + 16);
+    const int coder = (mode >> 5) & 7, sorter = mode & 0x1f;
+    if (payload < 1) return LIBBSC_DATA_CORRUPT;
+
+    int lzSize = stage_coder_decompress(ctx, d_block + LIBBSC_HEADER_SIZE, payload, d_out, dataSize, coder, features);
+    if (lzSize < 0) return lzSize;
+    int r;
+    if (sorter == 1) r = stage_bwt_decode(ctx, d_out, lzSize, index);
+    else return LIBBSC_NOT_SUPPORTED;                                    // bsc_st_decode: SURVEY 8(f) next #2
+    if (r < 0) return r;
+    if (lzSize != dataSize) return LIBBSC_DATA_CORRUPT;
+    return adler_data == stage_adler32(ctx, d_out, dataSize) ? LIBBSC_NO_ERROR : LIBBSC_DATA_CORRUPT;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// exported C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int bsc_platform_init(int features, void *(*malloc_fn)(size_t), void *(*zero_malloc_fn)(size_t), void (*free_fn)(void *))
+{
+    (void)features;
+    if (malloc_fn && zero_malloc_fn && free_fn) { g_malloc = malloc_fn; g_zero_malloc = zero_malloc_fn; g_free = free_fn; }
+    return LIBBSC_NO_ERROR;
+}
+void *bsc_malloc(size_t size) { return g_malloc ? g_malloc(size) : malloc(size); }
+void *bsc_zero_malloc(size_t size) { return g_zero_malloc ? g_zero_malloc(size) : calloc(1, size); }
+void bsc_free(void *p) { if (g_free) g_free(p); else free(p); }
+
+int bsc_init_full(int features, void *(*malloc_fn)(size_t), void *(*zero_malloc_fn)(size_t), void (*free_fn)(void *))
+{
+    bsc_platform_init(features, malloc_fn, zero_malloc_fn, free_fn);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) { cudaGetLastError(); return LIBBSC_GPU_NOT_SUPPORTED; }
+    g_features = features; g_initialised = true;
+    return LIBBSC_NO_ERROR;
+}
+int bsc_init(int features) { return bsc_init_full(features, nullptr, nullptr, nullptr); }
+int bsc_bwt_init(int) { return LIBBSC_NO_ERROR; }
+int bsc_st_init(int) { return LIBBSC_NO_ERROR; }
+int bsc_coder_init(int) { return LIBBSC_NO_ERROR; }
+int bsc_qlfc_init(int) { return LIBBSC_NO_ERROR; }
+
+unsigned int bsc_adler32(const unsigned char *T, int n, int features)
+{
+    (void)features;
+    if (n < (1 << 16)) return host_adler32(T, (size_t)(n > 0 ? n : 0));   // headers / tiny buffers
+    unsigned int value = 0;
+    int r = with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve((size_t)n + (1u << 20));
+        u8 *d = ctx->arena.get<u8>((size_t)n + 64);
+        CUDA_TRY(cudaMemcpyAsync(d, T, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        value = stage_adler32(ctx, d, n);
+        return 0;
+    });
+    return r == 0 ? value : host_adler32(T, (size_t)n);
+}
+
+int bsc_store(const unsigned char *input, unsigned char *output, int n, int features)
+{
+    (void)features;
+    if (n < 0) return LIBBSC_BAD_PARAMETER;
+    unsigned int a = bsc_adler32(input, n, features);
+    memmove(output + LIBBSC_HEADER_SIZE, input, (size_t)n);
+    put32(output, (u32)(n + LIBBSC_HEADER_SIZE)); put32(output + 4, (u32)n); put32(output + 8, 0); put32(output + 12, 0);
+    put32(output + 16, a); put32(output + 20, a); put32(output + 24, host_adler32(output, 24));
+    return n + LIBBSC_HEADER_SIZE;
+}
+
+int bsc_block_info(const unsigned char *blockHeader, int headerSize, int *pBlockSize, int *pDataSize, int features)
+{
+    (void)features;
+    return block_info_host(blockHeader, headerSize, pBlockSize, pDataSize);
+}
+
+int bsc_compress(const unsigned char *input, unsigned char *output, int n, int lzpHashSize, int lzpMinLen, int blockSorter, int coder, int features)
+{
+    if (!sorter_valid(blockSorter)) return LIBBSC_BAD_PARAMETER;
+    if (coder < 1 || coder > 3) return LIBBSC_BAD_PARAMETER;
+    if (lzpMinLen != 0 || lzpHashSize != 0) {
+        if (lzpMinLen < 4 || lzpMinLen > 255) return LIBBSC_BAD_PARAMETER;
+        if (lzpHashSize < 10 || lzpHashSize > 28) return LIBBSC_BAD_PARAMETER;
+        return LIBBSC_NOT_SUPPORTED;                       // LZP is outside this library (stays in host libbsc)
+    }
+    const bool inplace = (input == output);
+    if (n < 0 || n > (inplace ? 2146435072 : 1073741824)) return LIBBSC_BAD_PARAMETER;
+    if (n > 1073741824) return LIBBSC_NOT_SUPPORTED;
+    if (n <= LIBBSC_HEADER_SIZE) return bsc_store(input, output, n, features);
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve(2 * (size_t)n + 8192 + (blockSorter == 1 ? need_bwt_encode(n) : need_st_encode(n)) + need_coder(n));
+        u8 *d_in = ctx->arena.get<u8>((size_t)n + 64);
+        u8 *d_out = ctx->arena.get<u8>((size_t)n + 4096) + 4;      // payload (offset 28) lands 16-byte aligned
+        CUDA_TRY(cudaMemcpyAsync(d_in, input, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        int r = compress_dev(ctx, d_in, n, d_out, blockSorter, coder, features, inplace);
+        if (r > 0) { CUDA_TRY(cudaMemcpyAsync(output, d_out, (size_t)r, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+
+int bsc_decompress(const unsigned char *input, int inputSize, unsigned char *output, int outputSize, int features)
+{
+    int blockSize = 0, dataSize = 0;
+    int info = block_info_host(input, inputSize, &blockSize, &dataSize);
+    if (info != LIBBSC_NO_ERROR) return info;
+    if (inputSize < blockSize || outputSize < dataSize) return LIBBSC_UNEXPECTED_EOB;
+    unsigned char h[LIBBSC_HEADER_SIZE]; memcpy(h, input, LIBBSC_HEADER_SIZE);
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve((size_t)blockSize + (size_t)dataSize + 8192 + need_bwt_decode((size_t)dataSize) + need_coder((size_t)dataSize));
+        u8 *d_blk = ctx->arena.get<u8>((size_t)blockSize + 128) + 4;
+        u8 *d_out = ctx->arena.get<u8>((size_t)dataSize + 128);
+        CUDA_TRY(cudaMemcpyAsync(d_blk, input, (size_t)blockSize, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(d_blk + blockSize, 0, 64, ctx->stream));
+        int r = decompress_dev(ctx, h, d_blk, blockSize, d_out, dataSize, features);
+        if (r == LIBBSC_NO_ERROR && dataSize > 0) { CUDA_TRY(cudaMemcpyAsync(output, d_out, (size_t)dataSize, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+
+int bsc_bwt_encode(unsigned char *T, int n, unsigned char *num_indexes, int *indexes, int features)
+{
+    (void)features;
+    if (T == nullptr || n < 0) return LIBBSC_BAD_PARAMETER;
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve((size_t)n + 4096 + need_bwt_encode(n));
+        u8 *d = ctx->arena.get<u8>((size_t)n + 64);
+        if (n > 0) CUDA_TRY(cudaMemcpyAsync(d, T, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        int r = stage_bwt_encode(ctx, d, n, num_indexes, indexes);
+        if (r >= 0 && n > 0) { CUDA_TRY(cudaMemcpyAsync(T, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+
+int bsc_bwt_decode(unsigned char *T, int n, int index, unsigned char num_indexes, int *indexes, int features)
+{
+    (void)num_indexes; (void)indexes; (void)features;    // secondary indexes are CPU accelerators only (bwt.cpp:263 ignores them on the GPU too)
+    if (T == nullptr || n < 0 || index <= 0 || index > n) return LIBBSC_BAD_PARAMETER;
+    if (n <= 1) return LIBBSC_NO_ERROR;
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve((size_t)n + 4096 + need_bwt_decode(n));
+        u8 *d = ctx->arena.get<u8>((size_t)n + 64);
+        CUDA_TRY(cudaMemcpyAsync(d, T, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        int r = stage_bwt_decode(ctx, d, n, index);
+        if (r == 0) { CUDA_TRY(cudaMemcpyAsync(T, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+
+int bsc_st_encode(unsigned char *T, int n, int k, int features)
+{
+    (void)features;
+    if (T == nullptr || n < 0) return LIBBSC_BAD_PARAMETER;
+    if (k < 3 || k > 8) return LIBBSC_BAD_PARAMETER;
+    if (n <= 1) return 0;
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve((size_t)n + 4096 + need_st_encode(n));
+        u8 *d = ctx->arena.get<u8>((size_t)n + 64);
+        CUDA_TRY(cudaMemcpyAsync(d, T, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        int r = stage_st_encode(ctx, d, n, k);
+        if (r >= 0) { CUDA_TRY(cudaMemcpyAsync(T, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+
+int bsc_st_decode(unsigned char *T, int n, int k, int index, int features)
+{
+    (void)T; (void)n; (void)k; (void)index; (void)features;
+    return LIBBSC_NOT_SUPPORTED;
+}
+
+int bsc_coder_compress(const unsigned char *input, unsigned char *output, int n, int coder, int features)
+{
+    if (coder < 1 || coder > 3) return LIBBSC_BAD_PARAMETER;
+    if (n <= 0) return LIBBSC_BAD_PARAMETER;
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve(2 * (size_t)n + 16384 + need_coder(n));
+        u8 *d_in = ctx->arena.get<u8>((size_t)n + 64);
+        u8 *d_out = ctx->arena.get<u8>((size_t)n + 4096);
+        CUDA_TRY(cudaMemcpyAsync(d_in, input, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        int r = stage_coder_compress(ctx, d_in, d_out, n, coder, features);
+        if (r > 0) { CUDA_TRY(cudaMemcpyAsync(output, d_out, (size_t)r, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+
+// Size-aware variant used by bsc_decompress and exported for integrators.
+int bscb200_coder_decompress(const unsigned char *input, int inputSize, unsigned char *output, int outputCapacity, int coder, int features)
+{
+    if (coder < 1 || coder > 3) return LIBBSC_BAD_PARAMETER;
+    if (inputSize < 1 || outputCapacity < 0) return LIBBSC_BAD_PARAMETER;
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve((size_t)inputSize + (size_t)outputCapacity + 16384 + need_coder((size_t)outputCapacity));
+        u8 *d_in = ctx->arena.get<u8>((size_t)inputSize + 128);
+        u8 *d_out = ctx->arena.get<u8>((size_t)outputCapacity + 128);
+        CUDA_TRY(cudaMemcpyAsync(d_in, input, (size_t)inputSize, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(d_in + inputSize, 0, 64, ctx->stream));
+        int r = stage_coder_decompress(ctx, d_in, inputSize, d_out, outputCapacity, coder, features);
+        if (r > 0) { CUDA_TRY(cudaMemcpyAsync(output, d_out, (size_t)r, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+
+// libbsc's own signature carries no sizes (coder.h:66).  They are recovered from the container:
+// the sub-block table for nBlocks > 1; for a single sub-block the uncompressed size n is the first
+// 32 range-coded bits of the stream (qlfc.cpp:852) and the stream is shorter than n.
+int bsc_coder_decompress(const unsigned char *input, unsigned char *output, int coder, int features)
+{
+    if (coder < 1 || coder > 3) return LIBBSC_BAD_PARAMETER;
+    int nBlocks = input[0];
+    long long inSize = 0, outSize = 0;
+    if (nBlocks == 1) {
+        // decode the 32 equiprobable bits of n on the host (rangecoder.h:203-240 with p = 2048)
+        const unsigned char *p = input + 1;
+        unsigned int code = ((unsigned)p[2] | ((unsigned)p[3] << 8)) << 16 | ((unsigned)p[4] | ((unsigned)p[5] << 8));
+        unsigned int range = 0xffffffffu, nn = 0; int pos = 6;
+        for (int b = 0; b < 32; ++b) {
+            if (range < 0x10000u) { range <<= 16; code = (code << 16) | ((unsigned)p[pos] | ((unsigned)p[pos + 1] << 8)); pos += 2; }
+            unsigned int r = (range >> 12) * 2048u;
+            if (code >= r) { code -= r; range -= r; nn = (nn << 1) | 1u; } else { range = r; nn <<= 1; }
+        }
+        if (nn > 0x7fffffffu) return LIBBSC_DATA_CORRUPT;
+        outSize = nn;
+        inSize = (long long)readable_prefix(input, (size_t)nn + 1 + 16);  // the stream is < n bytes; never touch unmapped pages
+    } else {
+        if (nBlocks == 0 || nBlocks > 8) return LIBBSC_DATA_CORRUPT;
+        inSize = 1 + 8 * nBlocks;
+        for (int b = 0; b < nBlocks; ++b) { outSize += (int)get32(input + 1 + 8 * b); inSize += (int)get32(input + 5 + 8 * b); }
+    }
+    if (inSize > 0x7fffffffLL || outSize > 0x7fffffffLL) return LIBBSC_DATA_CORRUPT;
+    return bscb200_coder_decompress(input, (int)inSize, output, (int)outSize, coder, features);
+}
+
+// ---- extensions: explicit contexts and device-resident operation ------------------------------
+void *bscb200_ctx_create(int device, void *cuda_stream)
+{
+    try { return ctx_new(device, (cudaStream_t)cuda_stream, cuda_stream == nullptr); } catch (...) { cudaGetLastError(); return nullptr; }
+}
+void bscb200_ctx_destroy(void *ctx)
+{
+    Ctx *c = (Ctx *)ctx;
+    if (c) { std::lock_guard<std::mutex> lk(g_pool_mutex); g_launches_retired += c->kernels_launched; }
+    ctx_delete(c);
+}
+int bscb200_ctx_reserve(void *ctx, long long bytes)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() { CUDA_TRY(cudaSetDevice(c->device)); c->arena.reset(); c->arena.reserve((size_t)bytes); return 0; });
+}
+long long bscb200_workspace_bytes(int n, int blockSorter)
+{
+    size_t s = (blockSorter == 1 ? need_bwt_encode((size_t)n) : need_st_encode((size_t)n));
+    size_t d = need_bwt_decode((size_t)n);
+    return (long long)((s > d ? s : d) + need_coder((size_t)n) + (size_t)n + 8192);
+}
+unsigned long long bscb200_ctx_kernel_launches(void *ctx) { return ((Ctx *)ctx)->kernels_launched; }
+
+int bscb200_compress_device(void *ctx, const unsigned char *d_input, unsigned char *d_output, int n, int blockSorter, int coder, int features)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve((size_t)bscb200_workspace_bytes(n, blockSorter)); return compress_dev(c, d_input, n, d_output, blockSorter, coder, features, false); });
+}
+int bscb200_decompress_device(void *ctx, const unsigned char *d_input, int inputSize, unsigned char *d_output, int outputSize, int features)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() {
+        if (inputSize < LIBBSC_HEADER_SIZE) return LIBBSC_UNEXPECTED_EOB;
+        unsigned char h[LIBBSC_HEADER_SIZE];
+        CUDA_TRY(cudaMemcpyAsync(c->h_mail + 64, d_input, LIBBSC_HEADER_SIZE, cudaMemcpyDeviceToHost, c->stream));
+        c->sync(); memcpy(h, c->h_mail + 64, LIBBSC_HEADER_SIZE);
+        c->arena.reset(); c->arena.reserve((size_t)bscb200_workspace_bytes(outputSize, 1));
+        return decompress_dev(c, h, d_input, inputSize, d_output, outputSize, features);
+    });
+}
+int bscb200_bwt_encode_device(void *ctx, unsigned char *d_T, int n, unsigned char *num_indexes, int *indexes)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_bwt_encode((size_t)n)); return stage_bwt_encode(c, d_T, n, num_indexes, indexes); });
+}
+int bscb200_bwt_decode_device(void *ctx, unsigned char *d_T, int n, int index)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_bwt_decode((size_t)n)); int r = stage_bwt_decode(c, d_T, n, index); c->sync(); return r; });
+}
+int bscb200_st_encode_device(void *ctx, unsigned char *d_T, int n, int k)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_st_encode((size_t)n)); return stage_st_encode(c, d_T, n, k); });
+}
+int bscb200_coder_compress_device(void *ctx, const unsigned char *d_in, unsigned char *d_out, int n, int coder, int features)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_coder((size_t)n)); return stage_coder_compress(c, d_in, d_out, n, coder, features); });
+}
+int bscb200_coder_decompress_device(void *ctx, const unsigned char *d_in, int inputSize, unsigned char *d_out, int outputCapacity, int coder, int features)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_coder((size_t)outputCapacity)); return stage_coder_decompress(c, d_in, inputSize, d_out, outputCapacity, coder, features); });
+}
+unsigned int bscb200_adler32_device(void *ctx, const unsigned char *d_p, int n)
+{
+    Ctx *c = (Ctx *)ctx; unsigned int v = 0;
+    guarded(c, [&]() { v = stage_adler32(c, d_p, n); return 0; });
+    return v;
+}
+
+// total kernel launches issued through pooled + destroyed contexts (bench.py's gpu_launches)
+unsigned long long bscb200_total_kernel_launches(void)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    unsigned long long t = g_launches_retired;
+    for (int d = 0; d < MAX_DEVICES; ++d) for (Ctx *c : g_pool[d]) t += c->kernels_launched;
+    return t;
+}
+const char *bscb200_version(void) { return "libbsc_b200 0.1 (libbsc 3.3.5 block format)"; }
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// libbsc_b200/csrc/common.cuh -- shared device/host plumbing for the B200 block-sorting path.
+//
+// One `Ctx` = one CUDA stream + one bump-allocated HBM arena + small pinned mailboxes.  Every
+// stage takes a Ctx and enqueues its kernels on ctx->stream; nothing here is global except the
+// per-device context pool in api.cu.  Blocks are independent, so concurrency is
+// simply "several Ctx in flight".
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef uint8_t  u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// libbsc error codes (libbsc/libbsc.h:41-51)
+#define LIBBSC_NO_ERROR                0
+#define LIBBSC_BAD_PARAMETER          -1
+#define LIBBSC_NOT_ENOUGH_MEMORY      -2
+#define LIBBSC_NOT_COMPRESSIBLE       -3
+#define LIBBSC_NOT_SUPPORTED          -4
+#define LIBBSC_UNEXPECTED_EOB         -5
+#define LIBBSC_DATA_CORRUPT           -6
+#define LIBBSC_GPU_ERROR              -7
+#define LIBBSC_GPU_NOT_SUPPORTED      -8
+#define LIBBSC_GPU_NOT_ENOUGH_MEMORY  -9
+
+#define LIBBSC_FEATURE_FASTMODE        1
+#define LIBBSC_FEATURE_MULTITHREADING  2
+#define LIBBSC_FEATURE_LARGEPAGES      4
+#define LIBBSC_FEATURE_CUDA            8
+
+#define LIBBSC_HEADER_SIZE 28
+
+#define B200_SMS 148
+
+struct CudaFail { cudaError_t err; const char *file; int line; };
+
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+        if (getenv("BSCB200_DEBUG")) fprintf(stderr, "[libbsc_b200] %s:%d: %s -> %s\n", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+        throw CudaFail{e_, __FILE__, __LINE__}; } } while (0)
+
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline u32 ceil_div(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+static inline int bits_for(u64 max_value) { int b = 0; while (b < 64 && (max_value >> b) != 0) ++b; return b > 0 ? b : 1; }
+
+// Bump allocator over one cudaMalloc'd slab.  reset() between blocks; grows (realloc) on demand
+// only while empty, so pointers handed out stay valid for the duration of a block.
+struct Arena {
+    u8    *base = nullptr;
+    size_t cap = 0, used = 0;
+
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (used != 0) throw CudaFail{cudaErrorMemoryAllocation, __FILE__, __LINE__};
+        if (base) { cudaFree(base); base = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&base, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); throw CudaFail{cudaErrorMemoryAllocation, __FILE__, __LINE__}; }
+        cap = bytes;
+    }
+    template <typename T> T *get(size_t count) {
+        size_t bytes = align_up(count * sizeof(T) + 256, 256);      // 256 B slack after every buffer
+        if (used + bytes > cap) throw CudaFail{cudaErrorMemoryAllocation, __FILE__, __LINE__};
+        T *p = (T *)(base + used); used += bytes; return p;
+    }
+    size_t mark() const { return used; }
+    void release(size_t m) { used = m; }
+    void reset() { used = 0; }
+    void destroy() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
+};
+
+struct Ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    bool         owns_stream = false;
+    Arena        arena;
+    u32         *h_mail = nullptr;      // pinned host mailbox (64 words) for small D2H read-backs
+    u32         *d_mail = nullptr;      // device mailbox (64 words)
+    u8          *h_stage = nullptr;     // pinned staging for host<->device block copies
+    size_t       h_stage_cap = 0;
+    void        *qlfc_tables = nullptr; // device copy of the QLFC state tables (lazily uploaded)
+    u64          kernels_launched = 0;  // our own kernel launches enqueued through this ctx
+
+    void sync() { CUDA_TRY(cudaStreamSynchronize(stream)); }
+    // Read `words` u32 from the device mailbox (blocks the host on this stream only).
+    void fetch_mail(int words) {
+        CUDA_TRY(cudaMemcpyAsync(h_mail, d_mail, sizeof(u32) * words, cudaMemcpyDeviceToHost, stream));
+        sync();
+    }
+    u8 *stage(size_t bytes) {
+        if (bytes > h_stage_cap) {
+            if (h_stage) cudaFreeHost(h_stage);
+            h_stage = nullptr; h_stage_cap = 0;
+            size_t want = align_up(bytes + (bytes >> 3) + 65536, 1 << 20);
+            CUDA_TRY(cudaMallocHost((void **)&h_stage, want));
+            h_stage_cap = want;
+        }
+        return h_stage;
+    }
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); KERNEL_CHECK(); (ctx)->kernels_launched++; } while (0)
+
+// ---- small device helpers ------------------------------------------------------------------
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// relaxed, device-scope single-word accesses for decoupled look-back descriptors
+__device__ __forceinline__ u64 ld_relaxed(const u64 *p) { u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_relaxed(u64 *p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+
+// streaming 128-bit loads that do not pollute L1 (inputs that are read exactly once)
+__device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
+    uint4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}

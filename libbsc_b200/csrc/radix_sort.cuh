@@ -1,0 +1,280 @@
+// libbsc_b200/csrc/radix_sort.cuh -- device-wide stable LSD radix sort, "onesweep" style.
+//
+// This is the workhorse of the forward BWT (prefix-doubling suffix sort) and of ST-k.  It replaces
+// the reference's cub::DeviceRadixSort / DeviceSegmentedSort calls (libcubwt.cu:713-739,
+// 1686-1703, 2136-2163; st.cu:187-193, 273-279) with our own kernels:
+//
+//   rs_histogram  : ONE read of the keys builds the 256-bin histograms of every digit pass.
+//   rs_scan       : exclusive scan of each pass's histogram -> global digit bases.
+//   rs_onesweep   : per digit pass, ONE read + ONE write of every (key,value): each CTA ranks a
+//                   tile with warp match-any multisplit, obtains its per-digit global offsets by
+//                   decoupled look-back over the preceding tiles (single pass, no separate
+//                   upsweep), reorders the tile in shared memory and stores digit-contiguous,
+//                   fully coalesced runs.
+//
+// Keys come from a "source" functor so that the first pass can synthesise keys on the fly (text
+// 8-grams, ST context words) instead of reading a materialised key array: that removes one write
+// + two reads of 8n bytes from every sort.
+//
+// HBM traffic per pass: (sizeof(K) + 4) bytes read + the same written per element -- the
+// algorithmic floor for an LSD pass -- plus 2 KB of look-back descriptors per 4096-element tile.
+#pragma once
+
+#include "common.cuh"
+
+#define RS_THREADS 256
+#define RS_ITEMS   16
+#define RS_TILE    (RS_THREADS * RS_ITEMS)
+#define RS_WARPS   (RS_THREADS / 32)
+#define RS_MAX_PASSES 8
+
+struct DigitPasses {
+    int count;
+    unsigned char shift[RS_MAX_PASSES];
+    unsigned char bits[RS_MAX_PASSES];
+};
+
+// Build the list of <=8-bit digit passes covering key bit ranges [lo0,hi0) then [lo1,hi1) (LSD order).
+static inline DigitPasses make_passes(int lo0, int hi0, int lo1 = 0, int hi1 = 0)
+{
+    DigitPasses p; p.count = 0;
+    int lo[2] = {lo0, lo1}, hi[2] = {hi0, hi1};
+    for (int f = 0; f < 2; ++f) {
+        int total = hi[f] - lo[f];
+        if (total <= 0) continue;
+        int np = (total + 7) / 8;
+        for (int s = lo[f], k = 0; k < np; ++k) {      // spread the bits evenly over the passes
+            int b = (total + np - 1 - k) / np; if (b > hi[f] - s) b = hi[f] - s;
+            p.shift[p.count] = (unsigned char)s; p.bits[p.count] = (unsigned char)b; p.count++; s += b;
+        }
+    }
+    return p;
+}
+
+// ---- key sources ---------------------------------------------------------------------------
+template <typename K, bool HAS_VAL> struct SrcArray {
+    const K *keys; const u32 *vals;
+    __device__ __forceinline__ K   key(u32 i) const { return keys[i]; }
+    __device__ __forceinline__ u32 val(u32 i) const { return HAS_VAL ? vals[i] : 0u; }
+};
+
+// 8 bytes T[pos..pos+7] as one big-endian word.  T must be 8-byte aligned and readable (zero
+// padded) up to pos+15.
+__device__ __forceinline__ u64 load_be64(const u8 *T, u32 pos)
+{
+    const u64 *W = (const u64 *)T;
+    u64 a = W[pos >> 3], b = W[(pos >> 3) + 1];
+    u32 sh = (pos & 7u) * 8u;
+    u64 v = sh ? ((a >> sh) | (b << (64u - sh))) : a;   // little-endian bytes pos..pos+7
+    u32 lo = (u32)v, hi = (u32)(v >> 32);
+    return ((u64)__byte_perm(lo, 0, 0x0123) << 32) | (u64)__byte_perm(hi, 0, 0x0123);
+}
+
+// ---- histogram of all digit passes in one read ------------------------------------------------
+template <class Src>
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram(Src src, u32 n, DigitPasses passes, u32 *ghist)
+{
+    __shared__ u32 sh[RS_MAX_PASSES * 256];
+    for (int i = threadIdx.x; i < passes.count * 256; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    const u32 stride = gridDim.x * RS_THREADS;
+    for (u32 i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
+        auto k = src.key(i);
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASSES; ++p) {
+            if (p < passes.count) {
+                u32 d = (u32)(k >> passes.shift[p]) & ((1u << passes.bits[p]) - 1u);
+                // warp-aggregate equal digits (text keys are extremely skewed in the high bytes)
+                u32 m = __match_any_sync(__activemask(), d);
+                if ((m & lanemask_lt()) == 0) atomicAdd(&sh[p * 256 + d], __popc(m));
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes.count * 256; i += RS_THREADS) if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+}
+
+static __global__ void rs_scan(u32 *ghist, int npasses)
+{
+    // one warp per pass; 256 bins = 8 per lane
+    int p = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p >= npasses) return;
+    u32 *h = ghist + p * 256;
+    u32 v[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = h[lane * 8 + j]; sum += v[j]; }
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    u32 run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { h[lane * 8 + j] = run; run += v[j]; }
+}
+
+// ---- one digit pass ------------------------------------------------------------------------
+#define RS_FLAG_AGG    (1ull << 62)
+#define RS_FLAG_PREFIX (2ull << 62)
+#define RS_FLAG_MASK   (3ull << 62)
+
+template <typename K> __device__ __forceinline__ K rs_all_ones();
+template <> __device__ __forceinline__ u64 rs_all_ones<u64>() { return ~0ull; }
+template <> __device__ __forceinline__ u32 rs_all_ones<u32>() { return ~0u; }
+
+template <typename K, bool HAS_VAL> struct RsSmem {
+    u32 whist[RS_WARPS][256];
+    u32 dstart[256];
+    u32 gbase[256];
+    u32 scan_tmp[RS_WARPS];
+    u32 tile;
+    K   keys[RS_TILE];
+    u32 vals[HAS_VAL ? RS_TILE : 1];
+};
+
+template <typename K, bool HAS_VAL, class Src>
+__global__ void __launch_bounds__(RS_THREADS, 3)
+rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int shift, int bits,
+            const u32 *__restrict__ gbase_in, u32 *tile_counter, u64 *lookback)
+{
+    extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+    RsSmem<K, HAS_VAL> &S = *reinterpret_cast<RsSmem<K, HAS_VAL> *>(rs_smem_raw);
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 dmask = (1u << bits) - 1u;
+
+    if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&S.whist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 tile = S.tile;
+    const u32 base = tile * RS_TILE;                     // n <= 2^30 so this cannot overflow
+    const u32 valid = min((u32)RS_TILE, n - base);
+    const u32 wbase = warp * (32 * RS_ITEMS) + lane;     // warp-striped: item i of this lane = wbase + 32*i
+
+    K keys[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        u32 off = wbase + 32 * i;
+        keys[i] = off < valid ? src.key(base + off) : rs_all_ones<K>();
+    }
+
+    // --- warp-level multisplit ranking (stable: items in (i, lane) order) ---
+    u32 pos[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        u32 d = (u32)(keys[i] >> shift) & dmask;
+        u32 m = __match_any_sync(0xffffffffu, d);
+        u32 leader = __ffs(m) - 1;
+        u32 pre = 0;
+        if (lane == leader) { pre = S.whist[warp][d]; S.whist[warp][d] = pre + __popc(m); }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        pos[i] = pre + __popc(m & lanemask_lt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // --- per digit (thread = digit): warp offsets, tile offsets, decoupled look-back ---
+    {
+        const u32 d = tid;                               // RS_THREADS == 256 digits
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { u32 t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
+        const u32 count = run;
+        // block exclusive scan of `count` over the 256 digits
+        u32 incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) S.scan_tmp[warp] = incl;
+        __syncthreads();
+        u32 woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) if (w < (int)warp) woff += S.scan_tmp[w];
+        const u32 excl = woff + incl - count;
+        S.dstart[d] = excl;
+
+        u64 *mine = lookback + (size_t)tile * 256 + d;
+        u32 gexcl = 0;
+        if (tile == 0) {
+            st_relaxed(mine, RS_FLAG_PREFIX | (u64)count);
+        } else {
+            st_relaxed(mine, RS_FLAG_AGG | (u64)count);
+            for (u32 t = tile; t-- > 0; ) {
+                const u64 *theirs = lookback + (size_t)t * 256 + d;
+                u64 v;
+                do { v = ld_relaxed(theirs); } while ((v & RS_FLAG_MASK) == 0);
+                gexcl += (u32)v;
+                if ((v & RS_FLAG_MASK) == RS_FLAG_PREFIX) break;
+            }
+            st_relaxed(mine, RS_FLAG_PREFIX | (u64)(gexcl + count));
+        }
+        S.gbase[d] = gbase_in[d] + gexcl - excl;         // u32 wrap-around arithmetic is intended
+    }
+    __syncthreads();
+
+    // --- reorder the tile in shared memory, then store digit-contiguous runs ---
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        u32 d = (u32)(keys[i] >> shift) & dmask;
+        pos[i] += S.dstart[d] + S.whist[warp][d];
+        S.keys[pos[i]] = keys[i];
+    }
+    if (HAS_VAL) {
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            u32 off = wbase + 32 * i;
+            if (off < valid) S.vals[pos[i]] = src.val(base + off);
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (u32 j = tid; j < valid; j += RS_THREADS) {
+        K k = S.keys[j];
+        u32 d = (u32)(k >> shift) & dmask;
+        u32 g = S.gbase[d] + j;
+        kout[g] = k;
+        if (HAS_VAL) vout[g] = S.vals[j];
+    }
+}
+
+// ---- host driver ---------------------------------------------------------------------------
+// Scratch needed by one sort (histograms, tile counters, look-back descriptors).
+static inline size_t rs_scratch_bytes(u32 n, int npasses)
+{
+    size_t tiles = ceil_div(n, RS_TILE);
+    return align_up(sizeof(u32) * 256 * RS_MAX_PASSES + sizeof(u32) * 64, 256) + (size_t)npasses * tiles * 256 * sizeof(u64);
+}
+
+// Sort n elements.  Pass 0 reads from `first`; later passes ping-pong between (k[0],v[0]) and
+// (k[1],v[1]), pass p writing to buffer (p & 1).  Returns the index of the buffer holding the
+// sorted result.  `scratch` must hold rs_scratch_bytes(n, passes.count).
+template <typename K, bool HAS_VAL, class FirstSrc>
+static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32 n, const DigitPasses &passes, void *scratch)
+{
+    if (passes.count == 0 || n == 0) return -1;
+    const u32 tiles = ceil_div(n, RS_TILE);
+    u32 *ghist = (u32 *)scratch;
+    u32 *counters = ghist + 256 * RS_MAX_PASSES;
+    u64 *lookback = (u64 *)((u8 *)scratch + align_up(sizeof(u32) * 256 * RS_MAX_PASSES + sizeof(u32) * 64, 256));
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, rs_scratch_bytes(n, passes.count), ctx->stream));
+
+    u32 hgrid = min(tiles, (u32)(B200_SMS * 8));
+    LAUNCH(ctx, (rs_histogram<FirstSrc>), hgrid, RS_THREADS, 0, first, n, passes, ghist);
+    LAUNCH(ctx, rs_scan, 1, 32 * RS_MAX_PASSES, 0, ghist, passes.count);
+
+    const size_t smem = sizeof(RsSmem<K, HAS_VAL>);
+    // (per device, cheap) allow the > 48 KB dynamic shared memory the tile needs
+    CUDA_TRY(cudaFuncSetAttribute(rs_onesweep<K, HAS_VAL, FirstSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    for (int p = 0; p < passes.count; ++p) {
+        int dst = p & 1;
+        u64 *lb = lookback + (size_t)p * tiles * 256;
+        if (p == 0) {
+            LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, FirstSrc>), tiles, RS_THREADS, smem,
+                   first, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, counters + p, lb);
+        } else {
+            SrcArray<K, HAS_VAL> src{k[dst ^ 1], v[dst ^ 1]};
+            LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>), tiles, RS_THREADS, smem,
+                   src, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, counters + p, lb);
+        }
+    }
+    return (passes.count - 1) & 1;
+}

@@ -1,0 +1,177 @@
+"""GPU parity tests (run on the B200 box): every stage of the CUDA path, called through the C ABI
+(host-pointer bsc_* entry points of include/libbsc_b200.h), must be bit-identical to the oracle --
+the unmodified reference when oracle/_ref was built, else our C port -- on the same seeded inputs,
+to the known-answer values of SURVEY.md Appendix C at BASELINE.json's full sizes, and must satisfy
+the size-independent round-trip properties."""
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def small_inputs(gen):
+    rng = np.random.default_rng(11)
+    yield "text300k", gen.text(7, 300000)
+    yield "text1M", gen.text(2, 1 << 20)
+    yield "skew300k", gen.skew(3, 300000)
+    yield "rand70k", gen.rand(1, 70000)
+    yield "alpha4", rng.integers(0, 4, 5000, dtype=np.uint8)
+    yield "alpha2_64k", rng.integers(0, 2, 65536, dtype=np.uint8)
+    yield "allsame3000", np.full(3000, 65, dtype=np.uint8)
+    yield "zeros1000", np.zeros(1000, dtype=np.uint8)
+    yield "period7", np.tile(np.frombuffer(b"abcabcd", dtype=np.uint8), 3000)
+    yield "withzeros", np.concatenate([gen.text(3, 5000), np.zeros(40, np.uint8), gen.text(4, 3000), np.zeros(9, np.uint8)])
+    yield "ragged4097", gen.text(8, 4097)
+    yield "tiny29", gen.text(1, 29)
+    yield "tiny100", gen.text(1, 100)
+
+
+def test_adler32_device(bsc):
+    rng = np.random.default_rng(3)
+    for n in (1 << 16, (1 << 16) + 1, 100000, (1 << 20) + 37, 5 << 20):
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        assert bsc.adler32(a) == zlib.adler32(a.tobytes()), n
+    assert bsc.adler32(np.full(3 << 20, 255, dtype=np.uint8)) == zlib.adler32(b"\xff" * (3 << 20))
+
+
+def test_st_encode_matches_oracle(bsc, gen, port, checker):
+    for name, a in small_inputs(gen):
+        for k in (3, 4, 5, 6, 7, 8):
+            ref_impl = checker if k <= 6 else port          # k = 7, 8 exist only in the reference's CUDA build
+            i2, L2 = ref_impl.st_encode(a, k)
+            i1, L1 = bsc.st_encode(a, k)
+            assert i1 == i2, (name, k, i1, i2)
+            assert np.array_equal(L1, L2), (name, k)
+
+
+def test_st_tiny_sizes(bsc, port):
+    for n in (2, 3, 4, 5, 7, 8, 9, 16, 17):
+        a = ((np.arange(n) * 5 + 1) % 3).astype(np.uint8)
+        for k in (3, 6, 8):
+            i2, L2 = port.st_encode(a, k)
+            i1, L1 = bsc.st_encode(a, k)
+            assert i1 == i2 and np.array_equal(L1, L2), (n, k)
+
+
+def test_bwt_encode_matches_oracle(bsc, gen, checker):
+    for name, a in small_inputs(gen):
+        r2, L2, x2 = checker.bwt_encode(a)
+        r1, L1, x1 = bsc.bwt_encode(a)
+        assert r1 == r2, (name, r1, r2)
+        assert x1 == x2, (name, x1, x2)
+        assert np.array_equal(L1, L2), name
+
+
+def test_bwt_small_n_conventions(bsc, port):
+    for n in (0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 33):
+        a = ((np.arange(n) * 7 + 3) % 5).astype(np.uint8)
+        assert bsc.bwt_encode(a, aux=True)[0] == port.bwt_encode(a, aux=True)[0], n
+        r1, L1, _ = bsc.bwt_encode(a, aux=False)
+        r2, L2, _ = port.bwt_encode(a, aux=False)
+        assert r1 == r2 and np.array_equal(L1, L2), n
+
+
+def test_bwt_decode_matches_oracle(bsc, gen, checker):
+    for name, a in small_inputs(gen):
+        r, L, _ = checker.bwt_encode(a)
+        d, T = bsc.bwt_decode(L, r)
+        assert d == 0 and np.array_equal(T, a), name
+    assert bsc.bwt_decode(np.zeros(10, np.uint8), 0)[0] == -1
+    assert bsc.bwt_decode(np.zeros(10, np.uint8), 11)[0] == -1
+
+
+def test_coder_compress_matches_oracle(bsc, gen, checker):
+    for name, a in list(small_inputs(gen)) + [("text5M", gen.text(9, 5 << 20))]:
+        _, L, _ = checker.bwt_encode(a)
+        for feats in (3, 1):
+            c2, s2 = checker.coder_compress(L, 1, feats)
+            c1, s1 = bsc.coder_compress(L, 1, feats)
+            assert c1 == c2, (name, feats, c1, c2)
+            if c2 > 0:
+                assert np.array_equal(s1, s2), (name, feats)
+
+
+def test_coder_decompress_matches_oracle(bsc, gen, checker):
+    for name, a in list(small_inputs(gen)) + [("text5M", gen.text(9, 5 << 20))]:
+        _, L, _ = checker.bwt_encode(a)
+        c, s = checker.coder_compress(L, 1, 3)
+        if c <= 0:
+            continue
+        n, out = bsc.coder_decompress(s, L.size)
+        assert n == L.size, (name, n)
+        assert np.array_equal(out, L), name
+
+
+def test_block_bytes_and_cross_decoding(bsc, gen, checker):
+    for name, a in small_inputs(gen):
+        for sorter in (1, 6):
+            z2, b2 = checker.compress(a, sorter, 1, 3)
+            z1, b1 = bsc.compress(a, sorter, 1, 3)
+            assert z1 == z2, (name, sorter, z1, z2)
+            assert np.array_equal(b1, b2), (name, sorter)
+        z, blk = bsc.compress(a, 1, 1, 3)
+        q, u = checker.decompress(blk)                    # ours -> reference decoder
+        assert q == 0 and np.array_equal(u, a), name
+        z, blk = checker.compress(a, 1, 1, 3)
+        q, u = bsc.decompress(blk)                        # reference -> our decoder
+        assert q == 0 and np.array_equal(u, a), name
+
+
+def test_error_codes(bsc, gen):
+    a = gen.text(1, 1000)
+    assert bsc.compress(a, sorter=2)[0] == -1
+    assert bsc.compress(a, coder=0)[0] == -1
+    assert bsc.compress(a, lzp_hash=15, lzp_min=128)[0] == -4     # LZP is outside the replaced path
+    assert bsc.compress(a, lzp_hash=5, lzp_min=128)[0] == -1
+    z, blk = bsc.compress(a)
+    bad = blk.copy(); bad[40] ^= 1
+    assert bsc.decompress(bad)[0] == -6
+    bad = blk.copy(); bad[3] ^= 1
+    assert bsc.block_info(bad)[0] == -6
+    r, s = bsc.compress(gen.text(1, 20))                          # n <= 28: stored
+    assert r == 48 and int.from_bytes(bytes(s[8:12]), "little") == 0
+
+
+def test_k1_random_block_is_stored(bsc, gen):
+    a = gen.rand(1, 1048576)
+    r, L, aux = bsc.bwt_encode(a)
+    assert r == 791385 and aux == [633903, 252159, 118572, 805028, 426935, 565037, 575571]
+    assert gen.adler32(L) == 0x5ce80fec
+    assert bsc.coder_compress(L, 1, 3)[0] == -3
+    z, blk = bsc.compress(a)
+    assert z == 1048604 and gen.adler32(blk) == 0x242115a8
+    q, u = bsc.decompress(blk)
+    assert q == 0 and np.array_equal(u, a)
+
+
+def test_k2_text_25mb(bsc, gen):
+    a = gen.text(2, 26214400)
+    r, L, aux = bsc.bwt_encode(a)
+    assert r == 4197692
+    assert aux == [19656645, 17965358, 3119786, 16132698, 10774871, 18082751, 1296587, 1120570, 2626855, 2680633, 25151113, 17332296]
+    assert gen.adler32(L) == 0x77ffc0f7
+    c, s = bsc.coder_compress(L, 1, 3)
+    assert c == 5019497 and gen.adler32(s) == 0xe6f2f8c5
+    z, blk = bsc.compress(a)
+    assert z == 5019574 and gen.adler32(blk) == 0xed300f73
+    q, u = bsc.decompress(blk)
+    assert q == 0 and np.array_equal(u, a)
+
+
+def test_k3_text_64mb(bsc, gen):
+    a = gen.text(2, 67108864)
+    z, blk = bsc.compress(a)
+    assert z == 12686186 and gen.adler32(blk) == 0xf21848c1
+    assert int.from_bytes(bytes(blk[12:16]), "little") == 10745360
+    q, u = bsc.decompress(blk)
+    assert q == 0 and np.array_equal(u, a)
+
+
+def test_k5_st6_skew_32mb(bsc, gen):
+    a = gen.skew(3, 33554432)
+    i, L = bsc.st_encode(a, 6)
+    assert i == 28690215 and gen.adler32(L) == 0x3141fea1
+    z, blk = bsc.compress(a, sorter=6)
+    assert z == 32294018 and gen.adler32(blk) == 0x8d12e56b

@@ -1,0 +1,141 @@
+"""CPU-only tests: the oracle is pinned against the known-answer values of SURVEY.md Appendix C and
+against the unmodified reference (oracle/_ref, when built); the C-ABI library loads and exports
+every symbol include/libbsc_b200.h declares.  No GPU work here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- generators (Appendix C adler32 values) -------------------------------------------------
+def test_generators_match_appendix_c(gen):
+    assert gen.adler32(gen.rand(1, 1048576)) == 0x90fa0fec
+    assert gen.adler32(gen.skew(3, 1 << 22)) == gen.adler32(gen.skew(3, 33554432)[: 1 << 22])
+    t = gen.text(2, 4 << 20)
+    assert bytes(t[:8]) == b"Oumrefue"
+    assert gen.adler32(t) == gen.adler32(gen.text(2, 6 << 20)[: 4 << 20])     # sequential generator
+
+
+@pytest.mark.slow
+def test_generators_full_kats(gen):
+    assert gen.adler32(gen.skew(3, 33554432)) == 0x82fefea1
+    t = gen.text(2, 67108864)
+    assert gen.adler32(t) == 0x2762809f
+    assert gen.adler32(t[:26214400]) == 0x5cf8c0f7
+
+
+# ---- K1 known answers (1 MiB random) against the port ---------------------------------------
+def test_port_k1(gen, port):
+    a = gen.rand(1, 1048576)
+    idx, L, aux = port.bwt_encode(a)
+    assert idx == 791385
+    assert aux == [633903, 252159, 118572, 805028, 426935, 565037, 575571]
+    assert gen.adler32(L) == 0x5ce80fec
+    r, _ = port.coder_compress(L, 1, 3)
+    assert r == -3
+    r, blk = port.compress(a, 1, 1, 3)
+    assert r == 1048604 and gen.adler32(blk) == 0x242115a8
+    assert int.from_bytes(bytes(blk[8:12]), "little") == 0                   # stored block
+
+
+def test_port_k5_prefix_st6(gen, port, ref):
+    a = gen.skew(3, 1 << 20)
+    i1, L1 = port.st_encode(a, 6)
+    i2, L2 = ref.st_encode(a, 6)
+    assert i1 == i2 and np.array_equal(L1, L2)
+
+
+# ---- port vs unmodified reference -----------------------------------------------------------
+def _inputs(gen):
+    rng = np.random.default_rng(0)
+    yield "text300k", gen.text(7, 300000)
+    yield "text1M", gen.text(2, 1 << 20)
+    yield "skew300k", gen.skew(3, 300000)
+    yield "rand70k", gen.rand(1, 70000)
+    yield "alpha4", rng.integers(0, 4, 5000, dtype=np.uint8)
+    yield "allsame", np.full(3000, 65, dtype=np.uint8)
+    yield "zeros", np.zeros(1000, dtype=np.uint8)
+    yield "tiny29", gen.text(1, 29)
+    yield "tiny100", gen.text(1, 100)
+    yield "withzeros", np.concatenate([gen.text(3, 5000), np.zeros(40, np.uint8), gen.text(4, 3000), np.zeros(9, np.uint8)])
+
+
+def test_port_matches_reference_stages(gen, port, ref):
+    for name, a in _inputs(gen):
+        r1, L1, i1 = port.bwt_encode(a)
+        r2, L2, i2 = ref.bwt_encode(a)
+        assert r1 == r2 and i1 == i2 and np.array_equal(L1, L2), name
+        d, T = port.bwt_decode(L2, r2)
+        assert d == 0 and np.array_equal(T, a), name
+        for feats in (1, 3):
+            c1, s1 = port.coder_compress(L2, 1, feats)
+            c2, s2 = ref.coder_compress(L2, 1, feats)
+            assert c1 == c2, (name, feats)
+            if c2 > 0:
+                assert np.array_equal(s1, s2), (name, feats)
+                n1, o1 = port.coder_decompress(s2, a.size)
+                assert n1 == a.size and np.array_equal(o1, L2), name
+        for k in (3, 4, 5, 6):
+            x1, y1 = port.st_encode(a, k)
+            x2, y2 = ref.st_encode(a, k)
+            assert x1 == x2 and np.array_equal(y1, y2), (name, k)
+
+
+def test_port_matches_reference_blocks(gen, port, ref):
+    for name, a in _inputs(gen):
+        for sorter in (1, 5):
+            z1, b1 = port.compress(a, sorter, 1, 3)
+            z2, b2 = ref.compress(a, sorter, 1, 3)
+            assert z1 == z2 and np.array_equal(b1, b2), (name, sorter)
+        z, b = ref.compress(a, 1, 1, 3)
+        q, u = port.decompress(b)
+        assert q == 0 and np.array_equal(u, a), name
+
+
+def test_port_transform_and_split(gen, port, ref):
+    a = gen.text(5, 400000)
+    _, L, _ = ref.bwt_encode(a)
+    ranks, mtf = port.transform(L)
+    assert ranks.size > 0 and ranks[-1] == 1
+    st, sz = port.split_blocks(L, 2)
+    assert st[0] == 0 and st[1] == sz[0] and sz[0] + sz[1] == L.size
+    # single sub-block streams of the port equal the reference's
+    for piece in (L[:st[1]], L[st[1]:]):
+        r1, s1 = port.encode_block(piece)
+        r2, s2 = ref.encode_block(piece)
+        assert r1 == r2 and np.array_equal(s1, s2)
+
+
+def test_small_n_bwt_conventions(port, ref):
+    for n in (0, 1, 2, 3, 7, 8, 15, 16, 17, 31, 33):
+        a = (np.arange(n, dtype=np.uint8) * 7 + 3) % 5
+        assert port.bwt_encode(a, aux=True)[0] == ref.bwt_encode(a, aux=True)[0], n
+        r1, L1, _ = port.bwt_encode(a, aux=False)
+        r2, L2, _ = ref.bwt_encode(a, aux=False)
+        assert r1 == r2 and np.array_equal(L1, L2), n
+
+
+# ---- boundary: the library loads and exports the declared ABI -------------------------------
+def test_library_exports_declared_abi():
+    import libbsc_b200
+    assert os.path.exists(libbsc_b200.LIB_PATH), "run __graft_entry__.build() first"
+    L = ctypes.CDLL(libbsc_b200.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "libbsc_b200.h")).read()
+    declared = set(re.findall(r"\b(bsc_\w+|bscb200_\w+)\s*\(", header))
+    assert len(declared) >= 35
+    for name in sorted(declared):
+        assert hasattr(L, name), "missing export: " + name
+    assert declared == set(libbsc_b200.EXPORTED_SYMBOLS)
+
+
+def test_host_only_entry_points_need_no_gpu():
+    """Pure header logic (no device work): bsc_block_info validation mirrors libbsc.cpp:340-418."""
+    import libbsc_b200
+    L = libbsc_b200.lib()
+    hdr = np.zeros(28, dtype=np.uint8)
+    assert L.bsc_block_info(hdr.ctypes.data, 10, None, None, 0) == -5          # UNEXPECTED_EOB
+    assert L.bsc_block_info(hdr.ctypes.data, 28, None, None, 0) == -6          # bad header adler
