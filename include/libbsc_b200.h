@@ -100,6 +100,9 @@ int                bscb200_ctx_reserve(void *ctx, long long bytes);
 long long          bscb200_workspace_bytes(int n, int blockSorter);
 unsigned long long bscb200_ctx_kernel_launches(void *ctx);
 unsigned long long bscb200_total_kernel_launches(void);
+/* per-kernel CUDA-event timing of everything launched through ctx (bench.py's roofline leg) */
+void               bscb200_ctx_set_profile(void *ctx, int on);
+int                bscb200_ctx_profile_report(void *ctx, char *buf, int cap);
 const char        *bscb200_version(void);
 
 /* Device-resident variants: all d_* pointers are device pointers on the context's device.

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "bscb200_workspace_bytes": ([ci, ci], ctypes.c_longlong),
     "bscb200_ctx_kernel_launches": ([vp], ctypes.c_ulonglong),
     "bscb200_total_kernel_launches": ([], ctypes.c_ulonglong),
+    "bscb200_ctx_set_profile": ([vp, ci], None),
+    "bscb200_ctx_profile_report": ([vp, ctypes.c_char_p, ci], ci),
     "bscb200_version": ([], ctypes.c_char_p),
     "bscb200_compress_device": ([vp, vp, vp, ci, ci, ci, ci], ci),
     "bscb200_decompress_device": ([vp, vp, ci, vp, ci, ci], ci),
@@ -187,6 +189,22 @@ class DeviceCtx:
 
     def launches(self):
         return int(self.lib.bscb200_ctx_kernel_launches(self.handle))
+
+    def set_profile(self, on):
+        self.lib.bscb200_ctx_set_profile(self.handle, 1 if on else 0)
+
+    def profile_report(self):
+        """{kernel name: (launches, total_ms, algorithmic_bytes)} since set_profile(True)."""
+        import re
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self.lib.bscb200_ctx_profile_report(self.handle, buf, len(buf))
+        out = {}
+        for line in buf.raw[:n].decode().splitlines():
+            name, cnt, ms, b = line.split("\t")
+            name = re.match(r"\(?\s*([A-Za-z_0-9]+)", name).group(1)
+            c0, m0, b0 = out.get(name, (0, 0.0, 0.0))
+            out[name] = (c0 + int(cnt), m0 + float(ms), b0 + float(b))
+        return out
 
     def compress(self, d_in, d_out, n, sorter=1, coder=1, features=3):
         return self.lib.bscb200_compress_device(self.handle, d_in, d_out, n, sorter, coder, features)

@@ -58,6 +58,7 @@ void ctx_delete(Ctx *c)
     if (c->d_mail) cudaFree(c->d_mail);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->qlfc_tables) cudaFree(c->qlfc_tables);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -535,6 +536,30 @@ unsigned int bscb200_adler32_device(void *ctx, const unsigned char *d_p, int n)
     Ctx *c = (Ctx *)ctx; unsigned int v = 0;
     guarded(c, [&]() { v = stage_adler32(c, d_p, n); return 0; });
     return v;
+}
+
+// Per-kernel timing: bracket every launch of this context with CUDA events on its stream.
+void bscb200_ctx_set_profile(void *ctx, int on)
+{
+    Ctx *c = (Ctx *)ctx; c->profile = on != 0; c->prof.clear(); c->ev_used = 0;
+}
+// Writes one line per kernel name: "<name>\t<launches>\t<total_ms>\t<algorithmic_bytes>\n"; returns bytes written.
+int bscb200_ctx_profile_report(void *ctx, char *buf, int cap)
+{
+    Ctx *c = (Ctx *)ctx;
+    cudaStreamSynchronize(c->stream);
+    struct Acc { const char *name; int n; double ms, bytes; };
+    std::vector<Acc> acc;
+    for (const ProfRec &r : c->prof) {
+        float ms = 0; if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        size_t i = 0; for (; i < acc.size(); ++i) if (strcmp(acc[i].name, r.name) == 0) break;
+        if (i == acc.size()) acc.push_back(Acc{r.name, 0, 0, 0});
+        acc[i].n++; acc[i].ms += ms; acc[i].bytes += r.bytes;
+    }
+    int w = 0;
+    for (const Acc &a : acc) { int k = snprintf(buf + w, cap > w ? (size_t)(cap - w) : 0, "%s\t%d\t%.6f\t%.0f\n", a.name, a.n, a.ms, a.bytes); if (k < 0 || w + k >= cap) break; w += k; }
+    c->prof.clear(); c->ev_used = 0;
+    return w;
 }
 
 // total kernel launches issued through pooled + destroyed contexts (bench.py's gpu_launches)

@@ -197,8 +197,10 @@ int stage_bwt_decode(Ctx *ctx, u8 *d_T, int n_, int index_)
 
     LAUNCH(ctx, unbwt_hist, min(ceil_div(n, 256 * 64), (u32)(B200_SMS * 8)), 256, 0, Lp, n, hist);
     LAUNCH(ctx, unbwt_scan256, 1, 32, 0, hist);
+    PROF_BYTES(ctx, 5.0 * n);
     LAUNCH(ctx, unbwt_lf, tiles, LF_THREADS, 0, Lp, n, index, hist, hist + 256, lb, LF);
 
+    PROF_BYTES(ctx, 4.0 * n);
     LAUNCH(ctx, unbwt_walk<false>, ceil_div(K, 256), 256, 0, LF, Lp, n, index, stride, K, dist[0], next[0], (const u32 *)nullptr, (u8 *)nullptr);
     LAUNCH(ctx, unbwt_init_sentinel, 1, 1, 0, dist[0], next[0], K);
     int cur = 0;
@@ -206,6 +208,7 @@ int stage_bwt_decode(Ctx *ctx, u8 *d_T, int n_, int index_)
         LAUNCH(ctx, unbwt_jump, ceil_div(K + 1, 256), 256, 0, dist[cur], next[cur], dist[cur ^ 1], next[cur ^ 1], K);
         cur ^= 1;
     }
+    PROF_BYTES(ctx, 6.0 * n);
     LAUNCH(ctx, unbwt_walk<true>, ceil_div(K, 256), 256, 0, LF, Lp, n, index, stride, K, (u32 *)nullptr, (u32 *)nullptr, dist[cur], d_T);
     A.release(mark);
     return LIBBSC_NO_ERROR;

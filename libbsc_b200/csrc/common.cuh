@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <vector>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -75,6 +76,9 @@ struct Arena {
     void destroy() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
 };
 
+// one timed kernel launch (profiling mode only): CUDA events on the launching stream
+struct ProfRec { const char *name; cudaEvent_t a, b; double bytes; };
+
 struct Ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
@@ -86,6 +90,15 @@ struct Ctx {
     size_t       h_stage_cap = 0;
     void        *qlfc_tables = nullptr; // device copy of the QLFC state tables (lazily uploaded)
     u64          kernels_launched = 0;  // our own kernel launches enqueued through this ctx
+    bool         profile = false;       // bracket every launch with CUDA events (bench.py roofline leg)
+    double       next_bytes = 0;        // algorithmic bytes of the next launch (PROF_BYTES)
+    std::vector<ProfRec>     prof;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t       ev_used = 0;
+    cudaEvent_t ev() {
+        if (ev_used == ev_pool.size()) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ev_pool.push_back(e); }
+        return ev_pool[ev_used++];
+    }
 
     void sync() { CUDA_TRY(cudaStreamSynchronize(stream)); }
     // Read `words` u32 from the device mailbox (blocks the host on this stream only).
@@ -105,8 +118,13 @@ struct Ctx {
     }
 };
 
+#define PROF_BYTES(ctx, b) do { (ctx)->next_bytes = (double)(b); } while (0)
 #define LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); KERNEL_CHECK(); (ctx)->kernels_launched++; } while (0)
+        Ctx *c_ = (ctx); cudaEvent_t ea_ = nullptr, eb_ = nullptr; const bool p_ = c_->profile; \
+        if (p_) { ea_ = c_->ev(); eb_ = c_->ev(); CUDA_TRY(cudaEventRecord(ea_, c_->stream)); } \
+        kernel<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__); KERNEL_CHECK(); \
+        if (p_) { CUDA_TRY(cudaEventRecord(eb_, c_->stream)); c_->prof.push_back(ProfRec{#kernel, ea_, eb_, c_->next_bytes}); } \
+        c_->next_bytes = 0; c_->kernels_launched++; } while (0)
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }

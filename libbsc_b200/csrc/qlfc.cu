@@ -654,9 +654,11 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     }
     CUDA_TRY(cudaMemcpyAsync(d_sb, h_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyHostToDevice, ctx->stream));
     // 3. ranks, 4. encode
+    PROF_BYTES(ctx, 2.0 * R);
     LAUNCH(ctx, q_ranks, nBlocks, 32, 0, run_sym, run_rank, d_sb, mtf);
     init_models(ctx, models, nBlocks);
     CUDA_TRY(cudaFuncSetAttribute(q_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QTables)));
+    PROF_BYTES(ctx, (double)n);                          // + c written; the launch is latency-, not bandwidth-bound
     LAUNCH(ctx, q_encode, nBlocks, 32, sizeof(QTables), run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
@@ -768,6 +770,7 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         ctx->sync();
         init_models(ctx, models, nlist);
         CUDA_TRY(cudaFuncSetAttribute(q_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QTables)));
+        PROF_BYTES(ctx, (double)in_size + (double)out_cap);
         LAUNCH(ctx, q_decode, nlist, 32, sizeof(QTables), d_in, d_sb, models, tables, d_out, d_list);
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof h_sb, cudaMemcpyDeviceToHost, ctx->stream));
     }

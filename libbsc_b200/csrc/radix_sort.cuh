@@ -256,6 +256,8 @@ static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32
     CUDA_TRY(cudaMemsetAsync(scratch, 0, rs_scratch_bytes(n, passes.count), ctx->stream));
 
     u32 hgrid = min(tiles, (u32)(B200_SMS * 8));
+    const double pass_bytes = 2.0 * (double)n * (sizeof(K) + (HAS_VAL ? 4 : 0));   // read + write of every element
+    PROF_BYTES(ctx, (double)n * sizeof(K));
     LAUNCH(ctx, (rs_histogram<FirstSrc>), hgrid, RS_THREADS, 0, first, n, passes, ghist);
     LAUNCH(ctx, rs_scan, 1, 32 * RS_MAX_PASSES, 0, ghist, passes.count);
 
@@ -267,6 +269,7 @@ static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32
     for (int p = 0; p < passes.count; ++p) {
         int dst = p & 1;
         u64 *lb = lookback + (size_t)p * tiles * 256;
+        PROF_BYTES(ctx, pass_bytes);
         if (p == 0) {
             LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, FirstSrc>), tiles, RS_THREADS, smem,
                    first, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, counters + p, lb);

@@ -30,7 +30,7 @@ def _ptr(a):
 def build(force=False):
     """(Re)build liboracle.so, libbscgen.so and -- when /root/reference exists -- _ref/libbsc_ref.so."""
     if force or not os.path.exists(os.path.join(HERE, "liboracle.so")) or \
-            (os.path.exists("/root/reference/libbsc/libbsc.h") and not os.path.exists(os.path.join(HERE, "_ref", "libbsc_ref.so"))):
+            (os.path.exists("/root/reference/libbsc/libbsc.h") and not (os.path.exists(os.path.join(HERE, "_ref", "libbsc_ref.so")) and os.path.exists(os.path.join(HERE, "_ref", "librefdrv.so")))):
         subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
     gen = os.path.join(ROOT, "tools", "libbscgen.so")
     if force or not os.path.exists(gen):
