@@ -26,20 +26,7 @@
 
 namespace {
 
-// ---------------------------------------------------------------------------------------------
-// counter layout (int16, all start at 2048) -- our own flat layout
-// ---------------------------------------------------------------------------------------------
-constexpr u32 WIDE  = 256 + 65536 + 65536;               // shared[256] | by_state[256][256] | by_char[256][256]
-constexpr u32 NARROW = 32 + 8192 + 8192;                 // shared[32]  | by_state[256][32]  | by_char[256][32]
-constexpr u32 O_RT_SHARED = 0, O_RT_STATE = 2, O_RT_CHAR = O_RT_STATE + 256;
-constexpr u32 O_RE_SHARED = O_RT_CHAR + 256, O_RE_STATE = O_RE_SHARED + 8, O_RE_CHAR = O_RE_STATE + 2048;
-constexpr u32 O_RM = O_RE_CHAR + 2048;                   // 8 wide banks (mantissa by exponent)
-constexpr u32 O_RP = O_RM + 8 * WIDE;                    // escape bank
-constexpr u32 O_UT_SHARED = O_RP + WIDE, O_UT_STATE = O_UT_SHARED + 2, O_UT_CHAR = O_UT_STATE + 256;
-constexpr u32 O_UE = O_UT_CHAR + 256;                    // narrow bank (run exponent)
-constexpr u32 O_UM = O_UE + NARROW;                      // 32 narrow banks (run mantissa by exponent)
-constexpr u32 MODEL_SHORTS = O_UM + 32 * NARROW;
-constexpr u32 MODEL_SHORTS_PAD = (MODEL_SHORTS + 127) & ~127u;
+
 
 enum { K_RANK_T, K_RANK_E, K_RANK_M, K_RANK_P, K_RUN_T, K_RUN_E, K_RUN_M };
 
@@ -51,6 +38,7 @@ struct SubBlock {
     u32 out_off, out_cap;        // slice of the temp output / (decode) input stream offset, size
     int result;                  // bytes produced or error
     u32 nsym;
+    u32 tile_base, tiles;        // slice of the rank tiles (qlfc_ranks.cuh)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -246,82 +234,6 @@ __global__ void __launch_bounds__(256) q_model_init(short *__restrict__ models, 
     else for (; i < total_shorts; ++i) models[i] = 2048;
 }
 
-template <int K> __device__ __forceinline__ int mix3(int s, int c, int g)
-{
-    return (c * c_params[K][0] + s * c_params[K][1] + g * c_params[K][2]) >> 5;
-}
-template <int K, int WHO> __device__ __forceinline__ int learn(int p, u32 bit)
-{
-    const short *q = &c_params[K][3 + 4 * WHO];
-    return bit ? p - (((p - q[2]) * q[3]) >> 12) : p + (((4096 - q[0] - p) * q[1]) >> 12);
-}
-
-struct Counters3 { short *s, *c, *g; };
-
-// ---------------------------------------------------------------------------------------------
-// range coder (rangecoder.h:38-271), 16-bit output units
-// ---------------------------------------------------------------------------------------------
-struct RcEnc {
-    u32 low32, carry, range, cache, pending, pos;
-    u8 *out;
-    __device__ __forceinline__ void put16(u32 v) { if (lane_id() == 0) *(u16 *)(out + pos) = (u16)v; pos += 2; }
-    __device__ void shift() {
-        if (low32 < 0xffff0000u || carry) {
-            put16(cache + carry);
-            for (; pending; --pending) put16(carry - 1);
-            cache = low32 >> 16; carry = 0;
-        } else pending++;
-        low32 <<= 16;
-    }
-    __device__ __forceinline__ void encode(u32 bit, int p) {
-        if (range < 0x10000u) { shift(); range <<= 16; }
-        u32 r = (range >> 12) * (u32)p;
-        if (bit) { u32 s = low32 + r; carry += (s < low32); low32 = s; range -= r; }
-        else range = r;
-    }
-    __device__ u32 finish() {
-        if (range < 0x10000u) shift();
-        shift(); shift(); shift();
-        return pos;
-    }
-};
-
-struct RcDec {
-    const u8 *in; u32 pos, limit, code, range;
-    __device__ __forceinline__ u32 get16() { u32 v = 0; if (pos + 1 < limit) v = (u32)in[pos] | ((u32)in[pos + 1] << 8); pos += 2; return v; }
-    __device__ __forceinline__ u32 decode(int p) {
-        if (range < 0x10000u) { range <<= 16; code = (code << 16) | get16(); }
-        u32 r = (range >> 12) * (u32)p;
-        u32 bit = code >= r;
-        if (bit) { code -= r; range -= r; } else range = r;
-        return bit;
-    }
-};
-
-// encode/decode one binary decision against three counters
-template <int K> __device__ __forceinline__ void enc_decision(RcEnc &rc, short *ps, short *pc, short *pg, u32 bit)
-{
-    int s = *ps, c = *pc, g = *pg;
-    int p = mix3<K>(s, c, g);
-    s = learn<K, 0>(s, bit); c = learn<K, 1>(c, bit); g = learn<K, 2>(g, bit);
-    if (lane_id() == 0) { *ps = (short)s; *pc = (short)c; *pg = (short)g; }
-    __syncwarp();
-    rc.encode(bit, p);
-}
-template <int K> __device__ __forceinline__ u32 dec_decision(RcDec &rc, short *ps, short *pc, short *pg)
-{
-    int s = *ps, c = *pc, g = *pg;
-    u32 bit = rc.decode(mix3<K>(s, c, g));
-    s = learn<K, 0>(s, bit); c = learn<K, 1>(c, bit); g = learn<K, 2>(g, bit);
-    if (lane_id() == 0) { *ps = (short)s; *pc = (short)c; *pg = (short)g; }
-    __syncwarp();
-    return bit;
-}
-
-struct RunCtx {
-    int ctxRank0, ctxRank4, ctxRun, maxRank, avgRank;
-};
-
 __device__ __forceinline__ int ilog2_dev(u32 v) { return 31 - __clz(v | 1u); }
 
 // which symbols can still appear in the MTF-order header (qlfc.cpp:857-891): lane l owns symbols 8l..8l+7
@@ -339,241 +251,10 @@ __device__ __forceinline__ void header_options(u32 used8, int prev, int prefix, 
 
 struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 
-__device__ __forceinline__ void load_tables(u8 *s_tab, const QTables *__restrict__ g)
-{
-    const uint4 *src = (const uint4 *)g; uint4 *dst = (uint4 *)s_tab;
-    for (u32 i = threadIdx.x; i < sizeof(QTables) / 16; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-}
+#include "qlfc_ranks.cuh"
+#include "qlfc_coder.cuh"
 
-// ---------------------------------------------------------------------------------------------
-// QLFC stage 2 encoder (qlfc.cpp:829-1129).  One warp per sub-block, lock-step.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) q_encode(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
-                                               SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ models,
-                                               const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
-{
-    extern __shared__ __align__(16) u8 s_tab[];
-    load_tables(s_tab, tables);
-    const u8 *t_rank = s_tab, *t_run = s_tab + 32768;
-    __shared__ u8 s_rankHist[256], s_runHist[256];
-
-    const u32 sid = sb_list ? sb_list[blockIdx.x] : blockIdx.x;
-    SubBlock &sb = sbs[sid];
-    short *M = models + (size_t)sid * MODEL_SHORTS_PAD;
-    const u32 lane = threadIdx.x;
-    for (int i = lane; i < 256; i += 32) { s_rankHist[i] = 0; s_runHist[i] = 0; }
-    __syncwarp();
-
-    RcEnc rc; rc.low32 = 0; rc.carry = 0; rc.range = 0xffffffffu; rc.cache = 0; rc.pending = 0; rc.pos = 0; rc.out = out_all + sb.out_off;
-    const long long eob = (long long)sb.out_cap - 16;
-    RunCtx x; x.ctxRank0 = x.ctxRank4 = x.ctxRun = 0; x.maxRank = 7; x.avgRank = 0;
-
-    const u32 n = sb.in_size;
-    for (int b = 31; b >= 0; --b) rc.encode((n >> b) & 1u, 2048);
-
-    {   // MTF-order header
-        const u8 *mtf = mtf_all + sid * 256;
-        u32 used8 = 0; int prev = -1;
-        for (int d = 0; d < 256; ++d) {
-            int c = mtf[d];
-            for (int bit = 7; bit >= 0; --bit) {
-                bool can0, can1; header_options(used8, prev, c >> (bit + 1), bit, can0, can1);
-                if (can0 && can1) rc.encode((c >> bit) & 1u, 2048);
-            }
-            if (c == prev) { x.maxRank = ilog2_dev((u32)(d - 1)); break; }
-            prev = c; if ((u32)(c >> 3) == lane) used8 |= 1u << (c & 7);
-        }
-    }
-
-    int result = 0;
-    const u32 rb = sb.run_begin, re = sb.run_end;
-    for (u32 t0 = rb; t0 < re && result == 0; t0 += 32) {
-        const u32 cnt = min(32u, re - t0);
-        // lane j prefetches run t0+j
-        u32 my_sym = 0, my_rank = 0, my_len = 0;
-        if (lane < cnt) { my_sym = run_sym[t0 + lane]; my_rank = run_rank[t0 + lane]; my_len = run_pos[t0 + lane + 1] - run_pos[t0 + lane]; }
-        for (u32 j = 0; j < cnt; ++j) {
-            if ((long long)rc.pos >= eob) { result = LIBBSC_NOT_COMPRESSIBLE; break; }   // qlfc.cpp:898-901
-            const int c = (int)__shfl_sync(0xffffffffu, my_sym, j);
-            const int rank = (int)__shfl_sync(0xffffffffu, my_rank, j);
-            const int run = (int)__shfl_sync(0xffffffffu, my_len, j);
-
-            int st = t_rank[(x.ctxRun << 11) | (x.ctxRank4 << 3) | s_rankHist[c]];
-            if (x.avgRank < 32) {
-                enc_decision<K_RANK_T>(rc, M + O_RT_STATE + st, M + O_RT_CHAR + c, M + O_RT_SHARED, rank != 1);
-                if (rank == 1) { if (lane == 0) s_rankHist[c] = 0; }
-                else {
-                    const int e = ilog2_dev((u32)rank);
-                    if (lane == 0) s_rankHist[c] = (u8)e;
-                    for (int b = 1; b < e; ++b) enc_decision<K_RANK_E>(rc, M + O_RE_STATE + st * 8 + b - 1, M + O_RE_CHAR + c * 8 + b - 1, M + O_RE_SHARED + b - 1, 1);
-                    if (e < x.maxRank)          enc_decision<K_RANK_E>(rc, M + O_RE_STATE + st * 8 + e - 1, M + O_RE_CHAR + c * 8 + e - 1, M + O_RE_SHARED + e - 1, 0);
-                    short *bank = M + O_RM + (u32)e * WIDE;
-                    for (int node = 1, bit = e - 1; bit >= 0; --bit) {
-                        u32 bb = ((u32)rank >> bit) & 1u;
-                        enc_decision<K_RANK_M>(rc, bank + 256 + st * 256 + node, bank + 256 + 65536 + c * 256 + node, bank + node, bb);
-                        node = 2 * node + (int)bb;
-                    }
-                }
-            } else {
-                if (lane == 0) s_rankHist[c] = (u8)ilog2_dev((u32)rank);
-                short *bank = M + O_RP;
-                for (int node = 1, bit = x.maxRank; bit >= 0; --bit) {
-                    u32 bb = ((u32)rank >> bit) & 1u;
-                    enc_decision<K_RANK_P>(rc, bank + 256 + st * 256 + node, bank + 256 + 65536 + c * 256 + node, bank + node, bb);
-                    node = 2 * node + (int)bb;
-                }
-            }
-            x.avgRank = (x.avgRank * 124 + rank * 4) >> 7;
-            const int rank0 = rank - 1;
-            const int rh = s_runHist[c];
-            st = t_run[(x.ctxRank0 << 10) | (x.ctxRun << 6) | ((rank0 < 7 ? rank0 : 7) << 3) | (rh < 7 ? rh : 7)];
-
-            enc_decision<K_RUN_T>(rc, M + O_UT_STATE + st, M + O_UT_CHAR + c, M + O_UT_SHARED, run != 1);
-            if (run == 1) { if (lane == 0) s_runHist[c] = (u8)((rh + 2) >> 2); }
-            else {
-                const int e = ilog2_dev((u32)run);
-                if (lane == 0) s_runHist[c] = (u8)((rh + 3 * e + 3) >> 2);
-                short *eb = M + O_UE;
-                for (int b = 1; b < e; ++b) enc_decision<K_RUN_E>(rc, eb + 32 + st * 32 + b - 1, eb + 32 + 8192 + c * 32 + b - 1, eb + b - 1, 1);
-                enc_decision<K_RUN_E>(rc, eb + 32 + st * 32 + e - 1, eb + 32 + 8192 + c * 32 + e - 1, eb + e - 1, 0);
-                short *bank = M + O_UM + (u32)e * NARROW;
-                for (int node = 1, bit = e - 1; bit >= 0; --bit) {
-                    u32 bb = ((u32)run >> bit) & 1u;
-                    enc_decision<K_RUN_M>(rc, bank + 32 + st * 32 + node, bank + 32 + 8192 + c * 32 + node, bank + node, bb);
-                    node = (e <= 5) ? 2 * node + (int)bb : node + 1;          // qlfc.cpp:1119
-                }
-            }
-            __syncwarp();
-            x.ctxRank0 = ((x.ctxRank0 << 1) | (rank0 == 0)) & 0x7;
-            x.ctxRank4 = ((x.ctxRank4 << 2) | (rank0 < 3 ? rank0 : 3)) & 0xff;
-            x.ctxRun   = ((x.ctxRun << 1) | (run < 3)) & 0xf;
-        }
-    }
-    if (result == 0) result = (int)rc.finish();
-    if (lane == 0) sb.result = result;
-}
-
-// ---------------------------------------------------------------------------------------------
-// decoder (qlfc.cpp:1672-1927).  One warp per sub-block, lock-step; runs are expanded warp-wide.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) q_decode(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ models,
-                                               const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
-{
-    extern __shared__ __align__(16) u8 s_tab[];
-    load_tables(s_tab, tables);
-    const u8 *t_rank = s_tab, *t_run = s_tab + 32768;
-    __shared__ u8 s_rankHist[256], s_runHist[256], s_mtf[256 + 32];
-
-    const u32 sid = sb_list[blockIdx.x];
-    SubBlock &sb = sbs[sid];
-    short *M = models + (size_t)blockIdx.x * MODEL_SHORTS_PAD;
-    const u32 lane = threadIdx.x;
-    for (int i = lane; i < 256; i += 32) { s_rankHist[i] = 0; s_runHist[i] = 0; s_mtf[i] = 0; }
-    __syncwarp();
-
-    RcDec rc; rc.in = in_all + sb.out_off; rc.pos = 0; rc.limit = sb.out_cap; rc.code = 0; rc.range = 0xffffffffu;
-    for (int i = 0; i < 3; ++i) rc.code = (rc.code << 16) | rc.get16();
-    u32 n = 0; for (int b = 0; b < 32; ++b) n = (n << 1) | rc.decode(2048);
-    if (n > sb.in_size) { if (lane == 0) sb.result = LIBBSC_DATA_CORRUPT; return; }   // would overrun the output slice
-
-    RunCtx x; x.ctxRank0 = x.ctxRank4 = x.ctxRun = 0; x.maxRank = 7; x.avgRank = 0;
-    {
-        u32 used8 = 0; int prev = -1;
-        for (int d = 0; d < 256; ++d) {
-            int c = 0;
-            for (int bit = 7; bit >= 0; --bit) {
-                bool can0, can1; header_options(used8, prev, c, bit, can0, can1);
-                if (can0 && can1) c = 2 * c + (int)rc.decode(2048);
-                else if (can1) c = 2 * c + 1;
-                else if (can0) c = 2 * c;
-            }
-            c &= 255;
-            if (lane == 0) s_mtf[d] = (u8)c;
-            if (c == prev) { x.maxRank = ilog2_dev((u32)(d - 1)); break; }
-            prev = c; if ((u32)(c >> 3) == lane) used8 |= 1u << (c & 7);
-        }
-    }
-    __syncwarp();
-
-    u8 *out = out_all + sb.in_start;
-    for (u32 i = 0; i < n; ) {
-        const int c = s_mtf[0];
-        int rank = 1; u32 b;
-        int st = t_rank[(x.ctxRun << 11) | (x.ctxRank4 << 3) | s_rankHist[c]];
-        if (x.avgRank < 32) {
-            b = dec_decision<K_RANK_T>(rc, M + O_RT_STATE + st, M + O_RT_CHAR + c, M + O_RT_SHARED);
-            if (!b) { if (lane == 0) s_rankHist[c] = 0; }
-            else {
-                int e = 1;
-                while (e != x.maxRank) {
-                    b = dec_decision<K_RANK_E>(rc, M + O_RE_STATE + st * 8 + e - 1, M + O_RE_CHAR + c * 8 + e - 1, M + O_RE_SHARED + e - 1);
-                    if (!b) break;
-                    if (++e >= 7) break;                                     // e <= maxRank <= 7 in valid streams
-                }
-                if (lane == 0) s_rankHist[c] = (u8)e;
-                short *bank = M + O_RM + (u32)e * WIDE;
-                for (int bit = e - 1; bit >= 0; --bit) {
-                    b = dec_decision<K_RANK_M>(rc, bank + 256 + st * 256 + rank, bank + 256 + 65536 + c * 256 + rank, bank + rank);
-                    rank = 2 * rank + (int)b;
-                }
-            }
-        } else {
-            rank = 0;
-            short *bank = M + O_RP;
-            for (int node = 1, bit = x.maxRank; bit >= 0; --bit) {
-                b = dec_decision<K_RANK_P>(rc, bank + 256 + st * 256 + node, bank + 256 + 65536 + c * 256 + node, bank + node);
-                node = 2 * node + (int)b; rank = 2 * rank + (int)b;
-            }
-            if (lane == 0) s_rankHist[c] = (u8)ilog2_dev((u32)rank);
-        }
-        rank &= 255;
-        __syncwarp();
-        // push c `rank` places back: mtf[0..rank-1] = mtf[1..rank]; mtf[rank] = c  (qlfc.cpp:1830-1860)
-        for (int basep = 0; basep < rank; basep += 32) {
-            int p = basep + (int)lane;
-            u8 v = s_mtf[p + 1];
-            __syncwarp();
-            if (p < rank) s_mtf[p] = v;
-            __syncwarp();
-        }
-        if (lane == 0) s_mtf[rank] = (u8)c;
-        __syncwarp();
-
-        x.avgRank = (x.avgRank * 124 + rank * 4) >> 7;
-        const int rank0 = rank - 1;
-        const int rh = s_runHist[c];
-        st = t_run[(x.ctxRank0 << 10) | (x.ctxRun << 6) | (((u32)rank0 < 7u ? rank0 : 7) << 3) | (rh < 7 ? rh : 7)];
-        u32 run = 1;
-        b = dec_decision<K_RUN_T>(rc, M + O_UT_STATE + st, M + O_UT_CHAR + c, M + O_UT_SHARED);
-        if (!b) { if (lane == 0) s_runHist[c] = (u8)((rh + 2) >> 2); }
-        else {
-            int e = 1;
-            short *eb = M + O_UE;
-            for (;;) {
-                b = dec_decision<K_RUN_E>(rc, eb + 32 + st * 32 + e - 1, eb + 32 + 8192 + c * 32 + e - 1, eb + e - 1);
-                if (!b) break;
-                if (++e >= 31) break;                                        // corrupt-input guard
-            }
-            if (lane == 0) s_runHist[c] = (u8)((rh + 3 * e + 3) >> 2);
-            short *bank = M + O_UM + (u32)e * NARROW;
-            for (int node = 1, bit = e - 1; bit >= 0; --bit) {
-                b = dec_decision<K_RUN_M>(rc, bank + 32 + st * 32 + node, bank + 32 + 8192 + c * 32 + node, bank + node);
-                run = 2 * run + b;
-                node = (e <= 5) ? 2 * node + (int)b : node + 1;
-            }
-        }
-        __syncwarp();
-        x.ctxRank0 = ((x.ctxRank0 << 1) | (rank0 == 0)) & 0x7;
-        x.ctxRank4 = ((x.ctxRank4 << 2) | ((u32)rank0 < 3u ? rank0 : 3)) & 0xff;
-        x.ctxRun   = ((x.ctxRun << 1) | (run < 3)) & 0xf;
-
-        if (run > n - i) run = n - i;                                        // never write past n
-        for (u32 k = lane; k < run; k += 32) out[i + k] = (u8)c;
-        i += run;
-    }
-    if (lane == 0) sb.result = (int)n;
-}
+constexpr size_t MODEL_SHORTS_PAD = 2 * (size_t)COLD_PAD;     // by-state + by-symbol cold arrays per stream
 
 }  // namespace
 
@@ -647,19 +328,26 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     SubBlock h_sb[Q_MAX_SUB];
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
+    u32 total_tiles = 0;
     for (u32 b = 0, off = 0; b < (u32)nBlocks; ++b) {
         h_sb[b].out_off = off; off += (u32)align_up((size_t)h_size[b] + 4096, 256);   // 16-bit stores need even offsets
         h_sb[b].out_cap = (nBlocks == 1) ? n - 1 : h_size[b];
         h_sb[b].result = 0; h_sb[b].nsym = 0;
+        h_sb[b].tile_base = total_tiles; h_sb[b].tiles = ceil_div(h_sb[b].run_end - h_sb[b].run_begin, RK_TILE); total_tiles += h_sb[b].tiles;
     }
     CUDA_TRY(cudaMemcpyAsync(d_sb, h_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyHostToDevice, ctx->stream));
     // 3. ranks, 4. encode
-    PROF_BYTES(ctx, 2.0 * R);
-    LAUNCH(ctx, q_ranks, nBlocks, 32, 0, run_sym, run_rank, d_sb, mtf);
+    {
+        u32 *first_tab = A.get<u32>((size_t)total_tiles * 256), *next_tab = A.get<u32>((size_t)total_tiles * 256);
+        LAUNCH(ctx, q_rank_first, ceil_div(total_tiles, 4), 128, 0, run_sym, d_sb, (u32)nBlocks, total_tiles, first_tab);
+        LAUNCH(ctx, q_rank_scan, nBlocks, 256, 0, d_sb, first_tab, next_tab, mtf);
+        PROF_BYTES(ctx, 2.0 * R);
+        LAUNCH(ctx, q_rank_tile, ceil_div(total_tiles, 4), 128, 0, run_sym, run_rank, d_sb, (u32)nBlocks, total_tiles, next_tab);
+    }
     init_models(ctx, models, nBlocks);
-    CUDA_TRY(cudaFuncSetAttribute(q_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QTables)));
+    CUDA_TRY(cudaFuncSetAttribute(q_encode2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoderSmem)));
     PROF_BYTES(ctx, (double)n);                          // + c written; the launch is latency-, not bandwidth-bound
-    LAUNCH(ctx, q_encode, nBlocks, 32, sizeof(QTables), run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+    LAUNCH(ctx, q_encode2, nBlocks, 32, sizeof(CoderSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
 
@@ -696,7 +384,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                 CUDA_TRY(cudaMemcpyAsync(d_list, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
                 ctx->sync();
                 init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                LAUNCH(ctx, q_encode, 1, 32, sizeof(QTables), run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                LAUNCH(ctx, q_encode2, 1, 32, sizeof(CoderSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
                 r = h_sb[b].result;
@@ -769,9 +457,9 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         CUDA_TRY(cudaMemcpyAsync(d_list, list, sizeof list, cudaMemcpyHostToDevice, ctx->stream));
         ctx->sync();
         init_models(ctx, models, nlist);
-        CUDA_TRY(cudaFuncSetAttribute(q_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QTables)));
+        CUDA_TRY(cudaFuncSetAttribute(q_decode2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoderSmem)));
         PROF_BYTES(ctx, (double)in_size + (double)out_cap);
-        LAUNCH(ctx, q_decode, nlist, 32, sizeof(QTables), d_in, d_sb, models, tables, d_out, d_list);
+        LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof h_sb, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->sync();
