@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 #include <vector>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -117,6 +118,18 @@ struct Ctx {
         return h_stage;
     }
 };
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the call is not free and
+// must not sit in front of every launch of a kernel that other streams are running.
+template <typename F> static inline void ensure_dyn_smem(F *kernel, int device, size_t bytes)
+{
+    static const void *seen[64]; static int seen_dev[64]; static int count = 0;   // per translation unit; tiny
+    static std::mutex m;
+    std::lock_guard<std::mutex> lk(m);
+    for (int i = 0; i < count; ++i) if (seen[i] == (const void *)kernel && seen_dev[i] == device) return;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (count < 64) { seen[count] = (const void *)kernel; seen_dev[count] = device; ++count; }
+}
 
 #define PROF_BYTES(ctx, b) do { (ctx)->next_bytes = (double)(b); } while (0)
 #define LAUNCH(ctx, kernel, grid, block, smem, ...) do { \

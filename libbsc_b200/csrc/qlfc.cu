@@ -345,7 +345,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         LAUNCH(ctx, q_rank_tile, ceil_div(total_tiles, 4), 128, 0, run_sym, run_rank, d_sb, (u32)nBlocks, total_tiles, next_tab);
     }
     init_models(ctx, models, nBlocks);
-    CUDA_TRY(cudaFuncSetAttribute(q_encode2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoderSmem)));
+    ensure_dyn_smem(q_encode2, ctx->device, sizeof(CoderSmem));
     PROF_BYTES(ctx, (double)n);                          // + c written; the launch is latency-, not bandwidth-bound
     LAUNCH(ctx, q_encode2, nBlocks, 32, sizeof(CoderSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
@@ -457,7 +457,7 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         CUDA_TRY(cudaMemcpyAsync(d_list, list, sizeof list, cudaMemcpyHostToDevice, ctx->stream));
         ctx->sync();
         init_models(ctx, models, nlist);
-        CUDA_TRY(cudaFuncSetAttribute(q_decode2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoderSmem)));
+        ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
         PROF_BYTES(ctx, (double)in_size + (double)out_cap);
         LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof h_sb, cudaMemcpyDeviceToHost, ctx->stream));

@@ -263,8 +263,8 @@ static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32
 
     const size_t smem = sizeof(RsSmem<K, HAS_VAL>);
     // (per device, cheap) allow the > 48 KB dynamic shared memory the tile needs
-    CUDA_TRY(cudaFuncSetAttribute(rs_onesweep<K, HAS_VAL, FirstSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dyn_smem(rs_onesweep<K, HAS_VAL, FirstSrc>, ctx->device, smem);
+    ensure_dyn_smem(rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>, ctx->device, smem);
 
     for (int p = 0; p < passes.count; ++p) {
         int dst = p & 1;
