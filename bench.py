@@ -26,6 +26,10 @@ import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
 
+# One hardware work queue per stream: with the default of 8, streams 9..16 alias onto the queues of
+# streams 1..8 and a long-running coder kernel falsely serialises the other block (measured: 2x).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -266,6 +266,9 @@ void bsc_free(void *p) { if (g_free) g_free(p); else free(p); }
 int bsc_init_full(int features, void *(*malloc_fn)(size_t), void *(*zero_malloc_fn)(size_t), void (*free_fn)(void *))
 {
     bsc_platform_init(features, malloc_fn, zero_malloc_fn, free_fn);
+    // Blocks run on independent streams; give every stream its own hardware queue (default 8 would
+    // alias streams and serialise long coder kernels).  Only effective before the CUDA context exists.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) { cudaGetLastError(); return LIBBSC_GPU_NOT_SUPPORTED; }
     g_features = features; g_initialised = true;

@@ -44,11 +44,12 @@ constexpr u32  COLD_PAD = (COLD_COUNT + 255) & ~255u;
 struct CoderSmem {
     u8    rank_state[32768];
     u8    run_state[8192];
-    short s16[S16_COUNT];
+    u16   s16[S16_COUNT];
     u8    tag_state[QC_SLOTS];
     u8    tag_char[QC_SLOTS];
     u8    rankHist[256], runHist[256];
     u8    mtf[256 + 32];
+    __align__(16) u8 inwin[256];     // decoder: staged window of the input stream
 };
 
 __device__ __forceinline__ void coder_smem_init(CoderSmem &S, const QTables *__restrict__ g)
@@ -77,23 +78,28 @@ __device__ __forceinline__ u32 cache_get(CoderSmem &S, u32 val_base, u8 *tags, s
 }
 
 // ---- counters ---------------------------------------------------------------------------------------
+// All parameters are compile-time immediates (bscb_param is constexpr).  Counters provably stay in
+// [1, 4095] from their start value 2048 for every parameter set, so they are kept as unsigned 16-bit.
 template <int K> __device__ __forceinline__ int q_mix(int s, int c, int g)
 {
-    return (c * c_params[K][0] + s * c_params[K][1] + g * c_params[K][2]) >> 5;
+    return (c * bscb_param(K, 0) + s * bscb_param(K, 1) + g * bscb_param(K, 2)) >> 5;
 }
-template <int K, int WHO> __device__ __forceinline__ int q_learn(int p, u32 bit)
+template <int K, int WHO> __device__ __forceinline__ int q_up(int p)      // the decision came out 0 (predictor.h:50-53)
 {
-    const int th0 = c_params[K][3 + 4 * WHO], ar0 = c_params[K][4 + 4 * WHO], th1 = c_params[K][5 + 4 * WHO], ar1 = c_params[K][6 + 4 * WHO];
-    const int up = p + (((4096 - th0 - p) * ar0) >> 12), down = p - (((p - th1) * ar1) >> 12);
-    return bit ? down : up;
+    return p + (((4096 - bscb_param(K, 3 + 4 * WHO) - p) * bscb_param(K, 4 + 4 * WHO)) >> 12);
 }
+template <int K, int WHO> __device__ __forceinline__ int q_down(int p)    // the decision came out 1 (predictor.h:55-58)
+{
+    return p - (((p - bscb_param(K, 5 + 4 * WHO)) * bscb_param(K, 6 + 4 * WHO)) >> 12);
+}
+template <int K, int WHO> __device__ __forceinline__ int q_learn(int p, u32 bit) { return bit ? q_down<K, WHO>(p) : q_up<K, WHO>(p); }
 
 // ---- range coder (rangecoder.h:38-271), 16-bit units -------------------------------------------------
 struct Rc2Enc {
     u32 low32, carry, range, cache, pending, pos;
     u8 *out;
     __device__ __forceinline__ void put16(u32 v) { *(u16 *)(out + pos) = (u16)v; pos += 2; }   // all lanes store the same value
-    __device__ __noinline__ void shift() {
+    __device__ __forceinline__ void shift() {
         if (low32 < 0xffff0000u || carry) {
             put16(cache + carry);
             for (; pending; --pending) put16(carry - 1);
@@ -110,9 +116,25 @@ struct Rc2Enc {
     __device__ u32 finish() { if (range < 0x10000u) shift(); shift(); shift(); shift(); return pos; }
 };
 
+// cold path of the decoder's input window (by-value arguments: keeps the coder state in registers)
+__device__ __noinline__ void rc_refill_window(const u8 *__restrict__ in, u8 *win, u32 base, u32 limit)
+{
+    const u32 lane = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const u32 o = base + lane * 8 + k; win[lane * 8 + k] = o < limit ? in[o] : (u8)0; }
+    __syncwarp();
+}
+
 struct Rc2Dec {
     const u8 *in; u32 pos, limit, code, range;
-    __device__ __forceinline__ u32 get16() { u32 v = 0; if (pos + 1 < limit) v = (u32)in[pos] | ((u32)in[pos + 1] << 8); pos += 2; return v; }
+    u8 *win; u32 wbase;              // 256-byte shared-memory window [wbase, wbase+256) of the stream (pos is always even)
+    __device__ __forceinline__ void refill() { wbase = pos; rc_refill_window(in, win, pos, limit); }
+    __device__ __forceinline__ u32 get16() {
+        if (pos - wbase >= 256u) refill();
+        const u32 v = *(const u16 *)(win + (pos - wbase));
+        pos += 2; return v;
+    }
     __device__ __forceinline__ u32 decode(int p) {
         if (range < 0x10000u) { range <<= 16; code = (code << 16) | get16(); }
         const u32 r = (range >> 12) * (u32)p;
@@ -134,7 +156,8 @@ template <int K> __device__ __forceinline__ u32 dec3(CoderSmem &S, Rc2Dec &rc, u
 {
     const int s = S.s16[is], c = S.s16[ic], g = S.s16[ig];
     const u32 bit = rc.decode(q_mix<K>(s, c, g));
-    S.s16[is] = (short)q_learn<K, 0>(s, bit); S.s16[ic] = (short)q_learn<K, 1>(c, bit); S.s16[ig] = (short)q_learn<K, 2>(g, bit);
+    if (bit) { S.s16[is] = (u16)q_down<K, 0>(s); S.s16[ic] = (u16)q_down<K, 1>(c); S.s16[ig] = (u16)q_down<K, 2>(g); }   // warp-uniform branch
+    else     { S.s16[is] = (u16)q_up<K, 0>(s);   S.s16[ic] = (u16)q_up<K, 1>(c);   S.s16[ig] = (u16)q_up<K, 2>(g); }
     return bit;
 }
 
@@ -262,6 +285,7 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
     const u32 lane = threadIdx.x;
 
     Rc2Dec rc; rc.in = in_all + sb.out_off; rc.pos = 0; rc.limit = sb.out_cap; rc.code = 0; rc.range = 0xffffffffu;
+    rc.win = S.inwin; rc.wbase = 0; rc.refill();
     for (int i = 0; i < 3; ++i) rc.code = (rc.code << 16) | rc.get16();
     u32 n = 0; for (int b = 0; b < 32; ++b) n = (n << 1) | rc.decode(2048);
     if (n > sb.in_size) { if (lane == 0) sb.result = LIBBSC_DATA_CORRUPT; return; }   // would overrun the output slice
@@ -363,4 +387,191 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
         i += run;
     }
     if (lane == 0) sb.result = (int)n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// encoder, two-warp pipeline (replaces q_encode2 on the hot path)
+//
+// Every context of the encoder is a function of the INPUT only (qlfc.cpp:949-955, 1048-1054,
+// 1123-1125), and within one run every decision touches a different counter.  So the model side
+// can evaluate all decisions of a run at once -- lane d of warp 0 owns decision d: it locates its
+// three counters, mixes the probability from their pre-update values, moves the counters and
+// emits a (bit, p) record -- while warp 1 does nothing but the one truly serial recurrence, the
+// range coder (range/low with 16-bit renormalisation, rangecoder.h:83-177), consuming the records
+// from a shared-memory ring.  Per stream the critical path shrinks from "~9 dependent model
+// look-ups per run" to "one parallel model step per run" || "one range step per decision".
+// ---------------------------------------------------------------------------------------------------
+#define QE_RING 8192                                       // records (u16) in the ring
+#define QE_REC_BIT   0x2000u                               // bit 13: the coded bit
+#define QE_REC_RUN   0x4000u                               // bit 14: first decision of a run (EOB check point)
+#define QE_REC_END   0xffffu
+
+struct EncPipe {
+    u16 ring[QE_RING];
+    volatile u32 head, tail, fail;                         // consumer / producer / "output full" flag
+    int params[7][16];
+};
+
+__device__ __forceinline__ void pipe_push(EncPipe &P, u32 &tail, u32 cnt, u32 rec, u32 lane)
+{
+    while ((int)(tail + cnt - P.head) > QE_RING) { }          // wait for room (consumer always drains; head jumps ahead when it quits)
+    if (lane < cnt) P.ring[(tail + lane) & (QE_RING - 1)] = (u16)rec;
+    __syncwarp();
+    __threadfence_block();
+    tail += cnt;
+    if (lane == 0) P.tail = tail;
+}
+
+__global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
+                                                   SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
+                                                   const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+{
+    extern __shared__ __align__(16) u8 q_smem_raw[];
+    CoderSmem &S = *reinterpret_cast<CoderSmem *>(q_smem_raw);
+    EncPipe &P = *reinterpret_cast<EncPipe *>(q_smem_raw + ((sizeof(CoderSmem) + 15) & ~(size_t)15));
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 sid = sb_list ? sb_list[blockIdx.x] : blockIdx.x;
+    SubBlock &sb = sbs[sid];
+
+    if (warp == 0) {
+        coder_smem_init(S, tables);
+        for (int i = lane; i < 7 * 16; i += 32) P.params[i / 16][i % 16] = (i % 16) < 15 ? (int)c_params[i / 16][i % 16] : 0;
+        if (lane == 0) { P.head = 0; P.tail = 0; P.fail = 0; }
+    }
+    __syncthreads();
+
+    if (warp == 1) {
+        // ------------------------------ consumer: the range coder ------------------------------
+        Rc2Enc rc; rc.low32 = 0; rc.carry = 0; rc.range = 0xffffffffu; rc.cache = 0; rc.pending = 0; rc.pos = 0; rc.out = out_all + sb.out_off;
+        const long long eob = (long long)sb.out_cap - 16;
+        u32 head = 0; int result = 0; bool done = false;
+        while (!done) {
+            u32 tail;
+            while ((tail = P.tail) == head) { }
+            __threadfence_block();
+            const u32 cnt = min(32u, tail - head);
+            const u32 mine = lane < cnt ? P.ring[(head + lane) & (QE_RING - 1)] : 0u;
+            for (u32 j = 0; j < cnt; ++j) {
+                const u32 rec = __shfl_sync(0xffffffffu, mine, j);
+                if (rec == QE_REC_END) { done = true; break; }
+                if ((rec & QE_REC_RUN) && (long long)rc.pos >= eob) { result = LIBBSC_NOT_COMPRESSIBLE; done = true; break; }   // qlfc.cpp:898-901
+                rc.encode((rec >> 13) & 1u, (int)(rec & 0x1fffu));
+            }
+            head += cnt;
+            if (lane == 0) P.head = head;
+        }
+        if (result == 0) result = (int)rc.finish();
+        else if (lane == 0) P.fail = 1;
+        if (lane == 0) { sb.result = result; P.head = 0x7fffffffu; }   // unblock a producer waiting for room
+        return;
+    }
+
+    // ---------------------------------- producer: the model ----------------------------------
+    short *cold_s = cold_all + (size_t)sid * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
+    u32 tail = 0;
+    int ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0, maxRank = 7, avgRank = 0;
+    const u32 n = sb.in_size;
+    pipe_push(P, tail, 32, 2048u | (((n >> (31 - lane)) & 1u) ? QE_REC_BIT : 0u), lane);
+    {   // MTF-order header (qlfc.cpp:857-891): few hundred records, pushed one at a time
+        const u8 *mtf = mtf_all + sid * 256;
+        u32 used8 = 0; int prev = -1;
+        for (int d = 0; d < 256; ++d) {
+            int c = mtf[d];
+            for (int bit = 7; bit >= 0; --bit) {
+                bool can0, can1; header_options(used8, prev, c >> (bit + 1), bit, can0, can1);
+                if (can0 && can1) pipe_push(P, tail, 1, 2048u | (((c >> bit) & 1) ? QE_REC_BIT : 0u), lane);
+            }
+            if (c == prev) { maxRank = ilog2_dev((u32)(d - 1)); break; }
+            prev = c; if ((u32)(c >> 3) == lane) used8 |= 1u << (c & 7);
+        }
+    }
+
+    const u32 rb = sb.run_begin, re = sb.run_end;
+    bool stop = false;
+    for (u32 t0 = rb; t0 < re && !stop; t0 += 32) {
+        const u32 cnt = min(32u, re - t0);
+        u32 my_sym = 0, my_rank = 0, my_len = 0;             // lane j prefetches run t0 + j
+        if (lane < cnt) { my_sym = run_sym[t0 + lane]; my_rank = run_rank[t0 + lane]; my_len = run_pos[t0 + lane + 1] - run_pos[t0 + lane]; }
+        if (P.fail) break;
+        for (u32 j = 0; j < cnt; ++j) {
+            const u32 c = __shfl_sync(0xffffffffu, my_sym, j);
+            const u32 rank = __shfl_sync(0xffffffffu, my_rank, j);
+            const u32 run = __shfl_sync(0xffffffffu, my_len, j);
+            // ---- per-run contexts (uniform) ----
+            const u32 st1 = S.rank_state[(ctxRun << 11) | (ctxRank4 << 3) | S.rankHist[c]];
+            const bool esc = avgRank >= 32;
+            const int er = ilog2_dev(rank), eu = ilog2_dev(run);
+            const int rank0 = (int)rank - 1;
+            const int rh = S.runHist[c];
+            const u32 st2 = S.run_state[(ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7 ? rank0 : 7) << 3) | (rh < 7 ? rh : 7)];
+            __syncwarp();
+            if (lane == 0) {
+                S.rankHist[c] = (u8)((esc || rank != 1) ? er : 0);
+                S.runHist[c] = (u8)(run == 1 ? (rh + 2) >> 2 : (rh + 3 * eu + 3) >> 2);
+            }
+            avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
+            ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0)) & 0x7;
+            ctxRank4 = ((ctxRank4 << 2) | (rank0 < 3 ? rank0 : 3)) & 0xff;
+            ctxRun   = ((ctxRun << 1) | (run < 3)) & 0xf;
+            // ---- decision layout of this run ----
+            const int nE = (!esc && rank != 1) ? (er - 1) + (er < maxRank) : 0;
+            const int nM = esc ? maxRank + 1 : (rank != 1 ? er : 0);
+            const int o1 = esc ? 0 : 1, o2 = o1 + nE, o3 = o2 + nM, o4 = o3 + 1, o5 = o4 + (run != 1 ? eu : 0), D = o5 + (run != 1 ? eu : 0);
+            for (int base = 0; base < D; base += 32) {
+                const int d = base + (int)lane;
+                const bool act = d < D;
+                int K = 0; u32 is = 0, ic = 0, ig = 0, bit = 0, cs = 0xffffffffu, cc = 0xffffffffu;   // cs/cc: cold indices when cached
+                if (act) {
+                    if (d < o1) { K = K_RANK_T; is = R_RT_STATE + st1; ic = R_RT_CHAR + c; ig = R_RT_SHARED; bit = rank != 1; }
+                    else if (d < o2) { const int k = d - o1; K = K_RANK_E; is = R_RE_STATE + st1 * 8 + k; ic = R_RE_CHAR + c * 8 + k; ig = R_RE_SHARED + k; bit = k < er - 1; }
+                    else if (d < o3) {
+                        const int l = d - o2;
+                        if (!esc) { const int bp = er - 1 - l; const u32 node = rank >> (bp + 1); bit = (rank >> bp) & 1u; K = K_RANK_M;
+                                    cs = wide_idx(er, st1, node); cc = wide_idx(er, c, node); ig = R_WIDE_SHARED + er * 256 + node; }
+                        else      { const int bp = maxRank - l; const u32 node = (1u << l) | (rank >> (bp + 1)); bit = (rank >> bp) & 1u; K = K_RANK_P;
+                                    cs = wide_idx(8, st1, node); cc = wide_idx(8, c, node); ig = R_WIDE_SHARED + 8 * 256 + node; }
+                    }
+                    else if (d < o4) { K = K_RUN_T; is = R_UT_STATE + st2; ic = R_UT_CHAR + c; ig = R_UT_SHARED; bit = run != 1; }
+                    else if (d < o5) { const int k = d - o4; K = K_RUN_E; is = R_UE_STATE + st2 * 32 + k; ic = R_UE_CHAR + c * 32 + k; ig = R_UE_SHARED + k; bit = k < eu - 1; }
+                    else { const int l = d - o5, bp = eu - 1 - l; const u32 node = eu <= 5 ? (run >> (bp + 1)) : (u32)(1 + l); bit = (run >> bp) & 1u; K = K_RUN_M;
+                           cs = narrow_idx(eu, st2, node); cc = narrow_idx(eu, c, node); ig = R_NARROW_SHARED + eu * 32 + node; }
+                }
+                // ---- cached counters: per-lane direct-mapped look-up; identical slots are serialised ----
+                const bool cached = cs != 0xffffffffu;
+                const u32 hs = cs >> QC_LOG, slot_s = (cs ^ (hs * 1237u)) & QC_MASK, hc = cc >> QC_LOG, slot_c = (cc ^ (hc * 1237u)) & QC_MASK;
+                const u32 cmask = __ballot_sync(0xffffffffu, cached);
+                bool clash = false;
+                if (cached) { clash = __popc(__match_any_sync(cmask, slot_s)) > 1 || __popc(__match_any_sync(cmask, slot_c)) > 1; }
+                const bool any_clash = __any_sync(0xffffffffu, clash);
+                u32 rec = 0;
+                for (int turn = 0; turn < (any_clash ? 32 : 1); ++turn) {
+                    const bool go = act && (!any_clash || (int)lane == turn);
+                    if (go) {
+                        if (cached) {
+                            u32 t = S.tag_state[slot_s];
+                            if (t != hs + 1) { if (t) cold_s[((t - 1) << QC_LOG) | ((slot_s ^ ((t - 1) * 1237u)) & QC_MASK)] = S.s16[C_STATE_VAL + slot_s];
+                                               S.s16[C_STATE_VAL + slot_s] = cold_s[cs]; S.tag_state[slot_s] = (u8)(hs + 1); }
+                            t = S.tag_char[slot_c];
+                            if (t != hc + 1) { if (t) cold_c[((t - 1) << QC_LOG) | ((slot_c ^ ((t - 1) * 1237u)) & QC_MASK)] = S.s16[C_CHAR_VAL + slot_c];
+                                               S.s16[C_CHAR_VAL + slot_c] = cold_c[cc]; S.tag_char[slot_c] = (u8)(hc + 1); }
+                            is = C_STATE_VAL + slot_s; ic = C_CHAR_VAL + slot_c;
+                        }
+                        const int *w = P.params[K];
+                        const int s = S.s16[is], cv = S.s16[ic], g = S.s16[ig];
+                        const int p = (cv * w[0] + s * w[1] + g * w[2]) >> 5;
+                        int ns, nc, ng;
+                        if (bit) { ns = s - (((s - w[5]) * w[6]) >> 12); nc = cv - (((cv - w[9]) * w[10]) >> 12); ng = g - (((g - w[13]) * w[14]) >> 12); }
+                        else     { ns = s + (((4096 - w[3] - s) * w[4]) >> 12); nc = cv + (((4096 - w[7] - cv) * w[8]) >> 12); ng = g + (((4096 - w[11] - g) * w[12]) >> 12); }
+                        S.s16[is] = (short)ns; S.s16[ic] = (short)nc; S.s16[ig] = (short)ng;
+                        rec = (u32)p | (bit ? QE_REC_BIT : 0u) | (d == 0 ? QE_REC_RUN : 0u);
+                    }
+                    if (any_clash) __syncwarp();
+                }
+                __syncwarp();
+                pipe_push(P, tail, (u32)min(32, D - base), rec, lane);
+            }
+            if ((j & 7) == 7 && P.fail) { stop = true; break; }
+        }
+    }
+    if (!P.fail) pipe_push(P, tail, 1, QE_REC_END, lane);
 }

@@ -6,6 +6,7 @@ import sys
 import time
 from concurrent.futures import ThreadPoolExecutor
 
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 import numpy as np
 import torch
 
