@@ -414,7 +414,9 @@ struct EncPipe {
 
 __device__ __forceinline__ void pipe_push(EncPipe &P, u32 &tail, u32 cnt, u32 rec, u32 lane)
 {
-    while ((int)(tail + cnt - P.head) > QE_RING) { }          // wait for room (consumer always drains; head jumps ahead when it quits)
+    // wait for room (the consumer always drains; head jumps ahead when it quits).  The spin is bounded so
+    // that a logic error can never hang the GPU: after ~1 s the stream is failed instead.
+    for (u32 spins = 0; (int)(tail + cnt - P.head) > QE_RING; ) if (++spins > (1u << 26)) { P.fail = 2; break; }
     if (lane < cnt) P.ring[(tail + lane) & (QE_RING - 1)] = (u16)rec;
     __syncwarp();
     __threadfence_block();
@@ -446,8 +448,9 @@ __global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_p
         const long long eob = (long long)sb.out_cap - 16;
         u32 head = 0; int result = 0; bool done = false;
         while (!done) {
-            u32 tail;
-            while ((tail = P.tail) == head) { }
+            u32 tail, spins = 0;
+            while ((tail = P.tail) == head) { if (P.fail == 2 || ++spins > (1u << 27)) { result = LIBBSC_GPU_ERROR; break; } }
+            if (result) { done = true; break; }
             __threadfence_block();
             const u32 cnt = min(32u, tail - head);
             const u32 mine = lane < cnt ? P.ring[(head + lane) & (QE_RING - 1)] : 0u;
@@ -541,7 +544,10 @@ __global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_p
                 const u32 hs = cs >> QC_LOG, slot_s = (cs ^ (hs * 1237u)) & QC_MASK, hc = cc >> QC_LOG, slot_c = (cc ^ (hc * 1237u)) & QC_MASK;
                 const u32 cmask = __ballot_sync(0xffffffffu, cached);
                 bool clash = false;
-                if (cached) { clash = __popc(__match_any_sync(cmask, slot_s)) > 1 || __popc(__match_any_sync(cmask, slot_c)) > 1; }
+                if (cached) {                                // both matches are executed by every lane of cmask (no short-circuit!)
+                    const u32 ms = __match_any_sync(cmask, slot_s), mc = __match_any_sync(cmask, slot_c);
+                    clash = (__popc(ms) > 1) | (__popc(mc) > 1);
+                }
                 const bool any_clash = __any_sync(0xffffffffu, clash);
                 u32 rec = 0;
                 for (int turn = 0; turn < (any_clash ? 32 : 1); ++turn) {
