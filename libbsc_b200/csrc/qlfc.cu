@@ -39,6 +39,7 @@ struct SubBlock {
     int result;                  // bytes produced or error
     u32 nsym;
     u32 tile_base, tiles;        // slice of the rank tiles (qlfc_ranks.cuh)
+    u32 stat_cached, stat_miss;  // rare-counter cache statistics of the coder kernel
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -352,6 +353,8 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
 
+    if (getenv("BSCB200_QSTATS"))
+        for (int b = 0; b < nBlocks; ++b) fprintf(stderr, "[qstats enc] sub %d: in %u runs %u out %d rare-accesses %u misses %u\n", b, h_sb[b].in_size, h_sb[b].run_end - h_sb[b].run_begin, h_sb[b].result, h_sb[b].stat_cached, h_sb[b].stat_miss);
     int result;
     if (nBlocks == 1) {                                   // coder.cpp:113-119
         result = h_sb[0].result;
@@ -464,6 +467,8 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof h_sb, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->sync();
+    if (getenv("BSCB200_QSTATS"))
+        for (int b = 0; b < (nBlocks == 1 ? 1 : nBlocks); ++b) fprintf(stderr, "[qstats dec] sub %d: out %d rare-accesses %u misses %u\n", b, h_sb[b].result, h_sb[b].stat_cached, h_sb[b].stat_miss);
     int total = 0, err = 0;
     for (int b = 0; b < (nBlocks == 1 ? 1 : nBlocks); ++b) { if (h_sb[b].result < 0) err = h_sb[b].result; total += h_sb[b].result; }
     A.release(mark);

@@ -1,45 +1,52 @@
 // libbsc_b200/csrc/qlfc_coder.cuh -- QLFC stage 2 (context model + binary range coder), device engine.
-// Included by qlfc.cu inside its anonymous namespace (needs SubBlock, QTables, c_params, K_*).
+// Included by qlfc.cu inside its anonymous namespace (needs SubBlock, QTables, K_*, bscb_param).
 //
 // Why this looks the way it does.  One coder stream is a strictly serial recurrence (every binary
 // decision reads three adaptive counters whose addresses depend on the previous decisions, then
 // updates them and the range coder).  The format allows only <= 8 streams per block
-// (coder.cpp:52-59), so per-stream LATENCY is everything.  First measurements (profiles/r1a_*)
-// showed ~370 cycles per decision with the counters in global memory (every dependent load is an
-// L2 round trip because the preceding store invalidates the L1 line).  Here the whole working set
-// lives in shared memory of one SM per stream:
+// (coder.cpp:52-59), so per-stream LATENCY is everything.  Measured history (profiles/):
+//   r1a  counters in global memory                 ~370 cycles / decision (each load an L2 round trip)
+//   r1b  16 K-entry shared-memory caches           ~200 cycles / decision (working set did not fit)
+// so the counter file is now laid out for shared memory: one SM per stream holds
 //
-//   * state tables                       40 KB   (tables.h data, qlfc_tables.inc)
-//   * "resident" counters                49 KB   every counter of the first-bit / unary-exponent
-//                                                decisions + all model-wide shared counters
-//   * two direct-mapped write-back caches 96 KB  for the mantissa/escape banks indexed by state and
-//                                                by symbol (1.7 M counters in HBM behind them;
-//                                                separate caches so the two lookups of one
-//                                                decision can never evict each other)
+//   * state tables                                  40 KB  (tables.h data, qlfc_tables.inc)
+//   * first-bit, unary-exponent (index < 8) and model-wide shared counters      25 KB
+//   * mantissa counters for exponents 1..5, stored COMPACTLY (2^e - 1 tree nodes per row instead of
+//     the reference's 256/32-wide rows: 62 entries per state / symbol)          124 KB
+//   * two small direct-mapped write-back caches (4 K entries each) for everything rare: rank
+//     exponents 6-7, the escape bank, run exponents >= 6 and run-exponent indices >= 8; the
+//     1.7 M counters behind them live in HBM                                    24 KB
 //
-// The warp runs in lock-step: all 32 lanes execute the same decision sequence on the same data
-// (shared-memory broadcasts), so no intra-warp synchronisation is needed on the model; lanes only
-// diverge to prefetch run records (encoder) and to expand runs / rotate the MTF list (decoder).
+// The decoder warp runs in lock-step: all 32 lanes execute the same decision sequence on the same
+// data (shared-memory broadcasts), lanes only diverge to expand runs / rotate the MTF list.
+// The encoder is a two-warp pipeline, see q_encode3 below.
 #pragma once
 
-// ---- shared-memory counter file (indices in int16 units) -------------------------------------------
+// ---- shared-memory counter file (indices in u16 units) ---------------------------------------------
 constexpr u32 R_RT_SHARED = 0, R_RT_STATE = 2, R_RT_CHAR = R_RT_STATE + 256;
 constexpr u32 R_RE_SHARED = R_RT_CHAR + 256, R_RE_STATE = R_RE_SHARED + 8, R_RE_CHAR = R_RE_STATE + 2048;
 constexpr u32 R_UT_SHARED = R_RE_CHAR + 2048, R_UT_STATE = R_UT_SHARED + 2, R_UT_CHAR = R_UT_STATE + 256;
-constexpr u32 R_UE_SHARED = R_UT_CHAR + 256, R_UE_STATE = R_UE_SHARED + 32, R_UE_CHAR = R_UE_STATE + 8192;
-constexpr u32 R_WIDE_SHARED = R_UE_CHAR + 8192;            // 9 banks x 256 (rank mantissa e=0..7, escape)
+constexpr u32 UE_RES = 8;                                   // run-exponent indices kept resident
+constexpr u32 R_UE_SHARED = R_UT_CHAR + 256, R_UE_STATE = R_UE_SHARED + 32, R_UE_CHAR = R_UE_STATE + 256 * UE_RES;
+constexpr u32 R_WIDE_SHARED = R_UE_CHAR + 256 * UE_RES;    // 9 banks x 256 (rank mantissa e=0..7, escape)
 constexpr u32 R_NARROW_SHARED = R_WIDE_SHARED + 9 * 256;   // 32 banks x 32 (run mantissa)
-constexpr u32 R_END = R_NARROW_SHARED + 32 * 32;
+constexpr u32 M_ROW = 62;                                   // compact row: exponents 1..5 -> offsets 2^e-2 .. 2^(e+1)-3
+constexpr u32 M_MAXE = 5;
+constexpr u32 R_RM_STATE = R_NARROW_SHARED + 32 * 32, R_RM_CHAR = R_RM_STATE + 256 * M_ROW;
+constexpr u32 R_UM_STATE = R_RM_CHAR + 256 * M_ROW, R_UM_CHAR = R_UM_STATE + 256 * M_ROW;
+constexpr u32 R_END = R_UM_CHAR + 256 * M_ROW;
 
-constexpr int  QC_LOG = 14;                                 // 16 K entries per cache
+constexpr int  QC_LOG = 12;                                 // 4 K entries per cache
 constexpr u32  QC_SLOTS = 1u << QC_LOG, QC_MASK = QC_SLOTS - 1;
-constexpr u32  C_STATE_VAL = R_END;                         // cache of the by-state banks
-constexpr u32  C_CHAR_VAL = C_STATE_VAL + QC_SLOTS;         // cache of the by-symbol banks
-constexpr u32  S16_COUNT = C_CHAR_VAL + QC_SLOTS;
-// index space behind each cache: 9 wide banks x [256][256], then 32 narrow banks x [256][32]
+constexpr u32  C_STATE_VAL = R_END;                         // cache of the by-state rare banks
+constexpr u32  C_CHAR_VAL = C_STATE_VAL + QC_SLOTS;         // cache of the by-symbol rare banks
+constexpr u32  S16_COUNT = (C_CHAR_VAL + QC_SLOTS + 1) & ~1u;
+// index space behind each cache: 9 wide banks x [256][256], 32 narrow banks x [256][32], run exponent [256][32]
 constexpr u32  COLD_WIDE = 65536, COLD_NARROW = 8192;
-constexpr u32  COLD_COUNT = 9 * COLD_WIDE + 32 * COLD_NARROW;          // 851968 counters per kind
+constexpr u32  COLD_UE = 9 * COLD_WIDE + 32 * COLD_NARROW;
+constexpr u32  COLD_COUNT = COLD_UE + 8192;
 constexpr u32  COLD_PAD = (COLD_COUNT + 255) & ~255u;
+static_assert((COLD_COUNT >> QC_LOG) + 1 < 256, "cache tag must fit a byte");
 
 struct CoderSmem {
     u8    rank_state[32768];
@@ -54,7 +61,7 @@ struct CoderSmem {
 
 __device__ __forceinline__ void coder_smem_init(CoderSmem &S, const QTables *__restrict__ g)
 {
-    const u32 lane = threadIdx.x;
+    const u32 lane = threadIdx.x & 31;
     const uint4 *src = (const uint4 *)g; uint4 *dst = (uint4 *)S.rank_state;      // rank_state and run_state are contiguous
     for (u32 i = lane; i < sizeof(QTables) / 16; i += 32) dst[i] = src[i];
     u32 *w = (u32 *)S.s16;
@@ -64,15 +71,22 @@ __device__ __forceinline__ void coder_smem_init(CoderSmem &S, const QTables *__r
     __syncwarp();
 }
 
-// Index (into S.s16) of counter `idx` of one kind, loading it through the direct-mapped cache.
-__device__ __forceinline__ u32 cache_get(CoderSmem &S, u32 val_base, u8 *tags, short *__restrict__ cold, u32 idx)
+__device__ __forceinline__ u32 wide_idx(u32 bank, u32 x, u32 node) { return bank * COLD_WIDE + x * 256 + node; }
+__device__ __forceinline__ u32 narrow_idx(u32 e, u32 x, u32 node) { return 9 * COLD_WIDE + e * COLD_NARROW + x * 32 + node; }
+__device__ __forceinline__ u32 ue_idx(u32 x, u32 k) { return COLD_UE + x * 32 + k; }
+__device__ __forceinline__ u32 m_off(u32 e, u32 node) { return (1u << e) - 2u + node; }   // position inside a compact row
+
+// Index (into S.s16) of rare counter `idx` of one kind, through the direct-mapped write-back cache.
+// Warp-uniform version (decoder): every lane performs the same accesses.
+__device__ __forceinline__ u32 cache_get(CoderSmem &S, u32 val_base, u8 *tags, short *__restrict__ cold, u32 idx, u32 &misses)
 {
     const u32 h = idx >> QC_LOG, slot = (idx ^ (h * 1237u)) & QC_MASK, want = h + 1;
     const u32 t = tags[slot];
-    if (t != want) {                                         // warp-uniform branch
-        if (t) cold[((t - 1) << QC_LOG) | ((slot ^ ((t - 1) * 1237u)) & QC_MASK)] = S.s16[val_base + slot];
-        S.s16[val_base + slot] = cold[idx];
+    if (t != want) {
+        if (t) cold[((t - 1) << QC_LOG) | ((slot ^ ((t - 1) * 1237u)) & QC_MASK)] = (short)S.s16[val_base + slot];
+        S.s16[val_base + slot] = (u16)cold[idx];
         tags[slot] = (u8)want;
+        ++misses;
     }
     return val_base + slot;
 }
@@ -92,7 +106,6 @@ template <int K, int WHO> __device__ __forceinline__ int q_down(int p)    // the
 {
     return p - (((p - bscb_param(K, 5 + 4 * WHO)) * bscb_param(K, 6 + 4 * WHO)) >> 12);
 }
-template <int K, int WHO> __device__ __forceinline__ int q_learn(int p, u32 bit) { return bit ? q_down<K, WHO>(p) : q_up<K, WHO>(p); }
 
 // ---- range coder (rangecoder.h:38-271), 16-bit units -------------------------------------------------
 struct Rc2Enc {
@@ -144,14 +157,7 @@ struct Rc2Dec {
     }
 };
 
-// one binary decision against three shared-memory counters (indices into S.s16)
-template <int K> __device__ __forceinline__ void enc3(CoderSmem &S, Rc2Enc &rc, u32 is, u32 ic, u32 ig, u32 bit)
-{
-    const int s = S.s16[is], c = S.s16[ic], g = S.s16[ig];
-    const int p = q_mix<K>(s, c, g);
-    S.s16[is] = (short)q_learn<K, 0>(s, bit); S.s16[ic] = (short)q_learn<K, 1>(c, bit); S.s16[ig] = (short)q_learn<K, 2>(g, bit);
-    rc.encode(bit, p);
-}
+// one binary decision against three shared-memory counters (indices into S.s16), decoder side
 template <int K> __device__ __forceinline__ u32 dec3(CoderSmem &S, Rc2Dec &rc, u32 is, u32 ic, u32 ig)
 {
     const int s = S.s16[is], c = S.s16[ic], g = S.s16[ig];
@@ -161,116 +167,8 @@ template <int K> __device__ __forceinline__ u32 dec3(CoderSmem &S, Rc2Dec &rc, u
     return bit;
 }
 
-// index helpers for the cached banks.  wide bank b = 0..7 rank mantissa by exponent, 8 = escape.
-__device__ __forceinline__ u32 wide_idx(u32 bank, u32 x, u32 node) { return bank * COLD_WIDE + x * 256 + node; }
-__device__ __forceinline__ u32 narrow_idx(u32 e, u32 x, u32 node) { return 9 * COLD_WIDE + e * COLD_NARROW + x * 32 + node; }
-
 // ---------------------------------------------------------------------------------------------------
-// encoder (qlfc.cpp:829-1129)
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 1) q_encode2(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
-                                                   SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
-                                                   const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
-{
-    extern __shared__ __align__(16) u8 q_smem_raw[];
-    CoderSmem &S = *reinterpret_cast<CoderSmem *>(q_smem_raw);
-    coder_smem_init(S, tables);
-
-    const u32 sid = sb_list ? sb_list[blockIdx.x] : blockIdx.x;
-    SubBlock &sb = sbs[sid];
-    short *cold_s = cold_all + (size_t)sid * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
-    const u32 lane = threadIdx.x;
-
-    Rc2Enc rc; rc.low32 = 0; rc.carry = 0; rc.range = 0xffffffffu; rc.cache = 0; rc.pending = 0; rc.pos = 0; rc.out = out_all + sb.out_off;
-    const long long eob = (long long)sb.out_cap - 16;
-    int ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0, maxRank = 7, avgRank = 0;
-
-    const u32 n = sb.in_size;
-    for (int b = 31; b >= 0; --b) rc.encode((n >> b) & 1u, 2048);
-    {   // MTF-order header (qlfc.cpp:857-891)
-        const u8 *mtf = mtf_all + sid * 256;
-        u32 used8 = 0; int prev = -1;
-        for (int d = 0; d < 256; ++d) {
-            int c = mtf[d];
-            for (int bit = 7; bit >= 0; --bit) {
-                bool can0, can1; header_options(used8, prev, c >> (bit + 1), bit, can0, can1);
-                if (can0 && can1) rc.encode((c >> bit) & 1u, 2048);
-            }
-            if (c == prev) { maxRank = ilog2_dev((u32)(d - 1)); break; }
-            prev = c; if ((u32)(c >> 3) == lane) used8 |= 1u << (c & 7);
-        }
-    }
-
-    int result = 0;
-    const u32 rb = sb.run_begin, re = sb.run_end;
-    for (u32 t0 = rb; t0 < re && result == 0; t0 += 32) {
-        const u32 cnt = min(32u, re - t0);
-        u32 my_sym = 0, my_rank = 0, my_len = 0;             // lane j prefetches run t0 + j
-        if (lane < cnt) { my_sym = run_sym[t0 + lane]; my_rank = run_rank[t0 + lane]; my_len = run_pos[t0 + lane + 1] - run_pos[t0 + lane]; }
-        for (u32 j = 0; j < cnt; ++j) {
-            if ((long long)rc.pos >= eob) { result = LIBBSC_NOT_COMPRESSIBLE; break; }   // qlfc.cpp:898-901
-            const u32 c = __shfl_sync(0xffffffffu, my_sym, j);
-            const int rank = (int)__shfl_sync(0xffffffffu, my_rank, j);
-            const int run = (int)__shfl_sync(0xffffffffu, my_len, j);
-
-            u32 st = S.rank_state[(ctxRun << 11) | (ctxRank4 << 3) | S.rankHist[c]];
-            if (avgRank < 32) {
-                enc3<K_RANK_T>(S, rc, R_RT_STATE + st, R_RT_CHAR + c, R_RT_SHARED, rank != 1);
-                if (rank == 1) S.rankHist[c] = 0;
-                else {
-                    const int e = ilog2_dev((u32)rank);
-                    S.rankHist[c] = (u8)e;
-                    for (int b = 1; b < e; ++b) enc3<K_RANK_E>(S, rc, R_RE_STATE + st * 8 + b - 1, R_RE_CHAR + c * 8 + b - 1, R_RE_SHARED + b - 1, 1);
-                    if (e < maxRank)          enc3<K_RANK_E>(S, rc, R_RE_STATE + st * 8 + e - 1, R_RE_CHAR + c * 8 + e - 1, R_RE_SHARED + e - 1, 0);
-                    for (int node = 1, bit = e - 1; bit >= 0; --bit) {
-                        const u32 bb = ((u32)rank >> bit) & 1u;
-                        const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, wide_idx(e, st, node));
-                        const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, wide_idx(e, c, node));
-                        enc3<K_RANK_M>(S, rc, is, ic, R_WIDE_SHARED + e * 256 + node, bb);
-                        node = 2 * node + (int)bb;
-                    }
-                }
-            } else {
-                S.rankHist[c] = (u8)ilog2_dev((u32)rank);
-                for (int node = 1, bit = maxRank; bit >= 0; --bit) {
-                    const u32 bb = ((u32)rank >> bit) & 1u;
-                    const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, wide_idx(8, st, node));
-                    const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, wide_idx(8, c, node));
-                    enc3<K_RANK_P>(S, rc, is, ic, R_WIDE_SHARED + 8 * 256 + node, bb);
-                    node = 2 * node + (int)bb;
-                }
-            }
-            avgRank = (avgRank * 124 + rank * 4) >> 7;
-            const int rank0 = rank - 1;
-            const int rh = S.runHist[c];
-            st = S.run_state[(ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7 ? rank0 : 7) << 3) | (rh < 7 ? rh : 7)];
-
-            enc3<K_RUN_T>(S, rc, R_UT_STATE + st, R_UT_CHAR + c, R_UT_SHARED, run != 1);
-            if (run == 1) S.runHist[c] = (u8)((rh + 2) >> 2);
-            else {
-                const int e = ilog2_dev((u32)run);
-                S.runHist[c] = (u8)((rh + 3 * e + 3) >> 2);
-                for (int b = 1; b < e; ++b) enc3<K_RUN_E>(S, rc, R_UE_STATE + st * 32 + b - 1, R_UE_CHAR + c * 32 + b - 1, R_UE_SHARED + b - 1, 1);
-                enc3<K_RUN_E>(S, rc, R_UE_STATE + st * 32 + e - 1, R_UE_CHAR + c * 32 + e - 1, R_UE_SHARED + e - 1, 0);
-                for (int node = 1, bit = e - 1; bit >= 0; --bit) {
-                    const u32 bb = ((u32)run >> bit) & 1u;
-                    const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, narrow_idx(e, st, node));
-                    const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, narrow_idx(e, c, node));
-                    enc3<K_RUN_M>(S, rc, is, ic, R_NARROW_SHARED + e * 32 + node, bb);
-                    node = (e <= 5) ? 2 * node + (int)bb : node + 1;          // qlfc.cpp:1119
-                }
-            }
-            ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0)) & 0x7;
-            ctxRank4 = ((ctxRank4 << 2) | (rank0 < 3 ? rank0 : 3)) & 0xff;
-            ctxRun   = ((ctxRun << 1) | (run < 3)) & 0xf;
-        }
-    }
-    if (result == 0) result = (int)rc.finish();
-    if (lane == 0) sb.result = result;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// decoder (qlfc.cpp:1672-1927)
+// decoder (qlfc.cpp:1672-1927).  One warp per sub-block, lock-step; runs are expanded warp-wide.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
                                                    const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
@@ -283,6 +181,7 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
     SubBlock &sb = sbs[sid];
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     const u32 lane = threadIdx.x;
+    u32 st_cached = 0, st_miss = 0;
 
     Rc2Dec rc; rc.in = in_all + sb.out_off; rc.pos = 0; rc.limit = sb.out_cap; rc.code = 0; rc.range = 0xffffffffu;
     rc.win = S.inwin; rc.wbase = 0; rc.refill();
@@ -318,25 +217,35 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
             b = dec3<K_RANK_T>(S, rc, R_RT_STATE + st, R_RT_CHAR + c, R_RT_SHARED);
             if (!b) S.rankHist[c] = 0;
             else {
-                int e = 1;
-                while (e != maxRank) {
+                u32 e = 1;
+                while ((int)e != maxRank) {
                     b = dec3<K_RANK_E>(S, rc, R_RE_STATE + st * 8 + e - 1, R_RE_CHAR + c * 8 + e - 1, R_RE_SHARED + e - 1);
                     if (!b) break;
                     if (++e >= 7) break;                                      // e <= maxRank <= 7 in valid streams
                 }
                 S.rankHist[c] = (u8)e;
-                for (int bit = e - 1; bit >= 0; --bit) {
-                    const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, wide_idx(e, st, rank));
-                    const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, wide_idx(e, c, rank));
-                    b = dec3<K_RANK_M>(S, rc, is, ic, R_WIDE_SHARED + e * 256 + rank);
-                    rank = 2 * rank + (int)b;
+                if (e <= M_MAXE) {
+                    const u32 bs = R_RM_STATE + st * M_ROW + (1u << e) - 2u, bc = R_RM_CHAR + c * M_ROW + (1u << e) - 2u, bg = R_WIDE_SHARED + e * 256;
+                    for (int bit = (int)e - 1; bit >= 0; --bit) {
+                        b = dec3<K_RANK_M>(S, rc, bs + rank, bc + rank, bg + rank);
+                        rank = 2 * rank + (int)b;
+                    }
+                } else {
+                    for (int bit = (int)e - 1; bit >= 0; --bit) {
+                        const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, wide_idx(e, st, rank), st_miss);
+                        const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, wide_idx(e, c, rank), st_miss);
+                        st_cached += 2;
+                        b = dec3<K_RANK_M>(S, rc, is, ic, R_WIDE_SHARED + e * 256 + rank);
+                        rank = 2 * rank + (int)b;
+                    }
                 }
             }
         } else {
             rank = 0;
             for (int node = 1, bit = maxRank; bit >= 0; --bit) {
-                const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, wide_idx(8, st, node));
-                const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, wide_idx(8, c, node));
+                const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, wide_idx(8, st, node), st_miss);
+                const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, wide_idx(8, c, node), st_miss);
+                st_cached += 2;
                 b = dec3<K_RANK_P>(S, rc, is, ic, R_WIDE_SHARED + 8 * 256 + node);
                 node = 2 * node + (int)b; rank = 2 * rank + (int)b;
             }
@@ -363,19 +272,34 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
         b = dec3<K_RUN_T>(S, rc, R_UT_STATE + st, R_UT_CHAR + c, R_UT_SHARED);
         if (!b) S.runHist[c] = (u8)((rh + 2) >> 2);
         else {
-            int e = 1;
+            u32 e = 1;
             for (;;) {
-                b = dec3<K_RUN_E>(S, rc, R_UE_STATE + st * 32 + e - 1, R_UE_CHAR + c * 32 + e - 1, R_UE_SHARED + e - 1);
+                const u32 k = e - 1;
+                if (k < UE_RES) b = dec3<K_RUN_E>(S, rc, R_UE_STATE + st * UE_RES + k, R_UE_CHAR + c * UE_RES + k, R_UE_SHARED + k);
+                else {
+                    const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, ue_idx(st, k), st_miss);
+                    const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, ue_idx(c, k), st_miss);
+                    st_cached += 2;
+                    b = dec3<K_RUN_E>(S, rc, is, ic, R_UE_SHARED + k);
+                }
                 if (!b) break;
                 if (++e >= 31) break;                                         // corrupt-input guard
             }
             S.runHist[c] = (u8)((rh + 3 * e + 3) >> 2);
-            for (int node = 1, bit = e - 1; bit >= 0; --bit) {
-                const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, narrow_idx(e, st, node));
-                const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, narrow_idx(e, c, node));
-                b = dec3<K_RUN_M>(S, rc, is, ic, R_NARROW_SHARED + e * 32 + node);
-                run = 2 * run + b;
-                node = (e <= 5) ? 2 * node + (int)b : node + 1;
+            if (e <= M_MAXE) {
+                const u32 bs = R_UM_STATE + st * M_ROW + (1u << e) - 2u, bc = R_UM_CHAR + c * M_ROW + (1u << e) - 2u, bg = R_NARROW_SHARED + e * 32;
+                for (int node = 1, bit = (int)e - 1; bit >= 0; --bit) {
+                    b = dec3<K_RUN_M>(S, rc, bs + node, bc + node, bg + node);
+                    run = 2 * run + b; node = 2 * node + (int)b;
+                }
+            } else {
+                for (int node = 1, bit = (int)e - 1; bit >= 0; --bit) {
+                    const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, narrow_idx(e, st, node), st_miss);
+                    const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, narrow_idx(e, c, node), st_miss);
+                    st_cached += 2;
+                    b = dec3<K_RUN_M>(S, rc, is, ic, R_NARROW_SHARED + e * 32 + node);
+                    run = 2 * run + b; node = node + 1;                       // qlfc.cpp:1119: linear contexts above 5 bits
+                }
             }
         }
         ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0)) & 0x7;
@@ -386,11 +310,11 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
         for (u32 k = lane; k < run; k += 32) out[i + k] = (u8)c;
         i += run;
     }
-    if (lane == 0) sb.result = (int)n;
+    if (lane == 0) { sb.result = (int)n; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// encoder, two-warp pipeline (replaces q_encode2 on the hot path)
+// encoder, two-warp pipeline
 //
 // Every context of the encoder is a function of the INPUT only (qlfc.cpp:949-955, 1048-1054,
 // 1123-1125), and within one run every decision touches a different counter.  So the model side
@@ -401,7 +325,7 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
 // from a shared-memory ring.  Per stream the critical path shrinks from "~9 dependent model
 // look-ups per run" to "one parallel model step per run" || "one range step per decision".
 // ---------------------------------------------------------------------------------------------------
-#define QE_RING 8192                                       // records (u16) in the ring
+#define QE_RING 4096                                       // records (u16) in the ring
 #define QE_REC_BIT   0x2000u                               // bit 13: the coded bit
 #define QE_REC_RUN   0x4000u                               // bit 14: first decision of a run (EOB check point)
 #define QE_REC_END   0xffffu
@@ -437,7 +361,7 @@ __global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_p
 
     if (warp == 0) {
         coder_smem_init(S, tables);
-        for (int i = lane; i < 7 * 16; i += 32) P.params[i / 16][i % 16] = (i % 16) < 15 ? (int)c_params[i / 16][i % 16] : 0;
+        for (int i = lane; i < 7 * 16; i += 32) P.params[i / 16][i % 16] = (i % 16) < 15 ? bscb_param(i / 16, i % 16) : 0;
         if (lane == 0) { P.head = 0; P.tail = 0; P.fail = 0; }
     }
     __syncthreads();
@@ -450,7 +374,7 @@ __global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_p
         while (!done) {
             u32 tail, spins = 0;
             while ((tail = P.tail) == head) { if (P.fail == 2 || ++spins > (1u << 27)) { result = LIBBSC_GPU_ERROR; break; } }
-            if (result) { done = true; break; }
+            if (result) break;
             __threadfence_block();
             const u32 cnt = min(32u, tail - head);
             const u32 mine = lane < cnt ? P.ring[(head + lane) & (QE_RING - 1)] : 0u;
@@ -471,7 +395,7 @@ __global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_p
 
     // ---------------------------------- producer: the model ----------------------------------
     short *cold_s = cold_all + (size_t)sid * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
-    u32 tail = 0;
+    u32 tail = 0, st_cached = 0, st_miss = 0;
     int ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0, maxRank = 7, avgRank = 0;
     const u32 n = sb.in_size;
     pipe_push(P, tail, 32, 2048u | (((n >> (31 - lane)) & 1u) ? QE_REC_BIT : 0u), lane);
@@ -503,63 +427,80 @@ __global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_p
             // ---- per-run contexts (uniform) ----
             const u32 st1 = S.rank_state[(ctxRun << 11) | (ctxRank4 << 3) | S.rankHist[c]];
             const bool esc = avgRank >= 32;
-            const int er = ilog2_dev(rank), eu = ilog2_dev(run);
+            const u32 er = (u32)ilog2_dev(rank), eu = (u32)ilog2_dev(run);
             const int rank0 = (int)rank - 1;
             const int rh = S.runHist[c];
             const u32 st2 = S.run_state[(ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7 ? rank0 : 7) << 3) | (rh < 7 ? rh : 7)];
             __syncwarp();
             if (lane == 0) {
                 S.rankHist[c] = (u8)((esc || rank != 1) ? er : 0);
-                S.runHist[c] = (u8)(run == 1 ? (rh + 2) >> 2 : (rh + 3 * eu + 3) >> 2);
+                S.runHist[c] = (u8)(run == 1 ? (rh + 2) >> 2 : (rh + 3 * (int)eu + 3) >> 2);
             }
             avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
             ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0)) & 0x7;
             ctxRank4 = ((ctxRank4 << 2) | (rank0 < 3 ? rank0 : 3)) & 0xff;
             ctxRun   = ((ctxRun << 1) | (run < 3)) & 0xf;
             // ---- decision layout of this run ----
-            const int nE = (!esc && rank != 1) ? (er - 1) + (er < maxRank) : 0;
-            const int nM = esc ? maxRank + 1 : (rank != 1 ? er : 0);
-            const int o1 = esc ? 0 : 1, o2 = o1 + nE, o3 = o2 + nM, o4 = o3 + 1, o5 = o4 + (run != 1 ? eu : 0), D = o5 + (run != 1 ? eu : 0);
+            const int nE = (!esc && rank != 1) ? ((int)er - 1) + ((int)er < maxRank) : 0;
+            const int nM = esc ? maxRank + 1 : (rank != 1 ? (int)er : 0);
+            const int o1 = esc ? 0 : 1, o2 = o1 + nE, o3 = o2 + nM, o4 = o3 + 1, o5 = o4 + (run != 1 ? (int)eu : 0), D = o5 + (run != 1 ? (int)eu : 0);
             for (int base = 0; base < D; base += 32) {
                 const int d = base + (int)lane;
                 const bool act = d < D;
                 int K = 0; u32 is = 0, ic = 0, ig = 0, bit = 0, cs = 0xffffffffu, cc = 0xffffffffu;   // cs/cc: cold indices when cached
                 if (act) {
                     if (d < o1) { K = K_RANK_T; is = R_RT_STATE + st1; ic = R_RT_CHAR + c; ig = R_RT_SHARED; bit = rank != 1; }
-                    else if (d < o2) { const int k = d - o1; K = K_RANK_E; is = R_RE_STATE + st1 * 8 + k; ic = R_RE_CHAR + c * 8 + k; ig = R_RE_SHARED + k; bit = k < er - 1; }
+                    else if (d < o2) { const u32 k = (u32)(d - o1); K = K_RANK_E; is = R_RE_STATE + st1 * 8 + k; ic = R_RE_CHAR + c * 8 + k; ig = R_RE_SHARED + k; bit = k + 1 < er; }
                     else if (d < o3) {
-                        const int l = d - o2;
-                        if (!esc) { const int bp = er - 1 - l; const u32 node = rank >> (bp + 1); bit = (rank >> bp) & 1u; K = K_RANK_M;
-                                    cs = wide_idx(er, st1, node); cc = wide_idx(er, c, node); ig = R_WIDE_SHARED + er * 256 + node; }
-                        else      { const int bp = maxRank - l; const u32 node = (1u << l) | (rank >> (bp + 1)); bit = (rank >> bp) & 1u; K = K_RANK_P;
-                                    cs = wide_idx(8, st1, node); cc = wide_idx(8, c, node); ig = R_WIDE_SHARED + 8 * 256 + node; }
+                        const u32 l = (u32)(d - o2);
+                        if (!esc) {
+                            const u32 bp = er - 1 - l, node = rank >> (bp + 1); bit = (rank >> bp) & 1u; K = K_RANK_M; ig = R_WIDE_SHARED + er * 256 + node;
+                            if (er <= M_MAXE) { is = R_RM_STATE + st1 * M_ROW + m_off(er, node); ic = R_RM_CHAR + c * M_ROW + m_off(er, node); }
+                            else { cs = wide_idx(er, st1, node); cc = wide_idx(er, c, node); }
+                        } else {
+                            const u32 bp = (u32)maxRank - l, node = (1u << l) | (rank >> (bp + 1)); bit = (rank >> bp) & 1u; K = K_RANK_P;
+                            cs = wide_idx(8, st1, node); cc = wide_idx(8, c, node); ig = R_WIDE_SHARED + 8 * 256 + node;
+                        }
                     }
                     else if (d < o4) { K = K_RUN_T; is = R_UT_STATE + st2; ic = R_UT_CHAR + c; ig = R_UT_SHARED; bit = run != 1; }
-                    else if (d < o5) { const int k = d - o4; K = K_RUN_E; is = R_UE_STATE + st2 * 32 + k; ic = R_UE_CHAR + c * 32 + k; ig = R_UE_SHARED + k; bit = k < eu - 1; }
-                    else { const int l = d - o5, bp = eu - 1 - l; const u32 node = eu <= 5 ? (run >> (bp + 1)) : (u32)(1 + l); bit = (run >> bp) & 1u; K = K_RUN_M;
-                           cs = narrow_idx(eu, st2, node); cc = narrow_idx(eu, c, node); ig = R_NARROW_SHARED + eu * 32 + node; }
+                    else if (d < o5) {
+                        const u32 k = (u32)(d - o4); K = K_RUN_E; ig = R_UE_SHARED + k; bit = k + 1 < eu;
+                        if (k < UE_RES) { is = R_UE_STATE + st2 * UE_RES + k; ic = R_UE_CHAR + c * UE_RES + k; }
+                        else { cs = ue_idx(st2, k); cc = ue_idx(c, k); }
+                    }
+                    else {
+                        const u32 l = (u32)(d - o5), bp = eu - 1 - l; bit = (run >> bp) & 1u; K = K_RUN_M;
+                        if (eu <= M_MAXE) { const u32 node = run >> (bp + 1); ig = R_NARROW_SHARED + eu * 32 + node;
+                                            is = R_UM_STATE + st2 * M_ROW + m_off(eu, node); ic = R_UM_CHAR + c * M_ROW + m_off(eu, node); }
+                        else { const u32 node = 1 + l; ig = R_NARROW_SHARED + eu * 32 + node; cs = narrow_idx(eu, st2, node); cc = narrow_idx(eu, c, node); }
+                    }
                 }
-                // ---- cached counters: per-lane direct-mapped look-up; identical slots are serialised ----
+                // ---- rare counters: per-lane direct-mapped look-up; identical slots are serialised ----
                 const bool cached = cs != 0xffffffffu;
-                const u32 hs = cs >> QC_LOG, slot_s = (cs ^ (hs * 1237u)) & QC_MASK, hc = cc >> QC_LOG, slot_c = (cc ^ (hc * 1237u)) & QC_MASK;
                 const u32 cmask = __ballot_sync(0xffffffffu, cached);
-                bool clash = false;
-                if (cached) {                                // both matches are executed by every lane of cmask (no short-circuit!)
-                    const u32 ms = __match_any_sync(cmask, slot_s), mc = __match_any_sync(cmask, slot_c);
-                    clash = (__popc(ms) > 1) | (__popc(mc) > 1);
-                }
-                const bool any_clash = __any_sync(0xffffffffu, clash);
                 u32 rec = 0;
+                bool any_clash = false;
+                u32 hs = 0, slot_s = 0, hc = 0, slot_c = 0;
+                if (cmask) {                                 // warp-uniform
+                    hs = cs >> QC_LOG; slot_s = (cs ^ (hs * 1237u)) & QC_MASK; hc = cc >> QC_LOG; slot_c = (cc ^ (hc * 1237u)) & QC_MASK;
+                    bool clash = false;
+                    if (cached) {                            // both matches are executed by every lane of cmask (no short-circuit!)
+                        const u32 ms = __match_any_sync(cmask, slot_s), mc = __match_any_sync(cmask, slot_c);
+                        clash = (__popc(ms) > 1) | (__popc(mc) > 1);
+                    }
+                    any_clash = __any_sync(0xffffffffu, clash);
+                    st_cached += 2 * __popc(cmask);
+                }
                 for (int turn = 0; turn < (any_clash ? 32 : 1); ++turn) {
                     const bool go = act && (!any_clash || (int)lane == turn);
                     if (go) {
                         if (cached) {
                             u32 t = S.tag_state[slot_s];
-                            if (t != hs + 1) { if (t) cold_s[((t - 1) << QC_LOG) | ((slot_s ^ ((t - 1) * 1237u)) & QC_MASK)] = S.s16[C_STATE_VAL + slot_s];
-                                               S.s16[C_STATE_VAL + slot_s] = cold_s[cs]; S.tag_state[slot_s] = (u8)(hs + 1); }
+                            if (t != hs + 1) { if (t) cold_s[((t - 1) << QC_LOG) | ((slot_s ^ ((t - 1) * 1237u)) & QC_MASK)] = (short)S.s16[C_STATE_VAL + slot_s];
+                                               S.s16[C_STATE_VAL + slot_s] = (u16)cold_s[cs]; S.tag_state[slot_s] = (u8)(hs + 1); ++st_miss; }
                             t = S.tag_char[slot_c];
-                            if (t != hc + 1) { if (t) cold_c[((t - 1) << QC_LOG) | ((slot_c ^ ((t - 1) * 1237u)) & QC_MASK)] = S.s16[C_CHAR_VAL + slot_c];
-                                               S.s16[C_CHAR_VAL + slot_c] = cold_c[cc]; S.tag_char[slot_c] = (u8)(hc + 1); }
+                            if (t != hc + 1) { if (t) cold_c[((t - 1) << QC_LOG) | ((slot_c ^ ((t - 1) * 1237u)) & QC_MASK)] = (short)S.s16[C_CHAR_VAL + slot_c];
+                                               S.s16[C_CHAR_VAL + slot_c] = (u16)cold_c[cc]; S.tag_char[slot_c] = (u8)(hc + 1); ++st_miss; }
                             is = C_STATE_VAL + slot_s; ic = C_CHAR_VAL + slot_c;
                         }
                         const int *w = P.params[K];
@@ -568,7 +509,7 @@ __global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_p
                         int ns, nc, ng;
                         if (bit) { ns = s - (((s - w[5]) * w[6]) >> 12); nc = cv - (((cv - w[9]) * w[10]) >> 12); ng = g - (((g - w[13]) * w[14]) >> 12); }
                         else     { ns = s + (((4096 - w[3] - s) * w[4]) >> 12); nc = cv + (((4096 - w[7] - cv) * w[8]) >> 12); ng = g + (((4096 - w[11] - g) * w[12]) >> 12); }
-                        S.s16[is] = (short)ns; S.s16[ic] = (short)nc; S.s16[ig] = (short)ng;
+                        S.s16[is] = (u16)ns; S.s16[ic] = (u16)nc; S.s16[ig] = (u16)ng;
                         rec = (u32)p | (bit ? QE_REC_BIT : 0u) | (d == 0 ? QE_REC_RUN : 0u);
                     }
                     if (any_clash) __syncwarp();
@@ -580,4 +521,6 @@ __global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_p
         }
     }
     if (!P.fail) pipe_push(P, tail, 1, QE_REC_END, lane);
+    st_miss = __reduce_add_sync(0xffffffffu, st_miss);
+    if (lane == 0) { sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
