@@ -254,6 +254,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 
 #include "qlfc_ranks.cuh"
 #include "qlfc_coder.cuh"
+#include "qlfc_encoder.cuh"
 
 constexpr size_t MODEL_SHORTS_PAD = 2 * (size_t)COLD_PAD;     // by-state + by-symbol cold arrays per stream
 
@@ -346,10 +347,10 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         LAUNCH(ctx, q_rank_tile, ceil_div(total_tiles, 4), 128, 0, run_sym, run_rank, d_sb, (u32)nBlocks, total_tiles, next_tab);
     }
     init_models(ctx, models, nBlocks);
-    const size_t enc_smem = ((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe);
-    ensure_dyn_smem(q_encode3, ctx->device, enc_smem);
+    const size_t enc_smem = ((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(Enc4Pipe);
+    ensure_dyn_smem(q_encode4, ctx->device, enc_smem);
     PROF_BYTES(ctx, (double)n);                          // + c written; the launch is latency-, not bandwidth-bound
-    LAUNCH(ctx, q_encode3, nBlocks, 64, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+    LAUNCH(ctx, q_encode4, nBlocks, 96, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
 
@@ -388,7 +389,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                 CUDA_TRY(cudaMemcpyAsync(d_list, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
                 ctx->sync();
                 init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                LAUNCH(ctx, q_encode3, 1, 64, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                LAUNCH(ctx, q_encode4, 1, 96, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
                 r = h_sb[b].result;

@@ -46,14 +46,18 @@ constexpr u32  COLD_WIDE = 65536, COLD_NARROW = 8192;
 constexpr u32  COLD_UE = 9 * COLD_WIDE + 32 * COLD_NARROW;
 constexpr u32  COLD_COUNT = COLD_UE + 8192;
 constexpr u32  COLD_PAD = (COLD_COUNT + 255) & ~255u;
-static_assert((COLD_COUNT >> QC_LOG) + 1 < 256, "cache tag must fit a byte");
+// Slot of a cold index: 11 hashed bits + 1 class bit (rank banks / run banks never share a slot, so the
+// encoder's rank-model warp and run-model warp can use the caches concurrently).
+__device__ __forceinline__ u32 cache_slot(u32 idx) { const u32 h = idx >> 11; return ((idx ^ (h * 1237u)) & 2047u) | (idx >= 9u * 65536u ? 2048u : 0u); }
+__device__ __forceinline__ u32 cache_tag(u32 idx) { return (idx >> 11) + 1u; }
+__device__ __forceinline__ u32 cache_unslot(u32 slot, u32 tag) { const u32 h = tag - 1u; return (h << 11) | (((slot & 2047u) ^ (h * 1237u)) & 2047u); }
 
 struct CoderSmem {
     u8    rank_state[32768];
     u8    run_state[8192];
     u16   s16[S16_COUNT];
-    u8    tag_state[QC_SLOTS];
-    u8    tag_char[QC_SLOTS];
+    u16   tag_state[QC_SLOTS];   // 0 = empty, else 1 + (cold index >> 11)
+    u16   tag_char[QC_SLOTS];
     u8    rankHist[256], runHist[256];
     u8    mtf[256 + 32];
     __align__(16) u8 inwin[256];     // decoder: staged window of the input stream
@@ -67,7 +71,7 @@ __device__ __forceinline__ void coder_smem_init(CoderSmem &S, const QTables *__r
     u32 *w = (u32 *)S.s16;
     for (u32 i = lane; i < S16_COUNT / 2; i += 32) w[i] = 0x08000800u;            // every counter starts at 2048
     u32 *t = (u32 *)S.tag_state;
-    for (u32 i = lane; i < (2 * QC_SLOTS + 512 + 288) / 4; i += 32) t[i] = 0;     // tags, histories, mtf
+    for (u32 i = lane; i < (2 * QC_SLOTS * 2 + 512 + 288) / 4; i += 32) t[i] = 0; // tags, histories, mtf
     __syncwarp();
 }
 
@@ -78,14 +82,14 @@ __device__ __forceinline__ u32 m_off(u32 e, u32 node) { return (1u << e) - 2u + 
 
 // Index (into S.s16) of rare counter `idx` of one kind, through the direct-mapped write-back cache.
 // Warp-uniform version (decoder): every lane performs the same accesses.
-__device__ __forceinline__ u32 cache_get(CoderSmem &S, u32 val_base, u8 *tags, short *__restrict__ cold, u32 idx, u32 &misses)
+__device__ __forceinline__ u32 cache_get(CoderSmem &S, u32 val_base, u16 *tags, short *__restrict__ cold, u32 idx, u32 &misses)
 {
-    const u32 h = idx >> QC_LOG, slot = (idx ^ (h * 1237u)) & QC_MASK, want = h + 1;
+    const u32 slot = cache_slot(idx), want = cache_tag(idx);
     const u32 t = tags[slot];
     if (t != want) {
-        if (t) cold[((t - 1) << QC_LOG) | ((slot ^ ((t - 1) * 1237u)) & QC_MASK)] = (short)S.s16[val_base + slot];
+        if (t) cold[cache_unslot(slot, t)] = (short)S.s16[val_base + slot];
         S.s16[val_base + slot] = (u16)cold[idx];
-        tags[slot] = (u8)want;
+        tags[slot] = (u16)want;
         ++misses;
     }
     return val_base + slot;
@@ -98,13 +102,17 @@ template <int K> __device__ __forceinline__ int q_mix(int s, int c, int g)
 {
     return (c * bscb_param(K, 0) + s * bscb_param(K, 1) + g * bscb_param(K, 2)) >> 5;
 }
-template <int K, int WHO> __device__ __forceinline__ int q_up(int p)      // the decision came out 0 (predictor.h:50-53)
+// Counter moves as ONE multiply-add and ONE shift.  With integer p:
+//   bit 0 (predictor.h:50-53):  p + floor(((4096-TH0-p)*AR0)/4096) = floor((p*(4096-AR0) + (4096-TH0)*AR0) / 4096)
+//   bit 1 (predictor.h:55-58):  p - floor(((p-TH1)*AR1)/4096)      = floor((p*(4096-AR1) + TH1*AR1 + 4095) / 4096)
+// (checked exhaustively for p in [0,4096] and all 21 parameter sets; tests/test_oracle.py)
+template <int K, int WHO> __device__ __forceinline__ int q_up(int p)
 {
-    return p + (((4096 - bscb_param(K, 3 + 4 * WHO) - p) * bscb_param(K, 4 + 4 * WHO)) >> 12);
+    return (p * (4096 - bscb_param(K, 4 + 4 * WHO)) + (4096 - bscb_param(K, 3 + 4 * WHO)) * bscb_param(K, 4 + 4 * WHO)) >> 12;
 }
-template <int K, int WHO> __device__ __forceinline__ int q_down(int p)    // the decision came out 1 (predictor.h:55-58)
+template <int K, int WHO> __device__ __forceinline__ int q_down(int p)
 {
-    return p - (((p - bscb_param(K, 5 + 4 * WHO)) * bscb_param(K, 6 + 4 * WHO)) >> 12);
+    return (p * (4096 - bscb_param(K, 6 + 4 * WHO)) + bscb_param(K, 5 + 4 * WHO) * bscb_param(K, 6 + 4 * WHO) + 4095) >> 12;
 }
 
 // ---- range coder (rangecoder.h:38-271), 16-bit units -------------------------------------------------
@@ -161,10 +169,17 @@ struct Rc2Dec {
 template <int K> __device__ __forceinline__ u32 dec3(CoderSmem &S, Rc2Dec &rc, u32 is, u32 ic, u32 ig)
 {
     const int s = S.s16[is], c = S.s16[ic], g = S.s16[ig];
-    const u32 bit = rc.decode(q_mix<K>(s, c, g));
-    if (bit) { S.s16[is] = (u16)q_down<K, 0>(s); S.s16[ic] = (u16)q_down<K, 1>(c); S.s16[ig] = (u16)q_down<K, 2>(g); }   // warp-uniform branch
-    else     { S.s16[is] = (u16)q_up<K, 0>(s);   S.s16[ic] = (u16)q_up<K, 1>(c);   S.s16[ig] = (u16)q_up<K, 2>(g); }
-    return bit;
+    const int p = q_mix<K>(s, c, g);
+    if (rc.range < 0x10000u) { rc.range <<= 16; rc.code = (rc.code << 16) | rc.get16(); }
+    const u32 r = (rc.range >> 12) * (u32)p;
+    if (rc.code >= r) {                                      // warp-uniform branch: one side does everything for its outcome
+        rc.code -= r; rc.range -= r;
+        S.s16[is] = (u16)q_down<K, 0>(s); S.s16[ic] = (u16)q_down<K, 1>(c); S.s16[ig] = (u16)q_down<K, 2>(g);
+        return 1u;
+    }
+    rc.range = r;
+    S.s16[is] = (u16)q_up<K, 0>(s); S.s16[ic] = (u16)q_up<K, 1>(c); S.s16[ig] = (u16)q_up<K, 2>(g);
+    return 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -252,17 +267,24 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
             S.rankHist[c] = (u8)ilog2_dev((u32)rank);
         }
         rank &= 255;
-        __syncwarp();
         // push c `rank` places back: mtf[0..rank-1] = mtf[1..rank]; mtf[rank] = c  (qlfc.cpp:1830-1860)
-        for (int basep = 0; basep < rank; basep += 32) {
-            const int p = basep + (int)lane;
-            const u8 v = S.mtf[p + 1];
+        if (rank >= 1 && rank <= 3) {                        // common case: every lane does the same few moves, no barrier needed
+            const u8 m1 = S.mtf[1], m2 = S.mtf[2], m3 = S.mtf[3];
+            S.mtf[0] = m1;
+            if (rank == 1) S.mtf[1] = (u8)c;
+            else { S.mtf[1] = m2; if (rank == 2) S.mtf[2] = (u8)c; else { S.mtf[2] = m3; S.mtf[3] = (u8)c; } }
+        } else {
             __syncwarp();
-            if (p < rank) S.mtf[p] = v;
+            for (int basep = 0; basep < rank; basep += 32) {
+                const int p = basep + (int)lane;
+                const u8 v = S.mtf[p + 1];
+                __syncwarp();
+                if (p < rank) S.mtf[p] = v;
+                __syncwarp();
+            }
+            if (lane == 0) S.mtf[rank] = (u8)c;
             __syncwarp();
         }
-        if (lane == 0) S.mtf[rank] = (u8)c;
-        __syncwarp();
 
         avgRank = (avgRank * 124 + rank * 4) >> 7;
         const int rank0 = rank - 1;
@@ -313,214 +335,3 @@ __global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all
     if (lane == 0) { sb.result = (int)n; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// encoder, two-warp pipeline
-//
-// Every context of the encoder is a function of the INPUT only (qlfc.cpp:949-955, 1048-1054,
-// 1123-1125), and within one run every decision touches a different counter.  So the model side
-// can evaluate all decisions of a run at once -- lane d of warp 0 owns decision d: it locates its
-// three counters, mixes the probability from their pre-update values, moves the counters and
-// emits a (bit, p) record -- while warp 1 does nothing but the one truly serial recurrence, the
-// range coder (range/low with 16-bit renormalisation, rangecoder.h:83-177), consuming the records
-// from a shared-memory ring.  Per stream the critical path shrinks from "~9 dependent model
-// look-ups per run" to "one parallel model step per run" || "one range step per decision".
-// ---------------------------------------------------------------------------------------------------
-#define QE_RING 4096                                       // records (u16) in the ring
-#define QE_REC_BIT   0x2000u                               // bit 13: the coded bit
-#define QE_REC_RUN   0x4000u                               // bit 14: first decision of a run (EOB check point)
-#define QE_REC_END   0xffffu
-
-struct EncPipe {
-    u16 ring[QE_RING];
-    volatile u32 head, tail, fail;                         // consumer / producer / "output full" flag
-    int params[7][16];
-};
-
-__device__ __forceinline__ void pipe_push(EncPipe &P, u32 &tail, u32 cnt, u32 rec, u32 lane)
-{
-    // wait for room (the consumer always drains; head jumps ahead when it quits).  The spin is bounded so
-    // that a logic error can never hang the GPU: after ~1 s the stream is failed instead.
-    for (u32 spins = 0; (int)(tail + cnt - P.head) > QE_RING; ) if (++spins > (1u << 26)) { P.fail = 2; break; }
-    if (lane < cnt) P.ring[(tail + lane) & (QE_RING - 1)] = (u16)rec;
-    __syncwarp();
-    __threadfence_block();
-    tail += cnt;
-    if (lane == 0) P.tail = tail;
-}
-
-__global__ void __launch_bounds__(64, 1) q_encode3(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
-                                                   SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
-                                                   const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
-{
-    extern __shared__ __align__(16) u8 q_smem_raw[];
-    CoderSmem &S = *reinterpret_cast<CoderSmem *>(q_smem_raw);
-    EncPipe &P = *reinterpret_cast<EncPipe *>(q_smem_raw + ((sizeof(CoderSmem) + 15) & ~(size_t)15));
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 sid = sb_list ? sb_list[blockIdx.x] : blockIdx.x;
-    SubBlock &sb = sbs[sid];
-
-    if (warp == 0) {
-        coder_smem_init(S, tables);
-        for (int i = lane; i < 7 * 16; i += 32) P.params[i / 16][i % 16] = (i % 16) < 15 ? bscb_param(i / 16, i % 16) : 0;
-        if (lane == 0) { P.head = 0; P.tail = 0; P.fail = 0; }
-    }
-    __syncthreads();
-
-    if (warp == 1) {
-        // ------------------------------ consumer: the range coder ------------------------------
-        Rc2Enc rc; rc.low32 = 0; rc.carry = 0; rc.range = 0xffffffffu; rc.cache = 0; rc.pending = 0; rc.pos = 0; rc.out = out_all + sb.out_off;
-        const long long eob = (long long)sb.out_cap - 16;
-        u32 head = 0; int result = 0; bool done = false;
-        while (!done) {
-            u32 tail, spins = 0;
-            while ((tail = P.tail) == head) { if (P.fail == 2 || ++spins > (1u << 27)) { result = LIBBSC_GPU_ERROR; break; } }
-            if (result) break;
-            __threadfence_block();
-            const u32 cnt = min(32u, tail - head);
-            const u32 mine = lane < cnt ? P.ring[(head + lane) & (QE_RING - 1)] : 0u;
-            for (u32 j = 0; j < cnt; ++j) {
-                const u32 rec = __shfl_sync(0xffffffffu, mine, j);
-                if (rec == QE_REC_END) { done = true; break; }
-                if ((rec & QE_REC_RUN) && (long long)rc.pos >= eob) { result = LIBBSC_NOT_COMPRESSIBLE; done = true; break; }   // qlfc.cpp:898-901
-                rc.encode((rec >> 13) & 1u, (int)(rec & 0x1fffu));
-            }
-            head += cnt;
-            if (lane == 0) P.head = head;
-        }
-        if (result == 0) result = (int)rc.finish();
-        else if (lane == 0) P.fail = 1;
-        if (lane == 0) { sb.result = result; P.head = 0x7fffffffu; }   // unblock a producer waiting for room
-        return;
-    }
-
-    // ---------------------------------- producer: the model ----------------------------------
-    short *cold_s = cold_all + (size_t)sid * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
-    u32 tail = 0, st_cached = 0, st_miss = 0;
-    int ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0, maxRank = 7, avgRank = 0;
-    const u32 n = sb.in_size;
-    pipe_push(P, tail, 32, 2048u | (((n >> (31 - lane)) & 1u) ? QE_REC_BIT : 0u), lane);
-    {   // MTF-order header (qlfc.cpp:857-891): few hundred records, pushed one at a time
-        const u8 *mtf = mtf_all + sid * 256;
-        u32 used8 = 0; int prev = -1;
-        for (int d = 0; d < 256; ++d) {
-            int c = mtf[d];
-            for (int bit = 7; bit >= 0; --bit) {
-                bool can0, can1; header_options(used8, prev, c >> (bit + 1), bit, can0, can1);
-                if (can0 && can1) pipe_push(P, tail, 1, 2048u | (((c >> bit) & 1) ? QE_REC_BIT : 0u), lane);
-            }
-            if (c == prev) { maxRank = ilog2_dev((u32)(d - 1)); break; }
-            prev = c; if ((u32)(c >> 3) == lane) used8 |= 1u << (c & 7);
-        }
-    }
-
-    const u32 rb = sb.run_begin, re = sb.run_end;
-    bool stop = false;
-    for (u32 t0 = rb; t0 < re && !stop; t0 += 32) {
-        const u32 cnt = min(32u, re - t0);
-        u32 my_sym = 0, my_rank = 0, my_len = 0;             // lane j prefetches run t0 + j
-        if (lane < cnt) { my_sym = run_sym[t0 + lane]; my_rank = run_rank[t0 + lane]; my_len = run_pos[t0 + lane + 1] - run_pos[t0 + lane]; }
-        if (P.fail) break;
-        for (u32 j = 0; j < cnt; ++j) {
-            const u32 c = __shfl_sync(0xffffffffu, my_sym, j);
-            const u32 rank = __shfl_sync(0xffffffffu, my_rank, j);
-            const u32 run = __shfl_sync(0xffffffffu, my_len, j);
-            // ---- per-run contexts (uniform) ----
-            const u32 st1 = S.rank_state[(ctxRun << 11) | (ctxRank4 << 3) | S.rankHist[c]];
-            const bool esc = avgRank >= 32;
-            const u32 er = (u32)ilog2_dev(rank), eu = (u32)ilog2_dev(run);
-            const int rank0 = (int)rank - 1;
-            const int rh = S.runHist[c];
-            const u32 st2 = S.run_state[(ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7 ? rank0 : 7) << 3) | (rh < 7 ? rh : 7)];
-            __syncwarp();
-            if (lane == 0) {
-                S.rankHist[c] = (u8)((esc || rank != 1) ? er : 0);
-                S.runHist[c] = (u8)(run == 1 ? (rh + 2) >> 2 : (rh + 3 * (int)eu + 3) >> 2);
-            }
-            avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
-            ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0)) & 0x7;
-            ctxRank4 = ((ctxRank4 << 2) | (rank0 < 3 ? rank0 : 3)) & 0xff;
-            ctxRun   = ((ctxRun << 1) | (run < 3)) & 0xf;
-            // ---- decision layout of this run ----
-            const int nE = (!esc && rank != 1) ? ((int)er - 1) + ((int)er < maxRank) : 0;
-            const int nM = esc ? maxRank + 1 : (rank != 1 ? (int)er : 0);
-            const int o1 = esc ? 0 : 1, o2 = o1 + nE, o3 = o2 + nM, o4 = o3 + 1, o5 = o4 + (run != 1 ? (int)eu : 0), D = o5 + (run != 1 ? (int)eu : 0);
-            for (int base = 0; base < D; base += 32) {
-                const int d = base + (int)lane;
-                const bool act = d < D;
-                int K = 0; u32 is = 0, ic = 0, ig = 0, bit = 0, cs = 0xffffffffu, cc = 0xffffffffu;   // cs/cc: cold indices when cached
-                if (act) {
-                    if (d < o1) { K = K_RANK_T; is = R_RT_STATE + st1; ic = R_RT_CHAR + c; ig = R_RT_SHARED; bit = rank != 1; }
-                    else if (d < o2) { const u32 k = (u32)(d - o1); K = K_RANK_E; is = R_RE_STATE + st1 * 8 + k; ic = R_RE_CHAR + c * 8 + k; ig = R_RE_SHARED + k; bit = k + 1 < er; }
-                    else if (d < o3) {
-                        const u32 l = (u32)(d - o2);
-                        if (!esc) {
-                            const u32 bp = er - 1 - l, node = rank >> (bp + 1); bit = (rank >> bp) & 1u; K = K_RANK_M; ig = R_WIDE_SHARED + er * 256 + node;
-                            if (er <= M_MAXE) { is = R_RM_STATE + st1 * M_ROW + m_off(er, node); ic = R_RM_CHAR + c * M_ROW + m_off(er, node); }
-                            else { cs = wide_idx(er, st1, node); cc = wide_idx(er, c, node); }
-                        } else {
-                            const u32 bp = (u32)maxRank - l, node = (1u << l) | (rank >> (bp + 1)); bit = (rank >> bp) & 1u; K = K_RANK_P;
-                            cs = wide_idx(8, st1, node); cc = wide_idx(8, c, node); ig = R_WIDE_SHARED + 8 * 256 + node;
-                        }
-                    }
-                    else if (d < o4) { K = K_RUN_T; is = R_UT_STATE + st2; ic = R_UT_CHAR + c; ig = R_UT_SHARED; bit = run != 1; }
-                    else if (d < o5) {
-                        const u32 k = (u32)(d - o4); K = K_RUN_E; ig = R_UE_SHARED + k; bit = k + 1 < eu;
-                        if (k < UE_RES) { is = R_UE_STATE + st2 * UE_RES + k; ic = R_UE_CHAR + c * UE_RES + k; }
-                        else { cs = ue_idx(st2, k); cc = ue_idx(c, k); }
-                    }
-                    else {
-                        const u32 l = (u32)(d - o5), bp = eu - 1 - l; bit = (run >> bp) & 1u; K = K_RUN_M;
-                        if (eu <= M_MAXE) { const u32 node = run >> (bp + 1); ig = R_NARROW_SHARED + eu * 32 + node;
-                                            is = R_UM_STATE + st2 * M_ROW + m_off(eu, node); ic = R_UM_CHAR + c * M_ROW + m_off(eu, node); }
-                        else { const u32 node = 1 + l; ig = R_NARROW_SHARED + eu * 32 + node; cs = narrow_idx(eu, st2, node); cc = narrow_idx(eu, c, node); }
-                    }
-                }
-                // ---- rare counters: per-lane direct-mapped look-up; identical slots are serialised ----
-                const bool cached = cs != 0xffffffffu;
-                const u32 cmask = __ballot_sync(0xffffffffu, cached);
-                u32 rec = 0;
-                bool any_clash = false;
-                u32 hs = 0, slot_s = 0, hc = 0, slot_c = 0;
-                if (cmask) {                                 // warp-uniform
-                    hs = cs >> QC_LOG; slot_s = (cs ^ (hs * 1237u)) & QC_MASK; hc = cc >> QC_LOG; slot_c = (cc ^ (hc * 1237u)) & QC_MASK;
-                    bool clash = false;
-                    if (cached) {                            // both matches are executed by every lane of cmask (no short-circuit!)
-                        const u32 ms = __match_any_sync(cmask, slot_s), mc = __match_any_sync(cmask, slot_c);
-                        clash = (__popc(ms) > 1) | (__popc(mc) > 1);
-                    }
-                    any_clash = __any_sync(0xffffffffu, clash);
-                    st_cached += 2 * __popc(cmask);
-                }
-                for (int turn = 0; turn < (any_clash ? 32 : 1); ++turn) {
-                    const bool go = act && (!any_clash || (int)lane == turn);
-                    if (go) {
-                        if (cached) {
-                            u32 t = S.tag_state[slot_s];
-                            if (t != hs + 1) { if (t) cold_s[((t - 1) << QC_LOG) | ((slot_s ^ ((t - 1) * 1237u)) & QC_MASK)] = (short)S.s16[C_STATE_VAL + slot_s];
-                                               S.s16[C_STATE_VAL + slot_s] = (u16)cold_s[cs]; S.tag_state[slot_s] = (u8)(hs + 1); ++st_miss; }
-                            t = S.tag_char[slot_c];
-                            if (t != hc + 1) { if (t) cold_c[((t - 1) << QC_LOG) | ((slot_c ^ ((t - 1) * 1237u)) & QC_MASK)] = (short)S.s16[C_CHAR_VAL + slot_c];
-                                               S.s16[C_CHAR_VAL + slot_c] = (u16)cold_c[cc]; S.tag_char[slot_c] = (u8)(hc + 1); ++st_miss; }
-                            is = C_STATE_VAL + slot_s; ic = C_CHAR_VAL + slot_c;
-                        }
-                        const int *w = P.params[K];
-                        const int s = S.s16[is], cv = S.s16[ic], g = S.s16[ig];
-                        const int p = (cv * w[0] + s * w[1] + g * w[2]) >> 5;
-                        int ns, nc, ng;
-                        if (bit) { ns = s - (((s - w[5]) * w[6]) >> 12); nc = cv - (((cv - w[9]) * w[10]) >> 12); ng = g - (((g - w[13]) * w[14]) >> 12); }
-                        else     { ns = s + (((4096 - w[3] - s) * w[4]) >> 12); nc = cv + (((4096 - w[7] - cv) * w[8]) >> 12); ng = g + (((4096 - w[11] - g) * w[12]) >> 12); }
-                        S.s16[is] = (u16)ns; S.s16[ic] = (u16)nc; S.s16[ig] = (u16)ng;
-                        rec = (u32)p | (bit ? QE_REC_BIT : 0u) | (d == 0 ? QE_REC_RUN : 0u);
-                    }
-                    if (any_clash) __syncwarp();
-                }
-                __syncwarp();
-                pipe_push(P, tail, (u32)min(32, D - base), rec, lane);
-            }
-            if ((j & 7) == 7 && P.fail) { stop = true; break; }
-        }
-    }
-    if (!P.fail) pipe_push(P, tail, 1, QE_REC_END, lane);
-    st_miss = __reduce_add_sync(0xffffffffu, st_miss);
-    if (lane == 0) { sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
-}
