@@ -311,7 +311,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
 
     // 1. split
     if (nBlocks > 1) LAUNCH(ctx, q_split, 1, 1024, 0, d_in, n, (u32)nBlocks, d_start, d_size);
-    else { u32 h[2] = {0, n}; CUDA_TRY(cudaMemcpyAsync(d_start, &h[0], 4, cudaMemcpyHostToDevice, ctx->stream)); CUDA_TRY(cudaMemcpyAsync(d_size, &h[1], 4, cudaMemcpyHostToDevice, ctx->stream)); ctx->sync(); }
+    else { u32 *h = ctx->h_mail + 240; h[0] = 0; h[1] = n;   /* pinned: pageable async copies serialise concurrent blocks */CUDA_TRY(cudaMemcpyAsync(d_start, &h[0], 4, cudaMemcpyHostToDevice, ctx->stream)); CUDA_TRY(cudaMemcpyAsync(d_size, &h[1], 4, cudaMemcpyHostToDevice, ctx->stream)); ctx->sync(); }
     // 2. runs
     LAUNCH(ctx, q_run_count, run_tiles, RUN_THREADS, 0, d_in, n, d_start, (u32)nBlocks, tile_cnt);
     LAUNCH(ctx, q_scan_tiles, 1, 1024, 0, tile_cnt, run_tiles, ctx->d_mail);
@@ -327,7 +327,10 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     LAUNCH(ctx, q_run_write, run_tiles, RUN_THREADS, 0, d_in, n, d_start, (u32)nBlocks, tile_cnt, run_pos, run_sym);
     LAUNCH(ctx, q_run_bounds, 1, 32, 0, run_pos, R, n, d_start, d_size, (u32)nBlocks, d_sb);
     // output slices in tmp (256-byte aligned, 4 KB slack each); capacity = the sub-block's input size (coder.cpp:193)
-    SubBlock h_sb[Q_MAX_SUB];
+    // All small host<->device copies go through the context's PINNED mailbox.  A cudaMemcpyAsync to or
+    // from pageable memory blocks inside the driver until the stream drains (here: a ~1 s coder
+    // kernel) and, measured, stalls the pageable copies of every other block's thread meanwhile.
+    SubBlock *h_sb = (SubBlock *)(ctx->h_mail + 128);
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
     u32 total_tiles = 0;
@@ -360,8 +363,8 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     if (nBlocks == 1) {                                   // coder.cpp:113-119
         result = h_sb[0].result;
         if (result >= 0) {
-            u8 one = 1;
-            CUDA_TRY(cudaMemcpyAsync(d_out, &one, 1, cudaMemcpyHostToDevice, ctx->stream));
+            u8 *one = (u8 *)(ctx->h_mail + 240); *one = 1;
+            CUDA_TRY(cudaMemcpyAsync(d_out, one, 1, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(cudaMemcpyAsync(d_out + 1, tmp + h_sb[0].out_off, (size_t)result, cudaMemcpyDeviceToDevice, ctx->stream));
             ctx->sync();
             result += 1;
@@ -384,7 +387,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
             int r = h_sb[b].result;
             if (room != (int)h_size[b]) {                 // clipped output size: redo this sub-block with the clipped room
                 h_sb[b].out_cap = (u32)(room > 0 ? room : 0); h_sb[b].result = 0;
-                u32 *d_list = A.get<u32>(1); u32 one = (u32)b;
+                u32 *d_list = A.get<u32>(1); u32 &one = ctx->h_mail[240]; one = (u32)b;
                 CUDA_TRY(cudaMemcpyAsync(d_sb + b, &h_sb[b], sizeof(SubBlock), cudaMemcpyHostToDevice, ctx->stream));
                 CUDA_TRY(cudaMemcpyAsync(d_list, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
                 ctx->sync();
@@ -437,8 +440,8 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         memcpy(hdr, ctx->h_mail + 32, (size_t)want);
     }
     const int nBlocks = hdr[0];
-    SubBlock h_sb[Q_MAX_SUB]; u32 list[Q_MAX_SUB]; int nlist = 0;
-    memset(h_sb, 0, sizeof h_sb);
+    SubBlock *h_sb = (SubBlock *)(ctx->h_mail + 128); u32 *list = ctx->h_mail + 232; int nlist = 0;   // pinned (see stage_coder_compress)
+    memset(h_sb, 0, sizeof(SubBlock) * Q_MAX_SUB); memset(list, 0, sizeof(u32) * Q_MAX_SUB);
     if (nBlocks == 1) {
         h_sb[0].in_start = 0; h_sb[0].in_size = (u32)out_cap; h_sb[0].out_off = 1; h_sb[0].out_cap = (u32)(in_size - 1);
         list[nlist++] = 0;
@@ -458,14 +461,14 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         SubBlock *d_sb = A.get<SubBlock>(Q_MAX_SUB);
         u32 *d_list = A.get<u32>(Q_MAX_SUB);
         short *models = A.get<short>((size_t)nlist * MODEL_SHORTS_PAD);
-        CUDA_TRY(cudaMemcpyAsync(d_sb, h_sb, sizeof h_sb, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(d_list, list, sizeof list, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_sb, h_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_list, list, sizeof(u32) * Q_MAX_SUB, cudaMemcpyHostToDevice, ctx->stream));
         ctx->sync();
         init_models(ctx, models, nlist);
         ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
         PROF_BYTES(ctx, (double)in_size + (double)out_cap);
         LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
-        CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof h_sb, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->sync();
     if (getenv("BSCB200_QSTATS"))

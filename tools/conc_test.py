@@ -64,7 +64,7 @@ def f_unbwt(i):
     assert r == 0
 
 
-for K in (1, 1, 2, 4, 8, 16):
+for K in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1,1,2,4,8,16".split(","))]:
     phase("bwt_encode", f_bwt, K)
     phase("coder_compress", f_enc, K)
     phase("coder_decompress", f_dec, K)
