@@ -50,17 +50,40 @@ __global__ void __launch_bounds__(256) bwt_gather_key2(const u32 *__restrict__ s
 
 struct TileAgg { u32 maxhead, active, groups, pad; };
 
-// per-slot classification shared by the reduce and apply kernels
+// A tile of SC_TILE slots (+ one neighbour on each side) staged in shared memory with coalesced loads.
+// Each thread then works on 8 CONSECUTIVE slots (what the scans want); one pad entry per 8 keeps the
+// 64-byte lane stride off the same banks (profile r1d: the unstaged version spent 3 ms per 64 M slots).
+struct ScTile {
+    u64 key[(SC_TILE + 2) + (SC_TILE + 2) / 8 + 1];
+    u32 sa[(SC_TILE + 2) + (SC_TILE + 2) / 8 + 1];
+    u32 idx[SC_TILE + SC_TILE / 8 + 1];
+};
+__device__ __forceinline__ u32 sc_pad(u32 i) { return i + (i >> 3); }
+
+// entry j of the staged arrays holds global slot base + j - 1
 template <bool INIT>
-__device__ __forceinline__ void classify(const u64 *__restrict__ key, const u32 *__restrict__ sa, u32 t, u32 m, u32 n,
-                                         bool &head, bool &single)
+__device__ __forceinline__ void sc_load(ScTile &S, const u64 *__restrict__ key, const u32 *__restrict__ sa, const u32 *__restrict__ idx, u32 base, u32 m)
 {
-    u64 k = key[t];
-    bool h0 = (t == 0) || key[t - 1] != k;
-    bool h1 = (t + 1 == m) || key[t + 1] != k;
+    for (u32 j = threadIdx.x; j < SC_TILE + 2; j += SC_THREADS) {
+        const long long g = (long long)base + j - 1;
+        const bool ok = g >= 0 && g < (long long)m;
+        S.key[sc_pad(j)] = ok ? key[g] : 0ull;
+        S.sa[sc_pad(j)] = ok ? sa[g] : 0u;
+    }
+    if (!INIT) for (u32 j = threadIdx.x; j < SC_TILE; j += SC_THREADS) S.idx[sc_pad(j)] = (base + j < m) ? idx[base + j] : 0u;
+    __syncthreads();
+}
+
+// per-slot classification shared by the reduce and apply kernels; i = slot index inside the tile
+template <bool INIT>
+__device__ __forceinline__ void classify(const ScTile &S, u32 i, u32 t, u32 m, u32 n, bool &head, bool &single)
+{
+    const u64 k = S.key[sc_pad(i + 1)];
+    bool h0 = (t == 0) || S.key[sc_pad(i)] != k;
+    bool h1 = (t + 1 == m) || S.key[sc_pad(i + 2)] != k;
     if (INIT) {                                          // suffixes shorter than 8 are complete: own group
-        if (t > 0 && (u64)sa[t - 1] + 8 > n) h0 = true;
-        if ((u64)sa[t] + 8 > n) h1 = true;
+        if (t > 0 && (u64)S.sa[sc_pad(i)] + 8 > n) h0 = true;
+        if ((u64)S.sa[sc_pad(i + 1)] + 8 > n) h1 = true;
     }
     head = h0; single = h0 && h1;
 }
@@ -70,14 +93,17 @@ __global__ void __launch_bounds__(SC_THREADS) bwt_tile_reduce(const u64 *__restr
                                                               u32 m, u32 n, TileAgg *__restrict__ agg)
 {
     __shared__ u32 s_max[SC_THREADS / 32], s_act[SC_THREADS / 32], s_grp[SC_THREADS / 32];
+    __shared__ ScTile T;
+    sc_load<INIT>(T, key, sa, idx, blockIdx.x * SC_TILE, m);
     u32 base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
     u32 mx = 0, act = 0, grp = 0;
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; ++i) {
         u32 t = base + i;
         if (t < m) {
-            bool head, single; classify<INIT>(key, sa, t, m, n, head, single);
-            u32 iv = INIT ? t : idx[t];
+            const u32 li = threadIdx.x * SC_ITEMS + i;
+            bool head, single; classify<INIT>(T, li, t, m, n, head, single);
+            u32 iv = INIT ? t : T.idx[sc_pad(li)];
             if (head) mx = iv + 1;                       // idx is increasing in t
             act += !single; grp += (head && !single);
         }
@@ -127,6 +153,8 @@ __global__ void __launch_bounds__(SC_THREADS) bwt_apply(const u64 *__restrict__ 
                                                         u32 *__restrict__ sa_out, u32 *__restrict__ idx_out, u32 *__restrict__ grp_out)
 {
     __shared__ u32 s_max[SC_THREADS / 32], s_act[SC_THREADS / 32], s_grp[SC_THREADS / 32];
+    __shared__ ScTile T;
+    sc_load<INIT>(T, key, sa, idx, blockIdx.x * SC_TILE, m);
     const u32 base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     bool head[SC_ITEMS], single[SC_ITEMS]; u32 iv[SC_ITEMS], sv[SC_ITEMS];
@@ -135,8 +163,9 @@ __global__ void __launch_bounds__(SC_THREADS) bwt_apply(const u64 *__restrict__ 
     for (int i = 0; i < SC_ITEMS; ++i) {
         u32 t = base + i; head[i] = false; single[i] = true; iv[i] = 0; sv[i] = 0;
         if (t < m) {
-            classify<INIT>(key, sa, t, m, n, head[i], single[i]);
-            iv[i] = INIT ? t : idx[t]; sv[i] = sa[t];
+            const u32 li = threadIdx.x * SC_ITEMS + i;
+            classify<INIT>(T, li, t, m, n, head[i], single[i]);
+            iv[i] = INIT ? t : T.idx[sc_pad(li)]; sv[i] = T.sa[sc_pad(li + 1)];
             if (head[i]) mx = iv[i] + 1;
             act += !single[i]; grp += (head[i] && !single[i]);
         }

@@ -4,20 +4,22 @@
 // the reference's cub::DeviceRadixSort / DeviceSegmentedSort calls (libcubwt.cu:713-739,
 // 1686-1703, 2136-2163; st.cu:187-193, 273-279) with our own kernels:
 //
-//   rs_histogram  : ONE read of the keys builds the 256-bin histograms of every digit pass.
-//   rs_scan       : exclusive scan of each pass's histogram -> global digit bases.
-//   rs_onesweep   : per digit pass, ONE read + ONE write of every (key,value): each CTA ranks a
-//                   tile with warp match-any multisplit, obtains its per-digit global offsets by
-//                   decoupled look-back over the preceding tiles (single pass, no separate
-//                   upsweep), reorders the tile in shared memory and stores digit-contiguous,
-//                   fully coalesced runs.
+//   rs_hist1      : 256-bin histogram of the FIRST digit only (one read of the source keys).
+//   rs_onesweep   : per digit pass, ONE read + ONE write of every (key,value): each CTA scans the
+//                   digit histogram into global bases, ranks a tile with warp match-any multisplit,
+//                   obtains its per-digit global offsets by decoupled look-back over the preceding
+//                   tiles (single pass, no separate upsweep), reorders the tile in shared memory and
+//                   stores digit-contiguous, fully coalesced runs.  While storing, it accumulates
+//                   the histogram of the NEXT digit, so no pass ever re-reads the keys for
+//                   counting (profile r1d: the up-front 8-digit histogram kernel cost 4 sort passes).
 //
 // Keys come from a "source" functor so that the first pass can synthesise keys on the fly (text
 // 8-grams, ST context words) instead of reading a materialised key array: that removes one write
 // + two reads of 8n bytes from every sort.
 //
 // HBM traffic per pass: (sizeof(K) + 4) bytes read + the same written per element -- the
-// algorithmic floor for an LSD pass -- plus 2 KB of look-back descriptors per 4096-element tile.
+// algorithmic floor for an LSD pass (ncu r1d: 1.615 GB measured vs 1.611 GB algorithmic for
+// n = 2^26 pairs) -- plus 2 KB of look-back descriptors per 4096-element tile.
 #pragma once
 
 #include "common.cuh"
@@ -70,45 +72,21 @@ __device__ __forceinline__ u64 load_be64(const u8 *T, u32 pos)
     return ((u64)__byte_perm(lo, 0, 0x0123) << 32) | (u64)__byte_perm(hi, 0, 0x0123);
 }
 
-// ---- histogram of all digit passes in one read ------------------------------------------------
+// ---- histogram of the first digit ------------------------------------------------------------
 template <class Src>
-__global__ void __launch_bounds__(RS_THREADS) rs_histogram(Src src, u32 n, DigitPasses passes, u32 *ghist)
+__global__ void __launch_bounds__(RS_THREADS) rs_hist1(Src src, u32 n, int shift, int bits, u32 *__restrict__ ghist)
 {
-    __shared__ u32 sh[RS_MAX_PASSES * 256];
-    for (int i = threadIdx.x; i < passes.count * 256; i += RS_THREADS) sh[i] = 0;
+    __shared__ u32 sh[256];
+    sh[threadIdx.x] = 0;
     __syncthreads();
-    const u32 stride = gridDim.x * RS_THREADS;
+    const u32 stride = gridDim.x * RS_THREADS, dmask = (1u << bits) - 1u;
     for (u32 i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
-        auto k = src.key(i);
-#pragma unroll
-        for (int p = 0; p < RS_MAX_PASSES; ++p) {
-            if (p < passes.count) {
-                u32 d = (u32)(k >> passes.shift[p]) & ((1u << passes.bits[p]) - 1u);
-                // warp-aggregate equal digits (text keys are extremely skewed in the high bytes)
-                u32 m = __match_any_sync(__activemask(), d);
-                if ((m & lanemask_lt()) == 0) atomicAdd(&sh[p * 256 + d], __popc(m));
-            }
-        }
+        const u32 d = (u32)(src.key(i) >> shift) & dmask;
+        const u32 m = __match_any_sync(__activemask(), d);           // warp-aggregate: text digits are skewed
+        if ((m & lanemask_lt()) == 0) atomicAdd(&sh[d], __popc(m));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < passes.count * 256; i += RS_THREADS) if (sh[i]) atomicAdd(&ghist[i], sh[i]);
-}
-
-static __global__ void rs_scan(u32 *ghist, int npasses)
-{
-    // one warp per pass; 256 bins = 8 per lane
-    int p = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (p >= npasses) return;
-    u32 *h = ghist + p * 256;
-    u32 v[8], sum = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { v[j] = h[lane * 8 + j]; sum += v[j]; }
-    u32 incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    u32 run = incl - sum;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { h[lane * 8 + j] = run; run += v[j]; }
+    if (sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
 }
 
 // ---- one digit pass ------------------------------------------------------------------------
@@ -124,16 +102,33 @@ template <typename K, bool HAS_VAL> struct RsSmem {
     u32 whist[RS_WARPS][256];
     u32 dstart[256];
     u32 gbase[256];
+    u32 nexthist[256];
     u32 scan_tmp[RS_WARPS];
     u32 tile;
     K   keys[RS_TILE];
     u32 vals[HAS_VAL ? RS_TILE : 1];
 };
 
+// exclusive scan of one value per thread over the 256 threads of the CTA (tmp: RS_WARPS words)
+__device__ __forceinline__ u32 rs_block_excl_scan(u32 v, u32 *tmp, u32 lane, u32 warp)
+{
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
+    if (lane == 31) tmp[warp] = incl;
+    __syncthreads();
+    u32 woff = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) if (w < (int)warp) woff += tmp[w];
+    __syncthreads();
+    return woff + incl - v;
+}
+
 template <typename K, bool HAS_VAL, class Src>
 __global__ void __launch_bounds__(RS_THREADS, 3)
 rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int shift, int bits,
-            const u32 *__restrict__ gbase_in, u32 *tile_counter, u64 *lookback)
+            const u32 *__restrict__ hist_in, u32 *__restrict__ hist_next, int shift2, int bits2,
+            u32 *tile_counter, u64 *lookback)
 {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
     RsSmem<K, HAS_VAL> &S = *reinterpret_cast<RsSmem<K, HAS_VAL> *>(rs_smem_raw);
@@ -143,7 +138,9 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
 
     if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&S.whist[0][0])[i] = 0;
-    __syncthreads();
+    S.nexthist[tid] = 0;
+    // global digit bases = exclusive scan of this digit's histogram (complete: the previous kernel ended)
+    const u32 gdigit_base = rs_block_excl_scan(hist_in[tid], S.scan_tmp, lane, warp);   // contains __syncthreads
     const u32 tile = S.tile;
     const u32 base = tile * RS_TILE;                     // n <= 2^30 so this cannot overflow
     const u32 valid = min((u32)RS_TILE, n - base);
@@ -178,16 +175,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { u32 t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
         const u32 count = run;
-        // block exclusive scan of `count` over the 256 digits
-        u32 incl = count;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) S.scan_tmp[warp] = incl;
-        __syncthreads();
-        u32 woff = 0;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) if (w < (int)warp) woff += S.scan_tmp[w];
-        const u32 excl = woff + incl - count;
+        const u32 excl = rs_block_excl_scan(count, S.scan_tmp, lane, warp);
         S.dstart[d] = excl;
 
         u64 *mine = lookback + (size_t)tile * 256 + d;
@@ -205,7 +193,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
             }
             st_relaxed(mine, RS_FLAG_PREFIX | (u64)(gexcl + count));
         }
-        S.gbase[d] = gbase_in[d] + gexcl - excl;         // u32 wrap-around arithmetic is intended
+        S.gbase[d] = gdigit_base + gexcl - excl;         // u32 wrap-around arithmetic is intended
     }
     __syncthreads();
 
@@ -224,6 +212,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
         }
     }
     __syncthreads();
+    const u32 dmask2 = (1u << bits2) - 1u;
 #pragma unroll 4
     for (u32 j = tid; j < valid; j += RS_THREADS) {
         K k = S.keys[j];
@@ -231,6 +220,12 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
         u32 g = S.gbase[d] + j;
         kout[g] = k;
         if (HAS_VAL) vout[g] = S.vals[j];
+        if (hist_next) atomicAdd(&S.nexthist[(u32)(k >> shift2) & dmask2], 1u);   // next digit's histogram, for free
+    }
+    if (hist_next) {
+        __syncthreads();
+        const u32 c = S.nexthist[tid];
+        if (c) atomicAdd(&hist_next[tid], c);
     }
 }
 
@@ -258,25 +253,26 @@ static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32
     u32 hgrid = min(tiles, (u32)(B200_SMS * 8));
     const double pass_bytes = 2.0 * (double)n * (sizeof(K) + (HAS_VAL ? 4 : 0));   // read + write of every element
     PROF_BYTES(ctx, (double)n * sizeof(K));
-    LAUNCH(ctx, (rs_histogram<FirstSrc>), hgrid, RS_THREADS, 0, first, n, passes, ghist);
-    LAUNCH(ctx, rs_scan, 1, 32 * RS_MAX_PASSES, 0, ghist, passes.count);
+    LAUNCH(ctx, (rs_hist1<FirstSrc>), hgrid, RS_THREADS, 0, first, n, (int)passes.shift[0], (int)passes.bits[0], ghist);
 
     const size_t smem = sizeof(RsSmem<K, HAS_VAL>);
-    // (per device, cheap) allow the > 48 KB dynamic shared memory the tile needs
     ensure_dyn_smem(rs_onesweep<K, HAS_VAL, FirstSrc>, ctx->device, smem);
     ensure_dyn_smem(rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>, ctx->device, smem);
 
     for (int p = 0; p < passes.count; ++p) {
         int dst = p & 1;
         u64 *lb = lookback + (size_t)p * tiles * 256;
+        const bool more = p + 1 < passes.count;
+        u32 *hnext = more ? ghist + 256 * (p + 1) : nullptr;
+        const int s2 = more ? (int)passes.shift[p + 1] : 0, b2 = more ? (int)passes.bits[p + 1] : 1;
         PROF_BYTES(ctx, pass_bytes);
         if (p == 0) {
             LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, FirstSrc>), tiles, RS_THREADS, smem,
-                   first, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, counters + p, lb);
+                   first, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, hnext, s2, b2, counters + p, lb);
         } else {
             SrcArray<K, HAS_VAL> src{k[dst ^ 1], v[dst ^ 1]};
             LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>), tiles, RS_THREADS, smem,
-                   src, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, counters + p, lb);
+                   src, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, hnext, s2, b2, counters + p, lb);
         }
     }
     return (passes.count - 1) & 1;
