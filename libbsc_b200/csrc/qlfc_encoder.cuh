@@ -17,8 +17,12 @@
 // Both model warps derive the ring position of every run from the same arithmetic (the number of
 // decisions of a run follows from rank, run length, maxRank and the escape flag), so they never
 // talk to each other; the coder consumes up to min(progress of warp 0, progress of warp 1).
-// The first profiled version of the encoder (one warp doing everything, profiles/r1b) executed
-// ~530 instructions per run on the critical warp; here the critical warp executes ~100.
+//
+// The per-run CONTEXTS are computed 32 runs at a time, one lane per run ("vector prologue"):
+// sliding-window contexts come from warp ballots, the per-symbol histories from match_any chains,
+// avgRank from a 32-step serial integer loop, ring offsets from a warp scan, and both state-table
+// look-ups are one vector shared-memory load.  History of the critical warp's instruction count per
+// run (ncu, profiles/): one warp doing everything 530 -> three warps, scalar prologue 205 -> this.
 #pragma once
 
 #define QE4_RING 2048
@@ -46,15 +50,6 @@ __device__ __forceinline__ void enc4_fill_params(Enc4Pipe &P, u32 lane)
             q[4 + 2 * who] = b ? th1 * ar1 + 4095 : (4096 - th0) * ar0;
         }
     }
-}
-
-// wait until records [pos, pos+cnt) of the ring may be overwritten; false = give up (failure / watchdog)
-__device__ __forceinline__ bool enc4_wait_room(Enc4Pipe &P, u32 pos, u32 cnt)
-{
-    for (u32 spins = 0; (int)(pos + cnt - P.head) > QE4_RING; ) {
-        if (P.fail || ++spins > (1u << 26)) { if (!P.fail) P.fail = 2; return false; }
-    }
-    return true;
 }
 
 // Evaluate one decision: counters at s16 indices (is, ic, ig); returns the record.  Rare counters
@@ -107,6 +102,9 @@ __device__ __forceinline__ u32 enc4_chunk(CoderSmem &S, Enc4Pipe &P, bool act, i
     __syncwarp();
     return rec;
 }
+
+// bits [32-lane, 32-lane+width) of (prev:cur): the flags of the `width` runs before this lane's run, most recent in bit 0
+__device__ __forceinline__ u32 enc4_window(u32 prev_rev, u32 cur_rev, u32 lane) { return (u32)((((u64)prev_rev << 32) | cur_rev) >> (32u - lane)); }
 
 __global__ void __launch_bounds__(96, 1) q_encode4(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                    SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
@@ -164,14 +162,14 @@ __global__ void __launch_bounds__(96, 1) q_encode4(const u32 *__restrict__ run_p
 
     short *cold_s = cold_all + (size_t)sid * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 n_cached = 0, misses = 0;
-    int ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0, avgRank = 0, maxRank = 7;
-    u32 off = 0;                                               // ring position (record index) of the current run
+    u32 maxRank = 7;
+    u32 base_off = 0;                                          // ring position (record index) of the current batch of runs
 
     if (warp == 0) {
         // ----------------------- stream header: n as 32 raw bits, then the MTF order (qlfc.cpp:851-891) -----------------------
         const u32 n = sb.in_size;
-        if (lane < 32) P.ring[lane] = (u16)(2048u | (((n >> (31 - lane)) & 1u) ? QE4_BIT : 0u));
-        off = 32;
+        P.ring[lane] = (u16)(2048u | (((n >> (31 - lane)) & 1u) ? QE4_BIT : 0u));
+        u32 off = 32;
         {
             const u8 *mtf = mtf_all + sid * 256;
             u32 used8 = 0; int prev = -1;
@@ -181,102 +179,156 @@ __global__ void __launch_bounds__(96, 1) q_encode4(const u32 *__restrict__ run_p
                     bool can0, can1; header_options(used8, prev, c >> (bit + 1), bit, can0, can1);
                     if (can0 && can1) { if (lane == 0) P.ring[off & (QE4_RING - 1)] = (u16)(2048u | (((c >> bit) & 1) ? QE4_BIT : 0u)); ++off; }   // <= 2048 records: fits the empty ring
                 }
-                if (c == prev) { maxRank = ilog2_dev((u32)(d - 1)); break; }
+                if (c == prev) { maxRank = (u32)ilog2_dev((u32)(d - 1)); break; }
                 prev = c; if ((u32)(c >> 3) == lane) used8 |= 1u << (c & 7);
             }
         }
+        base_off = off;
         __syncwarp();
         __threadfence_block();
-        if (lane == 0) { P.max_rank = (u32)maxRank; P.hdr_len = off; P.progA = off; __threadfence_block(); P.hdr_ready = 1; }
+        if (lane == 0) { P.max_rank = maxRank; P.hdr_len = off; P.progA = off; __threadfence_block(); P.hdr_ready = 1; }
     } else {
         for (u32 spins = 0; !P.hdr_ready; ) if (++spins > (1u << 27)) { P.fail = 2; break; }
         __threadfence_block();
-        maxRank = (int)P.max_rank; off = P.hdr_len;
-        if (lane == 0) P.progB = off;
+        maxRank = P.max_rank; base_off = P.hdr_len;
+        if (lane == 0) P.progB = base_off;
     }
 
+    // ---- state carried from batch to batch ----
+    u32 avg = 0;                                               // avgRank after the last run of the previous batch
+    u32 pf0 = 0, plo = 0, phi = 0, prn = 0;                    // bit-reversed flag ballots of the previous batch
+    u32 head_seen = 0;
     bool stop = false;
-    for (u32 t0 = rb; t0 < re && !stop; t0 += 32) {
-        const u32 cnt = min(32u, re - t0);
-        u32 my_sym = 0, my_rank = 0, my_len = 0;               // lane j prefetches run t0 + j
-        if (lane < cnt) { my_sym = run_sym[t0 + lane]; my_rank = run_rank[t0 + lane]; my_len = run_pos[t0 + lane + 1] - run_pos[t0 + lane]; }
-        for (u32 j = 0; j < cnt; ++j) {
-            const u32 c = __shfl_sync(0xffffffffu, my_sym, j);
-            const u32 rank = __shfl_sync(0xffffffffu, my_rank, j);
-            const u32 run = __shfl_sync(0xffffffffu, my_len, j);
-            const bool esc = avgRank >= 32;
-            const u32 er = (u32)ilog2_dev(rank), eu = (u32)ilog2_dev(run);
-            const int rank0 = (int)rank - 1;
-            // decisions of this run: [rank part nA][run part nB]
-            const u32 nE = (!esc && rank != 1) ? (er - 1) + ((int)er < maxRank ? 1u : 0u) : 0u;
-            const u32 nM = esc ? (u32)maxRank + 1u : (rank != 1 ? er : 0u);
-            const u32 nA = (esc ? 0u : 1u) + nE + nM;
-            const u32 nB = 1u + (run != 1 ? 2u * eu : 0u);
 
+    for (u32 t0 = rb; t0 < re && !stop; t0 += 32) {
+        // ================= vector prologue: lane j <-> run t0 + j =================
+        const u32 cnt = min(32u, re - t0);
+        const bool live = lane < cnt;
+        u32 sym = 256u + lane, rank = 1, len = 1;              // dead lanes: unique pseudo-symbols, no decisions
+        if (live) { sym = run_sym[t0 + lane]; rank = run_rank[t0 + lane]; len = run_pos[t0 + lane + 1] - run_pos[t0 + lane]; }
+        const u32 er = (u32)ilog2_dev(rank), eu = (u32)ilog2_dev(len), rank0 = rank - 1;
+        u32 my_avg = 0;                                        // avgRank seen by this lane's run (qlfc.cpp:1048: serial integer recurrence)
+        {
+            u32 a = avg;
+#pragma unroll 8
+            for (u32 j = 0; j < 32; ++j) {
+                const u32 r = __shfl_sync(0xffffffffu, rank, j);
+                if (lane == j) my_avg = a;
+                if (j < cnt) a = (a * 124u + r * 4u) >> 7;
+            }
+            avg = a;
+        }
+        const bool esc = my_avg >= 32u;
+        const u32 nE = (!esc && rank != 1) ? (er - 1) + (er < maxRank ? 1u : 0u) : 0u;
+        const u32 nM = esc ? maxRank + 1u : (rank != 1 ? er : 0u);
+        const u32 nA = live ? (esc ? 0u : 1u) + nE + nM : 0u;
+        const u32 nB = live ? 1u + (len != 1 ? 2u * eu : 0u) : 0u;
+        u32 incl = nA + nB;                                    // ring offsets: exclusive warp scan of the decision counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
+        const u32 my_off = incl - (nA + nB), batch_total = __shfl_sync(0xffffffffu, incl, 31);
+        // sliding-window contexts (qlfc.cpp:1123-1125) from ballots; most recent run in the low bits
+        const u32 q3 = rank0 < 3 ? rank0 : 3;
+        const u32 bf0 = __brev(__ballot_sync(0xffffffffu, live && rank0 == 0));
+        const u32 blo = __brev(__ballot_sync(0xffffffffu, live && (q3 & 1u))), bhi = __brev(__ballot_sync(0xffffffffu, live && (q3 & 2u)));
+        const u32 brn = __brev(__ballot_sync(0xffffffffu, live && len < 3));
+        const u32 ctxRank0 = enc4_window(pf0, bf0, lane) & 7u, ctxRun = enc4_window(prn, brn, lane) & 15u;
+        const u32 wl = enc4_window(plo, blo, lane) & 15u, wh = enc4_window(phi, bhi, lane) & 15u;
+        const u32 ctxRank4 = (wl & 1u) | ((wh & 1u) << 1) | ((wl & 2u) << 1) | ((wh & 2u) << 2) | ((wl & 4u) << 2) | ((wh & 4u) << 3) | ((wl & 8u) << 3) | ((wh & 8u) << 4);
+        pf0 = bf0; plo = blo; phi = bhi; prn = brn;
+        // per-symbol histories: value left by the previous run of the same symbol
+        const u32 same = __match_any_sync(0xffffffffu, sym);
+        const u32 below = same & lanemask_lt();
+        const u32 prevl = below ? 31u - (u32)__clz(below) : lane;
+        const bool last_of_sym = live && (same >> lane) == 1u;   // no later run of this symbol in the batch
+        u32 my_st;
+        if (warp == 0) {
+            const u32 er_prev = __shfl_sync(0xffffffffu, er, prevl);
+            const u32 rh = below ? er_prev : (u32)S.rankHist[sym & 255u];          // rankHistory = exponent of the previous rank (0 for rank 1)
+            my_st = S.rank_state[(ctxRun << 11) | (ctxRank4 << 3) | rh];
+            __syncwarp();
+            if (last_of_sym) S.rankHist[sym] = (u8)er;
+        } else {
+            const u32 occ = __popc(below), maxocc = __reduce_max_sync(0xffffffffu, live ? occ : 0u);
+            u32 vin = S.runHist[sym & 255u], vout = 0;
+            for (u32 round = 0; round <= maxocc; ++round) {       // resolve same-symbol chains in occurrence order
+                const u32 t = __shfl_sync(0xffffffffu, vout, prevl);
+                if (occ == round) { if (round) vin = t; vout = (len == 1) ? (vin + 2u) >> 2 : (vin + 3u * eu + 3u) >> 2; }
+            }
+            my_st = S.run_state[(ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7 ? rank0 : 7u) << 3) | (vin < 7 ? vin : 7u)];
+            __syncwarp();
+            if (last_of_sym) S.runHist[sym] = (u8)vout;
+        }
+        const u32 pack = er | (eu << 3) | ((esc ? 1u : 0u) << 8) | (nE << 9) | (nM << 12) | (nA << 16) | (nB << 20);
+        __syncwarp();
+
+        // ================= per run: one lane per decision =================
+        for (u32 j = 0; j < cnt; ++j) {
+            const u32 c = __shfl_sync(0xffffffffu, sym, j), rk = __shfl_sync(0xffffffffu, rank, j), run = __shfl_sync(0xffffffffu, len, j);
+            const u32 pk = __shfl_sync(0xffffffffu, pack, j), st = __shfl_sync(0xffffffffu, my_st, j);
+            const u32 off = base_off + __shfl_sync(0xffffffffu, my_off, j);
+            const u32 r_er = pk & 7u, r_eu = (pk >> 3) & 31u, r_nE = (pk >> 9) & 7u, r_nA = (pk >> 16) & 15u, r_nB = (pk >> 20) & 63u;
+            const bool r_esc = (pk >> 8) & 1u;
+            {   // room in the ring for this run's records (re-read the consumer's head only when needed)
+                const u32 end = off + (warp == 0 ? r_nA : r_nA + r_nB);
+                for (u32 spins = 0; (int)(end - head_seen) > QE4_RING; ) {
+                    head_seen = P.head;
+                    if (P.fail || ++spins > (1u << 26)) { if (!P.fail) P.fail = 2; stop = true; break; }
+                }
+                if (stop) break;
+            }
             if (warp == 0) {
-                const u32 st1 = S.rank_state[(ctxRun << 11) | (ctxRank4 << 3) | S.rankHist[c]];
-                S.rankHist[c] = (u8)((esc || rank != 1) ? er : 0);          // all lanes store the same value
-                if (!enc4_wait_room(P, off, nA)) { stop = true; break; }
                 // lane d: first bit | exponent index k | mantissa level l
                 const u32 d = lane;
-                const bool act = d < nA;
-                const u32 dT = esc ? 0xffffffffu : 0u;                    // escape mode has no first-bit decision
-                const bool isT = d == dT, isE = !esc && d >= 1 && d <= nE;
-                const u32 k = d - 1, l = esc ? d : d - 1 - nE;
-                const u32 e_m = esc ? (u32)maxRank + 1u : er, v = esc ? (rank | (1u << e_m)) : rank;
+                const bool act = d < r_nA;
+                const bool isT = !r_esc && d == 0, isE = !r_esc && d >= 1 && d <= r_nE;
+                const u32 k = d - 1, l = r_esc ? d : d - 1 - r_nE;
+                const u32 e_m = r_esc ? maxRank + 1u : r_er, v = r_esc ? (rk | (1u << e_m)) : rk;
                 const u32 bp = e_m - 1 - (l < e_m ? l : 0), node = v >> (bp + 1);
-                const int K = isT ? K_RANK_T : isE ? K_RANK_E : (esc ? K_RANK_P : K_RANK_M);
-                const u32 bit = isT ? (rank != 1) : isE ? (k + 1 < er) : ((v >> bp) & 1u);
-                const u32 bank = esc ? 8u : er;
-                const bool cached = !isT && !isE && (esc || er > M_MAXE);
+                const int K = isT ? K_RANK_T : isE ? K_RANK_E : (r_esc ? K_RANK_P : K_RANK_M);
+                const u32 bit = isT ? (rk != 1) : isE ? (k + 1 < r_er) : ((v >> bp) & 1u);
+                const u32 bank = r_esc ? 8u : r_er;
+                const bool cached = !isT && !isE && (r_esc || r_er > M_MAXE);
                 const u32 pos = isT ? 0u : isE ? k : node;
-                const u32 is = (isT ? R_RT_STATE + st1 : isE ? R_RE_STATE + st1 * 8 : R_RM_STATE + st1 * M_ROW + (1u << er) - 2u) + pos;
-                const u32 ic = (isT ? R_RT_CHAR + c : isE ? R_RE_CHAR + c * 8 : R_RM_CHAR + c * M_ROW + (1u << er) - 2u) + pos;
+                const u32 is = (isT ? R_RT_STATE + st : isE ? R_RE_STATE + st * 8 : R_RM_STATE + st * M_ROW + (1u << r_er) - 2u) + pos;
+                const u32 ic = (isT ? R_RT_CHAR + c : isE ? R_RE_CHAR + c * 8 : R_RM_CHAR + c * M_ROW + (1u << r_er) - 2u) + pos;
                 const u32 ig = (isT ? R_RT_SHARED : isE ? R_RE_SHARED : R_WIDE_SHARED + bank * 256) + pos;
-                u32 rec = enc4_chunk(S, P, act, K, bit, is, ic, ig, cached, wide_idx(bank, st1, node), wide_idx(bank, c, node), cold_s, cold_c, lane, n_cached, misses);
+                u32 rec = enc4_chunk(S, P, act, K, bit, is, ic, ig, cached, wide_idx(bank, st, node), wide_idx(bank, c, node), cold_s, cold_c, lane, n_cached, misses);
                 if (d == 0) rec |= QE4_RUN;
                 if (act) P.ring[(off + d) & (QE4_RING - 1)] = (u16)rec;
             } else {
-                const int rh = S.runHist[c];
-                const u32 st2 = S.run_state[(ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7 ? rank0 : 7) << 3) | (rh < 7 ? rh : 7)];
-                S.runHist[c] = (u8)(run == 1 ? (rh + 2) >> 2 : (rh + 3 * (int)eu + 3) >> 2);
-                if (!enc4_wait_room(P, off, nA + nB)) { stop = true; break; }
-                for (u32 base = 0; base < nB; base += 32) {              // nB <= 61; one chunk unless the run is >= 64 Ki long
+                for (u32 base = 0; base < r_nB; base += 32) {           // nB <= 61; one chunk unless the run is >= 64 Ki long
                     const u32 d = base + lane;
-                    const bool act = d < nB;
-                    const bool isT = d == 0, isE = d >= 1 && d <= eu;
-                    const u32 k = d - 1, l = d - 1 - eu;
-                    const u32 bp = eu - 1 - (l < eu ? l : 0);
-                    const bool tree = eu <= M_MAXE;
+                    const bool act = d < r_nB;
+                    const bool isT = d == 0, isE = d >= 1 && d <= r_eu;
+                    const u32 k = d - 1, l = d - 1 - r_eu;
+                    const u32 bp = r_eu - 1 - (l < r_eu ? l : 0);
+                    const bool tree = r_eu <= M_MAXE;
                     const u32 node = tree ? (run >> (bp + 1)) : 1u + l;
                     const int K = isT ? K_RUN_T : isE ? K_RUN_E : K_RUN_M;
-                    const u32 bit = isT ? (run != 1) : isE ? (k + 1 < eu) : ((run >> bp) & 1u);
+                    const u32 bit = isT ? (run != 1) : isE ? (k + 1 < r_eu) : ((run >> bp) & 1u);
                     const bool cached = isE ? (k >= UE_RES) : (!isT && !tree);
                     const u32 pos = isT ? 0u : isE ? k : node;
-                    const u32 is = (isT ? R_UT_STATE + st2 : isE ? R_UE_STATE + st2 * UE_RES : R_UM_STATE + st2 * M_ROW + (1u << eu) - 2u) + pos;
-                    const u32 ic = (isT ? R_UT_CHAR + c : isE ? R_UE_CHAR + c * UE_RES : R_UM_CHAR + c * M_ROW + (1u << eu) - 2u) + pos;
-                    const u32 ig = (isT ? R_UT_SHARED : isE ? R_UE_SHARED : R_NARROW_SHARED + eu * 32) + pos;
-                    const u32 cs = isE ? ue_idx(st2, k) : narrow_idx(eu, st2, node), cc = isE ? ue_idx(c, k) : narrow_idx(eu, c, node);
+                    const u32 is = (isT ? R_UT_STATE + st : isE ? R_UE_STATE + st * UE_RES : R_UM_STATE + st * M_ROW + (1u << r_eu) - 2u) + pos;
+                    const u32 ic = (isT ? R_UT_CHAR + c : isE ? R_UE_CHAR + c * UE_RES : R_UM_CHAR + c * M_ROW + (1u << r_eu) - 2u) + pos;
+                    const u32 ig = (isT ? R_UT_SHARED : isE ? R_UE_SHARED : R_NARROW_SHARED + r_eu * 32) + pos;
+                    const u32 cs = isE ? ue_idx(st, k) : narrow_idx(r_eu, st, node), cc = isE ? ue_idx(c, k) : narrow_idx(r_eu, c, node);
                     const u32 rec = enc4_chunk(S, P, act, K, bit, is, ic, ig, cached, cs, cc, cold_s, cold_c, lane, n_cached, misses);
-                    if (act) P.ring[(off + nA + d) & (QE4_RING - 1)] = (u16)rec;
+                    if (act) P.ring[(off + r_nA + d) & (QE4_RING - 1)] = (u16)rec;
                 }
             }
-            off += nA + nB;
-            avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
-            ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0)) & 0x7;
-            ctxRank4 = ((ctxRank4 << 2) | (rank0 < 3 ? rank0 : 3)) & 0xff;
-            ctxRun   = ((ctxRun << 1) | (run < 3)) & 0xf;
             if ((j & 3) == 3 || j + 1 == cnt) {                        // publish progress every 4 runs
                 __syncwarp();
                 __threadfence_block();
-                if (lane == 0) { if (warp == 0) P.progA = off; else P.progB = off; }
+                if (lane == 0) { if (warp == 0) P.progA = off + r_nA + r_nB; else P.progB = off + r_nA + r_nB; }
                 if (P.fail) { stop = true; break; }
             }
         }
+        base_off += batch_total;
     }
     __syncwarp();
     __threadfence_block();
-    if (lane == 0) { if (warp == 0) { P.progA = off; P.doneA = 1; } else { P.progB = off; P.doneB = 1; } }
+    if (lane == 0) { if (warp == 0) { P.progA = base_off; P.doneA = 1; } else { P.progB = base_off; P.doneB = 1; } }
     misses = __reduce_add_sync(0xffffffffu, misses);
     if (lane == 0) { if (warp == 0) sb.stat_cached = n_cached; else sb.stat_miss = misses; }
 }
