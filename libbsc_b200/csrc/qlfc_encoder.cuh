@@ -142,10 +142,25 @@ __global__ void __launch_bounds__(96, 1) q_encode4(const u32 *__restrict__ run_p
             }
             if (result || limit == h) break;
             __threadfence_block();
-            u32 nxt = P.ring[h & (QE4_RING - 1)];
             while (h != limit) {
-                const u32 rec = nxt; ++h;
-                nxt = P.ring[h & (QE4_RING - 1)];               // prefetch (harmless past `limit`)
+                if (!eob_hit && (h & 3u) == 0 && limit - h >= 4u) {
+                    // fast path: four records per 64-bit shared-memory load, no end-of-buffer test.  The
+                    // test of qlfc.cpp:898-901 can only start to matter after a renormalisation moved the
+                    // write position past the limit; from then on the checked path below takes over.
+                    const uint2 q = *reinterpret_cast<const uint2 *>(&P.ring[h & (QE4_RING - 1)]);
+                    const u32 recs[4] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const u32 rec = recs[k]; ++h;
+                        if (rc.range < 0x10000u) { rc.shift(); rc.range <<= 16; eob_hit = (long long)rc.pos >= eob; }
+                        const u32 r = (rc.range >> 12) * (rec & 0x1fffu);
+                        if (rec & QE4_BIT) { const u32 s = rc.low32 + r; rc.carry += (s < rc.low32); rc.low32 = s; rc.range -= r; }
+                        else rc.range = r;
+                        if (eob_hit) break;
+                    }
+                    continue;
+                }
+                const u32 rec = P.ring[h & (QE4_RING - 1)]; ++h;
                 if (eob_hit && (rec & QE4_RUN)) { result = LIBBSC_NOT_COMPRESSIBLE; break; }   // qlfc.cpp:898-901
                 if (rc.range < 0x10000u) { rc.shift(); rc.range <<= 16; eob_hit = (long long)rc.pos >= eob; }
                 const u32 r = (rc.range >> 12) * (rec & 0x1fffu);
