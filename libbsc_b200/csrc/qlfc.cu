@@ -337,7 +337,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     for (u32 b = 0, off = 0; b < (u32)nBlocks; ++b) {
         h_sb[b].out_off = off; off += (u32)align_up((size_t)h_size[b] + 4096, 256);   // 16-bit stores need even offsets
         h_sb[b].out_cap = (nBlocks == 1) ? n - 1 : h_size[b];
-        h_sb[b].result = 0; h_sb[b].nsym = 0;
+        h_sb[b].result = 0; h_sb[b].nsym = 0; h_sb[b].stat_cached = 0; h_sb[b].stat_miss = 0;
         h_sb[b].tile_base = total_tiles; h_sb[b].tiles = ceil_div(h_sb[b].run_end - h_sb[b].run_begin, RK_TILE); total_tiles += h_sb[b].tiles;
     }
     CUDA_TRY(cudaMemcpyAsync(d_sb, h_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyHostToDevice, ctx->stream));
@@ -350,10 +350,11 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         LAUNCH(ctx, q_rank_tile, ceil_div(total_tiles, 4), 128, 0, run_sym, run_rank, d_sb, (u32)nBlocks, total_tiles, next_tab);
     }
     init_models(ctx, models, nBlocks);
-    const size_t enc_smem = ((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(Enc4Pipe);
-    ensure_dyn_smem(q_encode4, ctx->device, enc_smem);
+    const size_t enc_smem = ((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe);
+    static_assert(((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448, "encoder working set must fit the 227 KB of one SM");
+    ensure_dyn_smem(q_encode5, ctx->device, enc_smem);
     PROF_BYTES(ctx, (double)n);                          // + c written; the launch is latency-, not bandwidth-bound
-    LAUNCH(ctx, q_encode4, nBlocks, 96, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+    LAUNCH(ctx, q_encode5, nBlocks, 160, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
 
@@ -392,7 +393,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                 CUDA_TRY(cudaMemcpyAsync(d_list, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
                 ctx->sync();
                 init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                LAUNCH(ctx, q_encode4, 1, 96, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                LAUNCH(ctx, q_encode5, 1, 160, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
                 r = h_sb[b].result;

@@ -48,9 +48,17 @@ constexpr u32  COLD_COUNT = COLD_UE + 8192;
 constexpr u32  COLD_PAD = (COLD_COUNT + 255) & ~255u;
 // Slot of a cold index: 11 hashed bits + 1 class bit (rank banks / run banks never share a slot, so the
 // encoder's rank-model warp and run-model warp can use the caches concurrently).
-__device__ __forceinline__ u32 cache_slot(u32 idx) { const u32 h = idx >> 11; return ((idx ^ (h * 1237u)) & 2047u) | (idx >= 9u * 65536u ? 2048u : 0u); }
-__device__ __forceinline__ u32 cache_tag(u32 idx) { return (idx >> 11) + 1u; }
-__device__ __forceinline__ u32 cache_unslot(u32 slot, u32 tag) { const u32 h = tag - 1u; return (h << 11) | (((slot & 2047u) ^ (h * 1237u)) & 2047u); }
+// 10 hashed bits + 2 class bits: classes 0,1 = rank banks (rank mantissa e>5, escape), 2 = run mantissa
+// e>5, 3 = run exponent index >= 8.  The encoder's model warps each touch exactly one class group, so
+// they can use the caches concurrently without ever sharing a slot.
+__device__ __forceinline__ u32 cache_slot(u32 idx)
+{
+    const u32 h = idx >> 10;
+    const u32 cls = idx < 9u * 65536u ? (h & 1u) : (idx < 9u * 65536u + 32u * 8192u ? 2u : 3u);
+    return (cls << 10) | ((idx ^ (h * 1237u)) & 1023u);
+}
+__device__ __forceinline__ u32 cache_tag(u32 idx) { return (idx >> 10) + 1u; }
+__device__ __forceinline__ u32 cache_unslot(u32 slot, u32 tag) { const u32 h = tag - 1u; return (h << 10) | (((slot & 1023u) ^ (h * 1237u)) & 1023u); }
 
 struct CoderSmem {
     u8    rank_state[32768];
