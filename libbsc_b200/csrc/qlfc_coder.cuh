@@ -125,22 +125,29 @@ template <int K, int WHO> __device__ __forceinline__ int q_down(int p)
 
 // ---- range coder (rangecoder.h:38-271), 16-bit units -------------------------------------------------
 struct Rc2Enc {
-    u32 low32, carry, range, cache, pending, pos;
+    u64 low;                          // bits 0..31 = low32, bit 32 = pending carry (rangecoder.h:43-52 `ari.low`)
+    u32 range, cache, pending, pos;
     u8 *out;
+    __device__ __forceinline__ void init(u8 *o) { low = 0; range = 0xffffffffu; cache = 0; pending = 0; pos = 0; out = o; }
     __device__ __forceinline__ void put16(u32 v) { *(u16 *)(out + pos) = (u16)v; pos += 2; }   // all lanes store the same value
     __device__ __forceinline__ void shift() {
+        const u32 low32 = (u32)low, carry = (u32)(low >> 32);
         if (low32 < 0xffff0000u || carry) {
             put16(cache + carry);
             for (; pending; --pending) put16(carry - 1);
-            cache = low32 >> 16; carry = 0;
+            cache = low32 >> 16;
         } else pending++;
-        low32 <<= 16;
+        low = (u64)(u32)(low32 << 16);
+    }
+    // branch-free step: low += bit ? r : 0 ; range = bit ? range - r : r
+    __device__ __forceinline__ void step(u32 bit, u32 p) {
+        const u32 r = (range >> 12) * p;
+        low += bit ? (u64)r : 0ull;
+        range = bit ? range - r : r;
     }
     __device__ __forceinline__ void encode(u32 bit, int p) {
         if (range < 0x10000u) { shift(); range <<= 16; }
-        const u32 r = (range >> 12) * (u32)p;
-        if (bit) { const u32 s = low32 + r; carry += (s < low32); low32 = s; range -= r; }
-        else range = r;
+        step(bit, (u32)p);
     }
     __device__ u32 finish() { if (range < 0x10000u) shift(); shift(); shift(); shift(); return pos; }
 };

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
 
     if (warp == QE_MODELS) {
         // ---------------------------------------- coder ----------------------------------------
-        Rc2Enc rc; rc.low32 = 0; rc.carry = 0; rc.range = 0xffffffffu; rc.cache = 0; rc.pending = 0; rc.pos = 0; rc.out = out_all + sb.out_off;
+        Rc2Enc rc; rc.init(out_all + sb.out_off);
         const long long eob = (long long)sb.out_cap - 16;
         u32 h = 0; int result = 0; bool eob_hit = eob <= 0;
         for (;;) {
@@ -158,9 +158,7 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
                     for (int k = 0; k < 4; ++k) {
                         const u32 rec = recs[k]; ++h;
                         if (rc.range < 0x10000u) { rc.shift(); rc.range <<= 16; eob_hit = (long long)rc.pos >= eob; }
-                        const u32 r = (rc.range >> 12) * (rec & 0x1fffu);
-                        if (rec & QE_BIT) { const u32 s = rc.low32 + r; rc.carry += (s < rc.low32); rc.low32 = s; rc.range -= r; }
-                        else rc.range = r;
+                        rc.step((rec >> 13) & 1u, rec & 0x1fffu);
                         if (eob_hit) break;
                     }
                     continue;
@@ -168,9 +166,7 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
                 const u32 rec = P.ring[h & (QE_RING - 1)]; ++h;
                 if (eob_hit && (rec & QE_RUN)) { result = LIBBSC_NOT_COMPRESSIBLE; break; }   // qlfc.cpp:898-901
                 if (rc.range < 0x10000u) { rc.shift(); rc.range <<= 16; eob_hit = (long long)rc.pos >= eob; }
-                const u32 r = (rc.range >> 12) * (rec & 0x1fffu);
-                if (rec & QE_BIT) { const u32 s = rc.low32 + r; rc.carry += (s < rc.low32); rc.low32 = s; rc.range -= r; }
-                else rc.range = r;
+                rc.step((rec >> 13) & 1u, rec & 0x1fffu);
             }
             if (lane == 0) P.head = h;
             if (result) break;
