@@ -4,26 +4,33 @@
 // Facts this design rests on (qlfc.cpp:829-1129):
 //   * every model context is a function of the INPUT (symbols, ranks, run lengths) only -- never of
 //     the coder state -- so probabilities can be produced ahead of the range coder;
-//   * within one run every binary decision touches a different counter, so all decisions of a run
-//     can be evaluated simultaneously, one lane per decision;
+//   * a probability is a weighted sum of THREE counters (by state, by symbol, shared) and each counter
+//     moves as a function of its own value and the coded bit only -- never of the mixed probability --
+//     so the three counter files evolve independently of each other;
 //   * the four decision groups of a run -- rank first-bit + exponent, rank mantissa (or escape),
 //     run-length first-bit + exponent, run-length mantissa -- use disjoint counter arrays, so four
 //     different warps can evaluate them without any ordering between them;
 //   * the only truly serial recurrence is the range coder (range/low, rangecoder.h:83-177).
 //
-//   warp 0..3  "model" : per run, lane d evaluates decision d of this warp's group
+//   warp 0..3  "model" : 32 decisions of this warp's group at a time, one lane per decision
 //   warp 4     "coder" : consumes the (bit, p) records in stream order from a shared-memory ring
 //
-// All model warps derive the ring position of every run from the same arithmetic (the number of
-// decisions of a run follows from rank, run length, maxRank and the escape flag), so they never
-// talk to each other; the coder consumes up to the minimum of the four progress counters.
+// Work is organised in batches of (up to) 32 runs.  The per-run CONTEXTS are computed one lane per run
+// ("vector prologue"): sliding-window contexts come from warp ballots, the per-symbol histories from
+// match_any chains, avgRank from a 32-step serial integer loop, ring offsets from a warp scan, and
+// the state-table look-ups are one vector shared-memory load.  Then each model warp flattens the
+// decisions of its group over the whole batch and evaluates them 32 at a time, one lane per DECISION:
+// decisions that hit the same counter inside a chunk are ordered by __match_any_sync and resolved in
+// occurrence order (usually a single round), separately for each of the three counter kinds.
 //
-// The per-run CONTEXTS are computed 32 runs at a time, one lane per run ("vector prologue"):
-// sliding-window contexts come from warp ballots, the per-symbol histories from match_any chains,
-// avgRank from a 32-step serial integer loop, ring offsets from a warp scan, and the state-table
-// look-ups are one vector shared-memory load.  History of the critical warp's instruction count per
-// run (ncu, profiles/): one warp doing everything 530 -> 2 model warps 205 -> vector prologue 170
-// -> 4 model warps (this file).
+// All model warps derive the ring position of every decision from the same arithmetic (the number of
+// decisions of a run follows from rank, run length, maxRank and the escape flag), so they never talk
+// to each other; the coder consumes up to the minimum of the four progress counters.  A batch is cut
+// short so that its records never exceed half the ring.
+//
+// History of the critical model warp's instruction count per run (ncu, profiles/): one warp doing
+// everything 530 -> 2 model warps 205 -> vector prologue 170 -> 4 model warps, lane per decision of one
+// run ~100 -> lane per decision of 32 runs (this file) ~25; the range-coder warp is now the limit.
 #pragma once
 
 #define QE_RING 2048
@@ -33,11 +40,11 @@
 
 struct EncPipe {
     u16 ring[QE_RING];
+    alignas(16) int prm[7][2][12];                          // [class][bit] = w0 w1 w2 | Ms Ks | Mc Kc | Mg Kg
     volatile u32 prog[QE_MODELS], done[QE_MODELS];          // records completed by each model warp / its end flag
     volatile u32 head;                                      // records consumed by the coder
     volatile u32 hdr_len, hdr_ready, max_rank;              // published by warp 0 after the stream header
     volatile u32 fail;
-    int prm[7][2][12];                                      // [class][bit] = w0 w1 w2 | Ms Ks | Mc Kc | Mg Kg
     u8  hist2[2][256];                                      // private history copies of warps 1 and 3 (warps 0, 2 use CoderSmem's)
 };
 
@@ -53,58 +60,39 @@ __device__ __forceinline__ void enc_fill_params(EncPipe &P, u32 lane)
             q[3 + 2 * who] = b ? 4096 - ar1 : 4096 - ar0;
             q[4 + 2 * who] = b ? th1 * ar1 + 4095 : (4096 - th0) * ar0;
         }
+        q[9] = q[10] = q[11] = 0;
     }
 }
 
-// Evaluate one decision: counters at s16 indices (is, ic, ig); returns the record.  Rare counters
-// (cached == true) go through the direct-mapped caches; the caller guarantees that no two lanes of
-// the same call use the same cache slot (else it serialises the lanes).
-__device__ __forceinline__ u32 enc_decide(CoderSmem &S, EncPipe &P, int K, u32 bit, u32 is, u32 ic, u32 ig, bool cached, u32 cs, u32 cc,
-                                          short *__restrict__ cold_s, short *__restrict__ cold_c, u32 &misses)
+// One counter kind of one chunk of decisions.  Lane `act` uses counter S.s16[x] (or, when `cached`, the
+// rare counter `key` through this kind's direct-mapped write-back cache): returns the counter's value
+// BEFORE this lane's decision and applies the move (v*M + Kc) >> 12.  Lanes that share a counter -- or
+// a cache slot -- are served in lane (= stream) order, one per round.
+template <int KIND>   // 0 by state, 1 by symbol, 2 shared (never cached)
+__device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool cached, u32 key, int M, int Kc, short *__restrict__ cold, u32 lane, u32 &misses)
 {
-    if (cached) {
-        const u32 slot_s = cache_slot(cs), slot_c = cache_slot(cc);
-        u32 t = S.tag_state[slot_s];
-        if (t != cache_tag(cs)) { if (t) cold_s[cache_unslot(slot_s, t)] = (short)S.s16[C_STATE_VAL + slot_s];
-                                  S.s16[C_STATE_VAL + slot_s] = (u16)cold_s[cs]; S.tag_state[slot_s] = (u16)cache_tag(cs); ++misses; }
-        t = S.tag_char[slot_c];
-        if (t != cache_tag(cc)) { if (t) cold_c[cache_unslot(slot_c, t)] = (short)S.s16[C_CHAR_VAL + slot_c];
-                                  S.s16[C_CHAR_VAL + slot_c] = (u16)cold_c[cc]; S.tag_char[slot_c] = (u16)cache_tag(cc); ++misses; }
-        is = C_STATE_VAL + slot_s; ic = C_CHAR_VAL + slot_c;
-    }
-    const int *q = P.prm[K][bit];
-    const int s = S.s16[is], c = S.s16[ic], g = S.s16[ig];
-    const int p = (c * q[0] + s * q[1] + g * q[2]) >> 5;
-    S.s16[is] = (u16)((s * q[3] + q[4]) >> 12);
-    S.s16[ic] = (u16)((c * q[5] + q[6]) >> 12);
-    S.s16[ig] = (u16)((g * q[7] + q[8]) >> 12);
-    return (u32)p | (bit ? QE_BIT : 0u);
-}
-
-// run the per-lane decisions of one chunk; lanes with cached counters that collide on a cache slot are serialised
-__device__ __forceinline__ u32 enc_chunk(CoderSmem &S, EncPipe &P, bool act, int K, u32 bit, u32 is, u32 ic, u32 ig, bool cached, u32 cs, u32 cc,
-                                         short *__restrict__ cold_s, short *__restrict__ cold_c, u32 lane, u32 &n_cached, u32 &misses)
-{
-    const u32 cmask = __ballot_sync(0xffffffffu, act && cached);
-    bool any_clash = false;
-    if (cmask) {                                            // warp-uniform, rare
-        bool clash = false;
-        if (act && cached) {
-            const u32 slot_s = cache_slot(cs), slot_c = cache_slot(cc);
-            const u32 ms = __match_any_sync(cmask, slot_s), mc = __match_any_sync(cmask, slot_c);   // both executed by all lanes of cmask
-            clash = (__popc(ms) > 1) | (__popc(mc) > 1);
+    u16 *tags = KIND == 0 ? S.tag_state : S.tag_char;
+    const u32 vbase = KIND == 0 ? C_STATE_VAL : C_CHAR_VAL;
+    if (KIND != 2 && cached) x = vbase + cache_slot(key);
+    const u32 m = __match_any_sync(0xffffffffu, act ? x : (0x80000000u | lane));
+    const u32 occ = __popc(m & lanemask_lt());
+    const u32 maxocc = __reduce_max_sync(0xffffffffu, act ? occ : 0u);
+    int v = 0;
+    for (u32 round = 0; round <= maxocc; ++round) {
+        if (act && occ == round) {
+            if (KIND != 2 && cached) {
+                const u32 slot = x - vbase, t = tags[slot];
+                if (t != cache_tag(key)) {
+                    if (t) cold[cache_unslot(slot, t)] = (short)S.s16[x];
+                    S.s16[x] = (u16)cold[key]; tags[slot] = (u16)cache_tag(key); ++misses;
+                }
+            }
+            v = S.s16[x];
+            S.s16[x] = (u16)((v * M + Kc) >> 12);
         }
-        any_clash = __any_sync(0xffffffffu, clash);
-        n_cached += 2 * __popc(cmask);
-    }
-    u32 rec = 0;
-    if (!any_clash) { if (act) rec = enc_decide(S, P, K, bit, is, ic, ig, cached, cs, cc, cold_s, cold_c, misses); }
-    else for (u32 turn = 0; turn < 32; ++turn) {
-        if (act && lane == turn) rec = enc_decide(S, P, K, bit, is, ic, ig, cached, cs, cc, cold_s, cold_c, misses);
         __syncwarp();
     }
-    __syncwarp();
-    return rec;
+    return v;
 }
 
 // bits [32-lane, ...) of (prev:cur): the flags of the runs before this lane's run, most recent in bit 0
@@ -161,6 +149,7 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
                         rc.step((rec >> 13) & 1u, rec & 0x1fffu);
                         if (eob_hit) break;
                     }
+                    if (lane == 0 && (h & 63u) == 0) P.head = h;
                     continue;
                 }
                 const u32 rec = P.ring[h & (QE_RING - 1)]; ++h;
@@ -219,13 +208,21 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
     u32 head_seen = 0;
     bool stop = false;
 
-    for (u32 t0 = rb; t0 < re && !stop; t0 += 32) {
+    for (u32 t0 = rb; t0 < re && !stop; ) {
         // ================= vector prologue: lane j <-> run t0 + j =================
-        const u32 cnt = min(32u, re - t0);
-        const bool live = lane < cnt;
+        u32 cnt = min(32u, re - t0);
+        bool live = lane < cnt;
         u32 sym = 256u + lane, rank = 1, len = 1;              // dead lanes: unique pseudo-symbols, no decisions
         if (live) { sym = run_sym[t0 + lane]; rank = run_rank[t0 + lane]; len = run_pos[t0 + lane + 1] - run_pos[t0 + lane]; }
-        const u32 er = (u32)ilog2_dev(rank), eu = (u32)ilog2_dev(len), rank0 = rank - 1;
+        u32 eu = (u32)ilog2_dev(len);
+        if (__any_sync(0xffffffffu, eu > 8u)) {                // long runs: cut the batch so that its records fit half the ring
+            u32 ub = live ? 16u + 2u * eu : 0u;                // upper bound of a run's decisions (15 rank + 1 + 2*eu)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, ub, o); if (lane >= (u32)o) ub += t; }
+            const u32 fit = (u32)__popc(__ballot_sync(0xffffffffu, live && ub <= QE_RING / 2));
+            if (fit < cnt) { cnt = fit; live = lane < cnt; if (!live) { sym = 256u + lane; rank = 1; len = 1; eu = 0; } }
+        }
+        const u32 er = (u32)ilog2_dev(rank), rank0 = rank - 1;
         u32 my_avg = 0;                                        // avgRank seen by this lane's run (qlfc.cpp:1048: serial integer recurrence)
         {
             u32 a = avg;
@@ -251,10 +248,13 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
         const u32 bf0 = __brev(__ballot_sync(0xffffffffu, live && rank0 == 0));
         const u32 blo = __brev(__ballot_sync(0xffffffffu, live && (q3 & 1u))), bhi = __brev(__ballot_sync(0xffffffffu, live && (q3 & 2u)));
         const u32 brn = __brev(__ballot_sync(0xffffffffu, live && len < 3));
+        const u32 sh = 32u - cnt;                              // a short batch shifts less history out of the windows
         const u32 ctxRank0 = enc_window(pf0, bf0, lane) & 7u, ctxRun = enc_window(prn, brn, lane) & 15u;
         const u32 wl = enc_window(plo, blo, lane) & 15u, wh = enc_window(phi, bhi, lane) & 15u;
         const u32 ctxRank4 = (wl & 1u) | ((wh & 1u) << 1) | ((wl & 2u) << 1) | ((wh & 2u) << 2) | ((wl & 4u) << 2) | ((wh & 4u) << 3) | ((wl & 8u) << 3) | ((wh & 8u) << 4);
-        pf0 = bf0; plo = blo; phi = bhi; prn = brn;
+        // carry: the flags of the last 32 runs, most recent in bit 0 (for a full batch this is just the new ballot)
+        pf0 = (u32)(((((u64)pf0 << 32) | bf0) >> sh)); plo = (u32)(((((u64)plo << 32) | blo) >> sh));
+        phi = (u32)(((((u64)phi << 32) | bhi) >> sh)); prn = (u32)(((((u64)prn << 32) | brn) >> sh));
         // per-symbol histories: value left by the previous run of the same symbol
         const u32 same = __match_any_sync(0xffffffffu, sym);
         const u32 below = same & lanemask_lt();
@@ -278,77 +278,98 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
             __syncwarp();
             if (last_of_sym) my_hist[sym] = (u8)vout;
         }
-        const u32 pack = er | (eu << 3) | ((esc ? 1u : 0u) << 8) | (nE << 9) | (nM << 12) | (nA << 16) | (nB << 20);
+        const u32 pack = er | (eu << 3) | ((esc ? 1u : 0u) << 8) | (nE << 9) | (nM << 12);
+        // this warp's group: number of decisions per run, and where they sit inside the run's records
+        u32 gcnt, gpos;
+        if (warp == 0)      { gcnt = esc ? 0u : 1u + nE;               gpos = 0; }
+        else if (warp == 1) { gcnt = nM;                               gpos = esc ? 0u : 1u + nE; }
+        else if (warp == 2) { gcnt = len != 1 ? 1u + eu : 1u;          gpos = nA; }
+        else                { gcnt = len != 1 ? eu : 0u;               gpos = nA + 1u + eu; }
+        if (!live) gcnt = 0;
+        u32 gincl = gcnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, gincl, o); if (lane >= (u32)o) gincl += t; }
+        const u32 goff = gincl - gcnt, gtotal = __shfl_sync(0xffffffffu, gincl, 31);
+        const u32 rpos = my_off + gpos;                        // batch-relative record index of this run's first decision of the group
+        const u32 val = rank_side ? rank : len;
         __syncwarp();
 
-        // ================= per run: one lane per decision of this warp's group =================
-        for (u32 j = 0; j < cnt; ++j) {
-            const u32 c = __shfl_sync(0xffffffffu, sym, j);
-            const u32 val = __shfl_sync(0xffffffffu, rank_side ? rank : len, j);      // the coded value: rank or run length
-            const u32 pk = __shfl_sync(0xffffffffu, pack, j), st = __shfl_sync(0xffffffffu, my_st, j);
-            const u32 off = base_off + __shfl_sync(0xffffffffu, my_off, j);
-            const u32 r_er = pk & 7u, r_eu = (pk >> 3) & 31u, r_nE = (pk >> 9) & 7u, r_nM = (pk >> 12) & 15u, r_nA = (pk >> 16) & 15u, r_nB = (pk >> 20) & 63u;
+        // room in the ring for the whole batch (re-read the consumer's head only when needed)
+        for (u32 spins = 0; (int)(base_off + batch_total - head_seen) > QE_RING; ) {
+            head_seen = P.head;
+            if (P.fail || ++spins > (1u << 26)) { if (!P.fail) P.fail = 2; stop = true; break; }
+        }
+        if (stop) break;
+
+        // ================= 32 decisions of this warp's group at a time, one lane per decision =================
+        for (u32 cb = 0; cb < gtotal; cb += 32) {
+            const u32 g = cb + lane;
+            const bool act = g < gtotal;
+            u32 r = 0;                                         // the run of decision g: largest r with goff[r] <= g
+#pragma unroll
+            for (u32 step = 16; step; step >>= 1) { const u32 v = __shfl_sync(0xffffffffu, goff, r + step); if (v <= g) r += step; }
+            const u32 c = __shfl_sync(0xffffffffu, sym, r) & 255u, v_ = __shfl_sync(0xffffffffu, val, r);
+            const u32 pk = __shfl_sync(0xffffffffu, pack, r), st = __shfl_sync(0xffffffffu, my_st, r);
+            const u32 rp = __shfl_sync(0xffffffffu, rpos, r), go = __shfl_sync(0xffffffffu, goff, r);
+            const u32 d = act ? g - go : 0u;
+            const u32 r_er = pk & 7u, r_eu = (pk >> 3) & 31u;
             const bool r_esc = (pk >> 8) & 1u;
-            {   // room in the ring for this run's records (re-read the consumer's head only when needed)
-                const u32 end = off + r_nA + r_nB;
-                for (u32 spins = 0; (int)(end - head_seen) > QE_RING; ) {
-                    head_seen = P.head;
-                    if (P.fail || ++spins > (1u << 26)) { if (!P.fail) P.fail = 2; stop = true; break; }
-                }
-                if (stop) break;
-            }
-            if (warp == 0) {            // rank: first bit (lane 0) and unary exponent (lanes 1..nE); nothing in escape mode
-                const u32 d = lane, k = d - 1;
-                const bool act = !r_esc && d <= r_nE, isT = d == 0;
-                const u32 bit = isT ? (val != 1) : (k + 1 < r_er);
-                const u32 is = isT ? R_RT_STATE + st : R_RE_STATE + st * 8 + k;
-                const u32 ic = isT ? R_RT_CHAR + c : R_RE_CHAR + c * 8 + k;
-                const u32 ig = isT ? R_RT_SHARED : R_RE_SHARED + k;
-                u32 rec = enc_chunk(S, P, act, isT ? K_RANK_T : K_RANK_E, bit, is, ic, ig, false, 0, 0, cold_s, cold_c, lane, n_cached, misses);
-                if (isT) rec |= QE_RUN;
-                if (act) P.ring[(off + d) & (QE_RING - 1)] = (u16)rec;
+            int K; u32 bit, is, ic, ig, cs = 0, cc = 0; bool cached = false, runflag = false;
+            if (warp == 0) {            // rank: first bit (d = 0) and unary exponent (d = 1..nE)
+                const u32 k = d - 1; const bool isT = d == 0;
+                K = isT ? K_RANK_T : K_RANK_E;
+                bit = isT ? (v_ != 1) : (k + 1 < r_er);
+                is = isT ? R_RT_STATE + st : R_RE_STATE + st * 8 + k;
+                ic = isT ? R_RT_CHAR + c : R_RE_CHAR + c * 8 + k;
+                ig = isT ? R_RT_SHARED : R_RE_SHARED + k;
+                runflag = isT;
             } else if (warp == 1) {     // rank: mantissa tree of depth e (or the escape tree of depth maxRank+1)
-                const u32 l = lane;
-                const bool act = l < r_nM;
-                const u32 e_m = r_esc ? maxRank + 1u : r_er, v = r_esc ? (val | (1u << e_m)) : val;
-                const u32 bp = e_m - 1 - (l < e_m ? l : 0), node = v >> (bp + 1), bit = (v >> bp) & 1u;
+                const u32 e_m = r_esc ? maxRank + 1u : r_er, v = r_esc ? (v_ | (1u << e_m)) : v_;
+                const u32 bp = e_m - 1 - (d < e_m ? d : 0), node = v >> (bp + 1);
                 const u32 bank = r_esc ? 8u : r_er;
-                const bool cached = r_esc || r_er > M_MAXE;
                 const u32 rowoff = (1u << r_er) - 2u + node;
-                u32 rec = enc_chunk(S, P, act, r_esc ? K_RANK_P : K_RANK_M, bit, R_RM_STATE + st * M_ROW + rowoff, R_RM_CHAR + c * M_ROW + rowoff,
-                                    R_WIDE_SHARED + bank * 256 + node, cached, wide_idx(bank, st, node), wide_idx(bank, c, node), cold_s, cold_c, lane, n_cached, misses);
-                if (r_esc && l == 0) rec |= QE_RUN;
-                if (act) P.ring[(off + (r_esc ? 0u : 1u + r_nE) + l) & (QE_RING - 1)] = (u16)rec;
-            } else if (warp == 2) {     // run length: first bit (lane 0) and unary exponent (lanes 1..eu)
-                const u32 d = lane, k = d - 1;
-                const u32 nTE = val != 1 ? 1u + r_eu : 1u;
-                const bool act = d < nTE, isT = d == 0;
-                const u32 bit = isT ? (val != 1) : (k + 1 < r_eu);
-                const bool cached = !isT && k >= UE_RES;
-                const u32 is = isT ? R_UT_STATE + st : R_UE_STATE + st * UE_RES + k;
-                const u32 ic = isT ? R_UT_CHAR + c : R_UE_CHAR + c * UE_RES + k;
-                const u32 ig = isT ? R_UT_SHARED : R_UE_SHARED + k;
-                const u32 rec = enc_chunk(S, P, act, isT ? K_RUN_T : K_RUN_E, bit, is, ic, ig, cached, ue_idx(st, k), ue_idx(c, k), cold_s, cold_c, lane, n_cached, misses);
-                if (act) P.ring[(off + r_nA + d) & (QE_RING - 1)] = (u16)rec;
+                K = r_esc ? K_RANK_P : K_RANK_M;
+                bit = (v >> bp) & 1u;
+                cached = r_esc || r_er > M_MAXE;
+                is = R_RM_STATE + st * M_ROW + rowoff; ic = R_RM_CHAR + c * M_ROW + rowoff; ig = R_WIDE_SHARED + bank * 256 + node;
+                cs = wide_idx(bank, st, node); cc = wide_idx(bank, c, node);
+                runflag = r_esc && d == 0;
+            } else if (warp == 2) {     // run length: first bit (d = 0) and unary exponent (d = 1..eu)
+                const u32 k = d - 1; const bool isT = d == 0;
+                K = isT ? K_RUN_T : K_RUN_E;
+                bit = isT ? (v_ != 1) : (k + 1 < r_eu);
+                cached = !isT && k >= UE_RES;
+                is = isT ? R_UT_STATE + st : R_UE_STATE + st * UE_RES + k;
+                ic = isT ? R_UT_CHAR + c : R_UE_CHAR + c * UE_RES + k;
+                ig = isT ? R_UT_SHARED : R_UE_SHARED + k;
+                cs = ue_idx(st, k); cc = ue_idx(c, k);
             } else {                    // run length: mantissa (tree for exponents <= 5, linear contexts above; qlfc.cpp:1119)
-                const u32 l = lane;
-                const bool act = val != 1 && l < r_eu;
-                const u32 bp = r_eu - 1 - (l < r_eu ? l : 0), bit = (val >> bp) & 1u;
+                const u32 bp = r_eu - 1 - (d < r_eu ? d : 0);
                 const bool tree = r_eu <= M_MAXE;
-                const u32 node = tree ? (val >> (bp + 1)) : 1u + l;
+                const u32 node = tree ? (v_ >> (bp + 1)) : 1u + d;
                 const u32 rowoff = (1u << r_eu) - 2u + node;
-                const u32 rec = enc_chunk(S, P, act, K_RUN_M, bit, R_UM_STATE + st * M_ROW + rowoff, R_UM_CHAR + c * M_ROW + rowoff,
-                                          R_NARROW_SHARED + r_eu * 32 + node, !tree, narrow_idx(r_eu, st, node), narrow_idx(r_eu, c, node), cold_s, cold_c, lane, n_cached, misses);
-                if (act) P.ring[(off + r_nA + 1u + r_eu + l) & (QE_RING - 1)] = (u16)rec;
+                K = K_RUN_M;
+                bit = (v_ >> bp) & 1u;
+                cached = !tree;
+                is = R_UM_STATE + st * M_ROW + rowoff; ic = R_UM_CHAR + c * M_ROW + rowoff; ig = R_NARROW_SHARED + r_eu * 32 + node;
+                cs = narrow_idx(r_eu, st, node); cc = narrow_idx(r_eu, c, node);
             }
-            if ((j & 3) == 3 || j + 1 == cnt) {                        // publish progress every 4 runs
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) P.prog[warp] = off + r_nA + r_nB;
-                if (P.fail) { stop = true; break; }
-            }
+            cached = cached && act;
+            if (__any_sync(0xffffffffu, cached)) n_cached += 2u * (u32)__popc(__ballot_sync(0xffffffffu, cached));
+            const int4 *q = reinterpret_cast<const int4 *>(P.prm[K][bit & 1u]);
+            const int4 qa = q[0], qb = q[1]; const int qg = P.prm[K][bit & 1u][8];
+            const int vs = enc_resolve<0>(S, act, is, cached, cs, qa.w, qb.x, cold_s, lane, misses);
+            const int vc = enc_resolve<1>(S, act, ic, cached, cc, qb.y, qb.z, cold_c, lane, misses);
+            const int vg = enc_resolve<2>(S, act, ig, false, 0, qb.w, qg, nullptr, lane, misses);
+            const u32 p = (u32)((vc * qa.x + vs * qa.y + vg * qa.z) >> 5);
+            if (act) P.ring[(base_off + rp + d) & (QE_RING - 1)] = (u16)(p | (bit ? QE_BIT : 0u) | (runflag ? QE_RUN : 0u));
         }
         base_off += batch_total;
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) P.prog[warp] = base_off;
+        if (P.fail) stop = true;
+        t0 += cnt;
     }
     __syncwarp();
     __threadfence_block();
