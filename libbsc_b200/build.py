@@ -12,7 +12,7 @@ SOURCES = ["api.cu", "adler32.cu", "bwt_encode.cu", "bwt_decode.cu", "st_encode.
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-ccbin", "/usr/bin/g++",
-         "-Xptxas", "-v"]
+         "-Xptxas", "-v"] + os.environ.get("BSCB200_NVCC_EXTRA", "").split()      # e.g. -DQE_DIAG (diagnostic builds only)
 
 
 def _deps():

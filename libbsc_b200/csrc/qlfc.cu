@@ -354,7 +354,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     static_assert(((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448, "encoder working set must fit the 227 KB of one SM");
     ensure_dyn_smem(q_encode5, ctx->device, enc_smem);
     PROF_BYTES(ctx, (double)n);                          // + c written; the launch is latency-, not bandwidth-bound
-    LAUNCH(ctx, q_encode5, nBlocks, 160, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+    LAUNCH(ctx, q_encode5, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
 
@@ -393,7 +393,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                 CUDA_TRY(cudaMemcpyAsync(d_list, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
                 ctx->sync();
                 init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                LAUNCH(ctx, q_encode5, 1, 160, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                LAUNCH(ctx, q_encode5, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
                 r = h_sb[b].result;

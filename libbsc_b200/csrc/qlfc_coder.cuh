@@ -134,7 +134,8 @@ struct Rc2Enc {
         const u32 low32 = (u32)low, carry = (u32)(low >> 32);
         if (low32 < 0xffff0000u || carry) {
             put16(cache + carry);
-            for (; pending; --pending) put16(carry - 1);
+#pragma unroll 1
+            for (; pending; --pending) put16(carry - 1);        // one time in 65536: keep it small
             cache = low32 >> 16;
         } else pending++;
         low = (u64)(u32)(low32 << 16);

@@ -33,16 +33,29 @@
 // run ~100 -> lane per decision of 32 runs (this file) ~25; the range-coder warp is now the limit.
 #pragma once
 
-#define QE_RING 2048
+#define QE_RING 1024
 #define QE_BIT  0x2000u                                     // record: bits 0..12 p, bit 13 the coded bit, bit 14 run start
 #define QE_RUN  0x4000u
 #define QE_MODELS 4
+#define QE_THREADS ((QE_MODELS + 2) * 32)
+#ifdef QE_DIAG      // where does each warp spend its time?  (nvcc -DQE_DIAG; prints for sub-block 0)
+#define QE_DIAG_DECL long long dg_wait = 0, dg_t0 = 0, dg_start = clock64();
+#define QE_DIAG_T0 dg_t0 = clock64();
+#define QE_DIAG_T1 dg_wait += clock64() - dg_t0;
+#define QE_DIAG_END(name) if (sid == 0 && lane == 0) printf("%s warp %u: total %lld waiting %lld\n", name, warp, clock64() - dg_start, dg_wait);
+#else
+#define QE_DIAG_DECL
+#define QE_DIAG_T0
+#define QE_DIAG_T1
+#define QE_DIAG_END(name)
+#endif
 
 struct EncPipe {
-    u16 ring[QE_RING];
+    alignas(16) u32 ring[QE_RING];                          // model warps: record; after the range warp: the addend of `low`
     alignas(16) int prm[7][2][12];                          // [class][bit] = w0 w1 w2 | Ms Ks | Mc Kc | Mg Kg
     volatile u32 prog[QE_MODELS], done[QE_MODELS];          // records completed by each model warp / its end flag
-    volatile u32 head;                                      // records consumed by the coder
+    volatile u32 mid, mid_done, final_range;                // records passed through the range warp / its end flag / range at the end
+    volatile u32 head;                                      // records consumed by the low warp (ring space free again)
     volatile u32 hdr_len, hdr_ready, max_rank;              // published by warp 0 after the stream header
     volatile u32 fail;
     u8  hist2[2][256];                                      // private history copies of warps 1 and 3 (warps 0, 2 use CoderSmem's)
@@ -98,7 +111,7 @@ __device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool c
 // bits [32-lane, ...) of (prev:cur): the flags of the runs before this lane's run, most recent in bit 0
 __device__ __forceinline__ u32 enc_window(u32 prev_rev, u32 cur_rev, u32 lane) { return (u32)((((u64)prev_rev << 32) | cur_rev) >> (32u - lane)); }
 
-__global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
+__global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                     SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
                                                     const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
 {
@@ -113,54 +126,134 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
     if (warp == 1) {
         enc_fill_params(P, lane);
         for (int i = lane; i < 512; i += 32) (&P.hist2[0][0])[i] = 0;
-        if (lane < QE_MODELS) { P.prog[lane] = 0; P.done[lane] = 0; }
-        if (lane == 0) { P.head = 0; P.hdr_len = 0; P.hdr_ready = 0; P.max_rank = 7; P.fail = 0; }
+        if (lane < QE_MODELS) { P.prog[lane] = lane ? 0xffffffffu : 0u; P.done[lane] = 0; }
+        if (lane == 0) { P.head = 0; P.hdr_len = 0; P.hdr_ready = 0; P.max_rank = 7; P.fail = 0; P.mid = 0; P.mid_done = 0; P.final_range = 0; }
     }
     __syncthreads();
 
     const u32 rb = sb.run_begin, re = sb.run_end;
+    u8 *flg = S.inwin;                                         // 2 flags per record, 4 records per byte: bit k = renormalise before record k, bit 4+k = run start
 
     if (warp == QE_MODELS) {
-        // ---------------------------------------- coder ----------------------------------------
-        Rc2Enc rc; rc.init(out_all + sb.out_off);
-        const long long eob = (long long)sb.out_cap - 16;
-        u32 h = 0; int result = 0; bool eob_hit = eob <= 0;
+        // ------------------------- range warp: the `range` recurrence only (rangecoder.h:83-177) -------------------------
+        // Turns each record (bit, p) into the addend of `low` and a "renormalise first" flag, in place.
+        u32 range = 0xffffffffu, h = 0;
+        bool bad = false;
+        QE_DIAG_DECL
         for (;;) {
             u32 limit, spins = 0;
+            QE_DIAG_T0
             for (;;) {
                 limit = min(min(P.prog[0], P.prog[1]), min(P.prog[2], P.prog[3]));
                 if (limit != h) break;
                 if (P.done[0] && P.done[1] && P.done[2] && P.done[3] && min(min(P.prog[0], P.prog[1]), min(P.prog[2], P.prog[3])) == h) break;
+                if (P.fail || ++spins > (1u << 27)) { bad = true; break; }
+            }
+            QE_DIAG_T1
+            if (bad || limit == h) break;
+            __threadfence_block();
+            while (h != limit) {
+                const u32 slot = h & (QE_RING - 1);
+                if ((h & 3u) == 0 && limit - h >= 4u) {
+                    uint4 q = *reinterpret_cast<const uint4 *>(&P.ring[slot]);
+                    u32 recs[4] = {q.x, q.y, q.z, q.w}, f = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const u32 rec = recs[k];
+                        const bool sh = range < 0x10000u;
+                        if (sh) range <<= 16;
+                        const u32 r = (range >> 12) * (rec & 0x1fffu);
+                        const bool bit = rec & QE_BIT;
+                        range = bit ? range - r : r;
+                        recs[k] = bit ? r : 0u;
+                        f |= (sh ? 1u << k : 0u) | ((rec & QE_RUN) ? 16u << k : 0u);
+                    }
+                    *reinterpret_cast<uint4 *>(&P.ring[slot]) = make_uint4(recs[0], recs[1], recs[2], recs[3]);
+                    if (lane == 0) flg[slot >> 2] = (u8)f;
+                    h += 4;
+                    continue;
+                }
+                const u32 rec = P.ring[slot], k = h & 3u;
+                const bool sh = range < 0x10000u;
+                if (sh) range <<= 16;
+                const u32 r = (range >> 12) * (rec & 0x1fffu);
+                const bool bit = rec & QE_BIT;
+                range = bit ? range - r : r;
+                u32 f = k ? flg[slot >> 2] : 0u;
+                f |= (sh ? 1u << k : 0u) | ((rec & QE_RUN) ? 16u << k : 0u);
+                __syncwarp();
+                if (lane == 0) { P.ring[slot] = bit ? r : 0u; flg[slot >> 2] = (u8)f; }
+                __syncwarp();
+                ++h;
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) P.mid = h;
+        }
+        __syncwarp();
+        __threadfence_block();
+        QE_DIAG_END("range")
+        if (lane == 0) { P.final_range = range; P.mid = h; if (bad && !P.fail) P.fail = 2; __threadfence_block(); P.mid_done = 1; }
+        return;
+    }
+    if (warp == QE_MODELS + 1) {
+        // ------------------------- low warp: carries, output units and the end-of-buffer rule -------------------------
+        Rc2Enc rc; rc.init(out_all + sb.out_off);
+        const long long eob = (long long)sb.out_cap - 16;
+        u32 h = 0; int result = 0; bool eob_hit = eob <= 0;
+        QE_DIAG_DECL
+        for (;;) {
+            u32 limit, spins = 0;
+            QE_DIAG_T0
+            for (;;) {
+                limit = P.mid;
+                if (limit != h) break;
+                if (P.mid_done && P.mid == h) break;
                 if (P.fail == 2 || ++spins > (1u << 27)) { result = LIBBSC_GPU_ERROR; break; }
             }
+            QE_DIAG_T1
             if (result || limit == h) break;
             __threadfence_block();
             while (h != limit) {
+                const u32 slot = h & (QE_RING - 1);
                 if (!eob_hit && (h & 3u) == 0 && limit - h >= 4u) {
-                    // fast path: four records per 64-bit shared-memory load, no end-of-buffer test.  The
+                    // fast path: four records per 128-bit shared-memory load, no end-of-buffer test.  The
                     // test of qlfc.cpp:898-901 can only start to matter after a renormalisation moved the
                     // write position past the limit; from then on the checked path below takes over.
-                    const uint2 q = *reinterpret_cast<const uint2 *>(&P.ring[h & (QE_RING - 1)]);
-                    const u32 recs[4] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const u32 rec = recs[k]; ++h;
-                        if (rc.range < 0x10000u) { rc.shift(); rc.range <<= 16; eob_hit = (long long)rc.pos >= eob; }
-                        rc.step((rec >> 13) & 1u, rec & 0x1fffu);
-                        if (eob_hit) break;
+                    const uint4 q = *reinterpret_cast<const uint4 *>(&P.ring[slot]);
+                    const u32 f = flg[slot >> 2] & 15u;
+                    if (__builtin_expect(f == 0, 1)) {            // no renormalisation inside the group: just add
+                        rc.low += ((u64)q.x + q.y) + ((u64)q.z + q.w);
+                        h += 4;
+                    } else {
+                        u32 a0 = q.x, a1 = q.y, a2 = q.z, a3 = q.w;
+#pragma unroll 1
+                        for (u32 k = 0, ff = f; k < 4; ++k, ff >>= 1) {
+                            ++h;
+                            if (ff & 1u) { rc.shift(); eob_hit = (long long)rc.pos >= eob; }
+                            rc.low += a0; a0 = a1; a1 = a2; a2 = a3;
+                            if (eob_hit) break;
+                        }
                     }
                     if (lane == 0 && (h & 63u) == 0) P.head = h;
                     continue;
                 }
-                const u32 rec = P.ring[h & (QE_RING - 1)]; ++h;
-                if (eob_hit && (rec & QE_RUN)) { result = LIBBSC_NOT_COMPRESSIBLE; break; }   // qlfc.cpp:898-901
-                if (rc.range < 0x10000u) { rc.shift(); rc.range <<= 16; eob_hit = (long long)rc.pos >= eob; }
-                rc.step((rec >> 13) & 1u, rec & 0x1fffu);
+                const u32 a = P.ring[slot], f = (u32)flg[slot >> 2] >> (h & 3u); ++h;
+                if (eob_hit && (f & 16u)) { result = LIBBSC_NOT_COMPRESSIBLE; break; }        // qlfc.cpp:898-901
+                if (f & 1u) { rc.shift(); eob_hit = (long long)rc.pos >= eob; }
+                rc.low += a;
             }
             if (lane == 0) P.head = h;
             if (result) break;
         }
-        if (result == 0) result = (int)rc.finish();
+        QE_DIAG_END("low")
+        if (result == 0) {
+            for (u32 spins = 0; !P.mid_done; ) if (++spins > (1u << 27)) { result = LIBBSC_GPU_ERROR; break; }
+            __threadfence_block();
+            rc.range = P.final_range;
+            if (result == 0 && P.fail == 2) result = LIBBSC_GPU_ERROR;
+            if (result == 0) result = (int)rc.finish();
+        }
         if (lane == 0) { if (result < 0 && P.fail == 0) P.fail = 1; sb.result = result; }
         return;
     }
@@ -173,19 +266,32 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
     u32 maxRank = 7;
     u32 base_off = 0;                                          // ring position (record index) of the current batch of runs
 
+    u32 head_seen = 0;
+    bool stop = false;
     if (warp == 0) {
         // ----------------------- stream header: n as 32 raw bits, then the MTF order (qlfc.cpp:851-891) -----------------------
+        // Warps 1..3 keep their progress counters at "infinity" meanwhile, so the coder follows warp 0 alone.
         const u32 n = sb.in_size;
-        P.ring[lane] = (u16)(2048u | (((n >> (31 - lane)) & 1u) ? QE_BIT : 0u));
+        P.ring[lane] = 2048u | (((n >> (31 - lane)) & 1u) ? QE_BIT : 0u);
         u32 off = 32;
         {
             const u8 *mtf = mtf_all + sid * 256;
             u32 used8 = 0; int prev = -1;
-            for (int d = 0; d < 256; ++d) {
+            for (int d = 0; d < 256 && !stop; ++d) {
                 const int c = mtf[d];
                 for (int bit = 7; bit >= 0; --bit) {
                     bool can0, can1; header_options(used8, prev, c >> (bit + 1), bit, can0, can1);
-                    if (can0 && can1) { if (lane == 0) P.ring[off & (QE_RING - 1)] = (u16)(2048u | (((c >> bit) & 1) ? QE_BIT : 0u)); ++off; }   // <= 2048 records: fits the empty ring
+                    if (can0 && can1) {
+                        if (off - head_seen >= QE_RING) {       // the header can be longer than the ring: hand over what is there
+                            __syncwarp();
+                            __threadfence_block();
+                            if (lane == 0) P.prog[0] = off;
+                            for (u32 spins = 0; off - (head_seen = P.head) >= QE_RING; ) if (P.fail || ++spins > (1u << 26)) { if (!P.fail) P.fail = 2; stop = true; break; }
+                            if (stop) break;
+                        }
+                        if (lane == 0) P.ring[off & (QE_RING - 1)] = 2048u | (((c >> bit) & 1) ? QE_BIT : 0u);
+                        ++off;
+                    }
                 }
                 if (c == prev) { maxRank = (u32)ilog2_dev((u32)(d - 1)); break; }
                 prev = c; if ((u32)(c >> 3) == lane) used8 |= 1u << (c & 7);
@@ -195,18 +301,21 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
         __syncwarp();
         __threadfence_block();
         if (lane == 0) { P.max_rank = maxRank; P.hdr_len = off; P.prog[0] = off; __threadfence_block(); P.hdr_ready = 1; }
+        // nobody may publish beyond the header before every model warp has dropped from "infinity" to the header length
+        for (u32 spins = 0; !stop && (P.prog[1] == 0xffffffffu || P.prog[2] == 0xffffffffu || P.prog[3] == 0xffffffffu); )
+            if (P.fail || ++spins > (1u << 27)) { if (!P.fail) P.fail = 2; stop = true; }
     } else {
-        for (u32 spins = 0; !P.hdr_ready; ) if (++spins > (1u << 27)) { P.fail = 2; break; }
+        for (u32 spins = 0; !P.hdr_ready; ) if (P.fail || ++spins > (1u << 27)) { if (!P.fail) P.fail = 2; stop = true; break; }
         __threadfence_block();
         maxRank = P.max_rank; base_off = P.hdr_len;
+        __syncwarp();
         if (lane == 0) P.prog[warp] = base_off;
     }
 
     // ---- state carried from batch to batch ----
+    QE_DIAG_DECL
     u32 avg = 0;                                               // avgRank after the last run of the previous batch
     u32 pf0 = 0, plo = 0, phi = 0, prn = 0;                    // bit-reversed flag ballots of the previous batch
-    u32 head_seen = 0;
-    bool stop = false;
 
     for (u32 t0 = rb; t0 < re && !stop; ) {
         // ================= vector prologue: lane j <-> run t0 + j =================
@@ -214,15 +323,7 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
         bool live = lane < cnt;
         u32 sym = 256u + lane, rank = 1, len = 1;              // dead lanes: unique pseudo-symbols, no decisions
         if (live) { sym = run_sym[t0 + lane]; rank = run_rank[t0 + lane]; len = run_pos[t0 + lane + 1] - run_pos[t0 + lane]; }
-        u32 eu = (u32)ilog2_dev(len);
-        if (__any_sync(0xffffffffu, eu > 8u)) {                // long runs: cut the batch so that its records fit half the ring
-            u32 ub = live ? 16u + 2u * eu : 0u;                // upper bound of a run's decisions (15 rank + 1 + 2*eu)
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, ub, o); if (lane >= (u32)o) ub += t; }
-            const u32 fit = (u32)__popc(__ballot_sync(0xffffffffu, live && ub <= QE_RING / 2));
-            if (fit < cnt) { cnt = fit; live = lane < cnt; if (!live) { sym = 256u + lane; rank = 1; len = 1; eu = 0; } }
-        }
-        const u32 er = (u32)ilog2_dev(rank), rank0 = rank - 1;
+        const u32 er = (u32)ilog2_dev(rank), eu = (u32)ilog2_dev(len), rank0 = rank - 1;
         u32 my_avg = 0;                                        // avgRank seen by this lane's run (qlfc.cpp:1048: serial integer recurrence)
         {
             u32 a = avg;
@@ -237,12 +338,20 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
         const bool esc = my_avg >= 32u;
         const u32 nE = (!esc && rank != 1) ? (er - 1) + (er < maxRank ? 1u : 0u) : 0u;
         const u32 nM = esc ? maxRank + 1u : (rank != 1 ? er : 0u);
-        const u32 nA = live ? (esc ? 0u : 1u) + nE + nM : 0u;
-        const u32 nB = live ? 1u + (len != 1 ? 2u * eu : 0u) : 0u;
+        u32 nA = live ? (esc ? 0u : 1u) + nE + nM : 0u;
+        u32 nB = live ? 1u + (len != 1 ? 2u * eu : 0u) : 0u;
         u32 incl = nA + nB;                                    // ring offsets: exclusive warp scan of the decision counts
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
-        const u32 my_off = incl - (nA + nB), batch_total = __shfl_sync(0xffffffffu, incl, 31);
+        const u32 my_off = incl - (nA + nB);
+        u32 batch_total = __shfl_sync(0xffffffffu, incl, 31);
+        if (batch_total > QE_RING / 2) {                       // long runs: cut the batch so that its records fit half the ring
+            cnt = (u32)__popc(__ballot_sync(0xffffffffu, live && incl <= QE_RING / 2));   // >= 1: a run has at most 78 decisions
+            avg = __shfl_sync(0xffffffffu, my_avg, cnt);       // cnt < 32 here; nothing before this point had side effects
+            batch_total = __shfl_sync(0xffffffffu, incl, cnt - 1);
+            live = lane < cnt;
+            if (!live) { sym = 256u + lane; nA = nB = 0; }
+        }
         // sliding-window contexts (qlfc.cpp:1123-1125) from ballots; most recent run in the low bits
         const u32 q3 = rank0 < 3 ? rank0 : 3;
         const u32 bf0 = __brev(__ballot_sync(0xffffffffu, live && rank0 == 0));
@@ -295,10 +404,12 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
         __syncwarp();
 
         // room in the ring for the whole batch (re-read the consumer's head only when needed)
+        QE_DIAG_T0
         for (u32 spins = 0; (int)(base_off + batch_total - head_seen) > QE_RING; ) {
             head_seen = P.head;
             if (P.fail || ++spins > (1u << 26)) { if (!P.fail) P.fail = 2; stop = true; break; }
         }
+        QE_DIAG_T1
         if (stop) break;
 
         // ================= 32 decisions of this warp's group at a time, one lane per decision =================
@@ -362,7 +473,7 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
             const int vc = enc_resolve<1>(S, act, ic, cached, cc, qb.y, qb.z, cold_c, lane, misses);
             const int vg = enc_resolve<2>(S, act, ig, false, 0, qb.w, qg, nullptr, lane, misses);
             const u32 p = (u32)((vc * qa.x + vs * qa.y + vg * qa.z) >> 5);
-            if (act) P.ring[(base_off + rp + d) & (QE_RING - 1)] = (u16)(p | (bit ? QE_BIT : 0u) | (runflag ? QE_RUN : 0u));
+            if (act) P.ring[(base_off + rp + d) & (QE_RING - 1)] = p | (bit ? QE_BIT : 0u) | (runflag ? QE_RUN : 0u);
         }
         base_off += batch_total;
         __syncwarp();
@@ -374,6 +485,7 @@ __global__ void __launch_bounds__(160, 1) q_encode5(const u32 *__restrict__ run_
     __syncwarp();
     __threadfence_block();
     if (lane == 0) { P.prog[warp] = base_off; P.done[warp] = 1; }
+    QE_DIAG_END("model")
     misses = __reduce_add_sync(0xffffffffu, misses);
     if (lane == 0) { atomicAdd(&sb.stat_cached, n_cached); atomicAdd(&sb.stat_miss, misses); }
 }
