@@ -43,7 +43,13 @@
 #define QE_DIAG_T0 dg_t0 = clock64();
 #define QE_DIAG_T1 dg_wait += clock64() - dg_t0;
 #define QE_DIAG_END(name) if (sid == 0 && lane == 0) printf("%s warp %u: total %lld waiting %lld\n", name, warp, clock64() - dg_start, dg_wait);
+#define QE_DIAG_ROUNDS(k) , dg_rounds[k]
+#define QE_DIAG_ROUNDS_PARAM , unsigned long long &dg_r
+#define QE_DIAG_ROUNDS_ADD dg_r += maxocc + 1;
 #else
+#define QE_DIAG_ROUNDS(k)
+#define QE_DIAG_ROUNDS_PARAM
+#define QE_DIAG_ROUNDS_ADD
 #define QE_DIAG_DECL
 #define QE_DIAG_T0
 #define QE_DIAG_T1
@@ -82,7 +88,7 @@ __device__ __forceinline__ void enc_fill_params(EncPipe &P, u32 lane)
 // BEFORE this lane's decision and applies the move (v*M + Kc) >> 12.  Lanes that share a counter -- or
 // a cache slot -- are served in lane (= stream) order, one per round.
 template <int KIND>   // 0 by state, 1 by symbol, 2 shared (never cached)
-__device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool cached, u32 key, int M, int Kc, short *__restrict__ cold, u32 lane, u32 &misses)
+__device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool cached, u32 key, int M, int Kc, short *__restrict__ cold, u32 lane, u32 &misses QE_DIAG_ROUNDS_PARAM)
 {
     u16 *tags = KIND == 0 ? S.tag_state : S.tag_char;
     const u32 vbase = KIND == 0 ? C_STATE_VAL : C_CHAR_VAL;
@@ -91,6 +97,7 @@ __device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool c
     const u32 occ = __popc(m & lanemask_lt());
     const u32 maxocc = __reduce_max_sync(0xffffffffu, act ? occ : 0u);
     int v = 0;
+    QE_DIAG_ROUNDS_ADD
     for (u32 round = 0; round <= maxocc; ++round) {
         if (act && occ == round) {
             if (KIND != 2 && cached) {
@@ -142,20 +149,25 @@ __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict
         QE_DIAG_DECL
         for (;;) {
             u32 limit, spins = 0;
+            bool fin;
             QE_DIAG_T0
             for (;;) {
+                fin = P.done[0] && P.done[1] && P.done[2] && P.done[3];          // read before the counters: then they are final
                 limit = min(min(P.prog[0], P.prog[1]), min(P.prog[2], P.prog[3]));
-                if (limit != h) break;
-                if (P.done[0] && P.done[1] && P.done[2] && P.done[3] && min(min(P.prog[0], P.prog[1]), min(P.prog[2], P.prog[3])) == h) break;
+                if (!fin) limit &= ~3u;                                        // whole groups of four until the very end
+                if (limit != h || fin) break;
                 if (P.fail || ++spins > (1u << 27)) { bad = true; break; }
             }
             QE_DIAG_T1
             if (bad || limit == h) break;
             __threadfence_block();
-            while (h != limit) {
-                const u32 slot = h & (QE_RING - 1);
-                if ((h & 3u) == 0 && limit - h >= 4u) {
-                    uint4 q = *reinterpret_cast<const uint4 *>(&P.ring[slot]);
+            if ((h & 3u) == 0 && limit - h >= 4u) {
+                u32 groups = (limit - h) >> 2;
+                uint4 q = *reinterpret_cast<const uint4 *>(&P.ring[h & (QE_RING - 1)]);
+                for (; groups; --groups) {
+                    const u32 slot = h & (QE_RING - 1);
+                    uint4 nq = q;
+                    if (groups > 1) nq = *reinterpret_cast<const uint4 *>(&P.ring[(h + 4) & (QE_RING - 1)]);    // prefetch the next group
                     u32 recs[4] = {q.x, q.y, q.z, q.w}, f = 0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -170,9 +182,11 @@ __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict
                     }
                     *reinterpret_cast<uint4 *>(&P.ring[slot]) = make_uint4(recs[0], recs[1], recs[2], recs[3]);
                     if (lane == 0) flg[slot >> 2] = (u8)f;
-                    h += 4;
-                    continue;
+                    h += 4; q = nq;
                 }
+            }
+            while (h != limit) {                                               // the last few records of the stream
+                const u32 slot = h & (QE_RING - 1);
                 const u32 rec = P.ring[slot], k = h & 3u;
                 const bool sh = range < 0x10000u;
                 if (sh) range <<= 16;
@@ -220,22 +234,31 @@ __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict
                     // fast path: four records per 128-bit shared-memory load, no end-of-buffer test.  The
                     // test of qlfc.cpp:898-901 can only start to matter after a renormalisation moved the
                     // write position past the limit; from then on the checked path below takes over.
-                    const uint4 q = *reinterpret_cast<const uint4 *>(&P.ring[slot]);
-                    const u32 f = flg[slot >> 2] & 15u;
-                    if (__builtin_expect(f == 0, 1)) {            // no renormalisation inside the group: just add
-                        rc.low += ((u64)q.x + q.y) + ((u64)q.z + q.w);
-                        h += 4;
-                    } else {
-                        u32 a0 = q.x, a1 = q.y, a2 = q.z, a3 = q.w;
-#pragma unroll 1
-                        for (u32 k = 0, ff = f; k < 4; ++k, ff >>= 1) {
-                            ++h;
-                            if (ff & 1u) { rc.shift(); eob_hit = (long long)rc.pos >= eob; }
-                            rc.low += a0; a0 = a1; a1 = a2; a2 = a3;
-                            if (eob_hit) break;
+                    u32 groups = (limit - h) >> 2;
+                    uint4 q = *reinterpret_cast<const uint4 *>(&P.ring[slot]);
+                    u32 f = flg[slot >> 2];
+                    for (; groups && !eob_hit; --groups) {
+                        uint4 nq = q; u32 nf = f;
+                        if (groups > 1) {                             // prefetch the next group
+                            const u32 ns = (h + 4) & (QE_RING - 1);
+                            nq = *reinterpret_cast<const uint4 *>(&P.ring[ns]); nf = flg[ns >> 2];
                         }
+                        if (__builtin_expect((f & 15u) == 0, 1)) {    // no renormalisation inside the group: just add
+                            rc.low += ((u64)q.x + q.y) + ((u64)q.z + q.w);
+                            h += 4;
+                        } else {
+                            u32 a0 = q.x, a1 = q.y, a2 = q.z, a3 = q.w;
+#pragma unroll 1
+                            for (u32 k = 0, ff = f; k < 4; ++k, ff >>= 1) {
+                                ++h;
+                                if (ff & 1u) { rc.shift(); eob_hit = (long long)rc.pos >= eob; }
+                                rc.low += a0; a0 = a1; a1 = a2; a2 = a3;
+                                if (eob_hit) break;
+                            }
+                        }
+                        if (lane == 0 && (h & 63u) == 0) P.head = h;
+                        q = nq; f = nf;
                     }
-                    if (lane == 0 && (h & 63u) == 0) P.head = h;
                     continue;
                 }
                 const u32 a = P.ring[slot], f = (u32)flg[slot >> 2] >> (h & 3u); ++h;
@@ -314,6 +337,9 @@ __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict
 
     // ---- state carried from batch to batch ----
     QE_DIAG_DECL
+#ifdef QE_DIAG
+    unsigned long long dg_rounds[3] = {0, 0, 0}, dg_chunks = 0; long long dg_cyc = 0, dg_c0 = 0;
+#endif
     u32 avg = 0;                                               // avgRank after the last run of the previous batch
     u32 pf0 = 0, plo = 0, phi = 0, prn = 0;                    // bit-reversed flag ballots of the previous batch
 
@@ -413,6 +439,9 @@ __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict
         if (stop) break;
 
         // ================= 32 decisions of this warp's group at a time, one lane per decision =================
+#ifdef QE_DIAG
+        dg_c0 = clock64(); dg_chunks += (gtotal + 31) / 32;
+#endif
         for (u32 cb = 0; cb < gtotal; cb += 32) {
             const u32 g = cb + lane;
             const bool act = g < gtotal;
@@ -469,12 +498,15 @@ __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict
             if (__any_sync(0xffffffffu, cached)) n_cached += 2u * (u32)__popc(__ballot_sync(0xffffffffu, cached));
             const int4 *q = reinterpret_cast<const int4 *>(P.prm[K][bit & 1u]);
             const int4 qa = q[0], qb = q[1]; const int qg = P.prm[K][bit & 1u][8];
-            const int vs = enc_resolve<0>(S, act, is, cached, cs, qa.w, qb.x, cold_s, lane, misses);
-            const int vc = enc_resolve<1>(S, act, ic, cached, cc, qb.y, qb.z, cold_c, lane, misses);
-            const int vg = enc_resolve<2>(S, act, ig, false, 0, qb.w, qg, nullptr, lane, misses);
+            const int vs = enc_resolve<0>(S, act, is, cached, cs, qa.w, qb.x, cold_s, lane, misses QE_DIAG_ROUNDS(0));
+            const int vc = enc_resolve<1>(S, act, ic, cached, cc, qb.y, qb.z, cold_c, lane, misses QE_DIAG_ROUNDS(1));
+            const int vg = enc_resolve<2>(S, act, ig, false, 0, qb.w, qg, nullptr, lane, misses QE_DIAG_ROUNDS(2));
             const u32 p = (u32)((vc * qa.x + vs * qa.y + vg * qa.z) >> 5);
             if (act) P.ring[(base_off + rp + d) & (QE_RING - 1)] = p | (bit ? QE_BIT : 0u) | (runflag ? QE_RUN : 0u);
         }
+#ifdef QE_DIAG
+        dg_cyc += clock64() - dg_c0;
+#endif
         base_off += batch_total;
         __syncwarp();
         __threadfence_block();
@@ -486,6 +518,10 @@ __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict
     __threadfence_block();
     if (lane == 0) { P.prog[warp] = base_off; P.done[warp] = 1; }
     QE_DIAG_END("model")
+#ifdef QE_DIAG
+    if (sid == 0 && lane == 0 && warp == 0) printf("records %u runs %u\n", base_off, re - rb);
+    if (sid == 0 && lane == 0) printf("model warp %u: chunks %llu rounds s %llu c %llu g %llu, cycles in chunks %lld\n", warp, dg_chunks, dg_rounds[0], dg_rounds[1], dg_rounds[2], dg_cyc);
+#endif
     misses = __reduce_add_sync(0xffffffffu, misses);
     if (lane == 0) { atomicAdd(&sb.stat_cached, n_cached); atomicAdd(&sb.stat_miss, misses); }
 }
