@@ -94,10 +94,37 @@ __device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool c
     const u32 vbase = KIND == 0 ? C_STATE_VAL : C_CHAR_VAL;
     if (KIND != 2 && cached) x = vbase + cache_slot(key);
     const u32 m = __match_any_sync(0xffffffffu, act ? x : (0x80000000u | lane));
-    const u32 occ = __popc(m & lanemask_lt());
+    const u32 below = m & lanemask_lt();
+    const u32 occ = __popc(below);
     const u32 maxocc = __reduce_max_sync(0xffffffffu, act ? occ : 0u);
+    const u32 prevl = below ? 31u - (u32)__clz(below) : lane;      // the previous user of my counter
     int v = 0;
     QE_DIAG_ROUNDS_ADD
+    // two different rare counters on one cache slot inside a chunk (very rare): take turns through shared memory
+    bool clash = false;
+    if (KIND != 2) { const u32 pk = __shfl_sync(0xffffffffu, key, prevl); clash = __any_sync(0xffffffffu, act && cached && below && pk != key); }
+    if (!clash) {
+        // The first user of a counter reads it, the value then travels down the chain of users by shuffles,
+        // the last one writes it back: one round per link, no shared-memory round trip in between.
+        if (act && occ == 0) {
+            if (KIND != 2 && cached) {
+                const u32 slot = x - vbase, t = tags[slot];
+                if (t != cache_tag(key)) {
+                    if (t) cold[cache_unslot(slot, t)] = (short)S.s16[x];
+                    S.s16[x] = (u16)cold[key]; tags[slot] = (u16)cache_tag(key); ++misses;
+                }
+            }
+            v = S.s16[x];
+        }
+        int vn = (v * M + Kc) >> 12;
+        for (u32 round = 1; round <= maxocc; ++round) {
+            const int t = __shfl_sync(0xffffffffu, vn, prevl);
+            if (occ == round) { v = t; vn = (v * M + Kc) >> 12; }
+        }
+        if (act && (m >> lane) == 1u) S.s16[x] = (u16)vn;
+        __syncwarp();
+        return v;
+    }
     for (u32 round = 0; round <= maxocc; ++round) {
         if (act && occ == round) {
             if (KIND != 2 && cached) {
