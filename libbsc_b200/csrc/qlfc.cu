@@ -254,6 +254,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 
 #include "qlfc_ranks.cuh"
 #include "qlfc_coder.cuh"
+#include "qlfc_decoder.cuh"
 #include "qlfc_encoder.cuh"
 
 constexpr size_t MODEL_SHORTS_PAD = 2 * (size_t)COLD_PAD;     // by-state + by-symbol cold arrays per stream

@@ -17,9 +17,8 @@
 //     exponents 6-7, the escape bank, run exponents >= 6 and run-exponent indices >= 8; the
 //     1.7 M counters behind them live in HBM                                    24 KB
 //
-// The decoder warp runs in lock-step: all 32 lanes execute the same decision sequence on the same
-// data (shared-memory broadcasts), lanes only diverge to expand runs / rotate the MTF list.
-// The encoder is a two-warp pipeline, see q_encode3 below.
+// The decoder (qlfc_decoder.cuh) is one lock-step warp per stream; the encoder (qlfc_encoder.cuh) is a
+// six-warp pipeline per stream.
 #pragma once
 
 // ---- shared-memory counter file (indices in u16 units) ---------------------------------------------
@@ -88,21 +87,6 @@ __device__ __forceinline__ u32 narrow_idx(u32 e, u32 x, u32 node) { return 9 * C
 __device__ __forceinline__ u32 ue_idx(u32 x, u32 k) { return COLD_UE + x * 32 + k; }
 __device__ __forceinline__ u32 m_off(u32 e, u32 node) { return (1u << e) - 2u + node; }   // position inside a compact row
 
-// Index (into S.s16) of rare counter `idx` of one kind, through the direct-mapped write-back cache.
-// Warp-uniform version (decoder): every lane performs the same accesses.
-__device__ __forceinline__ u32 cache_get(CoderSmem &S, u32 val_base, u16 *tags, short *__restrict__ cold, u32 idx, u32 &misses)
-{
-    const u32 slot = cache_slot(idx), want = cache_tag(idx);
-    const u32 t = tags[slot];
-    if (t != want) {
-        if (t) cold[cache_unslot(slot, t)] = (short)S.s16[val_base + slot];
-        S.s16[val_base + slot] = (u16)cold[idx];
-        tags[slot] = (u16)want;
-        ++misses;
-    }
-    return val_base + slot;
-}
-
 // ---- counters ---------------------------------------------------------------------------------------
 // All parameters are compile-time immediates (bscb_param is constexpr).  Counters provably stay in
 // [1, 4095] from their start value 2048 for every parameter set, so they are kept as unsigned 16-bit.
@@ -152,202 +136,3 @@ struct Rc2Enc {
     }
     __device__ u32 finish() { if (range < 0x10000u) shift(); shift(); shift(); shift(); return pos; }
 };
-
-// cold path of the decoder's input window (by-value arguments: keeps the coder state in registers)
-__device__ __noinline__ void rc_refill_window(const u8 *__restrict__ in, u8 *win, u32 base, u32 limit)
-{
-    const u32 lane = threadIdx.x & 31;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { const u32 o = base + lane * 8 + k; win[lane * 8 + k] = o < limit ? in[o] : (u8)0; }
-    __syncwarp();
-}
-
-struct Rc2Dec {
-    const u8 *in; u32 pos, limit, code, range;
-    u8 *win; u32 wbase;              // 256-byte shared-memory window [wbase, wbase+256) of the stream (pos is always even)
-    __device__ __forceinline__ void refill() { wbase = pos; rc_refill_window(in, win, pos, limit); }
-    __device__ __forceinline__ u32 get16() {
-        if (pos - wbase >= 256u) refill();
-        const u32 v = *(const u16 *)(win + (pos - wbase));
-        pos += 2; return v;
-    }
-    __device__ __forceinline__ u32 decode(int p) {
-        if (range < 0x10000u) { range <<= 16; code = (code << 16) | get16(); }
-        const u32 r = (range >> 12) * (u32)p;
-        const u32 bit = code >= r;
-        code -= bit ? r : 0u; range = bit ? range - r : r;
-        return bit;
-    }
-};
-
-// one binary decision against three shared-memory counters (indices into S.s16), decoder side
-template <int K> __device__ __forceinline__ u32 dec3(CoderSmem &S, Rc2Dec &rc, u32 is, u32 ic, u32 ig)
-{
-    const int s = S.s16[is], c = S.s16[ic], g = S.s16[ig];
-    const int p = q_mix<K>(s, c, g);
-    if (rc.range < 0x10000u) { rc.range <<= 16; rc.code = (rc.code << 16) | rc.get16(); }
-    const u32 r = (rc.range >> 12) * (u32)p;
-    if (rc.code >= r) {                                      // warp-uniform branch: one side does everything for its outcome
-        rc.code -= r; rc.range -= r;
-        S.s16[is] = (u16)q_down<K, 0>(s); S.s16[ic] = (u16)q_down<K, 1>(c); S.s16[ig] = (u16)q_down<K, 2>(g);
-        return 1u;
-    }
-    rc.range = r;
-    S.s16[is] = (u16)q_up<K, 0>(s); S.s16[ic] = (u16)q_up<K, 1>(c); S.s16[ig] = (u16)q_up<K, 2>(g);
-    return 0u;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// decoder (qlfc.cpp:1672-1927).  One warp per sub-block, lock-step; runs are expanded warp-wide.
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 1) q_decode2(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
-                                                   const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
-{
-    extern __shared__ __align__(16) u8 q_smem_raw[];
-    CoderSmem &S = *reinterpret_cast<CoderSmem *>(q_smem_raw);
-    coder_smem_init(S, tables);
-
-    const u32 sid = sb_list[blockIdx.x];
-    SubBlock &sb = sbs[sid];
-    short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
-    const u32 lane = threadIdx.x;
-    u32 st_cached = 0, st_miss = 0;
-
-    Rc2Dec rc; rc.in = in_all + sb.out_off; rc.pos = 0; rc.limit = sb.out_cap; rc.code = 0; rc.range = 0xffffffffu;
-    rc.win = S.inwin; rc.wbase = 0; rc.refill();
-    for (int i = 0; i < 3; ++i) rc.code = (rc.code << 16) | rc.get16();
-    u32 n = 0; for (int b = 0; b < 32; ++b) n = (n << 1) | rc.decode(2048);
-    if (n > sb.in_size) { if (lane == 0) sb.result = LIBBSC_DATA_CORRUPT; return; }   // would overrun the output slice
-
-    int ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0, maxRank = 7, avgRank = 0;
-    {
-        u32 used8 = 0; int prev = -1;
-        for (int d = 0; d < 256; ++d) {
-            int c = 0;
-            for (int bit = 7; bit >= 0; --bit) {
-                bool can0, can1; header_options(used8, prev, c, bit, can0, can1);
-                if (can0 && can1) c = 2 * c + (int)rc.decode(2048);
-                else if (can1) c = 2 * c + 1;
-                else if (can0) c = 2 * c;
-            }
-            c &= 255;
-            S.mtf[d] = (u8)c;
-            if (c == prev) { maxRank = ilog2_dev((u32)(d - 1)); break; }
-            prev = c; if ((u32)(c >> 3) == lane) used8 |= 1u << (c & 7);
-        }
-    }
-    __syncwarp();
-
-    u8 *out = out_all + sb.in_start;
-    for (u32 i = 0; i < n; ) {
-        const u32 c = S.mtf[0];
-        int rank = 1; u32 b;
-        u32 st = S.rank_state[(ctxRun << 11) | (ctxRank4 << 3) | S.rankHist[c]];
-        if (avgRank < 32) {
-            b = dec3<K_RANK_T>(S, rc, R_RT_STATE + st, R_RT_CHAR + c, R_RT_SHARED);
-            if (!b) S.rankHist[c] = 0;
-            else {
-                u32 e = 1;
-                while ((int)e != maxRank) {
-                    b = dec3<K_RANK_E>(S, rc, R_RE_STATE + st * 8 + e - 1, R_RE_CHAR + c * 8 + e - 1, R_RE_SHARED + e - 1);
-                    if (!b) break;
-                    if (++e >= 7) break;                                      // e <= maxRank <= 7 in valid streams
-                }
-                S.rankHist[c] = (u8)e;
-                if (e <= M_MAXE) {
-                    const u32 bs = R_RM_STATE + st * M_ROW + (1u << e) - 2u, bc = R_RM_CHAR + c * M_ROW + (1u << e) - 2u, bg = R_WIDE_SHARED + e * 256;
-                    for (int bit = (int)e - 1; bit >= 0; --bit) {
-                        b = dec3<K_RANK_M>(S, rc, bs + rank, bc + rank, bg + rank);
-                        rank = 2 * rank + (int)b;
-                    }
-                } else {
-                    for (int bit = (int)e - 1; bit >= 0; --bit) {
-                        const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, wide_idx(e, st, rank), st_miss);
-                        const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, wide_idx(e, c, rank), st_miss);
-                        st_cached += 2;
-                        b = dec3<K_RANK_M>(S, rc, is, ic, R_WIDE_SHARED + e * 256 + rank);
-                        rank = 2 * rank + (int)b;
-                    }
-                }
-            }
-        } else {
-            rank = 0;
-            for (int node = 1, bit = maxRank; bit >= 0; --bit) {
-                const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, wide_idx(8, st, node), st_miss);
-                const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, wide_idx(8, c, node), st_miss);
-                st_cached += 2;
-                b = dec3<K_RANK_P>(S, rc, is, ic, R_WIDE_SHARED + 8 * 256 + node);
-                node = 2 * node + (int)b; rank = 2 * rank + (int)b;
-            }
-            S.rankHist[c] = (u8)ilog2_dev((u32)rank);
-        }
-        rank &= 255;
-        // push c `rank` places back: mtf[0..rank-1] = mtf[1..rank]; mtf[rank] = c  (qlfc.cpp:1830-1860)
-        if (rank >= 1 && rank <= 3) {                        // common case: every lane does the same few moves, no barrier needed
-            const u8 m1 = S.mtf[1], m2 = S.mtf[2], m3 = S.mtf[3];
-            S.mtf[0] = m1;
-            if (rank == 1) S.mtf[1] = (u8)c;
-            else { S.mtf[1] = m2; if (rank == 2) S.mtf[2] = (u8)c; else { S.mtf[2] = m3; S.mtf[3] = (u8)c; } }
-        } else {
-            __syncwarp();
-            for (int basep = 0; basep < rank; basep += 32) {
-                const int p = basep + (int)lane;
-                const u8 v = S.mtf[p + 1];
-                __syncwarp();
-                if (p < rank) S.mtf[p] = v;
-                __syncwarp();
-            }
-            if (lane == 0) S.mtf[rank] = (u8)c;
-            __syncwarp();
-        }
-
-        avgRank = (avgRank * 124 + rank * 4) >> 7;
-        const int rank0 = rank - 1;
-        const int rh = S.runHist[c];
-        st = S.run_state[(ctxRank0 << 10) | (ctxRun << 6) | (((u32)rank0 < 7u ? rank0 : 7) << 3) | (rh < 7 ? rh : 7)];
-        u32 run = 1;
-        b = dec3<K_RUN_T>(S, rc, R_UT_STATE + st, R_UT_CHAR + c, R_UT_SHARED);
-        if (!b) S.runHist[c] = (u8)((rh + 2) >> 2);
-        else {
-            u32 e = 1;
-            for (;;) {
-                const u32 k = e - 1;
-                if (k < UE_RES) b = dec3<K_RUN_E>(S, rc, R_UE_STATE + st * UE_RES + k, R_UE_CHAR + c * UE_RES + k, R_UE_SHARED + k);
-                else {
-                    const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, ue_idx(st, k), st_miss);
-                    const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, ue_idx(c, k), st_miss);
-                    st_cached += 2;
-                    b = dec3<K_RUN_E>(S, rc, is, ic, R_UE_SHARED + k);
-                }
-                if (!b) break;
-                if (++e >= 31) break;                                         // corrupt-input guard
-            }
-            S.runHist[c] = (u8)((rh + 3 * e + 3) >> 2);
-            if (e <= M_MAXE) {
-                const u32 bs = R_UM_STATE + st * M_ROW + (1u << e) - 2u, bc = R_UM_CHAR + c * M_ROW + (1u << e) - 2u, bg = R_NARROW_SHARED + e * 32;
-                for (int node = 1, bit = (int)e - 1; bit >= 0; --bit) {
-                    b = dec3<K_RUN_M>(S, rc, bs + node, bc + node, bg + node);
-                    run = 2 * run + b; node = 2 * node + (int)b;
-                }
-            } else {
-                for (int node = 1, bit = (int)e - 1; bit >= 0; --bit) {
-                    const u32 is = cache_get(S, C_STATE_VAL, S.tag_state, cold_s, narrow_idx(e, st, node), st_miss);
-                    const u32 ic = cache_get(S, C_CHAR_VAL, S.tag_char, cold_c, narrow_idx(e, c, node), st_miss);
-                    st_cached += 2;
-                    b = dec3<K_RUN_M>(S, rc, is, ic, R_NARROW_SHARED + e * 32 + node);
-                    run = 2 * run + b; node = node + 1;                       // qlfc.cpp:1119: linear contexts above 5 bits
-                }
-            }
-        }
-        ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0)) & 0x7;
-        ctxRank4 = ((ctxRank4 << 2) | ((u32)rank0 < 3u ? rank0 : 3)) & 0xff;
-        ctxRun   = ((ctxRun << 1) | (run < 3)) & 0xf;
-
-        if (run > n - i) run = n - i;                                         // never write past n
-        for (u32 k = lane; k < run; k += 32) out[i + k] = (u8)c;
-        i += run;
-    }
-    if (lane == 0) { sb.result = (int)n; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
-}
-
