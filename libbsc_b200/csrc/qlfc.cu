@@ -255,6 +255,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 #include "qlfc_ranks.cuh"
 #include "qlfc_coder.cuh"
 #include "qlfc_decoder.cuh"
+#include "qlfc_decoder3.cuh"
 #include "qlfc_encoder.cuh"
 
 constexpr size_t MODEL_SHORTS_PAD = 2 * (size_t)COLD_PAD;     // by-state + by-symbol cold arrays per stream
@@ -425,6 +426,13 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     return result;
 }
 
+// BSCB200_QDEC=2 selects the previous decoder kernel (serial decision-by-decision walk) for A/B measurements.
+static int decoder_generation()
+{
+    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); return (e && e[0] == '2') ? 2 : 3; }();
+    return gen;
+}
+
 int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int out_cap, int coder, int features)
 {
     (void)features;
@@ -467,9 +475,20 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         CUDA_TRY(cudaMemcpyAsync(d_list, list, sizeof(u32) * Q_MAX_SUB, cudaMemcpyHostToDevice, ctx->stream));
         ctx->sync();
         init_models(ctx, models, nlist);
-        ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
         PROF_BYTES(ctx, (double)in_size + (double)out_cap);
-        LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
+        if (decoder_generation() == 2) {
+            ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
+            LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
+        } else {
+            static const bool prof = getenv("BSCB200_QDEC_PROF") != nullptr;      // per-phase cycle counts (diagnostic)
+            if (prof) {
+                ensure_dyn_smem(q_decode3<true>, ctx->device, sizeof(Dec3Smem));
+                LAUNCH(ctx, q_decode3<true>, nlist, 32, sizeof(Dec3Smem), d_in, d_sb, models, tables, d_out, d_list);
+            } else {
+                ensure_dyn_smem(q_decode3<false>, ctx->device, sizeof(Dec3Smem));
+                LAUNCH(ctx, q_decode3<false>, nlist, 32, sizeof(Dec3Smem), d_in, d_sb, models, tables, d_out, d_list);
+            }
+        }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->sync();

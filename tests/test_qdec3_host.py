@@ -1,0 +1,76 @@
+"""Host emulation of the CUDA QLFC decoder (libbsc_b200/csrc/qlfc_decoder3.cuh compiled with QD3_HOST by
+tools/qdec3_host.cpp: the same source, the 32 lanes run one after the other) against the oracle, on the CPU.
+This pins the LANE LOGIC of the speculative decoder (who evaluates which candidate context, which lane owns
+which counter move, the pair-prefetching mantissa walk, the branch-free range-coder step) bit-for-bit; the
+GPU parity tests (tests/test_gpu_parity.py) then only have to confirm that the device executes it the same way."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tools", "qdec3_host.cpp")
+LIB = os.path.join(ROOT, "tools", "bin", "libqdec3_host.so")
+DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_decoder3.cuh", "qlfc_coder.cuh", "qlfc_tables.inc")]
+
+
+@pytest.fixture(scope="module")
+def qdec3():
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        subprocess.run(["g++", "-O2", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
+    lib = ctypes.CDLL(LIB)
+    lib.qdec3_host_decode.restype = ctypes.c_int
+    lib.qdec3_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+
+    def decode(stream, n):
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        out = np.full(n + 64, 0xAA, dtype=np.uint8)
+        stats = (ctypes.c_uint * 2)()
+        r = lib.qdec3_host_decode(stream.ctypes.data, stream.size, out.ctypes.data, n, stats)
+        assert np.all(out[n:] == 0xAA), "wrote past the output slice"
+        return r, out[:n], (stats[0], stats[1])
+    return decode
+
+
+def inputs(gen, checker):
+    rng = np.random.default_rng(5)
+
+    def bwt(a):
+        return checker.bwt_encode(a)[1]
+    yield "bwt(text 2M)", bwt(gen.text(2, 2 << 20))
+    yield "bwt(text 300k)", bwt(gen.text(7, 300000))
+    yield "bwt(skew 300k)", bwt(gen.skew(3, 300000))
+    yield "st6-like skew raw", gen.skew(3, 200000)                    # high-entropy: escape mode, wide banks
+    yield "alpha4", rng.integers(0, 4, 50000, dtype=np.uint8)
+    yield "alpha2", rng.integers(0, 2, 65536, dtype=np.uint8)
+    yield "allsame", np.full(3000, 65, dtype=np.uint8)
+    yield "zeros", np.zeros(1000, dtype=np.uint8)
+    yield "period7", np.tile(np.frombuffer(b"abcabcd", dtype=np.uint8), 3000)
+    yield "long runs", np.repeat(rng.integers(0, 200, 3000, dtype=np.uint8), rng.integers(1, 3000, 3000))
+    yield "huge run", np.concatenate([gen.text(3, 5000), np.full(3 << 20, 7, np.uint8), gen.text(4, 3000)])
+    yield "mixed ranks", np.concatenate([rng.integers(0, 256, 40000, dtype=np.uint8), bwt(gen.text(5, 100000)), rng.integers(0, 256, 40000, dtype=np.uint8)])
+    yield "tiny", gen.text(1, 40)
+
+
+def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
+    covered = 0
+    for name, a in inputs(gen, checker):
+        for enc in (checker, port):
+            r, s = enc.encode_block(a)
+            if r <= 0:
+                continue                                              # not compressible: the container stores it raw
+            n, out, stats = qdec3(s, a.size)
+            assert n == a.size, (name, n)
+            assert np.array_equal(out, a), name
+            covered += 1
+    assert covered >= 16
+
+
+def test_host_emulation_rejects_oversized_stream(qdec3, gen, checker):
+    a = checker.bwt_encode(gen.text(2, 100000))[1]
+    r, s = checker.encode_block(a)
+    n, _, _ = qdec3(s, a.size - 1)                                    # declared length exceeds the slice
+    assert n == -6
