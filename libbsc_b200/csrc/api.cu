@@ -560,7 +560,7 @@ int bscb200_ctx_profile_report(void *ctx, char *buf, int cap)
         acc[i].n++; acc[i].ms += ms; acc[i].bytes += r.bytes;
     }
     int w = 0;
-    for (const Acc &a : acc) { int k = snprintf(buf + w, cap > w ? (size_t)(cap - w) : 0, "%.*s\t%d\t%.6f\t%.0f\n", (int)strcspn(a.name, "<"), a.name, a.n, a.ms, a.bytes);   /* template arguments are not part of the reported name */ if (k < 0 || w + k >= cap) break; w += k; }
+    for (const Acc &a : acc) { int k = snprintf(buf + w, cap > w ? (size_t)(cap - w) : 0, "%.*s\t%d\t%.6f\t%.0f\n", (int)strcspn(a.name + (a.name[0] == '('), "<"), a.name + (a.name[0] == '('), a.n, a.ms, a.bytes);   /* template arguments are not part of the reported name */ if (k < 0 || w + k >= cap) break; w += k; }
     c->prof.clear(); c->ev_used = 0;
     return w;
 }

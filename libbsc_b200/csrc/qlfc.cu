@@ -426,10 +426,11 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     return result;
 }
 
-// BSCB200_QDEC=2 selects the previous decoder kernel (serial decision-by-decision walk) for A/B measurements.
+// Decoder kernel selection (A/B measurements): BSCB200_QDEC=2 q_decode2 (serial walk, two-sided branches),
+// 3 q_decode3<0> (speculative lane-parallel evaluation), 4 q_decode3<1> (serial walk on the branch-free plumbing).
 static int decoder_generation()
 {
-    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); return (e && e[0] == '2') ? 2 : 3; }();
+    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 4) ? g : 2; }();
     return gen;
 }
 
@@ -476,19 +477,16 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         ctx->sync();
         init_models(ctx, models, nlist);
         PROF_BYTES(ctx, (double)in_size + (double)out_cap);
-        if (decoder_generation() == 2) {
+        static const bool prof = getenv("BSCB200_QDEC_PROF") != nullptr;          // per-phase cycle counts (diagnostic)
+        const int gen = decoder_generation();
+#define LAUNCH_DEC3(MODE, PROF) do { ensure_dyn_smem(q_decode3<MODE, PROF>, ctx->device, sizeof(Dec3Smem)); \
+            LAUNCH(ctx, (q_decode3<MODE, PROF>), nlist, 32, sizeof(Dec3Smem), d_in, d_sb, models, tables, d_out, d_list); } while (0)
+        if (gen == 2) {
             ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
             LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
-        } else {
-            static const bool prof = getenv("BSCB200_QDEC_PROF") != nullptr;      // per-phase cycle counts (diagnostic)
-            if (prof) {
-                ensure_dyn_smem(q_decode3<true>, ctx->device, sizeof(Dec3Smem));
-                LAUNCH(ctx, q_decode3<true>, nlist, 32, sizeof(Dec3Smem), d_in, d_sb, models, tables, d_out, d_list);
-            } else {
-                ensure_dyn_smem(q_decode3<false>, ctx->device, sizeof(Dec3Smem));
-                LAUNCH(ctx, q_decode3<false>, nlist, 32, sizeof(Dec3Smem), d_in, d_sb, models, tables, d_out, d_list);
-            }
-        }
+        } else if (gen == 3) { if (prof) LAUNCH_DEC3(0, true); else LAUNCH_DEC3(0, false); }
+        else                 { if (prof) LAUNCH_DEC3(1, true); else LAUNCH_DEC3(1, false); }
+#undef LAUNCH_DEC3
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->sync();

@@ -180,8 +180,10 @@ QD3_FN void qd3_lane_init(Qd3Lane &r, u32 lane)
 
 #ifdef QD3_HOST
 #define QD3_LREGS Qd3Lane lr[32]
+#define QD3_LREGS_PARAM Qd3Lane (&lr)[32]
 #else
 #define QD3_LREGS Qd3Lane lr
+#define QD3_LREGS_PARAM Qd3Lane &lr
 #endif
 
 // (re)load the input window at rc.pos: 8 bytes per lane + 16 more by lanes 0..15
@@ -207,6 +209,45 @@ QD3_FN void qd3_lane_init(Qd3Lane &r, u32 lane)
 #else
 #define QD3_T(k) do { if (PROF) { const long long t_ = clock64(); prof_t[k] += t_ - prof_last; prof_last = t_; } } while (0)
 #endif
+// Stream prologue shared by both decoders: coder start-up, the 32-bit length, the MTF-order table.  Returns 0 or an error.
+QD3_FN int qd3_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PARAM, const u8 *__restrict__ in, u32 in_limit, u32 out_cap, u32 &n, int &maxRank)
+{
+#ifndef QD3_HOST
+    const u32 lane = threadIdx.x & 31u;
+#endif
+    QD3_LANES { qd3_lane_init(QD3_L(lr), lane); }
+
+    rc.in = in; rc.limit = in_limit; rc.code = 0; rc.range = 0xffffffffu; rc.pos = 0; rc.wbase = 0; rc.nx = 0;
+    QD3_REFILL();
+    rc.code = (sm.ld16(O3_WIN + 2) << 16) | sm.ld16(O3_WIN + 4);            // rangecoder.h:203-211: three units, the first falls out of 32 bits
+    rc.pos = 6; rc.nx = sm.ld16(O3_WIN + 6);
+    n = 0;
+    for (int b = 0; b < 32; ++b) n = (n << 1) | qd3_step(sm, rc, 2048u);
+    if (n > out_cap) return LIBBSC_DATA_CORRUPT;                            // would overrun the output slice
+
+    maxRank = 7;
+    int prev = -1;
+    for (int d = 0; d < 256; ++d) {
+        int c = 0;
+        for (int bit = 7; bit >= 0; --bit) {
+            bool can0, can1; QD3_HEADER_OPTIONS(prev, c, bit, can0, can1);
+            if (can0 && can1) {
+                if (rc.pos - rc.wbase > 256u) QD3_REFILL();
+                c = 2 * c + (int)qd3_step(sm, rc, 2048u);
+            }
+            else if (can1) c = 2 * c + 1;
+            else if (can0) c = 2 * c;
+        }
+        c &= 255;
+        sm.st8(O3_MTF + d, (u32)c);
+        if (c == prev) { maxRank = qd3_ilog2((u32)(d - 1)); break; }
+        prev = c;
+        QD3_LANES { if ((u32)(c >> 3) == lane) QD3_L(lr).used8 |= 1u << (c & 7); }
+    }
+    QD3_SYNC();
+    return 0;
+}
+
 template <bool PROF> QD3_FN int qd3_decode_stream(const SM3 &sm, const u8 *__restrict__ in, u32 in_limit, u8 *__restrict__ out, u32 out_cap,
                              short *__restrict__ cold_s, short *__restrict__ cold_c, u32 &st_cached, u32 &st_miss)
 {
@@ -214,38 +255,8 @@ template <bool PROF> QD3_FN int qd3_decode_stream(const SM3 &sm, const u8 *__res
 #ifndef QD3_HOST
     const u32 lane = threadIdx.x & 31u;
 #endif
-    QD3_LANES { qd3_lane_init(QD3_L(lr), lane); }
-
-    Rc3 rc; rc.in = in; rc.limit = in_limit; rc.code = 0; rc.range = 0xffffffffu; rc.pos = 0; rc.wbase = 0; rc.nx = 0;
-    QD3_REFILL();
-    rc.code = (sm.ld16(O3_WIN + 2) << 16) | sm.ld16(O3_WIN + 4);            // rangecoder.h:203-211: three units, the first falls out of 32 bits
-    rc.pos = 6; rc.nx = sm.ld16(O3_WIN + 6);
-    u32 n = 0;
-    for (int b = 0; b < 32; ++b) n = (n << 1) | qd3_step(sm, rc, 2048u);
-    if (n > out_cap) return LIBBSC_DATA_CORRUPT;                            // would overrun the output slice
-
-    int maxRank = 7;
-    {
-        int prev = -1;
-        for (int d = 0; d < 256; ++d) {
-            int c = 0;
-            for (int bit = 7; bit >= 0; --bit) {
-                bool can0, can1; QD3_HEADER_OPTIONS(prev, c, bit, can0, can1);
-                if (can0 && can1) {
-                    if (rc.pos - rc.wbase > 256u) QD3_REFILL();
-                    c = 2 * c + (int)qd3_step(sm, rc, 2048u);
-                }
-                else if (can1) c = 2 * c + 1;
-                else if (can0) c = 2 * c;
-            }
-            c &= 255;
-            sm.st8(O3_MTF + d, (u32)c);
-            if (c == prev) { maxRank = qd3_ilog2((u32)(d - 1)); break; }
-            prev = c;
-            QD3_LANES { if ((u32)(c >> 3) == lane) QD3_L(lr).used8 |= 1u << (c & 7); }
-        }
-    }
-    QD3_SYNC();
+    Rc3 rc; u32 n; int maxRank;
+    { const int err = qd3_prologue(sm, rc, lr, in, in_limit, out_cap, n, maxRank); if (err) return err; }
 
     u32 ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0; int avgRank = 0;
     u32 c = sm.ld8(O3_MTF), m1 = sm.ld8(O3_MTF + 1), m2 = sm.ld8(O3_MTF + 2), m3 = sm.ld8(O3_MTF + 3);
@@ -450,8 +461,192 @@ template <bool PROF> QD3_FN int qd3_decode_stream(const SM3 &sm, const u8 *__res
     return (int)n;
 }
 
+// ---- the serial decoder (decision-by-decision walk, the structure of q_decode2) on this file's plumbing -------------
+// Same prefetching as q_decode2 (the next run's first-decision counters and states are loaded while the current run
+// is still being decoded), but: the branch-free range-coder step with a preloaded next unit, counter moves as selects
+// (no two-sided branch per decision), the input window checked once per run, the front of the MTF list kept in
+// registers and written back only when a rank > 3 needs the list in shared memory, and run expansion as ONE
+// unconditional 32-byte store per run (later runs overwrite the excess; byte address A is always written by lane
+// A mod 32, so the order of two stores to one address is program order of one thread).
+template <int K> QD3_FN u32 qd3_dec3v(const SM3 &sm, Rc3 &rc, u32 is, u32 ic, u32 ig, int s, int c, int g)
+{
+    const u32 b = qd3_step(sm, rc, (u32)q_mix<K>(s, c, g));
+    sm.set(is, b ? q_down<K, 0>(s) : q_up<K, 0>(s));
+    sm.set(ic, b ? q_down<K, 1>(c) : q_up<K, 1>(c));
+    sm.set(ig, b ? q_down<K, 2>(g) : q_up<K, 2>(g));
+    return b;
+}
+
+template <bool PROF> QD3_FN int qd3_decode_stream_serial(const SM3 &sm, const u8 *__restrict__ in, u32 in_limit, u8 *__restrict__ out, u32 out_cap,
+                                    short *__restrict__ cold_s, short *__restrict__ cold_c, u32 &st_cached, u32 &st_miss)
+{
+    QD3_LREGS;
 #ifndef QD3_HOST
-template <bool PROF> __global__ void __launch_bounds__(32, 1) q_decode3(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
+    const u32 lane = threadIdx.x & 31u;
+#endif
+    Rc3 rc; u32 n; int maxRank;
+    { const int err = qd3_prologue(sm, rc, lr, in, in_limit, out_cap, n, maxRank); if (err) return err; }
+
+    u32 ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0; int avgRank = 0;
+    u32 c, m1, m2, m3;
+    { const u32 f = sm.ld32(O3_MTF); c = f & 255u; m1 = (f >> 8) & 255u; m2 = (f >> 16) & 255u; m3 = f >> 24; }
+    u32 rhU = sm.ld8(O3_RUN_HIST + c);
+    u32 st = sm.ld8(O3_RANK_STATE + ((ctxRun << 11) | (ctxRank4 << 3) | sm.ld8(O3_RANK_HIST + c)));
+    int tS = sm.cnt(R_RT_STATE + st), tC = sm.cnt(R_RT_CHAR + c), tG = sm.cnt(R_RT_SHARED);
+    u32 st2z = sm.ld8(O3_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));       // run state if rank == 1
+
+    long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = 0; u32 prof_runs = 0;
+    (void)prof_t; (void)prof_last; (void)prof_runs;
+#ifndef QD3_HOST
+    if (PROF) prof_last = clock64();
+#endif
+    for (u32 i = 0; i < n; ) {
+        u32 rank = 1, b;
+        const u32 rhq = rhU < 7 ? rhU : 7;
+        const bool plain = avgRank < 32;
+        if (rc.pos - rc.wbase > QD3_RUN_ROOM) QD3_REFILL();
+        // first-decision counters of the run length, should the rank turn out to be 1 (the rank decisions never touch them)
+        const int uS0 = sm.cnt(R_UT_STATE + st2z), uC0 = sm.cnt(R_UT_CHAR + c), uG0 = sm.cnt(R_UT_SHARED);
+        QD3_T(0);
+        if (plain) {
+            b = qd3_dec3v<K_RANK_T>(sm, rc, R_RT_STATE + st, R_RT_CHAR + c, R_RT_SHARED, tS, tC, tG);
+            if (!b) sm.st8(O3_RANK_HIST + c, 0);
+            else {
+                u32 e = 1;
+                while ((int)e != maxRank) {
+                    b = qd3_dec3<K_RANK_E>(sm, rc, R_RE_STATE + st * 8 + e - 1, R_RE_CHAR + c * 8 + e - 1, R_RE_SHARED + e - 1);
+                    if (!b) break;
+                    if (++e >= 7) break;                                      // e <= maxRank <= 7 in valid streams
+                }
+                sm.st8(O3_RANK_HIST + c, e);
+                if (e <= M_MAXE) {
+                    const u32 bs = R_RM_STATE + st * M_ROW + (1u << e) - 2u, bc = R_RM_CHAR + c * M_ROW + (1u << e) - 2u, bg = R_WIDE_SHARED + e * 256;
+                    for (int bit = (int)e - 1; bit >= 0; --bit) {
+                        b = qd3_dec3<K_RANK_M>(sm, rc, bs + rank, bc + rank, bg + rank);
+                        rank = 2u * rank + b;
+                    }
+                } else {
+                    for (int bit = (int)e - 1; bit >= 0; --bit) {
+                        const u32 is = qd3_cache_get(sm, C_STATE_VAL, O3_TAG_STATE, cold_s, wide_idx(e, st, rank), st_miss);
+                        const u32 ic = qd3_cache_get(sm, C_CHAR_VAL, O3_TAG_CHAR, cold_c, wide_idx(e, c, rank), st_miss);
+                        st_cached += 2;
+                        b = qd3_dec3<K_RANK_M>(sm, rc, is, ic, R_WIDE_SHARED + e * 256u + rank);
+                        rank = 2u * rank + b;
+                    }
+                }
+            }
+        } else {
+            rank = 0;
+            for (int node = 1, bit = maxRank; bit >= 0; --bit) {
+                const u32 is = qd3_cache_get(sm, C_STATE_VAL, O3_TAG_STATE, cold_s, wide_idx(8, st, (u32)node), st_miss);
+                const u32 ic = qd3_cache_get(sm, C_CHAR_VAL, O3_TAG_CHAR, cold_c, wide_idx(8, c, (u32)node), st_miss);
+                st_cached += 2;
+                b = qd3_dec3<K_RANK_P>(sm, rc, is, ic, R_WIDE_SHARED + 8u * 256u + (u32)node);
+                node = 2 * node + (int)b; rank = 2u * rank + b;
+            }
+            sm.st8(O3_RANK_HIST + c, (u32)qd3_ilog2(rank));
+        }
+        rank &= 255u;
+        QD3_T(1);
+
+        // push c `rank` places back (qlfc.cpp:1830-1860); positions 0..3 of the list live in (c, m1, m2, m3)
+        const u32 cur = c;
+        if (rank == 1) { c = m1; m1 = cur; }
+        else if (rank == 2) { c = m1; m1 = m2; m2 = cur; }
+        else if (rank == 3) { c = m1; m1 = m2; m2 = m3; m3 = cur; }
+        else if (rank != 0) {
+            sm.st8(O3_MTF, c); sm.st8(O3_MTF + 1, m1); sm.st8(O3_MTF + 2, m2); sm.st8(O3_MTF + 3, m3);
+            QD3_SYNC();
+            for (u32 basep = 0; basep < rank; basep += 32) {
+                QD3_LANES { QD3_L(lr).tmp = sm.ld8(O3_MTF + basep + lane + 1u); }
+                QD3_SYNC();
+                QD3_LANES { if (basep + lane < rank) sm.st8(O3_MTF + basep + lane, QD3_L(lr).tmp); }
+                QD3_SYNC();
+            }
+            sm.st8(O3_MTF + rank, cur);
+            QD3_SYNC();
+            const u32 f = sm.ld32(O3_MTF); c = f & 255u; m1 = (f >> 8) & 255u; m2 = (f >> 16) & 255u; m3 = f >> 24;
+        }
+        // (c, m1, m2, m3) now describe the NEXT run; `cur` is this run's symbol
+        const u32 rhRn = sm.ld8(O3_RANK_HIST + c), rhUn = sm.ld8(O3_RUN_HIST + c);
+        avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
+        const u32 rank0 = rank - 1u;
+        u32 st2 = st2z, run = 1;
+        QD3_T(4);
+        if (rank0 == 0) b = qd3_dec3v<K_RUN_T>(sm, rc, R_UT_STATE + st2z, R_UT_CHAR + cur, R_UT_SHARED, uS0, uC0, uG0);
+        else {
+            st2 = sm.ld8(O3_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7u ? rank0 : 7u) << 3) | rhq));
+            b = qd3_dec3<K_RUN_T>(sm, rc, R_UT_STATE + st2, R_UT_CHAR + cur, R_UT_SHARED);
+        }
+        // both candidates for the next run's rank state (its ctxRun gets one more bit: run < 3)
+        const u32 ctxRank4n = ((ctxRank4 << 2) | (rank0 < 3u ? rank0 : 3u)) & 0xffu;
+        const u32 ctxRunN = (ctxRun << 1) & 0xfu;
+        const u32 stA = sm.ld8(O3_RANK_STATE + (((ctxRunN | 1u) << 11) | (ctxRank4n << 3) | rhRn)), stB = sm.ld8(O3_RANK_STATE + ((ctxRunN << 11) | (ctxRank4n << 3) | rhRn));
+        QD3_T(2);
+        if (!b) sm.st8(O3_RUN_HIST + cur, (rhU + 2u) >> 2);
+        else {
+            u32 eu = 1;
+            for (;;) {
+                const u32 k = eu - 1u;
+                if (k < UE_RES) b = qd3_dec3<K_RUN_E>(sm, rc, R_UE_STATE + st2 * UE_RES + k, R_UE_CHAR + cur * UE_RES + k, R_UE_SHARED + k);
+                else {
+                    const u32 is = qd3_cache_get(sm, C_STATE_VAL, O3_TAG_STATE, cold_s, ue_idx(st2, k), st_miss);
+                    const u32 ic = qd3_cache_get(sm, C_CHAR_VAL, O3_TAG_CHAR, cold_c, ue_idx(cur, k), st_miss);
+                    st_cached += 2;
+                    b = qd3_dec3<K_RUN_E>(sm, rc, is, ic, R_UE_SHARED + k);
+                }
+                if (!b) break;
+                if (++eu >= 31u) break;                                          // corrupt-input guard
+            }
+            sm.st8(O3_RUN_HIST + cur, ((rhU + 3u * eu + 3u) >> 2) & 255u);
+            if (eu <= M_MAXE) {
+                const u32 bs = R_UM_STATE + st2 * M_ROW + (1u << eu) - 2u, bc = R_UM_CHAR + cur * M_ROW + (1u << eu) - 2u, bg = R_NARROW_SHARED + eu * 32u;
+                for (u32 node = 1, bit = eu; bit > 0; --bit) {
+                    b = qd3_dec3<K_RUN_M>(sm, rc, bs + node, bc + node, bg + node);
+                    run = 2u * run + b; node = 2u * node + b;
+                }
+            } else {
+                for (u32 node = 1, bit = eu; bit > 0; --bit) {
+                    const u32 is = qd3_cache_get(sm, C_STATE_VAL, O3_TAG_STATE, cold_s, narrow_idx(eu, st2, node), st_miss);
+                    const u32 ic = qd3_cache_get(sm, C_CHAR_VAL, O3_TAG_CHAR, cold_c, narrow_idx(eu, cur, node), st_miss);
+                    st_cached += 2;
+                    b = qd3_dec3<K_RUN_M>(sm, rc, is, ic, R_NARROW_SHARED + eu * 32u + node);
+                    run = 2u * run + b; node = node + 1u;                        // qlfc.cpp:1119: linear contexts above 5 bits
+                }
+            }
+        }
+        QD3_T(5);
+        const bool shortRun = run < 3u;
+        ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0u ? 1u : 0u)) & 0x7u;
+        ctxRank4 = ctxRank4n;
+        ctxRun   = ctxRunN | (shortRun ? 1u : 0u);
+        st = shortRun ? stA : stB;
+        rhU = rank != 0 ? rhUn : sm.ld8(O3_RUN_HIST + c);                         // rank 0 (corrupt input only): same symbol again
+        // first-decision counters of the next run (nothing writes the rank counters until then) and its run state for rank 1
+        tS = sm.cnt(R_RT_STATE + st); tC = sm.cnt(R_RT_CHAR + c); tG = sm.cnt(R_RT_SHARED);
+        st2z = sm.ld8(O3_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));
+
+        // run expansion: byte address A is always written by lane A mod 32
+        if (run <= 32u && i + 32u <= n) { QD3_LANES { out[i + ((lane - i) & 31u)] = (u8)cur; } }
+        else {
+            if (run > n - i) run = n - i;                                        // never write past n
+            QD3_LANES { for (u32 k = (lane - i) & 31u; k < run; k += 32) out[i + k] = (u8)cur; }
+        }
+        i += run;
+        QD3_T(6);
+        if (PROF) ++prof_runs;
+    }
+#ifndef QD3_HOST
+    if (PROF && blockIdx.x == 0 && threadIdx.x == 0)
+        printf("[qdec3 serial prof] runs %u; cycles/run: top %.1f rank %.1f runbit %.1f mtf+hist %.1f run>1 %.1f tail %.1f\n", prof_runs,
+               (double)prof_t[0] / prof_runs, (double)prof_t[1] / prof_runs, (double)prof_t[2] / prof_runs, (double)prof_t[4] / prof_runs,
+               (double)prof_t[5] / prof_runs, (double)prof_t[6] / prof_runs);
+#endif
+    return (int)n;
+}
+
+#ifndef QD3_HOST
+template <int MODE, bool PROF> __global__ void __launch_bounds__(32, 1) q_decode3(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
                                                    const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
@@ -469,7 +664,8 @@ template <bool PROF> __global__ void __launch_bounds__(32, 1) q_decode3(const u8
     SubBlock &sb = sbs[sid];
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 st_cached = 0, st_miss = 0;
-    const int r = qd3_decode_stream<PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss);
+    const int r = MODE == 0 ? qd3_decode_stream<PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss)
+                            : qd3_decode_stream_serial<PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss);
     if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
 #endif

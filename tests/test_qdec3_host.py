@@ -23,13 +23,13 @@ def qdec3():
         subprocess.run(["g++", "-O2", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
     lib = ctypes.CDLL(LIB)
     lib.qdec3_host_decode.restype = ctypes.c_int
-    lib.qdec3_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+    lib.qdec3_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int]
 
-    def decode(stream, n):
+    def decode(stream, n, mode):
         stream = np.ascontiguousarray(stream, dtype=np.uint8)
         out = np.full(n + 64, 0xAA, dtype=np.uint8)
         stats = (ctypes.c_uint * 2)()
-        r = lib.qdec3_host_decode(stream.ctypes.data, stream.size, out.ctypes.data, n, stats)
+        r = lib.qdec3_host_decode(stream.ctypes.data, stream.size, out.ctypes.data, n, stats, mode)
         assert np.all(out[n:] == 0xAA), "wrote past the output slice"
         return r, out[:n], (stats[0], stats[1])
     return decode
@@ -62,9 +62,10 @@ def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
             r, s = enc.encode_block(a)
             if r <= 0:
                 continue                                              # not compressible: the container stores it raw
-            n, out, stats = qdec3(s, a.size)
-            assert n == a.size, (name, n)
-            assert np.array_equal(out, a), name
+            for mode in (0, 1):                                       # speculative, serial
+                n, out, stats = qdec3(s, a.size, mode)
+                assert n == a.size, (name, mode, n)
+                assert np.array_equal(out, a), (name, mode)
             covered += 1
     assert covered >= 16
 
@@ -72,5 +73,6 @@ def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
 def test_host_emulation_rejects_oversized_stream(qdec3, gen, checker):
     a = checker.bwt_encode(gen.text(2, 100000))[1]
     r, s = checker.encode_block(a)
-    n, _, _ = qdec3(s, a.size - 1)                                    # declared length exceeds the slice
-    assert n == -6
+    for mode in (0, 1):
+        n, _, _ = qdec3(s, a.size - 1, mode)                          # declared length exceeds the slice
+        assert n == -6

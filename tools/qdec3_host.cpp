@@ -39,7 +39,8 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 }
 
 // Decodes one QLFC static stream (what bsc_qlfc_static_decode_block reads) of `in_size` bytes into out[0..out_cap).
-extern "C" int qdec3_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
+// mode 0: the speculative decoder, mode 1: the serial decoder
+extern "C" int qdec3_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats, int mode)
 {
     u8 *smem = (u8 *)calloc(1, sizeof(Dec3Smem));
     short *cold = (short *)malloc(sizeof(short) * 2 * (size_t)COLD_PAD);
@@ -51,7 +52,8 @@ extern "C" int qdec3_host_decode(const unsigned char *in, unsigned in_size, unsi
     for (size_t i = 0; i < 2 * (size_t)COLD_PAD; ++i) cold[i] = 2048;
     SM3 sm; sm.b = smem;
     u32 st_cached = 0, st_miss = 0;
-    const int r = qd3_decode_stream<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
+    const int r = mode == 0 ? qd3_decode_stream<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss)
+                            : qd3_decode_stream_serial<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
     if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
     free(smem); free(cold);
     return r;
