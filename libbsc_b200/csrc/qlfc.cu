@@ -427,10 +427,11 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
 }
 
 // Decoder kernel selection (A/B measurements): BSCB200_QDEC=2 q_decode2 (serial walk, two-sided branches),
-// 3 q_decode3<0> (speculative lane-parallel evaluation), 4 q_decode3<1> (serial walk on the branch-free plumbing).
+// 3 q_decode3<0> (speculative lane-parallel evaluation), 4 q_decode3<1> (serial walk on the branch-free plumbing),
+// 5 q_decode3<2> (serial walk with two-way speculation of the next decision's counters).
 static int decoder_generation()
 {
-    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 4) ? g : 2; }();
+    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 5) ? g : 2; }();
     return gen;
 }
 
@@ -485,7 +486,8 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
             LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
         } else if (gen == 3) { if (prof) LAUNCH_DEC3(0, true); else LAUNCH_DEC3(0, false); }
-        else                 { if (prof) LAUNCH_DEC3(1, true); else LAUNCH_DEC3(1, false); }
+        else if (gen == 4)   { if (prof) LAUNCH_DEC3(1, true); else LAUNCH_DEC3(1, false); }
+        else                 { if (prof) LAUNCH_DEC3(2, true); else LAUNCH_DEC3(2, false); }
 #undef LAUNCH_DEC3
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -645,6 +645,227 @@ template <bool PROF> QD3_FN int qd3_decode_stream_serial(const SM3 &sm, const u8
     return (int)n;
 }
 
+// ---- the pipelined serial decoder: two-way speculation inside the uniform instruction stream ---------------------------
+// Measured on q_decode3<1> (profiles/r1h): a rank decision costs ~138 cycles, most of it the chain address -> three
+// shared-memory loads -> three-term mix in front of the range-coder step.  Here the counters of BOTH possible next
+// decisions (exponent: next exponent decision | root of the mantissa tree; mantissa node: left | right child; last
+// mantissa decision: the two candidate run-length first-bit contexts) are loaded and mixed while the current decision
+// is being resolved; the outcome only selects.  More instructions, shorter chain.
+struct C3 { u32 is, ic, ig; int s, c, g; };
+QD3_FN C3 qd3_load3(const SM3 &sm, u32 is, u32 ic, u32 ig) { C3 x; x.is = is; x.ic = ic; x.ig = ig; x.s = sm.cnt(is); x.c = sm.cnt(ic); x.g = sm.cnt(ig); return x; }
+template <int K> QD3_FN u32 qd3_decide(const SM3 &sm, Rc3 &rc, const C3 &x, u32 p)
+{
+    const u32 b = qd3_step(sm, rc, p);
+    sm.set(x.is, b ? q_down<K, 0>(x.s) : q_up<K, 0>(x.s));
+    sm.set(x.ic, b ? q_down<K, 1>(x.c) : q_up<K, 1>(x.c));
+    sm.set(x.ig, b ? q_down<K, 2>(x.g) : q_up<K, 2>(x.g));
+    return b;
+}
+
+template <bool PROF> QD3_FN int qd3_decode_stream_pipe(const SM3 &sm, const u8 *__restrict__ in, u32 in_limit, u8 *__restrict__ out, u32 out_cap,
+                                    short *__restrict__ cold_s, short *__restrict__ cold_c, u32 &st_cached, u32 &st_miss)
+{
+    QD3_LREGS;
+#ifndef QD3_HOST
+    const u32 lane = threadIdx.x & 31u;
+#endif
+    Rc3 rc; u32 n; int maxRank;
+    { const int err = qd3_prologue(sm, rc, lr, in, in_limit, out_cap, n, maxRank); if (err) return err; }
+
+    u32 ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0; int avgRank = 0;
+    u32 c, m1, m2, m3;
+    { const u32 f = sm.ld32(O3_MTF); c = f & 255u; m1 = (f >> 8) & 255u; m2 = (f >> 16) & 255u; m3 = f >> 24; }
+    u32 rhU = sm.ld8(O3_RUN_HIST + c);
+    u32 st = sm.ld8(O3_RANK_STATE + ((ctxRun << 11) | (ctxRank4 << 3) | sm.ld8(O3_RANK_HIST + c)));
+    int tS = sm.cnt(R_RT_STATE + st), tC = sm.cnt(R_RT_CHAR + c), tG = sm.cnt(R_RT_SHARED);
+    u32 st2z = sm.ld8(O3_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));       // run state if rank == 1
+
+    long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = 0; u32 prof_runs = 0;
+    (void)prof_t; (void)prof_last; (void)prof_runs;
+#ifndef QD3_HOST
+    if (PROF) prof_last = clock64();
+#endif
+    for (u32 i = 0; i < n; ) {
+        u32 rank = 1, b;
+        const u32 rhq = rhU < 7 ? rhU : 7;
+        const bool plain = avgRank < 32;
+        if (rc.pos - rc.wbase > QD3_RUN_ROOM) QD3_REFILL();
+        // first-decision counters of the run length, should the rank turn out to be 1 (the rank decisions never touch them)
+        const int uS0 = sm.cnt(R_UT_STATE + st2z), uC0 = sm.cnt(R_UT_CHAR + c), uG0 = sm.cnt(R_UT_SHARED);
+        QD3_T(0);
+        bool haveU = false; u32 st2 = st2z, pU = 0; int uS = uS0;
+        if (plain) {
+            // Two-way speculation: while a decision is being resolved, the counters of BOTH possible next decisions are
+            // already loaded and mixed, so a load never sits between two decisions.
+            C3 T; T.is = R_RT_STATE + st; T.ic = R_RT_CHAR + c; T.ig = R_RT_SHARED; T.s = tS; T.c = tC; T.g = tG;
+            C3 E = qd3_load3(sm, R_RE_STATE + st * 8, R_RE_CHAR + c * 8, R_RE_SHARED);             // exponent decision 0, needed if the first bit is 1
+            u32 pE = (u32)q_mix<K_RANK_E>(E.s, E.c, E.g);
+            b = qd3_decide<K_RANK_T>(sm, rc, T, (u32)q_mix<K_RANK_T>(T.s, T.c, T.g));
+            if (!b) sm.st8(O3_RANK_HIST + c, 0);
+            else {
+                u32 e = 1;
+                C3 M; M.is = M.ic = M.ig = 0; M.s = M.c = M.g = 0; u32 pM = 0; bool haveM = false;
+                while ((int)e != maxRank) {
+                    // after exponent decision e-1: 1 -> exponent decision e, 0 -> the root of the mantissa tree of level e
+                    const C3 En = qd3_load3(sm, R_RE_STATE + st * 8 + e, R_RE_CHAR + c * 8 + e, R_RE_SHARED + e);
+                    const u32 pEn = (u32)q_mix<K_RANK_E>(En.s, En.c, En.g);
+                    C3 Mr = M; u32 pMr = 0;
+                    if (e <= M_MAXE) {
+                        Mr = qd3_load3(sm, R_RM_STATE + st * M_ROW + (1u << e) - 1u, R_RM_CHAR + c * M_ROW + (1u << e) - 1u, R_WIDE_SHARED + e * 256u + 1u);
+                        pMr = (u32)q_mix<K_RANK_M>(Mr.s, Mr.c, Mr.g);
+                    }
+                    b = qd3_decide<K_RANK_E>(sm, rc, E, pE);
+                    if (!b) { M = Mr; pM = pMr; haveM = e <= M_MAXE; break; }
+                    if (++e >= 7) break;                                      // e <= maxRank <= 7 in valid streams
+                    E = En; pE = pEn;
+                }
+                sm.st8(O3_RANK_HIST + c, e);
+                if (e <= M_MAXE) {
+                    const u32 bs = R_RM_STATE + st * M_ROW + (1u << e) - 2u, bc = R_RM_CHAR + c * M_ROW + (1u << e) - 2u, bg = R_WIDE_SHARED + e * 256u;
+                    if (!haveM) { M = qd3_load3(sm, bs + 1u, bc + 1u, bg + 1u); pM = (u32)q_mix<K_RANK_M>(M.s, M.c, M.g); }
+                    u32 node = 1;
+                    for (int bit = (int)e - 1; bit > 0; --bit) {
+                        const C3 c0 = qd3_load3(sm, bs + 2u * node, bc + 2u * node, bg + 2u * node), c1 = qd3_load3(sm, bs + 2u * node + 1u, bc + 2u * node + 1u, bg + 2u * node + 1u);
+                        const u32 p0 = (u32)q_mix<K_RANK_M>(c0.s, c0.c, c0.g), p1 = (u32)q_mix<K_RANK_M>(c1.s, c1.c, c1.g);
+                        b = qd3_decide<K_RANK_M>(sm, rc, M, pM);
+                        node = 2u * node + b;
+                        M.is = b ? c1.is : c0.is; M.ic = b ? c1.ic : c0.ic; M.ig = b ? c1.ig : c0.ig;
+                        M.s = b ? c1.s : c0.s; M.c = b ? c1.c : c0.c; M.g = b ? c1.g : c0.g; pM = b ? p1 : p0;
+                    }
+                    {   // last mantissa decision: rank = 2 node + b, so both candidates of the run-length first bit are known
+                        const u32 qa = 2u * node - 1u < 7u ? 2u * node - 1u : 7u, qb = 2u * node < 7u ? 2u * node : 7u;
+                        const u32 sb2 = O3_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | rhq);
+                        const u32 st2a = sm.ld8(sb2 + (qa << 3)), st2b = sm.ld8(sb2 + (qb << 3));
+                        const int ua = sm.cnt(R_UT_STATE + st2a), ub = sm.cnt(R_UT_STATE + st2b);
+                        const u32 pa = (u32)q_mix<K_RUN_T>(ua, uC0, uG0), pb = (u32)q_mix<K_RUN_T>(ub, uC0, uG0);
+                        b = qd3_decide<K_RANK_M>(sm, rc, M, pM);
+                        node = 2u * node + b;
+                        st2 = b ? st2b : st2a; uS = b ? ub : ua; pU = b ? pb : pa; haveU = true;
+                    }
+                    rank = node;
+                } else {
+                    for (int bit = (int)e - 1; bit >= 0; --bit) {
+                        const u32 is = qd3_cache_get(sm, C_STATE_VAL, O3_TAG_STATE, cold_s, wide_idx(e, st, rank), st_miss);
+                        const u32 ic = qd3_cache_get(sm, C_CHAR_VAL, O3_TAG_CHAR, cold_c, wide_idx(e, c, rank), st_miss);
+                        st_cached += 2;
+                        b = qd3_dec3<K_RANK_M>(sm, rc, is, ic, R_WIDE_SHARED + e * 256u + rank);
+                        rank = 2u * rank + b;
+                    }
+                }
+            }
+        } else {
+            rank = 0;
+            for (int node = 1, bit = maxRank; bit >= 0; --bit) {
+                const u32 is = qd3_cache_get(sm, C_STATE_VAL, O3_TAG_STATE, cold_s, wide_idx(8, st, (u32)node), st_miss);
+                const u32 ic = qd3_cache_get(sm, C_CHAR_VAL, O3_TAG_CHAR, cold_c, wide_idx(8, c, (u32)node), st_miss);
+                st_cached += 2;
+                b = qd3_dec3<K_RANK_P>(sm, rc, is, ic, R_WIDE_SHARED + 8u * 256u + (u32)node);
+                node = 2 * node + (int)b; rank = 2u * rank + b;
+            }
+            sm.st8(O3_RANK_HIST + c, (u32)qd3_ilog2(rank));
+        }
+        rank &= 255u;
+        QD3_T(1);
+
+        // push c `rank` places back (qlfc.cpp:1830-1860); positions 0..3 of the list live in (c, m1, m2, m3)
+        const u32 cur = c;
+        if (rank == 1) { c = m1; m1 = cur; }
+        else if (rank == 2) { c = m1; m1 = m2; m2 = cur; }
+        else if (rank == 3) { c = m1; m1 = m2; m2 = m3; m3 = cur; }
+        else if (rank != 0) {
+            sm.st8(O3_MTF, c); sm.st8(O3_MTF + 1, m1); sm.st8(O3_MTF + 2, m2); sm.st8(O3_MTF + 3, m3);
+            QD3_SYNC();
+            for (u32 basep = 0; basep < rank; basep += 32) {
+                QD3_LANES { QD3_L(lr).tmp = sm.ld8(O3_MTF + basep + lane + 1u); }
+                QD3_SYNC();
+                QD3_LANES { if (basep + lane < rank) sm.st8(O3_MTF + basep + lane, QD3_L(lr).tmp); }
+                QD3_SYNC();
+            }
+            sm.st8(O3_MTF + rank, cur);
+            QD3_SYNC();
+            const u32 f = sm.ld32(O3_MTF); c = f & 255u; m1 = (f >> 8) & 255u; m2 = (f >> 16) & 255u; m3 = f >> 24;
+        }
+        // (c, m1, m2, m3) now describe the NEXT run; `cur` is this run's symbol
+        const u32 rhRn = sm.ld8(O3_RANK_HIST + c), rhUn = sm.ld8(O3_RUN_HIST + c);
+        avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
+        const u32 rank0 = rank - 1u;
+        u32 run = 1;
+        QD3_T(4);
+        if (rank0 == 0) b = qd3_dec3v<K_RUN_T>(sm, rc, R_UT_STATE + st2z, R_UT_CHAR + cur, R_UT_SHARED, uS0, uC0, uG0);
+        else if (haveU) {
+            C3 U; U.is = R_UT_STATE + st2; U.ic = R_UT_CHAR + cur; U.ig = R_UT_SHARED; U.s = uS; U.c = uC0; U.g = uG0;
+            b = qd3_decide<K_RUN_T>(sm, rc, U, pU);
+        } else {
+            st2 = sm.ld8(O3_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7u ? rank0 : 7u) << 3) | rhq));
+            b = qd3_dec3<K_RUN_T>(sm, rc, R_UT_STATE + st2, R_UT_CHAR + cur, R_UT_SHARED);
+        }
+        // both candidates for the next run's rank state (its ctxRun gets one more bit: run < 3)
+        const u32 ctxRank4n = ((ctxRank4 << 2) | (rank0 < 3u ? rank0 : 3u)) & 0xffu;
+        const u32 ctxRunN = (ctxRun << 1) & 0xfu;
+        const u32 stA = sm.ld8(O3_RANK_STATE + (((ctxRunN | 1u) << 11) | (ctxRank4n << 3) | rhRn)), stB = sm.ld8(O3_RANK_STATE + ((ctxRunN << 11) | (ctxRank4n << 3) | rhRn));
+        QD3_T(2);
+        if (!b) sm.st8(O3_RUN_HIST + cur, (rhU + 2u) >> 2);
+        else {
+            u32 eu = 1;
+            for (;;) {
+                const u32 k = eu - 1u;
+                if (k < UE_RES) b = qd3_dec3<K_RUN_E>(sm, rc, R_UE_STATE + st2 * UE_RES + k, R_UE_CHAR + cur * UE_RES + k, R_UE_SHARED + k);
+                else {
+                    const u32 is = qd3_cache_get(sm, C_STATE_VAL, O3_TAG_STATE, cold_s, ue_idx(st2, k), st_miss);
+                    const u32 ic = qd3_cache_get(sm, C_CHAR_VAL, O3_TAG_CHAR, cold_c, ue_idx(cur, k), st_miss);
+                    st_cached += 2;
+                    b = qd3_dec3<K_RUN_E>(sm, rc, is, ic, R_UE_SHARED + k);
+                }
+                if (!b) break;
+                if (++eu >= 31u) break;                                          // corrupt-input guard
+            }
+            sm.st8(O3_RUN_HIST + cur, ((rhU + 3u * eu + 3u) >> 2) & 255u);
+            if (eu <= M_MAXE) {
+                const u32 bs = R_UM_STATE + st2 * M_ROW + (1u << eu) - 2u, bc = R_UM_CHAR + cur * M_ROW + (1u << eu) - 2u, bg = R_NARROW_SHARED + eu * 32u;
+                for (u32 node = 1, bit = eu; bit > 0; --bit) {
+                    b = qd3_dec3<K_RUN_M>(sm, rc, bs + node, bc + node, bg + node);
+                    run = 2u * run + b; node = 2u * node + b;
+                }
+            } else {
+                for (u32 node = 1, bit = eu; bit > 0; --bit) {
+                    const u32 is = qd3_cache_get(sm, C_STATE_VAL, O3_TAG_STATE, cold_s, narrow_idx(eu, st2, node), st_miss);
+                    const u32 ic = qd3_cache_get(sm, C_CHAR_VAL, O3_TAG_CHAR, cold_c, narrow_idx(eu, cur, node), st_miss);
+                    st_cached += 2;
+                    b = qd3_dec3<K_RUN_M>(sm, rc, is, ic, R_NARROW_SHARED + eu * 32u + node);
+                    run = 2u * run + b; node = node + 1u;                        // qlfc.cpp:1119: linear contexts above 5 bits
+                }
+            }
+        }
+        QD3_T(5);
+        const bool shortRun = run < 3u;
+        ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0u ? 1u : 0u)) & 0x7u;
+        ctxRank4 = ctxRank4n;
+        ctxRun   = ctxRunN | (shortRun ? 1u : 0u);
+        st = shortRun ? stA : stB;
+        rhU = rank != 0 ? rhUn : sm.ld8(O3_RUN_HIST + c);                         // rank 0 (corrupt input only): same symbol again
+        // first-decision counters of the next run (nothing writes the rank counters until then) and its run state for rank 1
+        tS = sm.cnt(R_RT_STATE + st); tC = sm.cnt(R_RT_CHAR + c); tG = sm.cnt(R_RT_SHARED);
+        st2z = sm.ld8(O3_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));
+
+        // run expansion: byte address A is always written by lane A mod 32
+        if (run <= 32u && i + 32u <= n) { QD3_LANES { out[i + ((lane - i) & 31u)] = (u8)cur; } }
+        else {
+            if (run > n - i) run = n - i;                                        // never write past n
+            QD3_LANES { for (u32 k = (lane - i) & 31u; k < run; k += 32) out[i + k] = (u8)cur; }
+        }
+        i += run;
+        QD3_T(6);
+        if (PROF) ++prof_runs;
+    }
+#ifndef QD3_HOST
+    if (PROF && blockIdx.x == 0 && threadIdx.x == 0)
+        printf("[qdec3 pipe prof] runs %u; cycles/run: top %.1f rank %.1f runbit %.1f mtf+hist %.1f run>1 %.1f tail %.1f\n", prof_runs,
+               (double)prof_t[0] / prof_runs, (double)prof_t[1] / prof_runs, (double)prof_t[2] / prof_runs, (double)prof_t[4] / prof_runs,
+               (double)prof_t[5] / prof_runs, (double)prof_t[6] / prof_runs);
+#endif
+    return (int)n;
+}
+
 #ifndef QD3_HOST
 template <int MODE, bool PROF> __global__ void __launch_bounds__(32, 1) q_decode3(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
                                                    const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
@@ -665,7 +886,8 @@ template <int MODE, bool PROF> __global__ void __launch_bounds__(32, 1) q_decode
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 st_cached = 0, st_miss = 0;
     const int r = MODE == 0 ? qd3_decode_stream<PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss)
-                            : qd3_decode_stream_serial<PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss);
+                : MODE == 1 ? qd3_decode_stream_serial<PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss)
+                            : qd3_decode_stream_pipe<PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss);
     if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
 #endif

@@ -62,7 +62,7 @@ def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
             r, s = enc.encode_block(a)
             if r <= 0:
                 continue                                              # not compressible: the container stores it raw
-            for mode in (0, 1):                                       # speculative, serial
+            for mode in (0, 1, 2):                                    # speculative, serial, pipelined serial
                 n, out, stats = qdec3(s, a.size, mode)
                 assert n == a.size, (name, mode, n)
                 assert np.array_equal(out, a), (name, mode)
@@ -73,6 +73,6 @@ def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
 def test_host_emulation_rejects_oversized_stream(qdec3, gen, checker):
     a = checker.bwt_encode(gen.text(2, 100000))[1]
     r, s = checker.encode_block(a)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         n, _, _ = qdec3(s, a.size - 1, mode)                          # declared length exceeds the slice
         assert n == -6

@@ -39,7 +39,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 }
 
 // Decodes one QLFC static stream (what bsc_qlfc_static_decode_block reads) of `in_size` bytes into out[0..out_cap).
-// mode 0: the speculative decoder, mode 1: the serial decoder
+// mode 0: the speculative decoder, mode 1: the serial decoder, mode 2: the pipelined serial decoder
 extern "C" int qdec3_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats, int mode)
 {
     u8 *smem = (u8 *)calloc(1, sizeof(Dec3Smem));
@@ -53,7 +53,8 @@ extern "C" int qdec3_host_decode(const unsigned char *in, unsigned in_size, unsi
     SM3 sm; sm.b = smem;
     u32 st_cached = 0, st_miss = 0;
     const int r = mode == 0 ? qd3_decode_stream<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss)
-                            : qd3_decode_stream_serial<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
+                : mode == 1 ? qd3_decode_stream_serial<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss)
+                            : qd3_decode_stream_pipe<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
     if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
     free(smem); free(cold);
     return r;
