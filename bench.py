@@ -13,8 +13,9 @@ decode -> inverse BWT -> adler32 check), all on the GPU through the C ABI of lib
   cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref) driven like its CLI
           (oracle/ref_driver.c) on the box's host cores.
 
-Workload (BASELINE.json config C3, per GPU): G_text(seed 2 + rank), 16 blocks of 64 MiB, sorter BWT,
-coder QLFC static, LZP off.  Weak scaling: every rank processes its own 1 GiB.
+Workload (BASELINE.json config C3, per GPU): G_text(seed 2 + rank), 18 blocks of 64 MiB, sorter BWT,
+coder QLFC static, LZP off.  18 blocks = 144 coder streams = one per SM on 144 of the 148 SMs (the coder stage is one
+SM per stream).  Weak scaling: every rank processes its own 1.125 GiB.
 """
 import argparse
 import ctypes
@@ -44,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--blocks", type=int, default=16, help="blocks per GPU")
+    ap.add_argument("--blocks", type=int, default=18, help="blocks per GPU (18 x 8 coder streams = 144 of the 148 SMs, one stream per SM)")
     ap.add_argument("--block-mib", type=int, default=64)
     ap.add_argument("--workers", type=int, default=0, help="concurrent blocks per GPU (0 = all)")
     ap.add_argument("--sorter", type=int, default=1)

@@ -4,6 +4,11 @@
  * oracle/_ref/libbsc_ref.so), mirroring what the reference CLI does (bsc.cpp:184-199, 354, 594):
  *   T = omp_get_max_threads(); if (T <= nBlocks) intra-block multithreading is switched off;
  *   T = min(T, nBlocks); one block per OpenMP thread.
+ * When the host has more threads than there are blocks, the CLI leaves FEATURE_MULTITHREADING on, i.e.
+ * the reference's own intra-block OpenMP regions (libsais, the <= 8 coder sub-blocks, the inverse BWT)
+ * are meant to use the spare threads.  OpenMP only does that when nested parallelism is enabled, so the
+ * driver enables two active levels and gives every block an inner team of max_threads / nBlocks threads:
+ * the reference gets ALL the host threads it can use (refdrv_set_nested(0) restores the stock CLI behaviour).
  * Used by bench.py for the `cpu_baseline` object and for `--impl reference`.
  * Links against libbsc_ref.so only (no product code, no oracle port).
  */
@@ -16,6 +21,14 @@ int bsc_decompress(const unsigned char *input, int inputSize, unsigned char *out
 
 #define FEATURE_FASTMODE 1
 #define FEATURE_MULTITHREADING 2
+
+static int g_nested = 1;
+void refdrv_set_nested(int on) { g_nested = on; }
+static int inner_threads(int nBlocks)
+{
+    int T = omp_get_max_threads();
+    return (g_nested && T > nBlocks && nBlocks > 0) ? T / nBlocks : 1;
+}
 
 static int cli_features(int nBlocks, int *threads_out)
 {
@@ -33,16 +46,18 @@ int refdrv_max_threads(void) { return omp_get_max_threads(); }
 /* compress nBlocks independent blocks; out[b] must hold size[b] + 28 bytes; outSize[b] = result */
 int refdrv_compress(const unsigned char *const *in, const int *size, int nBlocks, unsigned char *const *out, int *outSize, int sorter, int coder)
 {
-    int T, features = cli_features(nBlocks, &T), b;
+    int T, features = cli_features(nBlocks, &T), b, inner = inner_threads(nBlocks);
+    omp_set_max_active_levels(inner > 1 ? 2 : 1);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(T)
-    for (b = 0; b < nBlocks; ++b) outSize[b] = bsc_compress(in[b], out[b], size[b], 0, 0, sorter, coder, features);
-    return T;
+    for (b = 0; b < nBlocks; ++b) { omp_set_num_threads(inner); outSize[b] = bsc_compress(in[b], out[b], size[b], 0, 0, sorter, coder, features); }
+    return T * inner;
 }
 
 int refdrv_decompress(const unsigned char *const *in, const int *inSize, int nBlocks, unsigned char *const *out, const int *outSize, int *result)
 {
-    int T, features = cli_features(nBlocks, &T), b;
+    int T, features = cli_features(nBlocks, &T), b, inner = inner_threads(nBlocks);
+    omp_set_max_active_levels(inner > 1 ? 2 : 1);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(T)
-    for (b = 0; b < nBlocks; ++b) result[b] = bsc_decompress(in[b], inSize[b], out[b], outSize[b], features);
-    return T;
+    for (b = 0; b < nBlocks; ++b) { omp_set_num_threads(inner); result[b] = bsc_decompress(in[b], inSize[b], out[b], outSize[b], features); }
+    return T * inner;
 }
