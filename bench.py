@@ -139,6 +139,7 @@ def _reference_native(drv_path, blocks, steps, warmup, sorter):
     vp, ci = ctypes.c_void_p, ctypes.c_int
     d = ctypes.CDLL(drv_path)
     d.refdrv_init()
+    d.refdrv_set_nested(1 if os.environ.get("BSCB200_REF_NESTED") == "1" else 0)   # stock CLI behaviour by default (see oracle/ref_driver.c)
     nb = len(blocks)
     PP = ctypes.c_void_p * nb
     II = ci * nb

@@ -4,11 +4,12 @@
  * oracle/_ref/libbsc_ref.so), mirroring what the reference CLI does (bsc.cpp:184-199, 354, 594):
  *   T = omp_get_max_threads(); if (T <= nBlocks) intra-block multithreading is switched off;
  *   T = min(T, nBlocks); one block per OpenMP thread.
- * When the host has more threads than there are blocks, the CLI leaves FEATURE_MULTITHREADING on, i.e.
- * the reference's own intra-block OpenMP regions (libsais, the <= 8 coder sub-blocks, the inverse BWT)
- * are meant to use the spare threads.  OpenMP only does that when nested parallelism is enabled, so the
- * driver enables two active levels and gives every block an inner team of max_threads / nBlocks threads:
- * the reference gets ALL the host threads it can use (refdrv_set_nested(0) restores the stock CLI behaviour).
+ * When the host has more threads than there are blocks, the CLI leaves FEATURE_MULTITHREADING on, but
+ * its intra-block OpenMP regions only get threads if nested parallelism is enabled, which the CLI does
+ * not do.  refdrv_set_nested(1) enables two active levels with inner teams of max_threads / nBlocks
+ * threads.  Measured on the B200 box's host (Xeon 8562Y+, 64 threads): 18 blocks, nested, 54 threads:
+ * 134.7 MB/s round trip; 16 blocks, stock, 16 threads: 145.6 MB/s (profiles/r1h, r1g) -- nesting does not
+ * help the reference, so the default is the stock CLI behaviour (the faster configuration).
  * Used by bench.py for the `cpu_baseline` object and for `--impl reference`.
  * Links against libbsc_ref.so only (no product code, no oracle port).
  */
@@ -22,7 +23,7 @@ int bsc_decompress(const unsigned char *input, int inputSize, unsigned char *out
 #define FEATURE_FASTMODE 1
 #define FEATURE_MULTITHREADING 2
 
-static int g_nested = 1;
+static int g_nested = 0;
 void refdrv_set_nested(int on) { g_nested = on; }
 static int inner_threads(int nBlocks)
 {
