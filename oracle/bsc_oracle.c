@@ -512,6 +512,173 @@ int orc_qlfc_static_decode_block(const unsigned char *in, unsigned char *out)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Fast QLFC coder (coder id 3, `-e0`).  qlfc.cpp:1135-1336 (encoder), 1933-2127 (decoder),      */
+/* qlfc_model.h:243-259 (QlfcStatisticalModel2), qlfc_model.cpp:73-74 (start values),            */
+/* predictor.h:63-71 (shift updates), rangecoder.h:145-177, 213-240 (precision template P).      */
+/* One counter per decision, selected by the run's symbol and the position in the code only.    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    short re[256][8], rm[256][8][256];          /* rank: exponent / mantissa-tree counters, 13-bit probabilities */
+    short ue[256][32], um[256][32][32];         /* run length: exponent / mantissa counters, 11-bit probabilities */
+} orc_fast_model;
+
+/* what one decision kind does: precision of the coder step, speed of the counter, its two targets */
+typedef struct { int P, R, to0, to1; } fast_kind;
+static const fast_kind FK_RANK_T = {13, 4, 8016, 83}, FK_RANK_E = {13, 4, 8114, 122}, FK_RANK_M = {13, 7, 7999, 235};
+static const fast_kind FK_RUN_T = {11, 5, 2025, 42}, FK_RUN_E = {11, 4, 1962, 142}, FK_RUN_M = {11, 6, 1951, 147}, FK_RUN_L = {11, 5, 1987, 46};
+
+static orc_fast_model *fast_model_new(void)
+{
+    orc_fast_model *m = malloc(sizeof *m);
+    if (!m) return NULL;
+    short *p = (short *)m->re; for (size_t i = 0; i < (sizeof m->re + sizeof m->rm) / sizeof(short); ++i) p[i] = 4096;   /* re and rm are contiguous */
+    p = (short *)m->ue; for (size_t i = 0; i < (sizeof m->ue + sizeof m->um) / sizeof(short); ++i) p[i] = 1024;
+    return m;
+}
+
+static void fast_learn(short *x, const fast_kind *k, unsigned bit) { int p = *x; *x = (short)(p - ((p - (bit ? k->to1 : k->to0)) >> k->R)); }
+
+static void rc_add_low(rc_enc *e, uint32_t add) { uint32_t s = e->low32 + add; if (s < e->low32) e->carry++; e->low32 = s; }
+
+static void rc_encode_p(rc_enc *e, unsigned bit, int p, int P)
+{
+    if (e->range < 0x10000u) { rc_shift(e); e->range <<= 16; }
+    uint32_t r = (e->range >> P) * (uint32_t)p;
+    if (bit) { rc_add_low(e, r); e->range -= r; } else e->range = r;
+}
+
+/* rangecoder.h:165-177 called with an UNNORMALISED bit value (qlfc.cpp:1174 passes `c & (1 << bit)`): the    */
+/* reference uses (0 - bitval) as a mask, so for bitval = 2^k the low k bits of the addend are cleared.      */
+static void rc_encode_half_masked(rc_enc *e, uint32_t bitval)
+{
+    if (e->range < 0x10000u) { rc_shift(e); e->range <<= 16; }
+    uint32_t r = e->range >> 1, m = 0u - bitval;
+    rc_add_low(e, m & r);
+    e->range = r + (m & (e->range - r - r));
+}
+
+static unsigned rc_decode_p(rc_dec *d, int p, int P)
+{
+    if (d->range < 0x10000u) { d->range <<= 16; d->code = (d->code << 16) | rc_get16(d); }
+    uint32_t r = (d->range >> P) * (uint32_t)p;
+    if (d->code >= r) { d->code -= r; d->range -= r; return 1; }
+    d->range = r; return 0;
+}
+
+#define FENC(KIND, CTR, BIT) do { short *x_ = (CTR); unsigned b_ = (BIT); int p_ = *x_; fast_learn(x_, &(KIND), b_); rc_encode_p(&rc, b_, p_, (KIND).P); } while (0)
+#define FDEC(KIND, CTR, BITVAR) do { short *x_ = (CTR); (BITVAR) = rc_decode_p(&rc, *x_, (KIND).P); fast_learn(x_, &(KIND), (BITVAR)); } while (0)
+
+int orc_qlfc_fast_encode_block(const unsigned char *in, unsigned char *out, int inSize, int outSize)
+{
+    orc_fast_model *m = fast_model_new();
+    unsigned char *ranks = malloc((size_t)inSize > 0 ? (size_t)inSize : 1);
+    if (!m || !ranks) { free(m); free(ranks); return ORC_NOT_ENOUGH_MEMORY; }
+    unsigned char mtf[256];
+    int R = orc_qlfc_transform(in, inSize, ranks, mtf);
+
+    rc_enc rc; rc_enc_init(&rc, out, outSize);
+    for (int b = 31; b >= 0; --b) rc_encode(&rc, ((unsigned)inSize >> b) & 1, 2048);
+
+    unsigned char used[256]; memset(used, 0, sizeof used);
+    int prev = -1;
+    for (int d = 0; d < 256; ++d) {
+        int c = mtf[d];
+        for (int bit = 7; bit >= 0; --bit) {
+            int can0, can1; header_options(used, prev, c >> (bit + 1), bit, &can0, &can1);
+            if (can0 && can1) rc_encode_half_masked(&rc, (uint32_t)(c & (1 << bit)));
+        }
+        if (c == prev) break;
+        prev = c; used[c] = 1;
+    }
+
+    int pos = 0, result = 0;
+    for (int t = 0; t < R; ++t) {
+        if (rc.pos >= rc.eob) { result = ORC_NOT_COMPRESSIBLE; break; }   /* qlfc.cpp:1192-1195 */
+        int c = in[pos], run = 1;
+        while (pos + run < inSize && in[pos + run] == c) ++run;
+        pos += run;
+        int rank = ranks[t];
+
+        FENC(FK_RANK_T, &m->re[c][0], rank != 1);
+        if (rank != 1) {
+            int e = ilog2((unsigned)rank);
+            for (int b = 1; b < e; ++b) FENC(FK_RANK_E, &m->re[c][b], 1);
+            if (e < 7)                  FENC(FK_RANK_E, &m->re[c][e], 0);
+            for (int node = 1, bit = e - 1; bit >= 0; --bit) {
+                unsigned b = ((unsigned)rank >> bit) & 1;
+                FENC(FK_RANK_M, &m->rm[c][e][node], b);
+                node = 2 * node + (int)b;
+            }
+        }
+        FENC(FK_RUN_T, &m->ue[c][0], run != 1);
+        if (run != 1) {
+            int e = ilog2((unsigned)run);
+            for (int b = 1; b < e; ++b) FENC(FK_RUN_E, &m->ue[c][b], 1);
+            FENC(FK_RUN_E, &m->ue[c][e], 0);
+            for (int node = 1, bit = e - 1; bit >= 0; --bit) {
+                unsigned b = ((unsigned)run >> bit) & 1;
+                if (e <= 5) { FENC(FK_RUN_M, &m->um[c][e][node], b); node = 2 * node + (int)b; }
+                else        { FENC(FK_RUN_L, &m->um[c][e][node], b); node = node + 1; }
+            }
+        }
+    }
+    if (result == 0) result = rc_enc_finish(&rc);
+    free(m); free(ranks);
+    return result;
+}
+
+int orc_qlfc_fast_decode_block(const unsigned char *in, unsigned char *out)
+{
+    orc_fast_model *m = fast_model_new();
+    if (!m) return ORC_NOT_ENOUGH_MEMORY;
+    rc_dec rc; rc_dec_init(&rc, in);
+    uint32_t n32 = 0; for (int b = 0; b < 32; ++b) n32 = (n32 << 1) | rc_decode(&rc, 2048);
+    int n = (int)n32;
+
+    unsigned char mtf[256], used[256]; memset(used, 0, sizeof used); memset(mtf, 0, sizeof mtf);
+    int prev = -1;
+    for (int d = 0; d < 256; ++d) {
+        int c = 0;
+        for (int bit = 7; bit >= 0; --bit) {
+            int can0, can1; header_options(used, prev, c, bit, &can0, &can1);
+            if (can0 && can1) c = 2 * c + (int)rc_decode_p(&rc, 1, 1);
+            else if (can1) c = 2 * c + 1;
+            else if (can0) c = 2 * c;
+        }
+        mtf[d] = (unsigned char)c;
+        if (c == prev) break;
+        prev = c; used[c] = 1;
+    }
+
+    for (int i = 0; i < n; ) {
+        int c = mtf[0], rank = 1; unsigned b;
+        FDEC(FK_RANK_T, &m->re[c][0], b);
+        if (b) {
+            int e = 1;
+            while (e < 7) { FDEC(FK_RANK_E, &m->re[c][e], b); if (!b) break; ++e; }
+            for (int bit = e - 1; bit >= 0; --bit) { FDEC(FK_RANK_M, &m->rm[c][e][rank], b); rank = 2 * rank + (int)b; }
+        }
+        for (int r = 0; r < rank; ++r) mtf[r] = mtf[r + 1];
+        mtf[rank] = (unsigned char)c;
+
+        int run = 1;
+        FDEC(FK_RUN_T, &m->ue[c][0], b);
+        if (b) {
+            int e = 1;
+            for (;;) { FDEC(FK_RUN_E, &m->ue[c][e], b); if (!b) break; if (++e >= 31) break; }   /* 31: guard against corrupt input */
+            for (int node = 1, bit = e - 1; bit >= 0; --bit) {
+                if (e <= 5) { FDEC(FK_RUN_M, &m->um[c][e][node], b); node = 2 * node + (int)b; }
+                else        { FDEC(FK_RUN_L, &m->um[c][e][node], b); node = node + 1; }
+                run = 2 * run + (int)b;
+            }
+        }
+        for (; run > 0 && i < n; --run) out[i++] = (unsigned char)c;
+    }
+    free(m);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Coder container.  coder.cpp:52-59, 70-109, 111-155 (serial), 159-240 (parallel), 273-347.    */
 /* ------------------------------------------------------------------------------------------ */
 int orc_coder_num_blocks(int n)
@@ -541,12 +708,22 @@ void orc_coder_split_blocks(const unsigned char *in, int n, int nBlocks, int *st
     }
 }
 
+static int encode_block(int coder, const unsigned char *in, unsigned char *out, int inSize, int outSize)   /* coder.cpp:61-68 */
+{
+    return coder == 3 ? orc_qlfc_fast_encode_block(in, out, inSize, outSize) : orc_qlfc_static_encode_block(in, out, inSize, outSize);
+}
+static int decode_block(int coder, const unsigned char *in, unsigned char *out)                             /* coder.cpp:264-271 */
+{
+    return coder == 3 ? orc_qlfc_fast_decode_block(in, out) : orc_qlfc_static_decode_block(in, out);
+}
+
 int orc_coder_compress(const unsigned char *in, unsigned char *out, int n, int coder, int features)
 {
-    if (coder != 1) return ORC_BAD_PARAMETER;            /* static QLFC only in this oracle */
+    if (coder == 2) return ORC_NOT_SUPPORTED;            /* adaptive QLFC: not restated yet */
+    if (coder != 1 && coder != 3) return ORC_BAD_PARAMETER;
     int nBlocks = orc_coder_num_blocks(n);
     if (nBlocks == 1) {
-        int r = orc_qlfc_static_encode_block(in, out + 1, n, n - 1);
+        int r = encode_block(coder, in, out + 1, n, n - 1);
         if (r >= 0) { out[0] = 1; r += 1; }
         return r;
     }
@@ -559,7 +736,7 @@ int orc_coder_compress(const unsigned char *in, unsigned char *out, int n, int c
         int res[8], total = ptr;
         if (!tmp) return ORC_NOT_ENOUGH_MEMORY;
         for (int b = 0; b < nBlocks; ++b) {
-            res[b] = orc_qlfc_static_encode_block(in + start[b], tmp + start[b], size[b], size[b]);
+            res[b] = encode_block(coder, in + start[b], tmp + start[b], size[b], size[b]);
             if (res[b] < 0) res[b] = size[b];
             total += res[b];
         }
@@ -574,7 +751,7 @@ int orc_coder_compress(const unsigned char *in, unsigned char *out, int n, int c
     }
     for (int b = 0; b < nBlocks; ++b) {                  /* coder.cpp:111-155 */
         int room = size[b]; if (room > n - ptr) room = n - ptr;
-        int r = orc_qlfc_static_encode_block(in + start[b], out + ptr, size[b], room);
+        int r = encode_block(coder, in + start[b], out + ptr, size[b], room);
         if (r < 0) {
             if (ptr + size[b] >= n) return ORC_NOT_COMPRESSIBLE;
             r = size[b]; memcpy(out + ptr, in + start[b], (size_t)r);
@@ -587,13 +764,14 @@ int orc_coder_compress(const unsigned char *in, unsigned char *out, int n, int c
 
 int orc_coder_decompress(const unsigned char *in, unsigned char *out, int coder)
 {
-    if (coder != 1) return ORC_BAD_PARAMETER;
+    if (coder == 2) return ORC_NOT_SUPPORTED;
+    if (coder != 1 && coder != 3) return ORC_BAD_PARAMETER;
     int nBlocks = in[0];
-    if (nBlocks == 1) return orc_qlfc_static_decode_block(in + 1, out);
+    if (nBlocks == 1) return decode_block(coder, in + 1, out);
     int inPtr = 1 + 8 * nBlocks, outPtr = 0, total = 0, err = 0;
     for (int b = 0; b < nBlocks; ++b) {
         int rawSize = (int)get32(in + 1 + 8 * b), packed = (int)get32(in + 5 + 8 * b), r;
-        if (packed != rawSize) r = orc_qlfc_static_decode_block(in + inPtr, out + outPtr);
+        if (packed != rawSize) r = decode_block(coder, in + inPtr, out + outPtr);
         else { r = rawSize; memcpy(out + outPtr, in + inPtr, (size_t)rawSize); }
         if (r < 0) err = r;
         total += r; inPtr += packed; outPtr += rawSize;

@@ -148,6 +148,8 @@ class Port(_Api):
         self.f_transform = s("qlfc_transform", [vp, ci, vp, vp])
         self.f_enc_block = s("qlfc_static_encode_block", [vp, vp, ci, ci])
         self.f_dec_block = s("qlfc_static_decode_block", [vp, vp])
+        self.f_enc_fast = s("qlfc_fast_encode_block", [vp, vp, ci, ci])
+        self.f_dec_fast = s("qlfc_fast_decode_block", [vp, vp])
         self.f_split = s("coder_split_blocks", [vp, ci, ci, vp, vp], None)
         self.f_cc = s("coder_compress", [vp, vp, ci, ci, ci])
         self.f_cd = s("coder_decompress", [vp, vp, ci])
@@ -176,12 +178,22 @@ class Port(_Api):
         R = self.f_transform(_ptr(data), data.size, _ptr(ranks), _ptr(mtf))
         return ranks[:R].copy(), mtf
 
-    def encode_block(self, data, out_size=None):
+    def encode_block(self, data, out_size=None, coder=1):
+        """One QLFC stream (bsc_qlfc_{static,fast}_encode_block); coder 1 static, 3 fast."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         out_size = data.size if out_size is None else out_size
         out = np.empty(data.size + 4096, dtype=np.uint8)
-        r = self.f_enc_block(_ptr(data), _ptr(out), data.size, out_size)
+        f = self.f_enc_fast if coder == 3 else self.f_enc_block
+        r = f(_ptr(data), _ptr(out), data.size, out_size)
         return r, (out[:r].copy() if r > 0 else None)
+
+    def decode_block(self, stream, n, coder=1):
+        s = np.zeros(len(stream) + 64, dtype=np.uint8)
+        s[:len(stream)] = stream
+        out = np.empty(n + 64, dtype=np.uint8)
+        f = self.f_dec_fast if coder == 3 else self.f_dec_block
+        r = f(_ptr(s), _ptr(out))
+        return r, out[:max(r, 0)].copy()
 
     def split_blocks(self, data, nblocks):
         data = np.ascontiguousarray(data, dtype=np.uint8)
@@ -231,6 +243,8 @@ class Ref(_Api):
         self.f_st_dec = s("st_decode", [vp, ci, ci, ci, ci])
         self.f_enc_block = s("qlfc_static_encode_block", [vp, vp, ci, ci])
         self.f_dec_block = s("qlfc_static_decode_block", [vp, vp])
+        self.f_enc_fast = s("qlfc_fast_encode_block", [vp, vp, ci, ci])
+        self.f_dec_fast = s("qlfc_fast_decode_block", [vp, vp])
         self.f_cc = s("coder_compress", [vp, vp, ci, ci, ci])
         self.f_cd = s("coder_decompress", [vp, vp, ci, ci])
         self.f_store = s("store", [vp, vp, ci, ci])
@@ -258,12 +272,22 @@ class Ref(_Api):
         r = self.f_st_dec(_ptr(T), T.size, k, index, self.features)
         return r, T
 
-    def encode_block(self, data, out_size=None):
+    def encode_block(self, data, out_size=None, coder=1):
+        """One QLFC stream (bsc_qlfc_{static,fast}_encode_block); coder 1 static, 3 fast."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         out_size = data.size if out_size is None else out_size
         out = np.empty(data.size + 4096, dtype=np.uint8)
-        r = self.f_enc_block(_ptr(data), _ptr(out), data.size, out_size)
+        f = self.f_enc_fast if coder == 3 else self.f_enc_block
+        r = f(_ptr(data), _ptr(out), data.size, out_size)
         return r, (out[:r].copy() if r > 0 else None)
+
+    def decode_block(self, stream, n, coder=1):
+        s = np.zeros(len(stream) + 64, dtype=np.uint8)
+        s[:len(stream)] = stream
+        out = np.empty(n + 64, dtype=np.uint8)
+        f = self.f_dec_fast if coder == 3 else self.f_dec_block
+        r = f(_ptr(s), _ptr(out))
+        return r, out[:max(r, 0)].copy()
 
     def _coder_compress(self, i, o, n, coder, features):
         return self.f_cc(i, o, n, coder, features)
