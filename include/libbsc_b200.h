@@ -43,7 +43,7 @@ extern "C" {
 #define LIBBSC_BLOCKSORTER_BWT         1   /* 3..8 = ST3..ST8 */
 #define LIBBSC_CODER_QLFC_STATIC       1
 #define LIBBSC_CODER_QLFC_ADAPTIVE     2   /* not on the device yet: LIBBSC_NOT_SUPPORTED */
-#define LIBBSC_CODER_QLFC_FAST         3   /* not on the device yet: LIBBSC_NOT_SUPPORTED */
+#define LIBBSC_CODER_QLFC_FAST         3   /* experimental: LIBBSC_NOT_SUPPORTED unless BSCB200_ENABLE_FAST=1 (csrc/qlfc_fast.cuh) */
 
 /* ---- group 1: libbsc-compatible entry points -------------------------------------------- */
 
@@ -69,7 +69,7 @@ int bsc_bwt_decode(unsigned char *T, int n, int index, unsigned char num_indexes
 /* libbsc/st/st.h:47,57,68 ; libbsc/st/st.cpp:990-1012 (k = 3..8; st.cu:334 for 7, 8).  In place on T. */
 int bsc_st_init(int features);
 int bsc_st_encode(unsigned char *T, int n, int k, int features);
-int bsc_st_decode(unsigned char *T, int n, int k, int index, int features);   /* LIBBSC_NOT_SUPPORTED for now */
+int bsc_st_decode(unsigned char *T, int n, int k, int index, int features);   /* LIBBSC_NOT_SUPPORTED: see DESIGN.md 1 (stateful serial walk, stays on the host) */
 
 /* libbsc/coder/coder.h:45,56,66 ; libbsc/coder/coder.cpp:244-347.  output of compress holds n + 4096 bytes. */
 int bsc_coder_init(int features);

@@ -256,6 +256,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 #include "qlfc_coder.cuh"
 #include "qlfc_decoder.cuh"
 #include "qlfc_decoder3.cuh"
+#include "qlfc_fast.cuh"
 #include "qlfc_encoder.cuh"
 
 constexpr size_t MODEL_SHORTS_PAD = 2 * (size_t)COLD_PAD;     // by-state + by-symbol cold arrays per stream
@@ -287,6 +288,16 @@ static const QTables *get_tables(Ctx *ctx)
     return (const QTables *)ctx->qlfc_tables;
 }
 
+// Coder ids (libbsc.h:60-62): 1 static, 2 adaptive, 3 fast.  The fast coder's kernels (qlfc_fast.cuh) are bit-exact in host
+// emulation but have not run on a GPU yet, so they stay behind BSCB200_ENABLE_FAST=1 until the parity tests have seen them.
+static int coder_gate(int coder)
+{
+    if (coder == 1) return LIBBSC_NO_ERROR;
+    if (coder == 3) { static const bool on = [] { const char *e = getenv("BSCB200_ENABLE_FAST"); return e && e[0] == '1'; }(); return on ? LIBBSC_NO_ERROR : LIBBSC_NOT_SUPPORTED; }
+    return coder == 2 ? LIBBSC_NOT_SUPPORTED : LIBBSC_BAD_PARAMETER;
+}
+static_assert(QF_COLD <= 2 * (size_t)COLD_PAD, "the fast coder's cold counters must fit the per-stream model allocation");
+
 static void init_models(Ctx *ctx, short *models, int count)
 {
     size_t total = (size_t)count * MODEL_SHORTS_PAD;
@@ -295,7 +306,8 @@ static void init_models(Ctx *ctx, short *models, int count)
 
 int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder, int features)
 {
-    if (coder != 1) return (coder == 2 || coder == 3) ? LIBBSC_NOT_SUPPORTED : LIBBSC_BAD_PARAMETER;
+    { const int g = coder_gate(coder); if (g != LIBBSC_NO_ERROR) return g; }
+    const bool fast = coder == 3;
     if (n_ <= 0) return LIBBSC_BAD_PARAMETER;
     const u32 n = (u32)n_;
     const int nBlocks = coder_num_blocks(n_);
@@ -351,12 +363,18 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         PROF_BYTES(ctx, 2.0 * R);
         LAUNCH(ctx, q_rank_tile, ceil_div(total_tiles, 4), 128, 0, run_sym, run_rank, d_sb, (u32)nBlocks, total_tiles, next_tab);
     }
-    init_models(ctx, models, nBlocks);
     const size_t enc_smem = ((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe);
     static_assert(((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448, "encoder working set must fit the 227 KB of one SM");
-    ensure_dyn_smem(q_encode5, ctx->device, enc_smem);
     PROF_BYTES(ctx, (double)n);                          // + c written; the launch is latency-, not bandwidth-bound
-    LAUNCH(ctx, q_encode5, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+    if (fast) {
+        LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
+        ensure_dyn_smem(q_fast_encode, ctx->device, sizeof(FastSmem));
+        LAUNCH(ctx, q_fast_encode, nBlocks, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)nullptr);
+    } else {
+        init_models(ctx, models, nBlocks);
+        ensure_dyn_smem(q_encode5, ctx->device, enc_smem);
+        LAUNCH(ctx, q_encode5, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+    }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
 
@@ -394,8 +412,13 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                 CUDA_TRY(cudaMemcpyAsync(d_sb + b, &h_sb[b], sizeof(SubBlock), cudaMemcpyHostToDevice, ctx->stream));
                 CUDA_TRY(cudaMemcpyAsync(d_list, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
                 ctx->sync();
-                init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                LAUNCH(ctx, q_encode5, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                if (fast) {                                // q_fast_encode indexes the cold counters by sub-block id
+                    LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
+                    LAUNCH(ctx, q_fast_encode, 1, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)d_list);
+                } else {
+                    init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
+                    LAUNCH(ctx, q_encode5, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                }
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
                 r = h_sb[b].result;
@@ -438,7 +461,7 @@ static int decoder_generation()
 int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int out_cap, int coder, int features)
 {
     (void)features;
-    if (coder != 1) return (coder == 2 || coder == 3) ? LIBBSC_NOT_SUPPORTED : LIBBSC_BAD_PARAMETER;
+    { const int g = coder_gate(coder); if (g != LIBBSC_NO_ERROR) return g; }
     if (in_size < 1) return LIBBSC_UNEXPECTED_EOB;
     const QTables *tables = get_tables(ctx);
     Arena &A = ctx->arena;
@@ -476,19 +499,25 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         CUDA_TRY(cudaMemcpyAsync(d_sb, h_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(d_list, list, sizeof(u32) * Q_MAX_SUB, cudaMemcpyHostToDevice, ctx->stream));
         ctx->sync();
-        init_models(ctx, models, nlist);
         PROF_BYTES(ctx, (double)in_size + (double)out_cap);
-        static const bool prof = getenv("BSCB200_QDEC_PROF") != nullptr;          // per-phase cycle counts (diagnostic)
-        const int gen = decoder_generation();
+        if (coder == 3) {
+            LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nlist);
+            ensure_dyn_smem(q_fast_decode, ctx->device, sizeof(FastSmem));
+            LAUNCH(ctx, q_fast_decode, nlist, 32, sizeof(FastSmem), d_in, d_sb, models, d_out, (const u32 *)d_list);
+        } else {
+            init_models(ctx, models, nlist);
+            static const bool prof = getenv("BSCB200_QDEC_PROF") != nullptr;          // per-phase cycle counts (diagnostic)
+            const int gen = decoder_generation();
 #define LAUNCH_DEC3(MODE, PROF) do { ensure_dyn_smem(q_decode3<MODE, PROF>, ctx->device, sizeof(Dec3Smem)); \
-            LAUNCH(ctx, (q_decode3<MODE, PROF>), nlist, 32, sizeof(Dec3Smem), d_in, d_sb, models, tables, d_out, d_list); } while (0)
-        if (gen == 2) {
-            ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
-            LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
-        } else if (gen == 3) { if (prof) LAUNCH_DEC3(0, true); else LAUNCH_DEC3(0, false); }
-        else if (gen == 4)   { if (prof) LAUNCH_DEC3(1, true); else LAUNCH_DEC3(1, false); }
-        else                 { if (prof) LAUNCH_DEC3(2, true); else LAUNCH_DEC3(2, false); }
+                LAUNCH(ctx, (q_decode3<MODE, PROF>), nlist, 32, sizeof(Dec3Smem), d_in, d_sb, models, tables, d_out, d_list); } while (0)
+            if (gen == 2) {
+                ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
+                LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
+            } else if (gen == 3) { if (prof) LAUNCH_DEC3(0, true); else LAUNCH_DEC3(0, false); }
+            else if (gen == 4)   { if (prof) LAUNCH_DEC3(1, true); else LAUNCH_DEC3(1, false); }
+            else                 { if (prof) LAUNCH_DEC3(2, true); else LAUNCH_DEC3(2, false); }
 #undef LAUNCH_DEC3
+        }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->sync();

@@ -13,15 +13,19 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tools", "qdec3_host.cpp")
 LIB = os.path.join(ROOT, "tools", "bin", "libqdec3_host.so")
-DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_decoder3.cuh", "qlfc_coder.cuh", "qlfc_tables.inc")]
+DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_decoder3.cuh", "qlfc_fast.cuh", "qlfc_coder.cuh", "qlfc_tables.inc")]
+
+
+def _hostlib():
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        subprocess.run(["g++", "-O2", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
+    return ctypes.CDLL(LIB)
 
 
 @pytest.fixture(scope="module")
 def qdec3():
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
-        subprocess.run(["g++", "-O2", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
-    lib = ctypes.CDLL(LIB)
+    lib = _hostlib()
     lib.qdec3_host_decode.restype = ctypes.c_int
     lib.qdec3_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int]
 
@@ -76,3 +80,52 @@ def test_host_emulation_rejects_oversized_stream(qdec3, gen, checker):
     for mode in (0, 1, 2):
         n, _, _ = qdec3(s, a.size - 1, mode)                          # declared length exceeds the slice
         assert n == -6
+
+
+# ---- fast coder (coder id 3): libbsc_b200/csrc/qlfc_fast.cuh on the host -------------------------------------------------
+@pytest.fixture(scope="module")
+def qfast():
+    lib = _hostlib()
+    vp, cu = ctypes.c_void_p, ctypes.c_uint
+    lib.qfast_host_decode.restype = ctypes.c_int
+    lib.qfast_host_decode.argtypes = [vp, cu, vp, cu, vp]
+    lib.qfast_host_encode.restype = ctypes.c_int
+    lib.qfast_host_encode.argtypes = [vp, vp, vp, cu, cu, vp, vp, cu, vp]
+
+    def decode(stream, n):
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        out = np.full(n + 64, 0xAA, dtype=np.uint8)
+        r = lib.qfast_host_decode(stream.ctypes.data, stream.size, out.ctypes.data, n, None)
+        assert np.all(out[n:] == 0xAA), "wrote past the output slice"
+        return r, out[:n]
+
+    def encode(a, ranks, mtf, out_cap=None):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        heads = np.concatenate([[0], np.flatnonzero(np.diff(a) != 0) + 1]).astype(np.uint32)
+        run_pos = np.concatenate([heads, [a.size]]).astype(np.uint32)
+        run_sym = np.ascontiguousarray(a[heads])
+        assert ranks.size == heads.size
+        out_cap = a.size if out_cap is None else out_cap
+        out = np.full(a.size + 4096 + 256, 0xAA, dtype=np.uint8)
+        mtf = np.ascontiguousarray(mtf, dtype=np.uint8); ranks = np.ascontiguousarray(ranks, dtype=np.uint8)
+        r = lib.qfast_host_encode(run_pos.ctypes.data, run_sym.ctypes.data, ranks.ctypes.data, heads.size, a.size, mtf.ctypes.data, out.ctypes.data, out_cap, None)
+        return r, (out[:r].copy() if r > 0 else None)
+    return decode, encode
+
+
+def test_fast_coder_host_emulation_matches_oracle(qfast, gen, checker, port):
+    decode, encode = qfast
+    covered = 0
+    for name, a in list(inputs(gen, checker)) + [("rand", gen.rand(1, 70000))]:
+        r_ref, s_ref = checker.encode_block(a, coder=3)
+        ranks, mtf = port.transform(a)
+        r, s = encode(a, ranks, mtf)
+        assert r == r_ref, (name, r, r_ref)                            # same length, or the same NOT_COMPRESSIBLE (-3)
+        if r_ref > 0:
+            assert np.array_equal(s, s_ref), name
+            n, out = decode(s_ref, a.size)
+            assert n == a.size and np.array_equal(out, a), name
+            covered += 1
+    assert covered >= 10
+    a = checker.bwt_encode(gen.text(2, 100000))[1]
+    assert decode(checker.encode_block(a, coder=3)[1], a.size - 1)[0] == -6

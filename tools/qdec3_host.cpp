@@ -16,6 +16,7 @@ typedef uint64_t u64;
 
 #define LIBBSC_DATA_CORRUPT -6
 #define LIBBSC_NOT_ENOUGH_MEMORY -2
+#define LIBBSC_NOT_COMPRESSIBLE -3
 
 // just enough of the CUDA dialect for qlfc_tables.inc / qlfc_coder.cuh
 #define __CUDACC__ 1
@@ -36,6 +37,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 #include "../libbsc_b200/csrc/qlfc_coder.cuh"
 #define QD3_HOST 1
 #include "../libbsc_b200/csrc/qlfc_decoder3.cuh"
+#include "../libbsc_b200/csrc/qlfc_fast.cuh"
 }
 
 // Decodes one QLFC static stream (what bsc_qlfc_static_decode_block reads) of `in_size` bytes into out[0..out_cap).
@@ -55,6 +57,46 @@ extern "C" int qdec3_host_decode(const unsigned char *in, unsigned in_size, unsi
     const int r = mode == 0 ? qd3_decode_stream<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss)
                 : mode == 1 ? qd3_decode_stream_serial<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss)
                             : qd3_decode_stream_pipe<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
+    if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
+    free(smem); free(cold);
+    return r;
+}
+
+// ---- fast coder (coder id 3), libbsc_b200/csrc/qlfc_fast.cuh ---------------------------------------------------------
+static u8 *fast_smem_new(short **cold_out)
+{
+    FastSmem *F = (FastSmem *)calloc(1, sizeof(FastSmem));
+    short *cold = (short *)malloc(sizeof(short) * (size_t)QF_COLD);
+    if (!F || !cold) { free(F); free(cold); return nullptr; }
+    for (u32 i = 0; i < 256 * 8; ++i) F->re[i] = 4096;
+    for (u32 i = 0; i < 256 * QF_ROW; ++i) { F->rm[i] = 4096; F->um[i] = 1024; }
+    for (u32 i = 0; i < 256 * 32; ++i) F->ue[i] = 1024;
+    for (u32 i = 0; i < QF_COLD; ++i) cold[i] = i < QF_COLD_RANK ? 4096 : 1024;
+    *cold_out = cold;
+    return (u8 *)F;
+}
+
+extern "C" int qfast_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
+{
+    short *cold = nullptr; u8 *smem = fast_smem_new(&cold);
+    if (!smem) return LIBBSC_NOT_ENOUGH_MEMORY;
+    SM3 sm; sm.b = smem;
+    u32 st_cached = 0, st_miss = 0;
+    const int r = qf_decode_stream(sm, in, in_size, out, out_cap, cold, st_cached, st_miss);
+    if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
+    free(smem); free(cold);
+    return r;
+}
+
+// run_pos has nruns + 1 entries (the last one = in_size); mtf is the 256-byte MTF-order table of the transform
+extern "C" int qfast_host_encode(const unsigned *run_pos, const unsigned char *run_sym, const unsigned char *run_rank, unsigned nruns, unsigned in_size,
+                                 const unsigned char *mtf, unsigned char *out, unsigned out_cap, unsigned *stats)
+{
+    short *cold = nullptr; u8 *smem = fast_smem_new(&cold);
+    if (!smem) return LIBBSC_NOT_ENOUGH_MEMORY;
+    SM3 sm; sm.b = smem;
+    u32 st_cached = 0, st_miss = 0;
+    const int r = qf_encode_stream(sm, run_pos, run_sym, run_rank, 0, nruns, in_size, mtf, out, out_cap, cold, st_cached, st_miss);
     if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
     free(smem); free(cold);
     return r;
