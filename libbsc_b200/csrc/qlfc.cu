@@ -257,6 +257,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 #include "qlfc_decoder.cuh"
 #include "qlfc_decoder3.cuh"
 #include "qlfc_fast.cuh"
+#include "qlfc_decoder6.cuh"
 #include "qlfc_encoder.cuh"
 
 constexpr size_t MODEL_SHORTS_PAD = 2 * (size_t)COLD_PAD;     // by-state + by-symbol cold arrays per stream
@@ -451,10 +452,11 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
 
 // Decoder kernel selection (A/B measurements, profiles/r1h_decoder_ab.txt); default 4.  BSCB200_QDEC=2 q_decode2 (serial walk, two-sided branches),
 // 3 q_decode3<0> (speculative lane-parallel evaluation), 4 q_decode3<1> (serial walk on the branch-free plumbing),
-// 5 q_decode3<2> (serial walk with two-way speculation of the next decision's counters).
+// 5 q_decode3<2> (serial walk with two-way speculation of the next decision's counters),
+// 6 q_decode6<LayoutDiet> (gen 4 with a 110 KB counter file: two streams per SM; not yet run on a GPU), 7 q_decode6<LayoutFull> (refactoring check).
 static int decoder_generation()
 {
-    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 5) ? g : 4; }();
+    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 7) ? g : 4; }();
     return gen;
 }
 
@@ -515,7 +517,14 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
                 LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
             } else if (gen == 3) { if (prof) LAUNCH_DEC3(0, true); else LAUNCH_DEC3(0, false); }
             else if (gen == 4)   { if (prof) LAUNCH_DEC3(1, true); else LAUNCH_DEC3(1, false); }
-            else                 { if (prof) LAUNCH_DEC3(2, true); else LAUNCH_DEC3(2, false); }
+            else if (gen == 5)   { if (prof) LAUNCH_DEC3(2, true); else LAUNCH_DEC3(2, false); }
+            else if (gen == 6) {
+                ensure_dyn_smem(q_decode6<LayoutDiet, false>, ctx->device, LayoutDiet::BYTES);
+                LAUNCH(ctx, (q_decode6<LayoutDiet, false>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list);
+            } else {
+                ensure_dyn_smem(q_decode6<LayoutFull, false>, ctx->device, LayoutFull::BYTES);
+                LAUNCH(ctx, (q_decode6<LayoutFull, false>), nlist, 32, LayoutFull::BYTES, d_in, d_sb, models, tables, d_out, d_list);
+            }
 #undef LAUNCH_DEC3
         }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));

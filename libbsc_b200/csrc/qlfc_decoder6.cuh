@@ -1,0 +1,348 @@
+// libbsc_b200/csrc/qlfc_decoder6.cuh -- the serial QLFC static decoder (q_decode3<1>, qlfc_decoder3.cuh) with the LAYOUT of
+// the counter file as a template parameter, so that the same code runs with a shared-memory footprint small enough for
+// TWO streams per SM.  Included by qlfc.cu after qlfc_decoder3.cuh; also compiled for the host (tools/qdec3_host.cpp).
+//
+// Why: every measurement of round 1 says the coder kernels are bound by what one lone warp can issue,
+// and an SM has four schedulers.  q_decode3 needs 205 KB of shared memory per stream = one stream per SM.  The "diet"
+// layout keeps resident only what is hot:
+//     state tables 40 KB | first-bit / exponent / shared counters 25 KB | rank mantissa trees for exponents 1..4 (30 nodes
+//     per state / symbol) 30 KB | run mantissa trees for exponents 1..2 (6 nodes) 6 KB | two 1 K-entry write-back caches 8 KB
+// = 110 KB, i.e. two CTAs per SM.  Rank exponent 5 and run exponents 3..5 now go through the caches (same cold index space
+// in HBM as before).  Measured in host emulation on the bench data (64 MiB G_text block, sub-blocks 0 and 4): 0.00 / 0.20
+// cached accesses per run and 0.000 / 0.046 misses per run; the smaller QLayout<3, 2, 11> (102 KB) would take 1.8 / 0.9
+// accesses and 0.26 / 0.14 misses per run.  QLayout<5, 5, 12> is exactly the layout of qlfc_coder.cuh and is instantiated
+// too: it must behave like q_decode3<1> (a refactoring check for the A/B).
+// STATUS: bit-exact in host emulation with both layouts (tests/test_qdec3_host.py); not yet run on a GPU.  To profit from it
+// more than 148 streams have to be in flight (>= 19 blocks of >= 16 MiB per GPU): BSCB200_QDEC=6 selects it.
+#pragma once
+
+template <u32 MAXE_R_, u32 MAXE_U_, int CLOG_> struct QLayout {
+    static constexpr u32 MAXE_R = MAXE_R_, MAXE_U = MAXE_U_;                 // resident mantissa exponents (rank, run length)
+    static constexpr u32 ROW_R = (2u << MAXE_R_) - 2u, ROW_U = (2u << MAXE_U_) - 2u;   // compact row: exponent e at offsets 2^e-2 .. 2^(e+1)-3
+    // counter file, indices in u16 units (same order as qlfc_coder.cuh)
+    static constexpr u32 R_RT_SHARED = 0, R_RT_STATE = 2, R_RT_CHAR = R_RT_STATE + 256;
+    static constexpr u32 R_RE_SHARED = R_RT_CHAR + 256, R_RE_STATE = R_RE_SHARED + 8, R_RE_CHAR = R_RE_STATE + 2048;
+    static constexpr u32 R_UT_SHARED = R_RE_CHAR + 2048, R_UT_STATE = R_UT_SHARED + 2, R_UT_CHAR = R_UT_STATE + 256;
+    static constexpr u32 R_UE_SHARED = R_UT_CHAR + 256, R_UE_STATE = R_UE_SHARED + 32, R_UE_CHAR = R_UE_STATE + 256 * UE_RES;
+    static constexpr u32 R_WIDE_SHARED = R_UE_CHAR + 256 * UE_RES, R_NARROW_SHARED = R_WIDE_SHARED + 9 * 256;
+    static constexpr u32 R_RM_STATE = R_NARROW_SHARED + 32 * 32, R_RM_CHAR = R_RM_STATE + 256 * ROW_R;
+    static constexpr u32 R_UM_STATE = R_RM_CHAR + 256 * ROW_R, R_UM_CHAR = R_UM_STATE + 256 * ROW_U, R_END = R_UM_CHAR + 256 * ROW_U;
+    static constexpr u32 SLOTS = 1u << CLOG_, HB = CLOG_ - 2, HMASK = (1u << HB) - 1u;   // 2 class bits + HB hashed bits per cache
+    static constexpr u32 C_STATE_VAL = R_END, C_CHAR_VAL = C_STATE_VAL + SLOTS, S16_COUNT = (C_CHAR_VAL + SLOTS + 1) & ~1u;
+    // shared-memory image (byte offsets); the counters start where CoderSmem's do, so SM3::cnt / SM3::set apply
+    static constexpr u32 O_RANK_STATE = 0, O_RUN_STATE = 32768, O_S16 = 40960, O_TAG_STATE = O_S16 + 2 * S16_COUNT, O_TAG_CHAR = O_TAG_STATE + 2 * SLOTS;
+    static constexpr u32 O_RANK_HIST = O_TAG_CHAR + 2 * SLOTS, O_RUN_HIST = O_RANK_HIST + 256, O_MTF = (O_RUN_HIST + 256 + 15u) & ~15u, O_WIN = O_MTF + 288, BYTES = O_WIN + 272;
+    // cache slot of a cold index: classes as in qlfc_coder.cuh (0,1 rank banks, 2 run mantissa, 3 run exponent >= 8)
+    static QD3_FN_MEMBER u32 cache_slot(u32 idx)
+    {
+        const u32 h = idx >> HB;
+        const u32 cls = idx < 9u * 65536u ? (h & 1u) : (idx < 9u * 65536u + 32u * 8192u ? 2u : 3u);
+        return (cls << HB) | ((idx ^ (h * 1237u)) & HMASK);
+    }
+    static QD3_FN_MEMBER u32 cache_tag(u32 idx) { return (idx >> HB) + 1u; }
+    static QD3_FN_MEMBER u32 cache_unslot(u32 slot, u32 tag) { const u32 h = tag - 1u; return (h << HB) | (((slot & HMASK) ^ (h * 1237u)) & HMASK); }
+};
+typedef QLayout<5, 5, 12> LayoutFull;     // = qlfc_coder.cuh: 205 KB, one stream per SM
+typedef QLayout<4, 2, 10> LayoutDiet;     // 110 KB, two streams per SM
+static_assert(LayoutFull::R_END == R_END && LayoutFull::S16_COUNT == S16_COUNT && LayoutFull::O_S16 == O3_S16, "LayoutFull must reproduce qlfc_coder.cuh");
+static_assert(LayoutFull::R_RM_STATE == R_RM_STATE && LayoutFull::R_UM_CHAR == R_UM_CHAR && LayoutFull::C_CHAR_VAL == C_CHAR_VAL, "LayoutFull must reproduce qlfc_coder.cuh");
+static_assert(LayoutDiet::BYTES <= 113 * 1024, "two diet decoders must fit one SM (227 KB, 1 KB reserved per CTA)");
+static_assert(LayoutDiet::O_S16 == O3_S16 && (LayoutDiet::O_WIN & 15u) == 0 && (LayoutDiet::O_MTF & 3u) == 0, "alignment of the shared-memory image");
+
+// Index (into the counter file) of rare counter `idx` through the direct-mapped write-back cache (uniform).
+template <class LY> QD3_FN u32 qd6_cache_get(const SM3 &sm, u32 val_base, u32 tags_off, short *__restrict__ cold, u32 idx, u32 &misses)
+{
+    const u32 slot = LY::cache_slot(idx), want = LY::cache_tag(idx);
+    const u32 t = sm.ld16(tags_off + 2u * slot);
+    if (t != want) {
+        if (t) cold[LY::cache_unslot(slot, t)] = (short)sm.cnt(val_base + slot);
+        sm.set(val_base + slot, (u16)cold[idx]);
+        sm.st16(tags_off + 2u * slot, want);
+        ++misses;
+    }
+    return val_base + slot;
+}
+
+
+// one decision with P(bit = 0) = p / 4096
+template <class LY> QD3_FN u32 qd6_step(const SM3 &sm, Rc3 &rc, u32 p)
+{
+    const bool need = rc.range < 0x10000u;
+    rc.code = need ? (rc.code << 16) | rc.nx : rc.code;
+    rc.range = need ? rc.range << 16 : rc.range;
+    rc.pos += need ? 2u : 0u;
+    rc.nx = sm.ld16(LY::O_WIN + (rc.pos - rc.wbase));
+    const u32 r = (rc.range >> 12) * p;
+    const bool bit = rc.code >= r;
+    rc.code -= bit ? r : 0u;
+    rc.range = bit ? rc.range - r : r;
+    return bit ? 1u : 0u;
+}
+
+
+// one serial decision against three counters of the shared counter file (the rare paths)
+template <class LY, int K> QD3_FN u32 qd6_dec3(const SM3 &sm, Rc3 &rc, u32 is, u32 ic, u32 ig)
+{
+    const int s = sm.cnt(is), c = sm.cnt(ic), g = sm.cnt(ig);
+    const u32 b = qd6_step<LY>(sm, rc, (u32)q_mix<K>(s, c, g));
+    sm.set(is, b ? q_down<K, 0>(s) : q_up<K, 0>(s));
+    sm.set(ic, b ? q_down<K, 1>(c) : q_up<K, 1>(c));
+    sm.set(ig, b ? q_down<K, 2>(g) : q_up<K, 2>(g));
+    return b;
+}
+
+
+template <class LY, int K> QD3_FN u32 qd6_dec3v(const SM3 &sm, Rc3 &rc, u32 is, u32 ic, u32 ig, int s, int c, int g)
+{
+    const u32 b = qd6_step<LY>(sm, rc, (u32)q_mix<K>(s, c, g));
+    sm.set(is, b ? q_down<K, 0>(s) : q_up<K, 0>(s));
+    sm.set(ic, b ? q_down<K, 1>(c) : q_up<K, 1>(c));
+    sm.set(ig, b ? q_down<K, 2>(g) : q_up<K, 2>(g));
+    return b;
+}
+
+
+// (re)load the input window at rc.pos: 8 bytes per lane + 16 more by lanes 0..15
+#define QD6_REFILL() do { rc.wbase = rc.pos; QD3_SYNC(); \
+        QD3_LANES { for (u32 k_ = 0; k_ < 8; ++k_) { const u32 w_ = lane * 8u + k_, o_ = rc.wbase + w_; sm.st8(LY::O_WIN + w_, o_ < rc.limit ? rc.in[o_] : 0u); } \
+                    if (lane < 16u) { const u32 w_ = 256u + lane, o_ = rc.wbase + w_; sm.st8(LY::O_WIN + w_, o_ < rc.limit ? rc.in[o_] : 0u); } } \
+        QD3_SYNC(); } while (0)
+
+
+// Stream prologue shared by both decoders: coder start-up, the 32-bit length, the MTF-order table.  Returns 0 or an error.
+template <class LY> QD3_FN int qd6_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PARAM, const u8 *__restrict__ in, u32 in_limit, u32 out_cap, u32 &n, int &maxRank)
+{
+#ifndef QD3_HOST
+    const u32 lane = threadIdx.x & 31u;
+#endif
+    QD3_LANES { QD3_L(lr).used8 = 0; QD3_L(lr).tmp = 0; }
+
+    rc.in = in; rc.limit = in_limit; rc.code = 0; rc.range = 0xffffffffu; rc.pos = 0; rc.wbase = 0; rc.nx = 0;
+    QD6_REFILL();
+    rc.code = (sm.ld16(LY::O_WIN + 2) << 16) | sm.ld16(LY::O_WIN + 4);            // rangecoder.h:203-211: three units, the first falls out of 32 bits
+    rc.pos = 6; rc.nx = sm.ld16(LY::O_WIN + 6);
+    n = 0;
+    for (int b = 0; b < 32; ++b) n = (n << 1) | qd6_step<LY>(sm, rc, 2048u);
+    if (n > out_cap) return LIBBSC_DATA_CORRUPT;                            // would overrun the output slice
+
+    maxRank = 7;
+    int prev = -1;
+    for (int d = 0; d < 256; ++d) {
+        int c = 0;
+        for (int bit = 7; bit >= 0; --bit) {
+            bool can0, can1; QD3_HEADER_OPTIONS(prev, c, bit, can0, can1);
+            if (can0 && can1) {
+                if (rc.pos - rc.wbase > 256u) QD6_REFILL();
+                c = 2 * c + (int)qd6_step<LY>(sm, rc, 2048u);
+            }
+            else if (can1) c = 2 * c + 1;
+            else if (can0) c = 2 * c;
+        }
+        c &= 255;
+        sm.st8(LY::O_MTF + d, (u32)c);
+        if (c == prev) { maxRank = qd3_ilog2((u32)(d - 1)); break; }
+        prev = c;
+        QD3_LANES { if ((u32)(c >> 3) == lane) QD3_L(lr).used8 |= 1u << (c & 7); }
+    }
+    QD3_SYNC();
+    return 0;
+}
+
+
+template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const u8 *__restrict__ in, u32 in_limit, u8 *__restrict__ out, u32 out_cap,
+                                    short *__restrict__ cold_s, short *__restrict__ cold_c, u32 &st_cached, u32 &st_miss)
+{
+    QD3_LREGS;
+#ifndef QD3_HOST
+    const u32 lane = threadIdx.x & 31u;
+#endif
+    Rc3 rc; u32 n; int maxRank;
+    { const int err = qd6_prologue<LY>(sm, rc, lr, in, in_limit, out_cap, n, maxRank); if (err) return err; }
+
+    u32 ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0; int avgRank = 0;
+    u32 c, m1, m2, m3;
+    { const u32 f = sm.ld32(LY::O_MTF); c = f & 255u; m1 = (f >> 8) & 255u; m2 = (f >> 16) & 255u; m3 = f >> 24; }
+    u32 rhU = sm.ld8(LY::O_RUN_HIST + c);
+    u32 st = sm.ld8(LY::O_RANK_STATE + ((ctxRun << 11) | (ctxRank4 << 3) | sm.ld8(LY::O_RANK_HIST + c)));
+    int tS = sm.cnt(LY::R_RT_STATE + st), tC = sm.cnt(LY::R_RT_CHAR + c), tG = sm.cnt(LY::R_RT_SHARED);
+    u32 st2z = sm.ld8(LY::O_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));       // run state if rank == 1
+
+    long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = 0; u32 prof_runs = 0;
+    (void)prof_t; (void)prof_last; (void)prof_runs;
+#ifndef QD3_HOST
+    if (PROF) prof_last = clock64();
+#endif
+    for (u32 i = 0; i < n; ) {
+        u32 rank = 1, b;
+        const u32 rhq = rhU < 7 ? rhU : 7;
+        const bool plain = avgRank < 32;
+        if (rc.pos - rc.wbase > QD3_RUN_ROOM) QD6_REFILL();
+        // first-decision counters of the run length, should the rank turn out to be 1 (the rank decisions never touch them)
+        const int uS0 = sm.cnt(LY::R_UT_STATE + st2z), uC0 = sm.cnt(LY::R_UT_CHAR + c), uG0 = sm.cnt(LY::R_UT_SHARED);
+        QD3_T(0);
+        if (plain) {
+            b = qd6_dec3v<LY, K_RANK_T>(sm, rc, LY::R_RT_STATE + st, LY::R_RT_CHAR + c, LY::R_RT_SHARED, tS, tC, tG);
+            if (!b) sm.st8(LY::O_RANK_HIST + c, 0);
+            else {
+                u32 e = 1;
+                while ((int)e != maxRank) {
+                    b = qd6_dec3<LY, K_RANK_E>(sm, rc, LY::R_RE_STATE + st * 8 + e - 1, LY::R_RE_CHAR + c * 8 + e - 1, LY::R_RE_SHARED + e - 1);
+                    if (!b) break;
+                    if (++e >= 7) break;                                      // e <= maxRank <= 7 in valid streams
+                }
+                sm.st8(LY::O_RANK_HIST + c, e);
+                if (e <= LY::MAXE_R) {
+                    const u32 bs = LY::R_RM_STATE + st * LY::ROW_R + (1u << e) - 2u, bc = LY::R_RM_CHAR + c * LY::ROW_R + (1u << e) - 2u, bg = LY::R_WIDE_SHARED + e * 256;
+                    for (int bit = (int)e - 1; bit >= 0; --bit) {
+                        b = qd6_dec3<LY, K_RANK_M>(sm, rc, bs + rank, bc + rank, bg + rank);
+                        rank = 2u * rank + b;
+                    }
+                } else {
+                    for (int bit = (int)e - 1; bit >= 0; --bit) {
+                        const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, wide_idx(e, st, rank), st_miss);
+                        const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, wide_idx(e, c, rank), st_miss);
+                        st_cached += 2;
+                        b = qd6_dec3<LY, K_RANK_M>(sm, rc, is, ic, LY::R_WIDE_SHARED + e * 256u + rank);
+                        rank = 2u * rank + b;
+                    }
+                }
+            }
+        } else {
+            rank = 0;
+            for (int node = 1, bit = maxRank; bit >= 0; --bit) {
+                const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, wide_idx(8, st, (u32)node), st_miss);
+                const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, wide_idx(8, c, (u32)node), st_miss);
+                st_cached += 2;
+                b = qd6_dec3<LY, K_RANK_P>(sm, rc, is, ic, LY::R_WIDE_SHARED + 8u * 256u + (u32)node);
+                node = 2 * node + (int)b; rank = 2u * rank + b;
+            }
+            sm.st8(LY::O_RANK_HIST + c, (u32)qd3_ilog2(rank));
+        }
+        rank &= 255u;
+        QD3_T(1);
+
+        // push c `rank` places back (qlfc.cpp:1830-1860); positions 0..3 of the list live in (c, m1, m2, m3)
+        const u32 cur = c;
+        if (rank == 1) { c = m1; m1 = cur; }
+        else if (rank == 2) { c = m1; m1 = m2; m2 = cur; }
+        else if (rank == 3) { c = m1; m1 = m2; m2 = m3; m3 = cur; }
+        else if (rank != 0) {
+            sm.st8(LY::O_MTF, c); sm.st8(LY::O_MTF + 1, m1); sm.st8(LY::O_MTF + 2, m2); sm.st8(LY::O_MTF + 3, m3);
+            QD3_SYNC();
+            for (u32 basep = 0; basep < rank; basep += 32) {
+                QD3_LANES { QD3_L(lr).tmp = sm.ld8(LY::O_MTF + basep + lane + 1u); }
+                QD3_SYNC();
+                QD3_LANES { if (basep + lane < rank) sm.st8(LY::O_MTF + basep + lane, QD3_L(lr).tmp); }
+                QD3_SYNC();
+            }
+            sm.st8(LY::O_MTF + rank, cur);
+            QD3_SYNC();
+            const u32 f = sm.ld32(LY::O_MTF); c = f & 255u; m1 = (f >> 8) & 255u; m2 = (f >> 16) & 255u; m3 = f >> 24;
+        }
+        // (c, m1, m2, m3) now describe the NEXT run; `cur` is this run's symbol
+        const u32 rhRn = sm.ld8(LY::O_RANK_HIST + c), rhUn = sm.ld8(LY::O_RUN_HIST + c);
+        avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
+        const u32 rank0 = rank - 1u;
+        u32 st2 = st2z, run = 1;
+        QD3_T(4);
+        if (rank0 == 0) b = qd6_dec3v<LY, K_RUN_T>(sm, rc, LY::R_UT_STATE + st2z, LY::R_UT_CHAR + cur, LY::R_UT_SHARED, uS0, uC0, uG0);
+        else {
+            st2 = sm.ld8(LY::O_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7u ? rank0 : 7u) << 3) | rhq));
+            b = qd6_dec3<LY, K_RUN_T>(sm, rc, LY::R_UT_STATE + st2, LY::R_UT_CHAR + cur, LY::R_UT_SHARED);
+        }
+        // both candidates for the next run's rank state (its ctxRun gets one more bit: run < 3)
+        const u32 ctxRank4n = ((ctxRank4 << 2) | (rank0 < 3u ? rank0 : 3u)) & 0xffu;
+        const u32 ctxRunN = (ctxRun << 1) & 0xfu;
+        const u32 stA = sm.ld8(LY::O_RANK_STATE + (((ctxRunN | 1u) << 11) | (ctxRank4n << 3) | rhRn)), stB = sm.ld8(LY::O_RANK_STATE + ((ctxRunN << 11) | (ctxRank4n << 3) | rhRn));
+        QD3_T(2);
+        if (!b) sm.st8(LY::O_RUN_HIST + cur, (rhU + 2u) >> 2);
+        else {
+            u32 eu = 1;
+            for (;;) {
+                const u32 k = eu - 1u;
+                if (k < UE_RES) b = qd6_dec3<LY, K_RUN_E>(sm, rc, LY::R_UE_STATE + st2 * UE_RES + k, LY::R_UE_CHAR + cur * UE_RES + k, LY::R_UE_SHARED + k);
+                else {
+                    const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, ue_idx(st2, k), st_miss);
+                    const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, ue_idx(cur, k), st_miss);
+                    st_cached += 2;
+                    b = qd6_dec3<LY, K_RUN_E>(sm, rc, is, ic, LY::R_UE_SHARED + k);
+                }
+                if (!b) break;
+                if (++eu >= 31u) break;                                          // corrupt-input guard
+            }
+            sm.st8(LY::O_RUN_HIST + cur, ((rhU + 3u * eu + 3u) >> 2) & 255u);
+            if (eu <= LY::MAXE_U) {
+                const u32 bs = LY::R_UM_STATE + st2 * LY::ROW_U + (1u << eu) - 2u, bc = LY::R_UM_CHAR + cur * LY::ROW_U + (1u << eu) - 2u, bg = LY::R_NARROW_SHARED + eu * 32u;
+                for (u32 node = 1, bit = eu; bit > 0; --bit) {
+                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, bs + node, bc + node, bg + node);
+                    run = 2u * run + b; node = 2u * node + b;
+                }
+            } else {
+                for (u32 node = 1, bit = eu; bit > 0; --bit) {
+                    const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, narrow_idx(eu, st2, node), st_miss);
+                    const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, narrow_idx(eu, cur, node), st_miss);
+                    st_cached += 2;
+                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, is, ic, LY::R_NARROW_SHARED + eu * 32u + node);
+                    run = 2u * run + b; node = eu <= 5u ? 2u * node + b : node + 1u;   // qlfc.cpp:1119: tree contexts up to 5 bits, linear above
+                }
+            }
+        }
+        QD3_T(5);
+        const bool shortRun = run < 3u;
+        ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0u ? 1u : 0u)) & 0x7u;
+        ctxRank4 = ctxRank4n;
+        ctxRun   = ctxRunN | (shortRun ? 1u : 0u);
+        st = shortRun ? stA : stB;
+        rhU = rank != 0 ? rhUn : sm.ld8(LY::O_RUN_HIST + c);                         // rank 0 (corrupt input only): same symbol again
+        // first-decision counters of the next run (nothing writes the rank counters until then) and its run state for rank 1
+        tS = sm.cnt(LY::R_RT_STATE + st); tC = sm.cnt(LY::R_RT_CHAR + c); tG = sm.cnt(LY::R_RT_SHARED);
+        st2z = sm.ld8(LY::O_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));
+
+        // run expansion: byte address A is always written by lane A mod 32
+        if (run <= 32u && i + 32u <= n) { QD3_LANES { out[i + ((lane - i) & 31u)] = (u8)cur; } }
+        else {
+            if (run > n - i) run = n - i;                                        // never write past n
+            QD3_LANES { for (u32 k = (lane - i) & 31u; k < run; k += 32) out[i + k] = (u8)cur; }
+        }
+        i += run;
+        QD3_T(6);
+        if (PROF) ++prof_runs;
+    }
+#ifndef QD3_HOST
+    if (PROF && blockIdx.x == 0 && threadIdx.x == 0)
+        printf("[qdec6 prof] runs %u; cycles/run: top %.1f rank %.1f runbit %.1f mtf+hist %.1f run>1 %.1f tail %.1f\n", prof_runs,
+               (double)prof_t[0] / prof_runs, (double)prof_t[1] / prof_runs, (double)prof_t[2] / prof_runs, (double)prof_t[4] / prof_runs,
+               (double)prof_t[5] / prof_runs, (double)prof_t[6] / prof_runs);
+#endif
+    return (int)n;
+}
+
+
+#ifndef QD3_HOST
+template <class LY> __device__ __forceinline__ void qd6_smem_init(u8 *raw, const QTables *__restrict__ g)
+{
+    const u32 lane = threadIdx.x & 31;
+    const uint4 *src = (const uint4 *)g; uint4 *dst = (uint4 *)raw;                                   // rank_state and run_state are contiguous
+    for (u32 i = lane; i < sizeof(QTables) / 16; i += 32) dst[i] = src[i];
+    u32 *w = (u32 *)(raw + LY::O_S16);
+    for (u32 i = lane; i < LY::S16_COUNT / 2; i += 32) w[i] = 0x08000800u;                            // every counter starts at 2048
+    u32 *t = (u32 *)(raw + LY::O_TAG_STATE);
+    for (u32 i = lane; i < (LY::BYTES - LY::O_TAG_STATE) / 4; i += 32) t[i] = 0;                      // tags, histories, mtf, window
+    __syncwarp();
+}
+
+template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode6(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
+                                                                              const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+{
+    extern __shared__ __align__(16) u8 q_smem_raw[];
+    qd6_smem_init<LY>(q_smem_raw, tables);
+    SM3 sm; sm.b = (u32)__cvta_generic_to_shared(q_smem_raw);
+    asm volatile("" : "+r"(sm.b) :: "memory");
+    const u32 sid = sb_list[blockIdx.x];
+    SubBlock &sb = sbs[sid];
+    short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
+    u32 st_cached = 0, st_miss = 0;
+    const int r = qd6_decode_stream<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss);
+    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
+}
+#endif

@@ -13,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tools", "qdec3_host.cpp")
 LIB = os.path.join(ROOT, "tools", "bin", "libqdec3_host.so")
-DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_decoder3.cuh", "qlfc_fast.cuh", "qlfc_coder.cuh", "qlfc_tables.inc")]
+DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_decoder3.cuh", "qlfc_decoder6.cuh", "qlfc_fast.cuh", "qlfc_coder.cuh", "qlfc_tables.inc")]
 
 
 def _hostlib():
@@ -129,3 +129,27 @@ def test_fast_coder_host_emulation_matches_oracle(qfast, gen, checker, port):
     assert covered >= 10
     a = checker.bwt_encode(gen.text(2, 100000))[1]
     assert decode(checker.encode_block(a, coder=3)[1], a.size - 1)[0] == -6
+
+
+# ---- layout-templated decoder (qlfc_decoder6.cuh): full layout = refactoring check, diet layout = two streams per SM -------------
+def test_layout_templated_decoder_host_emulation(gen, checker, port):
+    lib = _hostlib()
+    lib.qdec6_host_decode.restype = ctypes.c_int
+    lib.qdec6_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int]
+    lib.qdec6_smem_bytes.restype = ctypes.c_uint
+    assert lib.qdec6_smem_bytes(1) <= 113 * 1024 < lib.qdec6_smem_bytes(0)       # diet: two CTAs per SM; full: one
+    covered, rare = 0, [0, 0]
+    for name, a in inputs(gen, checker):
+        r, s = checker.encode_block(a)
+        if r <= 0:
+            continue
+        for layout in (0, 1):
+            out = np.full(a.size + 64, 0xAA, dtype=np.uint8)
+            stats = (ctypes.c_uint * 2)()
+            s_ = np.ascontiguousarray(s)
+            n = lib.qdec6_host_decode(s_.ctypes.data, s_.size, out.ctypes.data, a.size, stats, layout)
+            assert n == a.size and np.array_equal(out[:a.size], a) and np.all(out[a.size:] == 0xAA), (name, layout)
+            rare[layout] += stats[0]
+        covered += 1
+    assert covered >= 8
+    assert rare[1] > rare[0]                                                      # the diet layout really sends more decisions through the caches

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """tools/dec_ab.py -- A/B timing of the QLFC decoder kernels on ONE block (CUDA events around every launch).
-    python tools/dec_ab.py [MiB] [gen ...]      gen: 2 q_decode2, 3 speculative q_decode3<0>, 4 serial q_decode3<1>
+    python tools/dec_ab.py [MiB] [gen ...]      gen: 2 q_decode2, 3 speculative q_decode3<0>, 4 serial q_decode3<1> (default), 5 q_decode3<2>, 6 q_decode6<LayoutDiet>, 7 q_decode6<LayoutFull>
 Each generation runs in its own process (the selection is read once from BSCB200_QDEC)."""
 import os
 import subprocess
@@ -37,7 +37,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     sys.exit(0)
 
 mib = sys.argv[1] if len(sys.argv) > 1 else "64"
-gens = sys.argv[2:] or ["2", "4", "3"]
+gens = sys.argv[2:] or ["2", "4", "7", "6"]
 for g in gens:
     env = dict(os.environ, BSCB200_QDEC=g)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--child", mib], env=env, check=False)

@@ -38,6 +38,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 #define QD3_HOST 1
 #include "../libbsc_b200/csrc/qlfc_decoder3.cuh"
 #include "../libbsc_b200/csrc/qlfc_fast.cuh"
+#include "../libbsc_b200/csrc/qlfc_decoder6.cuh"
 }
 
 // Decodes one QLFC static stream (what bsc_qlfc_static_decode_block reads) of `in_size` bytes into out[0..out_cap).
@@ -101,3 +102,26 @@ extern "C" int qfast_host_encode(const unsigned *run_pos, const unsigned char *r
     free(smem); free(cold);
     return r;
 }
+
+// ---- layout-templated serial decoder (libbsc_b200/csrc/qlfc_decoder6.cuh): layout 0 = full (205 KB), 1 = diet (101 KB) ------------
+template <class LY> static int qdec6_run(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
+{
+    u8 *smem = (u8 *)calloc(1, LY::BYTES);
+    short *cold = (short *)malloc(sizeof(short) * 2 * (size_t)COLD_PAD);
+    if (!smem || !cold) { free(smem); free(cold); return LIBBSC_NOT_ENOUGH_MEMORY; }
+    memcpy(smem + LY::O_RANK_STATE, bscb_rank_state_tab, 32768);
+    memcpy(smem + LY::O_RUN_STATE, bscb_run_state_tab, 8192);
+    for (u32 i = 0; i < LY::S16_COUNT; ++i) { const u16 v = 2048; memcpy(smem + LY::O_S16 + 2 * i, &v, 2); }
+    for (size_t i = 0; i < 2 * (size_t)COLD_PAD; ++i) cold[i] = 2048;
+    SM3 sm; sm.b = smem;
+    u32 st_cached = 0, st_miss = 0;
+    const int r = qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
+    if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
+    free(smem); free(cold);
+    return r;
+}
+extern "C" int qdec6_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats, int layout)
+{
+    return layout == 0 ? qdec6_run<LayoutFull>(in, in_size, out, out_cap, stats) : qdec6_run<LayoutDiet>(in, in_size, out, out_cap, stats);
+}
+extern "C" unsigned qdec6_smem_bytes(int layout) { return layout == 0 ? LayoutFull::BYTES : LayoutDiet::BYTES; }
