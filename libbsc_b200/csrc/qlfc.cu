@@ -279,9 +279,12 @@ static const QTables *get_tables(Ctx *ctx)
 {
     if (!ctx->qlfc_tables) {
         QTables *d = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&d, sizeof(QTables)));
+        static int h_moves[QD6_MOVES];                     // multipliers of the hot counter moves (qlfc_decoder6.cuh), stored right after the tables
+        qd6_fill_moves(h_moves);
+        CUDA_TRY(cudaMalloc((void **)&d, sizeof(QTables) + sizeof(h_moves)));
         CUDA_TRY(cudaMemcpyAsync(d->rank_state, bscb_rank_state_tab, 32768, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(d->run_state, bscb_run_state_tab, 8192, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d + 1, h_moves, sizeof(h_moves), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyToSymbolAsync(c_params, bscb_static_params, sizeof(c_params), 0, cudaMemcpyHostToDevice, ctx->stream));
         ctx->sync();
         ctx->qlfc_tables = d;

@@ -72,6 +72,9 @@ struct SM3 {
     U4  ld128(u32 off) const { U4 v; memcpy(&v, b + off, 16); return v; }
     void st8(u32 off, u32 v) const { b[off] = (u8)v; }
     void st16(u32 off, u32 v) const { u16 t = (u16)v; memcpy(b + off, &t, 2); }
+    u32 at(u32 off) const { return off; }                              // "absolute address" of an offset (host: the offset itself)
+    u32 ld16a(u32 a) const { return ld16(a); }
+    void st16a(u32 a, u32 v) const { st16(a, v); }
 #else
     u32 b;
     __device__ __forceinline__ u32 ld8(u32 off) const { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(b + off)); return v; }
@@ -81,6 +84,9 @@ struct SM3 {
     __device__ __forceinline__ U4  ld128(u32 off) const { U4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(b + off)); return v; }
     __device__ __forceinline__ void st8(u32 off, u32 v) const { asm volatile("st.shared.u8 [%0], %1;" :: "r"(b + off), "r"(v) : "memory"); }
     __device__ __forceinline__ void st16(u32 off, u32 v) const { asm volatile("st.shared.u16 [%0], %1;" :: "r"(b + off), "r"(v) : "memory"); }
+    __device__ __forceinline__ u32 at(u32 off) const { return b + off; }     // absolute shared-memory address of an offset
+    __device__ __forceinline__ u32 ld16a(u32 a) const { u32 v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+    __device__ __forceinline__ void st16a(u32 a, u32 v) const { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 #endif
     // counters (indices in u16 units, as in qlfc_coder.cuh)
     QD3_FN_MEMBER int cnt(u32 idx) const { return (int)ld16(O3_S16 + 2u * idx); }

@@ -12,6 +12,11 @@
 // cached accesses per run and 0.000 / 0.046 misses per run; the smaller QLayout<3, 2, 11> (102 KB) would take 1.8 / 0.9
 // accesses and 0.26 / 0.14 misses per run.  QLayout<5, 5, 12> is exactly the layout of qlfc_coder.cuh and is instantiated
 // too: it must behave like q_decode3<1> (a refactoring check for the A/B).
+// Besides the layout, two instruction-count measures (the cost model of DESIGN.md 4.5: a lone warp retires one instruction
+// per 4-5 cycles, so instructions are what counts): the multipliers of the hot counter moves live in registers (loaded from
+// a table, see q_move6), and the exponent / mantissa loops address their counters through absolute shared-memory
+// addresses that advance with the node.  SASS of the rank-mantissa loop: 53 instructions per decision in q_decode3<1>,
+// 28-42 here (cuobjdump, r1h).
 // STATUS: bit-exact in host emulation with both layouts (tests/test_qdec3_host.py); not yet run on a GPU.  To profit from it
 // more than 148 streams have to be in flight (>= 19 blocks of >= 16 MiB per GPU): BSCB200_QDEC=6 selects it.
 #pragma once
@@ -80,27 +85,63 @@ template <class LY> QD3_FN u32 qd6_step(const SM3 &sm, Rc3 &rc, u32 p)
 }
 
 
-// one serial decision against three counters of the shared counter file (the rare paths)
-template <class LY, int K> QD3_FN u32 qd6_dec3(const SM3 &sm, Rc3 &rc, u32 is, u32 ic, u32 ig)
+// Counter moves (p * M + K) >> 12 as in qlfc_coder.cuh.  IMAD takes ONE immediate (the addend), so ptxas re-materialises
+// every multiplier with a MOV in front of every use -- 6 of the 53 instructions of a mantissa decision in q_decode3<1>
+// (profiles/r1h), and it folds any constant it can see.  The multipliers of the four hot decision classes are therefore
+// LOADED (from a small table in global memory) into registers once per stream: 24 registers, no MOVs.
+QD3_FN constexpr int qd6_hot(int k) { return k == K_RANK_T ? 0 : k == K_RANK_E ? 1 : k == K_RANK_M ? 2 : k == K_RUN_T ? 3 : -1; }
+constexpr int QD6_HOT_CLASSES[4] = {K_RANK_T, K_RANK_E, K_RANK_M, K_RUN_T};
+constexpr int QD6_MOVES = 4 * 3 * 2;                                       // table layout: [hot class][state, symbol, shared][bit]
+struct Qd6Mv { int m[4][3][2]; };
+QD3_FN void qd6_load_moves(Qd6Mv &mv, const int *__restrict__ moves)
 {
-    const int s = sm.cnt(is), c = sm.cnt(ic), g = sm.cnt(ig);
-    const u32 b = qd6_step<LY>(sm, rc, (u32)q_mix<K>(s, c, g));
-    sm.set(is, b ? q_down<K, 0>(s) : q_up<K, 0>(s));
-    sm.set(ic, b ? q_down<K, 1>(c) : q_up<K, 1>(c));
-    sm.set(ig, b ? q_down<K, 2>(g) : q_up<K, 2>(g));
-    return b;
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+#pragma unroll
+        for (int w = 0; w < 3; ++w) { mv.m[h][w][0] = moves[(h * 3 + w) * 2]; mv.m[h][w][1] = moves[(h * 3 + w) * 2 + 1]; }
+}
+// host side of the table (also used by the host emulation): multiplier 4096 - AR0 for bit 0, 4096 - AR1 for bit 1
+static inline void qd6_fill_moves(int *moves)
+{
+    for (int h = 0; h < 4; ++h) for (int w = 0; w < 3; ++w) {
+        moves[(h * 3 + w) * 2]     = 4096 - bscb_static_params[QD6_HOT_CLASSES[h]][4 + 4 * w];
+        moves[(h * 3 + w) * 2 + 1] = 4096 - bscb_static_params[QD6_HOT_CLASSES[h]][6 + 4 * w];
+    }
+}
+template <int K, int WHO> QD3_FN int q_move6(int p, u32 bit, const Qd6Mv &mv)
+{
+    constexpr int h = qd6_hot(K);
+    const int m0 = h >= 0 ? mv.m[h >= 0 ? h : 0][WHO][0] : 4096 - bscb_param(K, 4 + 4 * WHO);
+    const int m1 = h >= 0 ? mv.m[h >= 0 ? h : 0][WHO][1] : 4096 - bscb_param(K, 6 + 4 * WHO);
+    const int up = p * m0 + (4096 - bscb_param(K, 3 + 4 * WHO)) * bscb_param(K, 4 + 4 * WHO);
+    const int dn = p * m1 + bscb_param(K, 5 + 4 * WHO) * bscb_param(K, 6 + 4 * WHO) + 4095;
+    return (bit ? dn : up) >> 12;
 }
 
-
-template <class LY, int K> QD3_FN u32 qd6_dec3v(const SM3 &sm, Rc3 &rc, u32 is, u32 ic, u32 ig, int s, int c, int g)
+// one serial decision against three counters given by their ABSOLUTE shared-memory addresses (SM3::at)
+template <class LY, int K> QD3_FN u32 qd6_dec3a(const SM3 &sm, Rc3 &rc, const Qd6Mv &mv, u32 as, u32 ac, u32 ag)
 {
+    const int s = (int)sm.ld16a(as), c = (int)sm.ld16a(ac), g = (int)sm.ld16a(ag);
     const u32 b = qd6_step<LY>(sm, rc, (u32)q_mix<K>(s, c, g));
-    sm.set(is, b ? q_down<K, 0>(s) : q_up<K, 0>(s));
-    sm.set(ic, b ? q_down<K, 1>(c) : q_up<K, 1>(c));
-    sm.set(ig, b ? q_down<K, 2>(g) : q_up<K, 2>(g));
+    sm.st16a(as, (u32)q_move6<K, 0>(s, b, mv));
+    sm.st16a(ac, (u32)q_move6<K, 1>(c, b, mv));
+    sm.st16a(ag, (u32)q_move6<K, 2>(g, b, mv));
     return b;
 }
-
+// the same by counter index
+template <class LY, int K> QD3_FN u32 qd6_dec3(const SM3 &sm, Rc3 &rc, const Qd6Mv &mv, u32 is, u32 ic, u32 ig)
+{
+    return qd6_dec3a<LY, K>(sm, rc, mv, sm.at(LY::O_S16 + 2u * is), sm.at(LY::O_S16 + 2u * ic), sm.at(LY::O_S16 + 2u * ig));
+}
+// ... with the counter values already loaded
+template <class LY, int K> QD3_FN u32 qd6_dec3v(const SM3 &sm, Rc3 &rc, const Qd6Mv &mv, u32 is, u32 ic, u32 ig, int s, int c, int g)
+{
+    const u32 b = qd6_step<LY>(sm, rc, (u32)q_mix<K>(s, c, g));
+    sm.set(is, q_move6<K, 0>(s, b, mv));
+    sm.set(ic, q_move6<K, 1>(c, b, mv));
+    sm.set(ig, q_move6<K, 2>(g, b, mv));
+    return b;
+}
 
 // (re)load the input window at rc.pos: 8 bytes per lane + 16 more by lanes 0..15
 #define QD6_REFILL() do { rc.wbase = rc.pos; QD3_SYNC(); \
@@ -150,9 +191,10 @@ template <class LY> QD3_FN int qd6_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PA
 
 
 template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const u8 *__restrict__ in, u32 in_limit, u8 *__restrict__ out, u32 out_cap,
-                                    short *__restrict__ cold_s, short *__restrict__ cold_c, u32 &st_cached, u32 &st_miss)
+                                    short *__restrict__ cold_s, short *__restrict__ cold_c, const int *__restrict__ moves, u32 &st_cached, u32 &st_miss)
 {
     QD3_LREGS;
+    Qd6Mv mv; qd6_load_moves(mv, moves);
 #ifndef QD3_HOST
     const u32 lane = threadIdx.x & 31u;
 #endif
@@ -181,28 +223,34 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
         const int uS0 = sm.cnt(LY::R_UT_STATE + st2z), uC0 = sm.cnt(LY::R_UT_CHAR + c), uG0 = sm.cnt(LY::R_UT_SHARED);
         QD3_T(0);
         if (plain) {
-            b = qd6_dec3v<LY, K_RANK_T>(sm, rc, LY::R_RT_STATE + st, LY::R_RT_CHAR + c, LY::R_RT_SHARED, tS, tC, tG);
+            b = qd6_dec3v<LY, K_RANK_T>(sm, rc, mv, LY::R_RT_STATE + st, LY::R_RT_CHAR + c, LY::R_RT_SHARED, tS, tC, tG);
             if (!b) sm.st8(LY::O_RANK_HIST + c, 0);
             else {
                 u32 e = 1;
-                while ((int)e != maxRank) {
-                    b = qd6_dec3<LY, K_RANK_E>(sm, rc, LY::R_RE_STATE + st * 8 + e - 1, LY::R_RE_CHAR + c * 8 + e - 1, LY::R_RE_SHARED + e - 1);
-                    if (!b) break;
-                    if (++e >= 7) break;                                      // e <= maxRank <= 7 in valid streams
+                {   // exponent decisions e-1 = 0, 1, ...: consecutive counters, addresses advance by 2 bytes
+                    u32 aS = sm.at(LY::O_S16 + 2u * (LY::R_RE_STATE + st * 8)), aC = sm.at(LY::O_S16 + 2u * (LY::R_RE_CHAR + c * 8)), aG = sm.at(LY::O_S16 + 2u * LY::R_RE_SHARED);
+                    while ((int)e != maxRank) {
+                        b = qd6_dec3a<LY, K_RANK_E>(sm, rc, mv, aS, aC, aG);
+                        if (!b) break;
+                        if (++e >= 7) break;                                  // e <= maxRank <= 7 in valid streams
+                        aS += 2u; aC += 2u; aG += 2u;
+                    }
                 }
                 sm.st8(LY::O_RANK_HIST + c, e);
                 if (e <= LY::MAXE_R) {
                     const u32 bs = LY::R_RM_STATE + st * LY::ROW_R + (1u << e) - 2u, bc = LY::R_RM_CHAR + c * LY::ROW_R + (1u << e) - 2u, bg = LY::R_WIDE_SHARED + e * 256;
+                    const u32 aS = sm.at(LY::O_S16 + 2u * bs), aC = sm.at(LY::O_S16 + 2u * bc), aG = sm.at(LY::O_S16 + 2u * bg);
                     for (int bit = (int)e - 1; bit >= 0; --bit) {
-                        b = qd6_dec3<LY, K_RANK_M>(sm, rc, bs + rank, bc + rank, bg + rank);
-                        rank = 2u * rank + b;
+                        const u32 r2 = 2u * rank;
+                        b = qd6_dec3a<LY, K_RANK_M>(sm, rc, mv, aS + r2, aC + r2, aG + r2);
+                        rank = r2 + b;
                     }
                 } else {
                     for (int bit = (int)e - 1; bit >= 0; --bit) {
                         const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, wide_idx(e, st, rank), st_miss);
                         const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, wide_idx(e, c, rank), st_miss);
                         st_cached += 2;
-                        b = qd6_dec3<LY, K_RANK_M>(sm, rc, is, ic, LY::R_WIDE_SHARED + e * 256u + rank);
+                        b = qd6_dec3<LY, K_RANK_M>(sm, rc, mv, is, ic, LY::R_WIDE_SHARED + e * 256u + rank);
                         rank = 2u * rank + b;
                     }
                 }
@@ -213,7 +261,7 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
                 const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, wide_idx(8, st, (u32)node), st_miss);
                 const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, wide_idx(8, c, (u32)node), st_miss);
                 st_cached += 2;
-                b = qd6_dec3<LY, K_RANK_P>(sm, rc, is, ic, LY::R_WIDE_SHARED + 8u * 256u + (u32)node);
+                b = qd6_dec3<LY, K_RANK_P>(sm, rc, mv, is, ic, LY::R_WIDE_SHARED + 8u * 256u + (u32)node);
                 node = 2 * node + (int)b; rank = 2u * rank + b;
             }
             sm.st8(LY::O_RANK_HIST + c, (u32)qd3_ilog2(rank));
@@ -245,10 +293,10 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
         const u32 rank0 = rank - 1u;
         u32 st2 = st2z, run = 1;
         QD3_T(4);
-        if (rank0 == 0) b = qd6_dec3v<LY, K_RUN_T>(sm, rc, LY::R_UT_STATE + st2z, LY::R_UT_CHAR + cur, LY::R_UT_SHARED, uS0, uC0, uG0);
+        if (rank0 == 0) b = qd6_dec3v<LY, K_RUN_T>(sm, rc, mv, LY::R_UT_STATE + st2z, LY::R_UT_CHAR + cur, LY::R_UT_SHARED, uS0, uC0, uG0);
         else {
             st2 = sm.ld8(LY::O_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7u ? rank0 : 7u) << 3) | rhq));
-            b = qd6_dec3<LY, K_RUN_T>(sm, rc, LY::R_UT_STATE + st2, LY::R_UT_CHAR + cur, LY::R_UT_SHARED);
+            b = qd6_dec3<LY, K_RUN_T>(sm, rc, mv, LY::R_UT_STATE + st2, LY::R_UT_CHAR + cur, LY::R_UT_SHARED);
         }
         // both candidates for the next run's rank state (its ctxRun gets one more bit: run < 3)
         const u32 ctxRank4n = ((ctxRank4 << 2) | (rank0 < 3u ? rank0 : 3u)) & 0xffu;
@@ -260,12 +308,12 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
             u32 eu = 1;
             for (;;) {
                 const u32 k = eu - 1u;
-                if (k < UE_RES) b = qd6_dec3<LY, K_RUN_E>(sm, rc, LY::R_UE_STATE + st2 * UE_RES + k, LY::R_UE_CHAR + cur * UE_RES + k, LY::R_UE_SHARED + k);
+                if (k < UE_RES) b = qd6_dec3<LY, K_RUN_E>(sm, rc, mv, LY::R_UE_STATE + st2 * UE_RES + k, LY::R_UE_CHAR + cur * UE_RES + k, LY::R_UE_SHARED + k);
                 else {
                     const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, ue_idx(st2, k), st_miss);
                     const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, ue_idx(cur, k), st_miss);
                     st_cached += 2;
-                    b = qd6_dec3<LY, K_RUN_E>(sm, rc, is, ic, LY::R_UE_SHARED + k);
+                    b = qd6_dec3<LY, K_RUN_E>(sm, rc, mv, is, ic, LY::R_UE_SHARED + k);
                 }
                 if (!b) break;
                 if (++eu >= 31u) break;                                          // corrupt-input guard
@@ -274,7 +322,7 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
             if (eu <= LY::MAXE_U) {
                 const u32 bs = LY::R_UM_STATE + st2 * LY::ROW_U + (1u << eu) - 2u, bc = LY::R_UM_CHAR + cur * LY::ROW_U + (1u << eu) - 2u, bg = LY::R_NARROW_SHARED + eu * 32u;
                 for (u32 node = 1, bit = eu; bit > 0; --bit) {
-                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, bs + node, bc + node, bg + node);
+                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, mv, bs + node, bc + node, bg + node);
                     run = 2u * run + b; node = 2u * node + b;
                 }
             } else {
@@ -282,7 +330,7 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
                     const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, narrow_idx(eu, st2, node), st_miss);
                     const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, narrow_idx(eu, cur, node), st_miss);
                     st_cached += 2;
-                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, is, ic, LY::R_NARROW_SHARED + eu * 32u + node);
+                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, mv, is, ic, LY::R_NARROW_SHARED + eu * 32u + node);
                     run = 2u * run + b; node = eu <= 5u ? 2u * node + b : node + 1u;   // qlfc.cpp:1119: tree contexts up to 5 bits, linear above
                 }
             }
@@ -332,7 +380,7 @@ template <class LY> __device__ __forceinline__ void qd6_smem_init(u8 *raw, const
 }
 
 template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode6(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
-                                                                              const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+                                                                              const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)   // the moves table (QD6_MOVES ints) follows the QTables
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
     qd6_smem_init<LY>(q_smem_raw, tables);
@@ -342,7 +390,7 @@ template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode6(c
     SubBlock &sb = sbs[sid];
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 st_cached = 0, st_miss = 0;
-    const int r = qd6_decode_stream<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss);
+    const int r = qd6_decode_stream<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), st_cached, st_miss);
     if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
 #endif

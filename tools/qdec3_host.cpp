@@ -115,7 +115,8 @@ template <class LY> static int qdec6_run(const unsigned char *in, unsigned in_si
     for (size_t i = 0; i < 2 * (size_t)COLD_PAD; ++i) cold[i] = 2048;
     SM3 sm; sm.b = smem;
     u32 st_cached = 0, st_miss = 0;
-    const int r = qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
+    int moves[QD6_MOVES]; qd6_fill_moves(moves);
+    const int r = qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss);
     if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
     free(smem); free(cold);
     return r;
