@@ -279,8 +279,10 @@ static const QTables *get_tables(Ctx *ctx)
 {
     if (!ctx->qlfc_tables) {
         QTables *d = nullptr;
-        static int h_moves[QD6_MOVES];                     // multipliers of the hot counter moves (qlfc_decoder6.cuh), stored right after the tables
-        qd6_fill_moves(h_moves);
+        // multipliers of the hot counter moves (qlfc_decoder6.cuh), stored right after the tables; filled once (thread-safe static init)
+        struct Moves { int v[QD6_MOVES]; };
+        static const Moves h_moves_ = [] { Moves m; qd6_fill_moves(m.v); return m; }();
+        const int (&h_moves)[QD6_MOVES] = h_moves_.v;
         CUDA_TRY(cudaMalloc((void **)&d, sizeof(QTables) + sizeof(h_moves)));
         CUDA_TRY(cudaMemcpyAsync(d->rank_state, bscb_rank_state_tab, 32768, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(d->run_state, bscb_run_state_tab, 8192, cudaMemcpyHostToDevice, ctx->stream));
