@@ -371,14 +371,15 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     }
     const size_t enc_smem = ((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe);
     static_assert(((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448, "encoder working set must fit the 227 KB of one SM");
-    PROF_BYTES(ctx, (double)n);                          // + c written; the launch is latency-, not bandwidth-bound
     if (fast) {
         LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
         ensure_dyn_smem(q_fast_encode, ctx->device, sizeof(FastSmem));
+        PROF_BYTES(ctx, (double)n);
         LAUNCH(ctx, q_fast_encode, nBlocks, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)nullptr);
     } else {
         init_models(ctx, models, nBlocks);
         ensure_dyn_smem(q_encode5, ctx->device, enc_smem);
+        PROF_BYTES(ctx, (double)n);                      // + c written; the launch is latency-, not bandwidth-bound
         LAUNCH(ctx, q_encode5, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
@@ -506,13 +507,14 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         CUDA_TRY(cudaMemcpyAsync(d_sb, h_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(d_list, list, sizeof(u32) * Q_MAX_SUB, cudaMemcpyHostToDevice, ctx->stream));
         ctx->sync();
-        PROF_BYTES(ctx, (double)in_size + (double)out_cap);
         if (coder == 3) {
             LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nlist);
             ensure_dyn_smem(q_fast_decode, ctx->device, sizeof(FastSmem));
+            PROF_BYTES(ctx, (double)in_size + (double)out_cap);
             LAUNCH(ctx, q_fast_decode, nlist, 32, sizeof(FastSmem), d_in, d_sb, models, d_out, (const u32 *)d_list);
         } else {
             init_models(ctx, models, nlist);
+            PROF_BYTES(ctx, (double)in_size + (double)out_cap);
             static const bool prof = getenv("BSCB200_QDEC_PROF") != nullptr;          // per-phase cycle counts (diagnostic)
             const int gen = decoder_generation();
 #define LAUNCH_DEC3(MODE, PROF) do { ensure_dyn_smem(q_decode3<MODE, PROF>, ctx->device, sizeof(Dec3Smem)); \
