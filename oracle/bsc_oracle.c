@@ -313,6 +313,50 @@ static void decide_learn(int k, short *s, short *c, short *g, unsigned bit)
     ctr_move(s, w + 3, bit); ctr_move(c, w + 7, bit); ctr_move(g, w + 11, bit);
 }
 
+/* ---- adaptive variant (coder id 2, `-e2`): same decisions and the same three counters, but their probabilities go   */
+/* through a per-context logistic mixer with on-line weights plus a 17-point probability map (predictor.h:74-213,      */
+/* qlfc_model.h:38-113 M_* constants, 225-231 mixer arrays, qlfc_model.cpp:49-68 start values).                         */
+extern const unsigned char orc_stretch_le16[], orc_squash_le16[];
+extern const short orc_adaptive_params[7][19];
+static int tab16(const unsigned char *t, int i) { return (int16_t)(uint16_t)(t[2 * i] | (t[2 * i + 1] << 8)); }
+static int stretch(int p) { return tab16(orc_stretch_le16, p); }              /* tables.h:1848 */
+static int squash(int s)  { return tab16(orc_squash_le16, 2048 + s); }        /* tables.h:1853 */
+
+typedef struct { int16_t s0, s1, s2; int mixed, index; short map[17]; int w0, w1, w2; } orc_mixer;
+typedef struct { orc_mixer rank[256], rankExp[8][8], rankMan[8], rankEsc[256], run[256], runExp[32][32], runMan[32]; } orc_mixers;
+
+static void mixer_init(orc_mixer *m)                                           /* predictor.h:96-103 */
+{
+    m->w0 = m->w1 = 2048 << 5; m->w2 = 0;
+    for (int p = 0; p < 17; ++p) m->map[p] = (short)squash((p - 8) * 256);
+}
+static orc_mixers *mixers_new(void)
+{
+    orc_mixers *x = calloc(1, sizeof *x);
+    if (x) { orc_mixer *m = (orc_mixer *)x; for (size_t i = 0; i < sizeof *x / sizeof *m; ++i) mixer_init(m + i); }
+    return x;
+}
+static int mixer_mixup(orc_mixer *m, int pChar, int pState, int pShared)       /* predictor.h:105-123: arguments in this order */
+{
+    m->s0 = (int16_t)stretch(pChar); m->s1 = (int16_t)stretch(pState); m->s2 = (int16_t)stretch(pShared);
+    int16_t sp = (int16_t)((m->s0 * m->w0 + m->s1 * m->w1 + m->s2 * m->w2) >> 17);   /* the reference keeps this in a short */
+    if (sp < -2047) sp = -2047;
+    if (sp > 2047) sp = 2047;
+    m->index = (sp + 2048) >> 8;
+    int weight = sp & 255, probability = squash(sp);
+    int mapped = m->map[m->index] + (((m->map[m->index + 1] - m->map[m->index]) * weight) >> 8);
+    return m->mixed = (3 * probability + mapped) >> 2;
+}
+static void mixer_learn(orc_mixer *m, const short *q, unsigned bit)            /* predictor.h:185-211; q = {TH0,AR0,TH1,AR1,LR0,LR1,LR2} */
+{
+    ctr_move(&m->map[m->index], q, bit); ctr_move(&m->map[m->index + 1], q, bit);
+    int eps = m->mixed - (bit ? 1 : 4095);
+    /* int products as the reference computes them (two's-complement wrap on overflow) */
+    m->w0 -= (int)((uint32_t)(q[4] * eps) * (uint32_t)(int)m->s0) >> 16;
+    m->w1 -= (int)((uint32_t)(q[5] * eps) * (uint32_t)(int)m->s1) >> 16;
+    m->w2 -= (int)((uint32_t)(q[6] * eps) * (uint32_t)(int)m->s2) >> 16;
+}
+
 typedef struct {
     int ctxRank0, ctxRank4, ctxRun, maxRank, avgRank;
     unsigned char rankHist[256], runHist[256];
@@ -341,14 +385,28 @@ static void header_options(const unsigned char *used, int prev, int prefix, int 
         if ((c == prev || !used[c]) && (c >> (bit + 1)) == prefix) { if (c & (1 << bit)) *can1 = 1; else *can0 = 1; }
 }
 
-#define ENC(K, S, C, G, BIT) do { short *s_ = (S), *c_ = (C), *g_ = (G); unsigned b_ = (BIT); \
-        int p_ = decide_p((K), s_, c_, g_); decide_learn((K), s_, c_, g_, b_); rc_encode(&rc, b_, p_); } while (0)
+/* one decision of either model-1 coder: static (mx == NULL) mixes with fixed weights, adaptive goes through mixer MIX */
+static int decide2_p(const orc_mixers *mx, int k, orc_mixer *mix, const short *s, const short *c, const short *g)
+{
+    return mx ? mixer_mixup(mix, *c, *s, *g) : decide_p(k, s, c, g);
+}
+static void decide2_learn(const orc_mixers *mx, int k, orc_mixer *mix, short *s, short *c, short *g, unsigned bit)
+{
+    if (!mx) { decide_learn(k, s, c, g, bit); return; }
+    const short *w = orc_adaptive_params[k];
+    ctr_move(s, w, bit); ctr_move(c, w + 4, bit); ctr_move(g, w + 8, bit);
+    mixer_learn(mix, w + 12, bit);
+}
+#define ENC(K, S, C, G, MIX, BIT) do { short *s_ = (S), *c_ = (C), *g_ = (G); unsigned b_ = (BIT); orc_mixer *m_ = mx ? (MIX) : NULL; \
+        int p_ = decide2_p(mx, (K), m_, s_, c_, g_); decide2_learn(mx, (K), m_, s_, c_, g_, b_); rc_encode(&rc, b_, p_); } while (0)
+#define MAXI(a, b) ((a) > (b) ? (a) : (b))
 
-int orc_qlfc_static_encode_block(const unsigned char *in, unsigned char *out, int inSize, int outSize)
+static int qlfc1_encode_block(const unsigned char *in, unsigned char *out, int inSize, int outSize, int adaptive)
 {
     orc_model *m = model_new();
+    orc_mixers *mx = adaptive ? mixers_new() : NULL;
     unsigned char *ranks = malloc((size_t)inSize > 0 ? (size_t)inSize : 1);
-    if (!m || !ranks) { free(m); free(ranks); return ORC_NOT_ENOUGH_MEMORY; }
+    if (!m || !ranks || (adaptive && !mx)) { free(m); free(ranks); free(mx); return ORC_NOT_ENOUGH_MEMORY; }
     unsigned char mtf[256];
     int R = orc_qlfc_transform(in, inSize, ranks, mtf);
 
@@ -375,19 +433,19 @@ int orc_qlfc_static_encode_block(const unsigned char *in, unsigned char *out, in
         while (pos + run < inSize && in[pos + run] == c) ++run;
         pos += run;
         int rank = ranks[t];
-        int st = rank_state(&x, c);
+        int st = rank_state(&x, c), h = x.rankHist[c];
 
         if (x.avgRank < 32) {
-            ENC(K_RANK_T, &m->rt_state[st], &m->rt_char[c], &m->rt_shared, rank != 1);
+            ENC(K_RANK_T, &m->rt_state[st], &m->rt_char[c], &m->rt_shared, &mx->rank[c], rank != 1);
             if (rank == 1) x.rankHist[c] = 0;
             else {
                 int e = ilog2((unsigned)rank); x.rankHist[c] = (unsigned char)e;
-                for (int b = 1; b < e; ++b) ENC(K_RANK_E, &m->re_state[st][b - 1], &m->re_char[c][b - 1], &m->re_shared[b - 1], 1);
-                if (e < x.maxRank)          ENC(K_RANK_E, &m->re_state[st][e - 1], &m->re_char[c][e - 1], &m->re_shared[e - 1], 0);
+                for (int b = 1; b < e; ++b) ENC(K_RANK_E, &m->re_state[st][b - 1], &m->re_char[c][b - 1], &m->re_shared[b - 1], &mx->rankExp[MAXI(h, b)][b], 1);
+                if (e < x.maxRank)          ENC(K_RANK_E, &m->re_state[st][e - 1], &m->re_char[c][e - 1], &m->re_shared[e - 1], &mx->rankExp[MAXI(h, e)][e], 0);
                 wide_bank *bk = &m->rm[e];
                 for (int node = 1, bit = e - 1; bit >= 0; --bit) {
                     unsigned b = ((unsigned)rank >> bit) & 1;
-                    ENC(K_RANK_M, &bk->by_state[st][node], &bk->by_char[c][node], &bk->shared[node], b);
+                    ENC(K_RANK_M, &bk->by_state[st][node], &bk->by_char[c][node], &bk->shared[node], &mx->rankMan[e], b);
                     node = 2 * node + (int)b;
                 }
             }
@@ -395,41 +453,44 @@ int orc_qlfc_static_encode_block(const unsigned char *in, unsigned char *out, in
             x.rankHist[c] = (unsigned char)ilog2((unsigned)rank);
             for (int node = 1, bit = x.maxRank; bit >= 0; --bit) {
                 unsigned b = ((unsigned)rank >> bit) & 1;
-                ENC(K_RANK_P, &m->rp.by_state[st][node], &m->rp.by_char[c][node], &m->rp.shared[node], b);
+                ENC(K_RANK_P, &m->rp.by_state[st][node], &m->rp.by_char[c][node], &m->rp.shared[node], &mx->rankEsc[node], b);
                 node = 2 * node + (int)b;
             }
         }
         x.avgRank = (x.avgRank * 124 + rank * 4) >> 7;
         int rank0 = rank - 1;
-        st = run_state(&x, c, rank0);
+        st = run_state(&x, c, rank0); h = x.runHist[c];
 
-        ENC(K_RUN_T, &m->ut_state[st], &m->ut_char[c], &m->ut_shared, run != 1);
+        ENC(K_RUN_T, &m->ut_state[st], &m->ut_char[c], &m->ut_shared, &mx->run[c], run != 1);
         if (run == 1) x.runHist[c] = (unsigned char)((x.runHist[c] + 2) >> 2);
         else {
             int e = ilog2((unsigned)run); x.runHist[c] = (unsigned char)((x.runHist[c] + 3 * e + 3) >> 2);
-            for (int b = 1; b < e; ++b) ENC(K_RUN_E, &m->ue.by_state[st][b - 1], &m->ue.by_char[c][b - 1], &m->ue.shared[b - 1], 1);
-            ENC(K_RUN_E, &m->ue.by_state[st][e - 1], &m->ue.by_char[c][e - 1], &m->ue.shared[e - 1], 0);
+            for (int b = 1; b < e; ++b) ENC(K_RUN_E, &m->ue.by_state[st][b - 1], &m->ue.by_char[c][b - 1], &m->ue.shared[b - 1], &mx->runExp[MAXI(h, b)][b], 1);
+            ENC(K_RUN_E, &m->ue.by_state[st][e - 1], &m->ue.by_char[c][e - 1], &m->ue.shared[e - 1], &mx->runExp[MAXI(h, e)][e], 0);
             narrow_bank *bk = &m->um[e];
             for (int node = 1, bit = e - 1; bit >= 0; --bit) {
                 unsigned b = ((unsigned)run >> bit) & 1;
-                ENC(K_RUN_M, &bk->by_state[st][node], &bk->by_char[c][node], &bk->shared[node], b);
+                ENC(K_RUN_M, &bk->by_state[st][node], &bk->by_char[c][node], &bk->shared[node], &mx->runMan[e], b);
                 node = (e <= 5) ? 2 * node + (int)b : node + 1;      /* qlfc.cpp:1119 */
             }
         }
         run_ctx_slide(&x, rank0, run);
     }
     if (result == 0) result = rc_enc_finish(&rc);
-    free(m); free(ranks);
+    free(m); free(ranks); free(mx);
     return result;
 }
+int orc_qlfc_static_encode_block(const unsigned char *in, unsigned char *out, int inSize, int outSize) { return qlfc1_encode_block(in, out, inSize, outSize, 0); }
+int orc_qlfc_adaptive_encode_block(const unsigned char *in, unsigned char *out, int inSize, int outSize) { return qlfc1_encode_block(in, out, inSize, outSize, 1); }
 
-#define DEC(K, S, C, G, BITVAR) do { short *s_ = (S), *c_ = (C), *g_ = (G); \
-        (BITVAR) = rc_decode(&rc, decide_p((K), s_, c_, g_)); decide_learn((K), s_, c_, g_, (BITVAR)); } while (0)
+#define DEC(K, S, C, G, MIX, BITVAR) do { short *s_ = (S), *c_ = (C), *g_ = (G); orc_mixer *m_ = mx ? (MIX) : NULL; \
+        (BITVAR) = rc_decode(&rc, decide2_p(mx, (K), m_, s_, c_, g_)); decide2_learn(mx, (K), m_, s_, c_, g_, (BITVAR)); } while (0)
 
-int orc_qlfc_static_decode_block(const unsigned char *in, unsigned char *out)
+static int qlfc1_decode_block(const unsigned char *in, unsigned char *out, int adaptive)
 {
     orc_model *m = model_new();
-    if (!m) return ORC_NOT_ENOUGH_MEMORY;
+    orc_mixers *mx = adaptive ? mixers_new() : NULL;
+    if (!m || (adaptive && !mx)) { free(m); free(mx); return ORC_NOT_ENOUGH_MEMORY; }
     run_ctx x; run_ctx_init(&x);
     rc_dec rc; rc_dec_init(&rc, in);
     uint32_t n32 = 0; for (int b = 0; b < 32; ++b) n32 = (n32 << 1) | rc_decode(&rc, 2048);
@@ -453,28 +514,28 @@ int orc_qlfc_static_decode_block(const unsigned char *in, unsigned char *out)
 
     for (int i = 0; i < n; ) {
         int c = mtf[0], rank = 1; unsigned b;
-        int st = rank_state(&x, c);
+        int st = rank_state(&x, c), h = x.rankHist[c];
         if (x.avgRank < 32) {
-            DEC(K_RANK_T, &m->rt_state[st], &m->rt_char[c], &m->rt_shared, b);
+            DEC(K_RANK_T, &m->rt_state[st], &m->rt_char[c], &m->rt_shared, &mx->rank[c], b);
             if (!b) x.rankHist[c] = 0;
             else {
                 int e = 1;
                 while (e != x.maxRank) {
-                    DEC(K_RANK_E, &m->re_state[st][e - 1], &m->re_char[c][e - 1], &m->re_shared[e - 1], b);
+                    DEC(K_RANK_E, &m->re_state[st][e - 1], &m->re_char[c][e - 1], &m->re_shared[e - 1], &mx->rankExp[MAXI(h, e) & 7][e & 7], b);
                     if (!b) break;
                     ++e;
                 }
                 x.rankHist[c] = (unsigned char)e;
                 wide_bank *bk = &m->rm[e];
                 for (int bit = e - 1; bit >= 0; --bit) {
-                    DEC(K_RANK_M, &bk->by_state[st][rank], &bk->by_char[c][rank], &bk->shared[rank], b);
+                    DEC(K_RANK_M, &bk->by_state[st][rank], &bk->by_char[c][rank], &bk->shared[rank], &mx->rankMan[e & 7], b);
                     rank = 2 * rank + (int)b;
                 }
             }
         } else {
             rank = 0;
             for (int node = 1, bit = x.maxRank; bit >= 0; --bit) {
-                DEC(K_RANK_P, &m->rp.by_state[st][node], &m->rp.by_char[c][node], &m->rp.shared[node], b);
+                DEC(K_RANK_P, &m->rp.by_state[st][node], &m->rp.by_char[c][node], &m->rp.shared[node], &mx->rankEsc[node & 255], b);
                 node = 2 * node + (int)b; rank = 2 * rank + (int)b;
             }
             x.rankHist[c] = (unsigned char)ilog2((unsigned)rank);
@@ -485,21 +546,21 @@ int orc_qlfc_static_decode_block(const unsigned char *in, unsigned char *out)
 
         x.avgRank = (x.avgRank * 124 + rank * 4) >> 7;
         int rank0 = rank - 1;
-        st = run_state(&x, c, rank0);
+        st = run_state(&x, c, rank0); h = x.runHist[c];
         int run = 1;
-        DEC(K_RUN_T, &m->ut_state[st], &m->ut_char[c], &m->ut_shared, b);
+        DEC(K_RUN_T, &m->ut_state[st], &m->ut_char[c], &m->ut_shared, &mx->run[c], b);
         if (!b) x.runHist[c] = (unsigned char)((x.runHist[c] + 2) >> 2);
         else {
             int e = 1;
             for (;;) {
-                DEC(K_RUN_E, &m->ue.by_state[st][e - 1], &m->ue.by_char[c][e - 1], &m->ue.shared[e - 1], b);
+                DEC(K_RUN_E, &m->ue.by_state[st][e - 1], &m->ue.by_char[c][e - 1], &m->ue.shared[e - 1], &mx->runExp[MAXI(h, e) & 31][e & 31], b);
                 if (!b) break;
                 ++e;
             }
             x.runHist[c] = (unsigned char)((x.runHist[c] + 3 * e + 3) >> 2);
             narrow_bank *bk = &m->um[e];
             for (int node = 1, bit = e - 1; bit >= 0; --bit) {
-                DEC(K_RUN_M, &bk->by_state[st][node], &bk->by_char[c][node], &bk->shared[node], b);
+                DEC(K_RUN_M, &bk->by_state[st][node], &bk->by_char[c][node], &bk->shared[node], &mx->runMan[e & 31], b);
                 run = 2 * run + (int)b;
                 node = (e <= 5) ? 2 * node + (int)b : node + 1;
             }
@@ -507,9 +568,11 @@ int orc_qlfc_static_decode_block(const unsigned char *in, unsigned char *out)
         run_ctx_slide(&x, rank0, run);
         for (; run > 0; --run) out[i++] = (unsigned char)c;
     }
-    free(m);
+    free(m); free(mx);
     return n;
 }
+int orc_qlfc_static_decode_block(const unsigned char *in, unsigned char *out) { return qlfc1_decode_block(in, out, 0); }
+int orc_qlfc_adaptive_decode_block(const unsigned char *in, unsigned char *out) { return qlfc1_decode_block(in, out, 1); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* Fast QLFC coder (coder id 3, `-e0`).  qlfc.cpp:1135-1336 (encoder), 1933-2127 (decoder),      */
@@ -710,17 +773,16 @@ void orc_coder_split_blocks(const unsigned char *in, int n, int nBlocks, int *st
 
 static int encode_block(int coder, const unsigned char *in, unsigned char *out, int inSize, int outSize)   /* coder.cpp:61-68 */
 {
-    return coder == 3 ? orc_qlfc_fast_encode_block(in, out, inSize, outSize) : orc_qlfc_static_encode_block(in, out, inSize, outSize);
+    return coder == 3 ? orc_qlfc_fast_encode_block(in, out, inSize, outSize) : qlfc1_encode_block(in, out, inSize, outSize, coder == 2);
 }
 static int decode_block(int coder, const unsigned char *in, unsigned char *out)                             /* coder.cpp:264-271 */
 {
-    return coder == 3 ? orc_qlfc_fast_decode_block(in, out) : orc_qlfc_static_decode_block(in, out);
+    return coder == 3 ? orc_qlfc_fast_decode_block(in, out) : qlfc1_decode_block(in, out, coder == 2);
 }
 
 int orc_coder_compress(const unsigned char *in, unsigned char *out, int n, int coder, int features)
 {
-    if (coder == 2) return ORC_NOT_SUPPORTED;            /* adaptive QLFC: not restated yet */
-    if (coder != 1 && coder != 3) return ORC_BAD_PARAMETER;
+    if (coder < 1 || coder > 3) return ORC_BAD_PARAMETER;
     int nBlocks = orc_coder_num_blocks(n);
     if (nBlocks == 1) {
         int r = encode_block(coder, in, out + 1, n, n - 1);
@@ -764,8 +826,7 @@ int orc_coder_compress(const unsigned char *in, unsigned char *out, int n, int c
 
 int orc_coder_decompress(const unsigned char *in, unsigned char *out, int coder)
 {
-    if (coder == 2) return ORC_NOT_SUPPORTED;
-    if (coder != 1 && coder != 3) return ORC_BAD_PARAMETER;
+    if (coder < 1 || coder > 3) return ORC_BAD_PARAMETER;
     int nBlocks = in[0];
     if (nBlocks == 1) return decode_block(coder, in + 1, out);
     int inPtr = 1 + 8 * nBlocks, outPtr = 0, total = 0, err = 0;

@@ -52,6 +52,10 @@ int orc_qlfc_static_encode_block(const unsigned char *in, unsigned char *out, in
 /* libbsc/coder/qlfc/qlfc.cpp:2186 / 1672 bsc_qlfc_static_decode_block */
 int orc_qlfc_static_decode_block(const unsigned char *in, unsigned char *out);
 
+/* libbsc/coder/qlfc/qlfc.cpp:2153 / 463 bsc_qlfc_adaptive_encode_block, 2200 / 1366 bsc_qlfc_adaptive_decode_block (coder id 2) */
+int orc_qlfc_adaptive_encode_block(const unsigned char *in, unsigned char *out, int inSize, int outSize);
+int orc_qlfc_adaptive_decode_block(const unsigned char *in, unsigned char *out);
+
 /* libbsc/coder/qlfc/qlfc.cpp:2168 / 1135 bsc_qlfc_fast_encode_block, 2213 / 1933 bsc_qlfc_fast_decode_block (coder id 3) */
 int orc_qlfc_fast_encode_block(const unsigned char *in, unsigned char *out, int inSize, int outSize);
 int orc_qlfc_fast_decode_block(const unsigned char *in, unsigned char *out);
@@ -59,7 +63,7 @@ int orc_qlfc_fast_decode_block(const unsigned char *in, unsigned char *out);
 /* libbsc/coder/coder.cpp:70 bsc_coder_split_blocks */
 int orc_coder_num_blocks(int n);
 void orc_coder_split_blocks(const unsigned char *in, int n, int nBlocks, int *start, int *size);
-/* libbsc/coder/coder.cpp:244 bsc_coder_compress (coder 1 static, 3 fast; 2 adaptive -> ORC_NOT_SUPPORTED) */
+/* libbsc/coder/coder.cpp:244 bsc_coder_compress (coder 1 static, 2 adaptive, 3 fast) */
 int orc_coder_compress(const unsigned char *in, unsigned char *out, int n, int coder, int features);
 /* libbsc/coder/coder.cpp:273 bsc_coder_decompress */
 int orc_coder_decompress(const unsigned char *in, unsigned char *out, int coder);

@@ -150,6 +150,8 @@ class Port(_Api):
         self.f_dec_block = s("qlfc_static_decode_block", [vp, vp])
         self.f_enc_fast = s("qlfc_fast_encode_block", [vp, vp, ci, ci])
         self.f_dec_fast = s("qlfc_fast_decode_block", [vp, vp])
+        self.f_enc_adapt = s("qlfc_adaptive_encode_block", [vp, vp, ci, ci])
+        self.f_dec_adapt = s("qlfc_adaptive_decode_block", [vp, vp])
         self.f_split = s("coder_split_blocks", [vp, ci, ci, vp, vp], None)
         self.f_cc = s("coder_compress", [vp, vp, ci, ci, ci])
         self.f_cd = s("coder_decompress", [vp, vp, ci])
@@ -179,11 +181,11 @@ class Port(_Api):
         return ranks[:R].copy(), mtf
 
     def encode_block(self, data, out_size=None, coder=1):
-        """One QLFC stream (bsc_qlfc_{static,fast}_encode_block); coder 1 static, 3 fast."""
+        """One QLFC stream (bsc_qlfc_{static,adaptive,fast}_encode_block); coder 1 static, 2 adaptive, 3 fast."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         out_size = data.size if out_size is None else out_size
         out = np.empty(data.size + 4096, dtype=np.uint8)
-        f = self.f_enc_fast if coder == 3 else self.f_enc_block
+        f = {1: self.f_enc_block, 2: self.f_enc_adapt, 3: self.f_enc_fast}[coder]
         r = f(_ptr(data), _ptr(out), data.size, out_size)
         return r, (out[:r].copy() if r > 0 else None)
 
@@ -191,7 +193,7 @@ class Port(_Api):
         s = np.zeros(len(stream) + 64, dtype=np.uint8)
         s[:len(stream)] = stream
         out = np.empty(n + 64, dtype=np.uint8)
-        f = self.f_dec_fast if coder == 3 else self.f_dec_block
+        f = {1: self.f_dec_block, 2: self.f_dec_adapt, 3: self.f_dec_fast}[coder]
         r = f(_ptr(s), _ptr(out))
         return r, out[:max(r, 0)].copy()
 
@@ -245,6 +247,8 @@ class Ref(_Api):
         self.f_dec_block = s("qlfc_static_decode_block", [vp, vp])
         self.f_enc_fast = s("qlfc_fast_encode_block", [vp, vp, ci, ci])
         self.f_dec_fast = s("qlfc_fast_decode_block", [vp, vp])
+        self.f_enc_adapt = s("qlfc_adaptive_encode_block", [vp, vp, ci, ci])
+        self.f_dec_adapt = s("qlfc_adaptive_decode_block", [vp, vp])
         self.f_cc = s("coder_compress", [vp, vp, ci, ci, ci])
         self.f_cd = s("coder_decompress", [vp, vp, ci, ci])
         self.f_store = s("store", [vp, vp, ci, ci])
@@ -273,11 +277,11 @@ class Ref(_Api):
         return r, T
 
     def encode_block(self, data, out_size=None, coder=1):
-        """One QLFC stream (bsc_qlfc_{static,fast}_encode_block); coder 1 static, 3 fast."""
+        """One QLFC stream (bsc_qlfc_{static,adaptive,fast}_encode_block); coder 1 static, 2 adaptive, 3 fast."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         out_size = data.size if out_size is None else out_size
         out = np.empty(data.size + 4096, dtype=np.uint8)
-        f = self.f_enc_fast if coder == 3 else self.f_enc_block
+        f = {1: self.f_enc_block, 2: self.f_enc_adapt, 3: self.f_enc_fast}[coder]
         r = f(_ptr(data), _ptr(out), data.size, out_size)
         return r, (out[:r].copy() if r > 0 else None)
 
@@ -285,7 +289,7 @@ class Ref(_Api):
         s = np.zeros(len(stream) + 64, dtype=np.uint8)
         s[:len(stream)] = stream
         out = np.empty(n + 64, dtype=np.uint8)
-        f = self.f_dec_fast if coder == 3 else self.f_dec_block
+        f = {1: self.f_dec_block, 2: self.f_dec_adapt, 3: self.f_dec_fast}[coder]
         r = f(_ptr(s), _ptr(out))
         return r, out[:max(r, 0)].copy()
 

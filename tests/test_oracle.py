@@ -110,33 +110,35 @@ def test_port_transform_and_split(gen, port, ref):
         assert r1 == r2 and np.array_equal(s1, s2)
 
 
-def test_port_fast_coder_matches_reference(gen, port, ref):
-    """Coder id 3 (`-e0`, qlfc.cpp:1135-1336 / 1933-2127): streams, container and blocks equal the reference's,
-    including the header's unnormalised-bit quirk (rangecoder.h:165-177 called with `c & (1 << bit)`)."""
+@pytest.mark.parametrize("coder", [2, 3])
+def test_port_other_coders_match_reference(gen, port, ref, coder):
+    """Coder ids 2 (adaptive `-e2`, qlfc.cpp:463-823 / 1366-1666, logistic mixing predictor.h:74-213) and 3 (fast `-e0`,
+    qlfc.cpp:1135-1336 / 1933-2127): streams, container and blocks equal the reference's -- for the fast coder including
+    the header's unnormalised-bit quirk (rangecoder.h:165-177 called with `c & (1 << bit)`)."""
     rng = np.random.default_rng(5)
     extra = [("long runs", np.repeat(rng.integers(0, 200, 2000, dtype=np.uint8), rng.integers(1, 3000, 2000))),
              ("huge run", np.concatenate([gen.text(3, 5000), np.full(3 << 20, 7, np.uint8), gen.text(4, 3000)])),
              ("alpha2", rng.integers(0, 2, 65536, dtype=np.uint8))]
     for name, a in list(_inputs(gen)) + extra:
         L = ref.bwt_encode(a)[1] if a.size < (1 << 20) + 1 else a
-        r1, s1 = port.encode_block(L, coder=3)
-        r2, s2 = ref.encode_block(L, coder=3)
+        r1, s1 = port.encode_block(L, coder=coder)
+        r2, s2 = ref.encode_block(L, coder=coder)
         assert r1 == r2, (name, r1, r2)
         if r2 > 0:
             assert np.array_equal(s1, s2), name
-            n, o = port.decode_block(s2, L.size, coder=3)
+            n, o = port.decode_block(s2, L.size, coder=coder)
             assert n == L.size and np.array_equal(o, L), name
         for feats in (1, 3):
-            c1, t1 = port.coder_compress(L, 3, feats)
-            c2, t2 = ref.coder_compress(L, 3, feats)
+            c1, t1 = port.coder_compress(L, coder, feats)
+            c2, t2 = ref.coder_compress(L, coder, feats)
             assert c1 == c2, (name, feats)
             if c2 > 0:
                 assert np.array_equal(t1, t2), (name, feats)
-                n, o = port.coder_decompress(t2, L.size, 3)
+                n, o = port.coder_decompress(t2, L.size, coder)
                 assert n == L.size and np.array_equal(o, L), name
     a = gen.text(2, 3 << 20)
-    z1, b1 = port.compress(a, 1, 3, 3)
-    z2, b2 = ref.compress(a, 1, 3, 3)
+    z1, b1 = port.compress(a, 1, coder, 3)
+    z2, b2 = ref.compress(a, 1, coder, 3)
     assert z1 == z2 and np.array_equal(b1, b2)
     assert port.decompress(b2)[0] == 0 and ref.decompress(b1)[0] == 0
 
