@@ -1,0 +1,18 @@
+#!/bin/bash
+# tools/round2_first_gpu_call.sh -- everything that was prepared WITHOUT a GPU at the end of round 1, in the order it should
+# meet one (gpurun --timeout 900 -- 'bash tools/round2_first_gpu_call.sh').  Each step is bounded by its own timeout and
+# writes to gpurun_out/; nothing here changes defaults.  Expected: ~6-8 minutes.
+mkdir -p gpurun_out
+{
+echo "== 1. default parity suite"
+timeout 200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+echo "== 2. fast coder (coder id 3): parity through the C ABI, then lift the gate in qlfc.cu:coder_gate"
+BSCB200_ENABLE_FAST=1 timeout 200 python -m pytest tests/test_gpu_fast_coder.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -3
+echo "== 3. decoder A/B on one 64 MiB block: 4 = default, 7 = tuned code + full layout, 6 = tuned code + diet layout (2 streams/SM)"
+timeout 200 python tools/dec_ab.py 64 4 7 6 2>&1 | tail -4
+echo "== 4. parity of the diet decoder as the default decoder"
+BSCB200_QDEC=6 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
+echo "== 5. does co-residency pay?  36 blocks per GPU: default decoder vs diet decoder"
+timeout 300 python bench.py --blocks 36 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench36_gen4.json 2> gpurun_out/r2_bench36_gen4.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench36_gen4.json'));print('gen4 36 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
+BSCB200_QDEC=6 timeout 300 python bench.py --blocks 36 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench36_gen6.json 2> gpurun_out/r2_bench36_gen6.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench36_gen6.json'));print('gen6 36 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
+} 2>&1 | tee gpurun_out/r2_first_call.log
