@@ -42,7 +42,7 @@ extern "C" {
 #endif
 #define LIBBSC_BLOCKSORTER_BWT         1   /* 3..8 = ST3..ST8 */
 #define LIBBSC_CODER_QLFC_STATIC       1
-#define LIBBSC_CODER_QLFC_ADAPTIVE     2   /* not on the device yet: LIBBSC_NOT_SUPPORTED */
+#define LIBBSC_CODER_QLFC_ADAPTIVE     2   /* experimental: LIBBSC_NOT_SUPPORTED unless BSCB200_ENABLE_ADAPTIVE=1 (csrc/qlfc_adaptive.cuh) */
 #define LIBBSC_CODER_QLFC_FAST         3   /* experimental: LIBBSC_NOT_SUPPORTED unless BSCB200_ENABLE_FAST=1 (csrc/qlfc_fast.cuh) */
 
 /* ---- group 1: libbsc-compatible entry points -------------------------------------------- */

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "stages.cuh"
 #include "qlfc_tables.inc"
+#include "qlfc_tables2.inc"
 
 #define Q_MAX_SUB 8
 
@@ -258,6 +259,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 #include "qlfc_decoder3.cuh"
 #include "qlfc_fast.cuh"
 #include "qlfc_decoder6.cuh"
+#include "qlfc_adaptive.cuh"
 #include "qlfc_encoder.cuh"
 
 constexpr size_t MODEL_SHORTS_PAD = 2 * (size_t)COLD_PAD;     // by-state + by-symbol cold arrays per stream
@@ -283,10 +285,14 @@ static const QTables *get_tables(Ctx *ctx)
         struct Moves { int v[QD6_MOVES]; };
         static const Moves h_moves_ = [] { Moves m; qd6_fill_moves(m.v); return m; }();
         const int (&h_moves)[QD6_MOVES] = h_moves_.v;
-        CUDA_TRY(cudaMalloc((void **)&d, sizeof(QTables) + sizeof(h_moves)));
+        // device image: QTables | moves (padded to 128 B) | stretch | squash (the adaptive coder's tables, qlfc_adaptive.cuh)
+        static_assert(sizeof(h_moves) <= 128, "moves table slot");
+        CUDA_TRY(cudaMalloc((void **)&d, sizeof(QTables) + 128 + 2 * QA_TAB_BYTES));
         CUDA_TRY(cudaMemcpyAsync(d->rank_state, bscb_rank_state_tab, 32768, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(d->run_state, bscb_run_state_tab, 8192, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(d + 1, h_moves, sizeof(h_moves), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync((u8 *)(d + 1) + 128, bscb_stretch_le16, 2 * 4097, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync((u8 *)(d + 1) + 128 + QA_TAB_BYTES, bscb_squash_le16, 2 * 4097, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyToSymbolAsync(c_params, bscb_static_params, sizeof(c_params), 0, cudaMemcpyHostToDevice, ctx->stream));
         ctx->sync();
         ctx->qlfc_tables = d;
@@ -294,13 +300,15 @@ static const QTables *get_tables(Ctx *ctx)
     return (const QTables *)ctx->qlfc_tables;
 }
 
-// Coder ids (libbsc.h:60-62): 1 static, 2 adaptive, 3 fast.  The fast coder's kernels (qlfc_fast.cuh) are bit-exact in host
-// emulation but have not run on a GPU yet, so they stay behind BSCB200_ENABLE_FAST=1 until the parity tests have seen them.
+// Coder ids (libbsc.h:60-62): 1 static, 2 adaptive, 3 fast.  The kernels of the adaptive and the fast coder (qlfc_adaptive.cuh,
+// qlfc_fast.cuh) are bit-exact in host emulation but have not run on a GPU yet, so they stay behind BSCB200_ENABLE_ADAPTIVE=1 /
+// BSCB200_ENABLE_FAST=1 until the parity tests have seen them.
 static int coder_gate(int coder)
 {
     if (coder == 1) return LIBBSC_NO_ERROR;
+    if (coder == 2) { static const bool on = [] { const char *e = getenv("BSCB200_ENABLE_ADAPTIVE"); return e && e[0] == '1'; }(); return on ? LIBBSC_NO_ERROR : LIBBSC_NOT_SUPPORTED; }
     if (coder == 3) { static const bool on = [] { const char *e = getenv("BSCB200_ENABLE_FAST"); return e && e[0] == '1'; }(); return on ? LIBBSC_NO_ERROR : LIBBSC_NOT_SUPPORTED; }
-    return coder == 2 ? LIBBSC_NOT_SUPPORTED : LIBBSC_BAD_PARAMETER;
+    return LIBBSC_BAD_PARAMETER;
 }
 static_assert(QF_COLD <= 2 * (size_t)COLD_PAD, "the fast coder's cold counters must fit the per-stream model allocation");
 
@@ -376,6 +384,11 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         ensure_dyn_smem(q_fast_encode, ctx->device, sizeof(FastSmem));
         PROF_BYTES(ctx, (double)n);
         LAUNCH(ctx, q_fast_encode, nBlocks, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)nullptr);
+    } else if (coder == 2) {
+        init_models(ctx, models, nBlocks);
+        ensure_dyn_smem(q_adaptive_encode, ctx->device, QA_BYTES);
+        PROF_BYTES(ctx, (double)n);
+        LAUNCH(ctx, q_adaptive_encode, nBlocks, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     } else {
         init_models(ctx, models, nBlocks);
         ensure_dyn_smem(q_encode5, ctx->device, enc_smem);
@@ -422,6 +435,9 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                 if (fast) {                                // q_fast_encode indexes the cold counters by sub-block id
                     LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
                     LAUNCH(ctx, q_fast_encode, 1, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)d_list);
+                } else if (coder == 2) {
+                    init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
+                    LAUNCH(ctx, q_adaptive_encode, 1, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 } else {
                     init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
                     LAUNCH(ctx, q_encode5, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
@@ -512,6 +528,11 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             ensure_dyn_smem(q_fast_decode, ctx->device, sizeof(FastSmem));
             PROF_BYTES(ctx, (double)in_size + (double)out_cap);
             LAUNCH(ctx, q_fast_decode, nlist, 32, sizeof(FastSmem), d_in, d_sb, models, d_out, (const u32 *)d_list);
+        } else if (coder == 2) {
+            init_models(ctx, models, nlist);
+            ensure_dyn_smem(q_adaptive_decode, ctx->device, QA_BYTES);
+            PROF_BYTES(ctx, (double)in_size + (double)out_cap);
+            LAUNCH(ctx, q_adaptive_decode, nlist, 32, QA_BYTES, d_in, d_sb, models, tables, d_out, (const u32 *)d_list);
         } else {
             init_models(ctx, models, nlist);
             PROF_BYTES(ctx, (double)in_size + (double)out_cap);

@@ -13,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tools", "qdec3_host.cpp")
 LIB = os.path.join(ROOT, "tools", "bin", "libqdec3_host.so")
-DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_decoder3.cuh", "qlfc_decoder6.cuh", "qlfc_fast.cuh", "qlfc_coder.cuh", "qlfc_tables.inc")]
+DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_decoder3.cuh", "qlfc_decoder6.cuh", "qlfc_fast.cuh", "qlfc_adaptive.cuh", "qlfc_tables2.inc", "qlfc_coder.cuh", "qlfc_tables.inc")]
 
 
 def _hostlib():
@@ -83,19 +83,19 @@ def test_host_emulation_rejects_oversized_stream(qdec3, gen, checker):
 
 
 # ---- fast coder (coder id 3): libbsc_b200/csrc/qlfc_fast.cuh on the host -------------------------------------------------
-@pytest.fixture(scope="module")
-def qfast():
+def _stream_codec(prefix):
     lib = _hostlib()
     vp, cu = ctypes.c_void_p, ctypes.c_uint
-    lib.qfast_host_decode.restype = ctypes.c_int
-    lib.qfast_host_decode.argtypes = [vp, cu, vp, cu, vp]
-    lib.qfast_host_encode.restype = ctypes.c_int
-    lib.qfast_host_encode.argtypes = [vp, vp, vp, cu, cu, vp, vp, cu, vp]
+    fdec, fenc = getattr(lib, prefix + "_host_decode"), getattr(lib, prefix + "_host_encode")
+    fdec.restype = ctypes.c_int
+    fdec.argtypes = [vp, cu, vp, cu, vp]
+    fenc.restype = ctypes.c_int
+    fenc.argtypes = [vp, vp, vp, cu, cu, vp, vp, cu, vp]
 
     def decode(stream, n):
         stream = np.ascontiguousarray(stream, dtype=np.uint8)
         out = np.full(n + 64, 0xAA, dtype=np.uint8)
-        r = lib.qfast_host_decode(stream.ctypes.data, stream.size, out.ctypes.data, n, None)
+        r = fdec(stream.ctypes.data, stream.size, out.ctypes.data, n, None)
         assert np.all(out[n:] == 0xAA), "wrote past the output slice"
         return r, out[:n]
 
@@ -108,16 +108,21 @@ def qfast():
         out_cap = a.size if out_cap is None else out_cap
         out = np.full(a.size + 4096 + 256, 0xAA, dtype=np.uint8)
         mtf = np.ascontiguousarray(mtf, dtype=np.uint8); ranks = np.ascontiguousarray(ranks, dtype=np.uint8)
-        r = lib.qfast_host_encode(run_pos.ctypes.data, run_sym.ctypes.data, ranks.ctypes.data, heads.size, a.size, mtf.ctypes.data, out.ctypes.data, out_cap, None)
+        r = fenc(run_pos.ctypes.data, run_sym.ctypes.data, ranks.ctypes.data, heads.size, a.size, mtf.ctypes.data, out.ctypes.data, out_cap, None)
         return r, (out[:r].copy() if r > 0 else None)
     return decode, encode
 
 
-def test_fast_coder_host_emulation_matches_oracle(qfast, gen, checker, port):
-    decode, encode = qfast
+@pytest.fixture(scope="module")
+def qfast():
+    return _stream_codec("qfast")
+
+
+def _check_stream_codec(codec, coder, gen, checker, port):
+    decode, encode = codec
     covered = 0
     for name, a in list(inputs(gen, checker)) + [("rand", gen.rand(1, 70000))]:
-        r_ref, s_ref = checker.encode_block(a, coder=3)
+        r_ref, s_ref = checker.encode_block(a, coder=coder)
         ranks, mtf = port.transform(a)
         r, s = encode(a, ranks, mtf)
         assert r == r_ref, (name, r, r_ref)                            # same length, or the same NOT_COMPRESSIBLE (-3)
@@ -128,7 +133,19 @@ def test_fast_coder_host_emulation_matches_oracle(qfast, gen, checker, port):
             covered += 1
     assert covered >= 10
     a = checker.bwt_encode(gen.text(2, 100000))[1]
-    assert decode(checker.encode_block(a, coder=3)[1], a.size - 1)[0] == -6
+    assert decode(checker.encode_block(a, coder=coder)[1], a.size - 1)[0] == -6
+
+
+def test_fast_coder_host_emulation_matches_oracle(qfast, gen, checker, port):
+    _check_stream_codec(qfast, 3, gen, checker, port)
+
+
+# ---- adaptive coder (coder id 2): libbsc_b200/csrc/qlfc_adaptive.cuh on the host ---------------------------------------
+def test_adaptive_coder_host_emulation_matches_oracle(gen, checker, port):
+    lib = _hostlib()
+    lib.qadapt_smem_bytes.restype = ctypes.c_uint
+    assert lib.qadapt_smem_bytes() <= 227 * 1024
+    _check_stream_codec(_stream_codec("qadapt"), 2, gen, checker, port)
 
 
 # ---- layout-templated decoder (qlfc_decoder6.cuh): full layout = refactoring check, diet layout = two streams per SM -------------

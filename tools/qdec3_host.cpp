@@ -29,6 +29,7 @@ static inline void __syncwarp() {}
 #define __align__(n) alignas(n)
 
 #include "../libbsc_b200/csrc/qlfc_tables.inc"
+#include "../libbsc_b200/csrc/qlfc_tables2.inc"
 
 namespace {
 enum { K_RANK_T, K_RANK_E, K_RANK_M, K_RANK_P, K_RUN_T, K_RUN_E, K_RUN_M };
@@ -39,6 +40,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 #include "../libbsc_b200/csrc/qlfc_decoder3.cuh"
 #include "../libbsc_b200/csrc/qlfc_fast.cuh"
 #include "../libbsc_b200/csrc/qlfc_decoder6.cuh"
+#include "../libbsc_b200/csrc/qlfc_adaptive.cuh"
 }
 
 // Decodes one QLFC static stream (what bsc_qlfc_static_decode_block reads) of `in_size` bytes into out[0..out_cap).
@@ -126,3 +128,45 @@ extern "C" int qdec6_host_decode(const unsigned char *in, unsigned in_size, unsi
     return layout == 0 ? qdec6_run<LayoutFull>(in, in_size, out, out_cap, stats) : qdec6_run<LayoutDiet>(in, in_size, out, out_cap, stats);
 }
 extern "C" unsigned qdec6_smem_bytes(int layout) { return layout == 0 ? LayoutFull::BYTES : LayoutDiet::BYTES; }
+
+// ---- adaptive coder (coder id 2), libbsc_b200/csrc/qlfc_adaptive.cuh ---------------------------------------------------
+static u8 *adaptive_smem_new(short **cold_out)
+{
+    u8 *smem = (u8 *)calloc(1, QA_BYTES);
+    short *cold = (short *)malloc(sizeof(short) * 2 * (size_t)COLD_PAD);
+    if (!smem || !cold) { free(smem); free(cold); return nullptr; }
+    memcpy(smem + ALY::O_RANK_STATE, bscb_rank_state_tab, 32768);
+    memcpy(smem + ALY::O_RUN_STATE, bscb_run_state_tab, 8192);
+    for (u32 i = 0; i < ALY::S16_COUNT; ++i) { const u16 v = 2048; memcpy(smem + ALY::O_S16 + 2 * i, &v, 2); }
+    memcpy(smem + OA_STRETCH, bscb_stretch_le16, 2 * 4097);
+    memcpy(smem + OA_SQUASH, bscb_squash_le16, 2 * 4097);
+    SM3 sm; sm.b = smem;
+    for (u32 m = 0; m < QA_MIXERS; ++m) qa_init_mixer(sm, m);
+    for (size_t i = 0; i < 2 * (size_t)COLD_PAD; ++i) cold[i] = 2048;
+    *cold_out = cold;
+    return smem;
+}
+extern "C" int qadapt_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
+{
+    short *cold = nullptr; u8 *smem = adaptive_smem_new(&cold);
+    if (!smem) return LIBBSC_NOT_ENOUGH_MEMORY;
+    SM3 sm; sm.b = smem;
+    u32 st_cached = 0, st_miss = 0;
+    const int r = qa_decode_stream(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
+    if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
+    free(smem); free(cold);
+    return r;
+}
+extern "C" int qadapt_host_encode(const unsigned *run_pos, const unsigned char *run_sym, const unsigned char *run_rank, unsigned nruns, unsigned in_size,
+                                  const unsigned char *mtf, unsigned char *out, unsigned out_cap, unsigned *stats)
+{
+    short *cold = nullptr; u8 *smem = adaptive_smem_new(&cold);
+    if (!smem) return LIBBSC_NOT_ENOUGH_MEMORY;
+    SM3 sm; sm.b = smem;
+    u32 st_cached = 0, st_miss = 0;
+    const int r = qa_encode_stream(sm, run_pos, run_sym, run_rank, 0, nruns, in_size, mtf, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
+    if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
+    free(smem); free(cold);
+    return r;
+}
+extern "C" unsigned qadapt_smem_bytes(void) { return QA_BYTES; }

@@ -6,8 +6,8 @@ mkdir -p gpurun_out
 {
 echo "== 1. default parity suite"
 timeout 200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-echo "== 2. fast coder (coder id 3): parity through the C ABI, then lift the gate in qlfc.cu:coder_gate"
-BSCB200_ENABLE_FAST=1 timeout 200 python -m pytest tests/test_gpu_fast_coder.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -3
+echo "== 2. adaptive + fast coders (coder ids 2, 3): parity through the C ABI, then lift the gates in qlfc.cu:coder_gate"
+BSCB200_ENABLE_ADAPTIVE=1 BSCB200_ENABLE_FAST=1 timeout 300 python -m pytest tests/test_gpu_other_coders.py tests/test_golden.py -m gpu -q 2>&1 | tail -5
 echo "== 3. decoder A/B on one 64 MiB block: 4 = default, 7 = tuned code + full layout, 6 = tuned code + diet layout (2 streams/SM)"
 timeout 200 python tools/dec_ab.py 64 4 7 6 2>&1 | tail -4
 echo "== 4. parity of the diet decoder as the default decoder"
