@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--blocks", type=int, default=18, help="blocks per GPU (18 x 8 coder streams = 144 of the 148 SMs, one stream per SM)")
     ap.add_argument("--block-mib", type=int, default=64)
     ap.add_argument("--workers", type=int, default=0, help="concurrent blocks per GPU (0 = all)")
+    ap.add_argument("--decode-workers", type=int, default=0,
+                    help="separate, smaller contexts for decompression (0 = reuse the compression contexts); e.g. --blocks 36 --workers 18 "
+                         "--decode-workers 36 keeps 288 decoder streams in flight where 36 full contexts (4.6 GiB each) would not fit")
     ap.add_argument("--sorter", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -206,8 +209,15 @@ def run_b200(args, rank, local_rank, world):
     ws = int(L.bscb200_workspace_bytes(bb, args.sorter))
     for c in ctxs:
         assert c.reserve(ws) == 0, "workspace allocation failed"
+    dworkers = args.decode_workers or workers
+    dctxs = ctxs
+    if args.decode_workers:
+        dctxs = [libbsc_b200.DeviceCtx(local_rank) for _ in range(dworkers)]
+        for c in dctxs:
+            assert c.reserve(int(L.bscb200_workspace_bytes_decode(bb))) == 0, "decode workspace allocation failed"
+    allctx = ctxs + ([] if dctxs is ctxs else dctxs)
     csize = [0] * nb
-    pool = ThreadPoolExecutor(max_workers=workers)
+    pool = ThreadPoolExecutor(max_workers=max(workers, dworkers))
 
     def dev_compress(i):
         torch.cuda.set_device(local_rank)
@@ -219,7 +229,7 @@ def run_b200(args, rank, local_rank, world):
 
     def dev_decompress(i):
         torch.cuda.set_device(local_rank)
-        c = ctxs[i % workers]
+        c = dctxs[i % dworkers]
         r = c.decompress(d_cmp[i].data_ptr() + 4, csize[i], d_back[i].data_ptr(), bb, 3)
         assert r == 0, "decompress failed: %d" % r
 
@@ -239,9 +249,9 @@ def run_b200(args, rank, local_rank, world):
 
     for _ in range(args.warmup):
         timed_phase(dev_compress); timed_phase(dev_decompress)
-    for c in ctxs:
+    for c in allctx:
         c.set_profile(True)
-    launches0 = sum(c.launches() for c in ctxs)
+    launches0 = sum(c.launches() for c in allctx)
     sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     t_c = t_d = 0.0
@@ -250,12 +260,12 @@ def run_b200(args, rank, local_rank, world):
         t_d += timed_phase(dev_decompress)
     barrier()
     clocks = sampler.stop()
-    launches = sum(c.launches() for c in ctxs) - launches0
+    launches = sum(c.launches() for c in allctx) - launches0
     for i in range(nb):
         assert torch.equal(d_back[i][:bb], d_in[i]), "round trip mismatch in block %d" % i
     # per-kernel CUDA-event timings gathered during the timed steps
     kern = {}
-    for c in ctxs:
+    for c in allctx:
         for name, (cnt, ms, by) in c.profile_report().items():
             a = kern.setdefault(name, [0, 0.0, 0.0]); a[0] += cnt; a[1] += ms; a[2] += by
         c.set_profile(False)
@@ -284,7 +294,7 @@ def run_b200(args, rank, local_rank, world):
     e2e = None
     comp_bytes = int(sum(csize))
     if not args.no_e2e:
-        for c in ctxs:
+        for c in allctx:
             c.close()
         del d_cmp, d_back
         torch.cuda.empty_cache()
@@ -384,7 +394,7 @@ def run_b200(args, rank, local_rank, world):
 
     line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_c + ms_d, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, {"concurrent_blocks_per_gpu": workers, "parallelism": "blocks round-robin over %d GPU(s), no collective" % world}),
+            "config": workload_config(args, {"concurrent_blocks_per_gpu": workers, "concurrent_decode_blocks_per_gpu": dworkers, "parallelism": "blocks round-robin over %d GPU(s), no collective" % world}),
             "compress_MBps": total_mb / (ms_c / 1e3), "decompress_MBps": total_mb / (ms_d / 1e3),
             "compressed_bytes_rank0": comp_bytes, "ratio": comp_bytes / float(nb * bb),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm_kernel": roofline_hbm,

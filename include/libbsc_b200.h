@@ -98,6 +98,7 @@ void              *bscb200_ctx_create(int device, void *cuda_stream);
 void               bscb200_ctx_destroy(void *ctx);
 int                bscb200_ctx_reserve(void *ctx, long long bytes);
 long long          bscb200_workspace_bytes(int n, int blockSorter);
+long long          bscb200_workspace_bytes_decode(int n);         /* a context that only decompresses */
 unsigned long long bscb200_ctx_kernel_launches(void *ctx);
 unsigned long long bscb200_total_kernel_launches(void);
 /* per-kernel CUDA-event timing of everything launched through ctx (bench.py's roofline leg) */

@@ -490,6 +490,8 @@ long long bscb200_workspace_bytes(int n, int blockSorter)
     size_t d = need_bwt_decode((size_t)n);
     return (long long)((s > d ? s : d) + need_coder((size_t)n) + (size_t)n + 8192);
 }
+// workspace of a context that only ever DEcompresses blocks of n bytes (inverse BWT + coder stage: ~21 n instead of ~71 n)
+long long bscb200_workspace_bytes_decode(int n) { return (long long)(need_bwt_decode((size_t)n) + need_coder((size_t)n) + (size_t)n + 8192); }
 unsigned long long bscb200_ctx_kernel_launches(void *ctx) { return ((Ctx *)ctx)->kernels_launched; }
 
 int bscb200_compress_device(void *ctx, const unsigned char *d_input, unsigned char *d_output, int n, int blockSorter, int coder, int features)
@@ -505,7 +507,7 @@ int bscb200_decompress_device(void *ctx, const unsigned char *d_input, int input
         unsigned char h[LIBBSC_HEADER_SIZE];
         CUDA_TRY(cudaMemcpyAsync(c->h_mail + 64, d_input, LIBBSC_HEADER_SIZE, cudaMemcpyDeviceToHost, c->stream));
         c->sync(); memcpy(h, c->h_mail + 64, LIBBSC_HEADER_SIZE);
-        c->arena.reset(); c->arena.reserve((size_t)bscb200_workspace_bytes(outputSize, 1));
+        c->arena.reset(); c->arena.reserve((size_t)bscb200_workspace_bytes_decode(outputSize));   // no-op for a context that already compressed
         return decompress_dev(c, h, d_input, inputSize, d_output, outputSize, features);
     });
 }

@@ -12,7 +12,7 @@ echo "== 3. decoder A/B on one 64 MiB block: 4 = default, 7 = tuned code + full 
 timeout 200 python tools/dec_ab.py 64 4 7 6 2>&1 | tail -4
 echo "== 4. parity of the diet decoder as the default decoder"
 BSCB200_QDEC=6 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
-echo "== 5. does co-residency pay?  36 blocks per GPU: default decoder vs diet decoder"
-timeout 300 python bench.py --blocks 36 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench36_gen4.json 2> gpurun_out/r2_bench36_gen4.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench36_gen4.json'));print('gen4 36 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
-BSCB200_QDEC=6 timeout 300 python bench.py --blocks 36 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench36_gen6.json 2> gpurun_out/r2_bench36_gen6.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench36_gen6.json'));print('gen6 36 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
+echo "== 5. does co-residency pay?  36 blocks per GPU (18 compression contexts of 4.6 GiB, 36 decode-only contexts of 1.4 GiB): default decoder vs diet decoder"
+timeout 300 python bench.py --blocks 36 --workers 18 --decode-workers 36 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench36_gen4.json 2> gpurun_out/r2_bench36_gen4.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench36_gen4.json'));print('gen4 36 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
+BSCB200_QDEC=6 timeout 300 python bench.py --blocks 36 --workers 18 --decode-workers 36 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench36_gen6.json 2> gpurun_out/r2_bench36_gen6.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench36_gen6.json'));print('gen6 36 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
 } 2>&1 | tee gpurun_out/r2_first_call.log
