@@ -216,6 +216,7 @@ def run_b200(args, rank, local_rank, world):
         for c in dctxs:
             assert c.reserve(int(L.bscb200_workspace_bytes_decode(bb))) == 0, "decode workspace allocation failed"
     allctx = ctxs + ([] if dctxs is ctxs else dctxs)
+    ctx_lock = {id(c): threading.Lock() for c in allctx}       # one block at a time per context (blocks > contexts share them)
     csize = [0] * nb
     pool = ThreadPoolExecutor(max_workers=max(workers, dworkers))
 
@@ -223,14 +224,16 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.set_device(local_rank)
         c = ctxs[i % workers]
         # +4: payload (offset 28) 16-byte aligned for the vectorised device adler32
-        r = c.compress(d_in[i].data_ptr(), d_cmp[i].data_ptr() + 4, bb, args.sorter, 1, 3)
+        with ctx_lock[id(c)]:
+            r = c.compress(d_in[i].data_ptr(), d_cmp[i].data_ptr() + 4, bb, args.sorter, 1, 3)
         assert r > 0, "compress failed: %d" % r
         csize[i] = r
 
     def dev_decompress(i):
         torch.cuda.set_device(local_rank)
         c = dctxs[i % dworkers]
-        r = c.decompress(d_cmp[i].data_ptr() + 4, csize[i], d_back[i].data_ptr(), bb, 3)
+        with ctx_lock[id(c)]:
+            r = c.decompress(d_cmp[i].data_ptr() + 4, csize[i], d_back[i].data_ptr(), bb, 3)
         assert r == 0, "decompress failed: %d" % r
 
     def barrier():
