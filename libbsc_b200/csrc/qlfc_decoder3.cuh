@@ -162,6 +162,7 @@ struct Qd3Lane {
     int sA, cA, gA, sB, cB, gB, sX, cX, gX;
     u32 iSX, iCX;
     u32 used8, tmp;
+    u32 mtfv;                        // qlfc_decoder6.cuh: lane l holds position l of the MTF list
 };
 
 QD3_FN void qd3_lane_init(Qd3Lane &r, u32 lane)

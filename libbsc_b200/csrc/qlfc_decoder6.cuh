@@ -12,10 +12,11 @@
 // cached accesses per run and 0.000 / 0.046 misses per run; the smaller QLayout<3, 2, 11> (102 KB) would take 1.8 / 0.9
 // accesses and 0.26 / 0.14 misses per run.  QLayout<5, 5, 12> is exactly the layout of qlfc_coder.cuh and is instantiated
 // too: it must behave like q_decode3<1> (a refactoring check for the A/B).
-// Besides the layout, two instruction-count measures (the cost model of DESIGN.md 4.5: a lone warp retires one instruction
+// Besides the layout, three instruction-count measures (the cost model of DESIGN.md 4.5: a lone warp retires one instruction
 // per 4-5 cycles, so instructions are what counts): the multipliers of the hot counter moves live in registers (loaded from
 // a table, see q_move6), and the exponent / mantissa loops address their counters through absolute shared-memory
-// addresses that advance with the node.  SASS of the rank-mantissa loop: 53 instructions per decision in q_decode3<1>,
+// addresses that advance with the node; positions 0..31 of the MTF list live in the lanes (one shuffle per run instead of
+// shared-memory traffic and three warp barriers for every rank > 3, i.e. 58 % of the runs on text).  SASS of the rank-mantissa loop: 53 instructions per decision in q_decode3<1>,
 // 28-42 here (cuobjdump, r1h).
 // STATUS: bit-exact in host emulation with both layouts (tests/test_qdec3_host.py); not yet run on a GPU.  To profit from it
 // more than 148 streams have to be in flight (>= 19 blocks of >= 16 MiB per GPU): BSCB200_QDEC=6 selects it.
@@ -202,8 +203,10 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
     { const int err = qd6_prologue<LY>(sm, rc, lr, in, in_limit, out_cap, n, maxRank); if (err) return err; }
 
     u32 ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0; int avgRank = 0;
-    u32 c, m1, m2, m3;
-    { const u32 f = sm.ld32(LY::O_MTF); c = f & 255u; m1 = (f >> 8) & 255u; m2 = (f >> 16) & 255u; m3 = f >> 24; }
+    // positions 0..31 of the MTF list live in the lanes (lane l holds position l; shared memory keeps 32..255), the front
+    // and its successor also as uniform values: c = list[0], m1 = list[1]
+    QD3_LANES { QD3_L(lr).mtfv = sm.ld8(LY::O_MTF + lane); }
+    u32 c = sm.ld8(LY::O_MTF), m1 = sm.ld8(LY::O_MTF + 1);
     u32 rhU = sm.ld8(LY::O_RUN_HIST + c);
     u32 st = sm.ld8(LY::O_RANK_STATE + ((ctxRun << 11) | (ctxRank4 << 3) | sm.ld8(LY::O_RANK_HIST + c)));
     int tS = sm.cnt(LY::R_RT_STATE + st), tC = sm.cnt(LY::R_RT_CHAR + c), tG = sm.cnt(LY::R_RT_SHARED);
@@ -269,25 +272,32 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
         rank &= 255u;
         QD3_T(1);
 
-        // push c `rank` places back (qlfc.cpp:1830-1860); positions 0..3 of the list live in (c, m1, m2, m3)
+        // push c `rank` places back (qlfc.cpp:1830-1860): positions 0..rank-1 take their successor, position rank takes c.
+        // One shuffle for the lanes' part; shared memory only moves for rank >= 32 (0.2 % of the runs on text).
         const u32 cur = c;
-        if (rank == 1) { c = m1; m1 = cur; }
-        else if (rank == 2) { c = m1; m1 = m2; m2 = cur; }
-        else if (rank == 3) { c = m1; m1 = m2; m2 = m3; m3 = cur; }
-        else if (rank != 0) {
-            sm.st8(LY::O_MTF, c); sm.st8(LY::O_MTF + 1, m1); sm.st8(LY::O_MTF + 2, m2); sm.st8(LY::O_MTF + 3, m3);
-            QD3_SYNC();
-            for (u32 basep = 0; basep < rank; basep += 32) {
-                QD3_LANES { QD3_L(lr).tmp = sm.ld8(LY::O_MTF + basep + lane + 1u); }
+        if (rank != 0) {
+#ifdef QD3_HOST
+            for (u32 lane = 0; lane < 32; ++lane) lr[lane].tmp = lr[lane < 31 ? lane + 1 : lane].mtfv;
+#else
+            lr.tmp = __shfl_down_sync(0xffffffffu, lr.mtfv, 1);
+#endif
+            if (rank >= 32u) {
+                QD3_LANES { if (lane == 31u) QD3_L(lr).tmp = sm.ld8(LY::O_MTF + 32u); }
                 QD3_SYNC();
-                QD3_LANES { if (basep + lane < rank) sm.st8(LY::O_MTF + basep + lane, QD3_L(lr).tmp); }
+                for (u32 basep = 32; basep < rank; basep += 32) {
+                    QD3_LANES { QD3_L(lr).used8 = sm.ld8(LY::O_MTF + basep + lane + 1u); }               // used8 is free after the header
+                    QD3_SYNC();
+                    QD3_LANES { if (basep + lane < rank) sm.st8(LY::O_MTF + basep + lane, QD3_L(lr).used8); }
+                    QD3_SYNC();
+                }
+                sm.st8(LY::O_MTF + rank, cur);
                 QD3_SYNC();
             }
-            sm.st8(LY::O_MTF + rank, cur);
-            QD3_SYNC();
-            const u32 f = sm.ld32(LY::O_MTF); c = f & 255u; m1 = (f >> 8) & 255u; m2 = (f >> 16) & 255u; m3 = f >> 24;
+            QD3_LANES { Qd3Lane &r = QD3_L(lr); r.mtfv = lane < rank ? r.tmp : (lane == rank ? cur : r.mtfv); }
+            c = m1;                                                            // the new front is the old second entry
+            m1 = QF_BCAST(mtfv, 1);
         }
-        // (c, m1, m2, m3) now describe the NEXT run; `cur` is this run's symbol
+        // (c, m1) now describe the NEXT run; `cur` is this run's symbol
         const u32 rhRn = sm.ld8(LY::O_RANK_HIST + c), rhUn = sm.ld8(LY::O_RUN_HIST + c);
         avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
         const u32 rank0 = rank - 1u;
