@@ -318,6 +318,13 @@ static void init_models(Ctx *ctx, short *models, int count)
     LAUNCH(ctx, q_model_init, ceil_div(total, 256 * 8), 256, 0, models, total);
 }
 
+// BSCB200_QENC=2: the static encoder's range warp with the one-multiply-add recurrence (qlfc_encoder.cuh, RANGE3) -- A/B only
+static bool encoder_range3()
+{
+    static const bool on = [] { const char *e = getenv("BSCB200_QENC"); return e && e[0] == '2'; }();
+    return on;
+}
+
 int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder, int features)
 {
     { const int g = coder_gate(coder); if (g != LIBBSC_NO_ERROR) return g; }
@@ -391,9 +398,14 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         LAUNCH(ctx, q_adaptive_encode, nBlocks, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
     } else {
         init_models(ctx, models, nBlocks);
-        ensure_dyn_smem(q_encode5, ctx->device, enc_smem);
         PROF_BYTES(ctx, (double)n);                      // + c written; the launch is latency-, not bandwidth-bound
-        LAUNCH(ctx, q_encode5, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+        if (encoder_range3()) {
+            ensure_dyn_smem(q_encode5<true>, ctx->device, enc_smem);
+            LAUNCH(ctx, q_encode5<true>, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+        } else {
+            ensure_dyn_smem(q_encode5<false>, ctx->device, enc_smem);
+            LAUNCH(ctx, q_encode5<false>, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+        }
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
@@ -440,7 +452,8 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                     LAUNCH(ctx, q_adaptive_encode, 1, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 } else {
                     init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                    LAUNCH(ctx, q_encode5, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                    if (encoder_range3()) LAUNCH(ctx, q_encode5<true>, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                    else                  LAUNCH(ctx, q_encode5<false>, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
                 }
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();

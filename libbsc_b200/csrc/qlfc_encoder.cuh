@@ -145,7 +145,12 @@ __device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool c
 // bits [32-lane, ...) of (prev:cur): the flags of the runs before this lane's run, most recent in bit 0
 __device__ __forceinline__ u32 enc_window(u32 prev_rev, u32 cur_rev, u32 lane) { return (u32)((((u64)prev_rev << 32) | cur_rev) >> (32u - lane)); }
 
-__global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
+// RANGE3 (BSCB200_QENC=2, not yet run on a GPU): the range recurrence of the range warp as ONE multiply-add per record.
+//   range' = bit ? range_s - (range_s >> 12) * p : (range_s >> 12) * p      with range_s = range renormalised
+//          = rin * (bit ? -p : p) + (bit ? range_s : 0),                    rin = range_s >> 12 = sh ? range << 4 : range >> 12
+// The multiplier and the addend mask come from the record (off the chain); the dependent chain through `range` shrinks from
+// six instructions per record (ISETP, shift, shift, IMAD, IADD, SEL -- cuobjdump of q_encode5) to about four.
+template <bool RANGE3> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                     SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
                                                     const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
 {
@@ -200,11 +205,19 @@ __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict
                     for (int k = 0; k < 4; ++k) {
                         const u32 rec = recs[k];
                         const bool sh = range < 0x10000u;
-                        if (sh) range <<= 16;
-                        const u32 r = (range >> 12) * (rec & 0x1fffu);
                         const bool bit = rec & QE_BIT;
-                        range = bit ? range - r : r;
-                        recs[k] = bit ? r : 0u;
+                        if (RANGE3) {
+                            const u32 p = rec & 0x1fffu, mul = bit ? 0u - p : p, keep = bit ? 0xffffffffu : 0u;
+                            const u32 rin = sh ? range << 4 : range >> 12;
+                            const u32 rs = sh ? range << 16 : range;
+                            recs[k] = (rin * p) & keep;                        // the addend of `low` (off the chain)
+                            range = rin * mul + (rs & keep);
+                        } else {
+                            if (sh) range <<= 16;
+                            const u32 r = (range >> 12) * (rec & 0x1fffu);
+                            range = bit ? range - r : r;
+                            recs[k] = bit ? r : 0u;
+                        }
                         f |= (sh ? 1u << k : 0u) | ((rec & QE_RUN) ? 16u << k : 0u);
                     }
                     *reinterpret_cast<uint4 *>(&P.ring[slot]) = make_uint4(recs[0], recs[1], recs[2], recs[3]);

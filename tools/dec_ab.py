@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""tools/dec_ab.py -- A/B timing of the QLFC decoder kernels on ONE block (CUDA events around every launch).
+"""tools/dec_ab.py -- A/B timing of the QLFC coder kernels on ONE block (CUDA events around every launch); the encoder variant
+is taken from the environment (BSCB200_QENC=2: one-multiply-add range recurrence).
     python tools/dec_ab.py [MiB] [gen ...]      gen: 2 q_decode2, 3 speculative q_decode3<0>, 4 serial q_decode3<1> (default), 5 q_decode3<2>, 6 q_decode6<LayoutDiet>, 7 q_decode6<LayoutFull>
 Each generation runs in its own process (the selection is read once from BSCB200_QDEC)."""
 import os
@@ -24,16 +25,17 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     back = torch.empty(n + 64, dtype=torch.uint8, device=dev)
     ctx = libbsc_b200.DeviceCtx(0)
     assert ctx.reserve(int(L.bscb200_workspace_bytes(n, 1))) == 0
-    size = ctx.compress(src.data_ptr(), blk.data_ptr() + 4, n, 1, 1, 3)
-    assert size > 0, size
     for rep in range(2):
         ctx.set_profile(rep == 1)
+        size = ctx.compress(src.data_ptr(), blk.data_ptr() + 4, n, 1, 1, 3)
+        assert size > 0, size
         r = ctx.decompress(blk.data_ptr() + 4, size, back.data_ptr(), n, 3)
         assert r == 0, r
         assert torch.equal(back[:n], src)
     for name, (cnt, ms, by) in ctx.profile_report().items():
-        if name.startswith("q_decode"):
-            print("gen %s  %-10s  %d launch(es)  %.1f ms  (%d MiB block, bit-exact)" % (os.environ.get("BSCB200_QDEC", "default"), name, cnt, ms, mib), flush=True)
+        if name.startswith(("q_decode", "q_encode")):
+            print("QDEC=%s QENC=%s  %-10s  %d launch(es)  %.1f ms  (%d MiB block, round trip bit-exact, %d bytes)" %
+                  (os.environ.get("BSCB200_QDEC", "default"), os.environ.get("BSCB200_QENC", "default"), name, cnt, ms, mib, size), flush=True)
     sys.exit(0)
 
 mib = sys.argv[1] if len(sys.argv) > 1 else "64"

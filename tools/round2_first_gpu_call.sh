@@ -10,6 +10,9 @@ echo "== 2. adaptive + fast coders (coder ids 2, 3): parity through the C ABI, t
 BSCB200_ENABLE_ADAPTIVE=1 BSCB200_ENABLE_FAST=1 timeout 300 python -m pytest tests/test_gpu_other_coders.py tests/test_golden.py -m gpu -q 2>&1 | tail -5
 echo "== 3. decoder A/B on one 64 MiB block: 4 = default, 7 = tuned code + full layout, 6 = tuned code + diet layout (2 streams/SM)"
 timeout 200 python tools/dec_ab.py 64 4 7 6 2>&1 | tail -4
+echo "== 3b. encoder range warp with the one-multiply-add recurrence: parity + time"
+BSCB200_QENC=2 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "coder_compress or block_bytes or k3" 2>&1 | tail -3
+BSCB200_QENC=2 timeout 100 python tools/dec_ab.py 64 4 2>&1 | tail -2
 echo "== 4. parity of the diet decoder as the default decoder"
 BSCB200_QDEC=6 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
 echo "== 5. does co-residency pay?  36 blocks per GPU (18 compression contexts of 4.6 GiB, 36 decode-only contexts of 1.4 GiB): default decoder vs diet decoder"
