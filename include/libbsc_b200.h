@@ -97,6 +97,8 @@ int bscb200_coder_decompress(const unsigned char *input, int inputSize, unsigned
 void              *bscb200_ctx_create(int device, void *cuda_stream);
 void               bscb200_ctx_destroy(void *ctx);
 int                bscb200_ctx_reserve(void *ctx, long long bytes);
+int                bscb200_device_count(void);                    /* CUDA devices visible to the process */
+int                bscb200_set_device(int device);                /* bind the calling thread: all entry points use the current device */
 long long          bscb200_workspace_bytes(int n, int blockSorter);
 long long          bscb200_workspace_bytes_decode(int n);         /* a context that only decompresses */
 unsigned long long bscb200_ctx_kernel_launches(void *ctx);

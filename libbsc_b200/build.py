@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbsc_b200.so")
+CLI = os.path.join(HERE, "bsc_b200")          # file-level front end (cli/bsc_b200.cpp), bsc1 container + multi-GPU block scheduler
 SOURCES = ["api.cu", "adler32.cu", "bwt_encode.cu", "bwt_decode.cu", "st_encode.cu", "qlfc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -52,6 +53,12 @@ def build(verbose=False):
                            capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))
+    cli_src = os.path.join(HERE, "cli", "bsc_b200.cpp")
+    if _stale(CLI, [cli_src, LIB, os.path.join(os.path.dirname(HERE), "include", "libbsc_b200.h")]):
+        p = subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-pthread", cli_src, "-o", CLI, "-L" + HERE, "-lbsc_b200", "-Wl,-rpath,$ORIGIN"],
+                           capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("CLI build failed:\n%s\n%s" % (p.stdout, p.stderr))
     return LIB
 
 

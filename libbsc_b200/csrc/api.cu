@@ -490,6 +490,11 @@ long long bscb200_workspace_bytes(int n, int blockSorter)
     size_t d = need_bwt_decode((size_t)n);
     return (long long)((s > d ? s : d) + need_coder((size_t)n) + (size_t)n + 8192);
 }
+// Multi-GPU callers (libbsc_b200/cli/bsc_b200.cpp, one worker thread per GPU slot): every entry point works on the CURRENT device
+// of the calling thread, so a worker only has to bind itself once.  Plain wrappers, so that callers need no CUDA headers.
+int bscb200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+int bscb200_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? LIBBSC_NO_ERROR : LIBBSC_GPU_ERROR; }
+
 // workspace of a context that only ever DEcompresses blocks of n bytes (inverse BWT + coder stage: ~21 n instead of ~71 n)
 long long bscb200_workspace_bytes_decode(int n) { return (long long)(need_bwt_decode((size_t)n) + need_coder((size_t)n) + (size_t)n + 8192); }
 unsigned long long bscb200_ctx_kernel_launches(void *ctx) { return ((Ctx *)ctx)->kernels_launched; }

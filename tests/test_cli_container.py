@@ -1,0 +1,103 @@
+"""The `bsc1` file container and the block scheduler of libbsc_b200/cli/bsc_b200.cpp.
+
+CPU part: the same CLI source is built against the UNMODIFIED reference library (-DBSCB200_CLI_REF: identical block API, no
+GPU) and its archives are compared with the reference's own CLI (oracle/_ref/bsc, built by oracle/Makefile from
+/root/reference/bsc.cpp): byte-identical containers when both write blocks in order (`bsc -t`), and each side decodes the
+other's archives.  That pins the container logic, option handling and the in-order writer without a GPU.
+GPU part (BSCB200_TEST_CLI=1, tools/round2_first_gpu_call.sh): the product binary libbsc_b200/bsc_b200 round-trips a file and
+produces the bytes of the reference CLI."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "libbsc_b200", "cli", "bsc_b200.cpp")
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+REFCLI = os.path.join(REFDIR, "bsc")
+TESTCLI = os.path.join(ROOT, "tools", "bin", "bsc_b200_ref")
+PRODUCT = os.path.join(ROOT, "libbsc_b200", "bsc_b200")
+
+
+def _run(*cmd):
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, (cmd, p.stdout[-300:], p.stderr[-300:])
+    return p.stdout
+
+
+@pytest.fixture(scope="module")
+def clis(tmp_path_factory):
+    if not (os.path.exists(REFCLI) and os.path.exists(os.path.join(REFDIR, "libbsc_ref.so"))):
+        pytest.skip("oracle/_ref (reference library + CLI) not built")
+    os.makedirs(os.path.dirname(TESTCLI), exist_ok=True)
+    if not os.path.exists(TESTCLI) or os.path.getmtime(SRC) > os.path.getmtime(TESTCLI):
+        _run("/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-fopenmp", "-DBSCB200_CLI_REF", SRC, "-o", TESTCLI,
+             "-L" + REFDIR, "-lbsc_ref", "-Wl,-rpath," + REFDIR)
+    return tmp_path_factory.mktemp("cli")
+
+
+def _files(gen, d):
+    rng = np.random.default_rng(3)
+    cases = {"text3M": gen.text(2, 3 << 20), "ragged": gen.text(5, (1 << 20) + 12345), "rand": gen.rand(1, 300000),
+             "tiny": gen.text(1, 20), "empty": np.zeros(0, np.uint8), "skew": gen.skew(3, 2 << 20),
+             "runs": np.repeat(rng.integers(0, 50, 4000, dtype=np.uint8), rng.integers(1, 2000, 4000))[: 3 << 20]}
+    out = {}
+    for name, a in cases.items():
+        p = str(d / (name + ".bin"))
+        a.tofile(p)
+        out[name] = p
+    return out
+
+
+def test_container_matches_reference_cli(clis, gen):
+    d = clis
+    for name, path in _files(gen, d).items():
+        for opts in (["-b1"], ["-b1", "-m5"], ["-b2", "-e0"], ["-b1", "-e2"]):
+            ours, theirs = str(d / "ours.bsc"), str(d / "theirs.bsc")
+            _run(TESTCLI, "e", path, ours, *opts, "-j3")
+            _run(REFCLI, "e", path, theirs, *opts, "-p", "-t")
+            a, b = open(ours, "rb").read(), open(theirs, "rb").read()
+            assert a == b, (name, opts, len(a), len(b))
+            if "-m5" in opts:
+                continue                                           # ST decoding stays in the reference
+            back1, back2 = str(d / "back1.bin"), str(d / "back2.bin")
+            _run(TESTCLI, "d", theirs, back1, "-j2")                   # their archive, our reader
+            _run(REFCLI, "d", ours, back2)                             # our archive, their reader
+            orig = open(path, "rb").read()
+            assert open(back1, "rb").read() == orig and open(back2, "rb").read() == orig, (name, opts)
+
+
+def test_reader_accepts_blocks_in_any_order(clis, gen):
+    """The reference writes blocks in completion order when it runs multithreaded (bsc.cpp:398-417)."""
+    d = clis
+    path = str(d / "mt.bin")
+    gen.text(9, 6 << 20).tofile(path)
+    arch, back = str(d / "mt.bsc"), str(d / "mt.back")
+    _run(REFCLI, "e", path, arch, "-b1", "-p")                          # parallel block loop of the reference
+    _run(TESTCLI, "d", arch, back, "-j4")
+    assert open(back, "rb").read() == open(path, "rb").read()
+
+
+def test_reader_refuses_host_side_preprocessing(clis, gen):
+    d = clis
+    path = str(d / "lzp.bin")
+    gen.text(4, 1 << 20).tofile(path)
+    arch = str(d / "lzp.bsc")
+    _run(REFCLI, "e", path, arch, "-b1", "-t", "-cp")                   # reversed contexts: a host-side filter of the reference
+    p = subprocess.run([TESTCLI, "d", arch, str(d / "x")], capture_output=True, text=True)
+    assert p.returncode != 0 and "stock bsc" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("BSCB200_TEST_CLI") != "1", reason="set BSCB200_TEST_CLI=1 (product CLI not yet run on a GPU)")
+def test_product_cli_round_trip_on_gpu(gen, tmp_path):
+    path, arch, back = str(tmp_path / "in.bin"), str(tmp_path / "a.bsc"), str(tmp_path / "back.bin")
+    gen.text(2, 40 << 20).tofile(path)
+    _run(PRODUCT, "e", path, arch, "-b8", "-j5")
+    _run(PRODUCT, "d", arch, back, "-j5")
+    assert open(back, "rb").read() == open(path, "rb").read()
+    if os.path.exists(REFCLI):
+        theirs = str(tmp_path / "t.bsc")
+        _run(REFCLI, "e", path, theirs, "-b8", "-p", "-t")
+        assert open(arch, "rb").read() == open(theirs, "rb").read()
