@@ -318,11 +318,12 @@ static void init_models(Ctx *ctx, short *models, int count)
     LAUNCH(ctx, q_model_init, ceil_div(total, 256 * 8), 256, 0, models, total);
 }
 
-// BSCB200_QENC=2: the static encoder's range warp with the one-multiply-add recurrence (qlfc_encoder.cuh, RANGE3) -- A/B only
-static bool encoder_range3()
+// BSCB200_QENC: static-encoder variants for A/B measurements (qlfc_encoder.cuh): 2 = one-multiply-add range recurrence (RANGE3),
+// 6 = diet counter file (two encoders per SM), 7 = both; default: the GPU-verified kernel.
+static int encoder_variant()
 {
-    static const bool on = [] { const char *e = getenv("BSCB200_QENC"); return e && e[0] == '2'; }();
-    return on;
+    static const int v = [] { const char *e = getenv("BSCB200_QENC"); return e ? atoi(e) : 0; }();
+    return v;
 }
 
 int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder, int features)
@@ -384,8 +385,15 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         PROF_BYTES(ctx, 2.0 * R);
         LAUNCH(ctx, q_rank_tile, ceil_div(total_tiles, 4), 128, 0, run_sym, run_rank, d_sb, (u32)nBlocks, total_tiles, next_tab);
     }
-    const size_t enc_smem = ((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe);
     static_assert(((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448, "encoder working set must fit the 227 KB of one SM");
+    static_assert(((sizeof(CoderSmemT<LayoutEncDiet>) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448 / 2 - 1024, "two diet encoders must fit one SM");
+    // static encoder variants (A/B): BSCB200_QENC = 2 RANGE3, 6 diet layout, 7 diet layout + RANGE3; anything else: the default
+#define LAUNCH_ENC(LY, R3, GRID, LIST) do { const size_t sm_ = ((sizeof(CoderSmemT<LY>) + 15) & ~(size_t)15) + sizeof(EncPipe); \
+        ensure_dyn_smem(q_encode5<LY, R3>, ctx->device, sm_); \
+        LAUNCH(ctx, (q_encode5<LY, R3>), (GRID), QE_THREADS, sm_, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)(LIST)); } while (0)
+#define LAUNCH_ENC_VARIANT(GRID, LIST) do { switch (encoder_variant()) { \
+        case 2: LAUNCH_ENC(LayoutFull, true, GRID, LIST); break; case 6: LAUNCH_ENC(LayoutEncDiet, false, GRID, LIST); break; \
+        case 7: LAUNCH_ENC(LayoutEncDiet, true, GRID, LIST); break; default: LAUNCH_ENC(LayoutFull, false, GRID, LIST); } } while (0)
     if (fast) {
         LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
         ensure_dyn_smem(q_fast_encode, ctx->device, sizeof(FastSmem));
@@ -399,13 +407,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     } else {
         init_models(ctx, models, nBlocks);
         PROF_BYTES(ctx, (double)n);                      // + c written; the launch is latency-, not bandwidth-bound
-        if (encoder_range3()) {
-            ensure_dyn_smem(q_encode5<true>, ctx->device, enc_smem);
-            LAUNCH(ctx, q_encode5<true>, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
-        } else {
-            ensure_dyn_smem(q_encode5<false>, ctx->device, enc_smem);
-            LAUNCH(ctx, q_encode5<false>, nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
-        }
+        LAUNCH_ENC_VARIANT(nBlocks, nullptr);
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
@@ -452,8 +454,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                     LAUNCH(ctx, q_adaptive_encode, 1, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 } else {
                     init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                    if (encoder_range3()) LAUNCH(ctx, q_encode5<true>, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
-                    else                  LAUNCH(ctx, q_encode5<false>, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, d_list);
+                    LAUNCH_ENC_VARIANT(1, d_list);
                 }
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();

@@ -48,10 +48,25 @@ template <u32 MAXE_R_, u32 MAXE_U_, int CLOG_> struct QLayout {
     static QD3_FN_MEMBER u32 cache_tag(u32 idx) { return (idx >> HB) + 1u; }
     static QD3_FN_MEMBER u32 cache_unslot(u32 slot, u32 tag) { const u32 h = tag - 1u; return (h << HB) | (((slot & HMASK) ^ (h * 1237u)) & HMASK); }
 };
+// the same image as a struct (what the encoder uses); for QLayout<5, 5, 12> it is CoderSmem, member for member
+template <class LY> struct CoderSmemT {
+    u8    rank_state[32768];
+    u8    run_state[8192];
+    u16   s16[LY::S16_COUNT];
+    u16   tag_state[LY::SLOTS];
+    u16   tag_char[LY::SLOTS];
+    u8    rankHist[256], runHist[256];
+    u8    mtf[256 + 32];
+    alignas(16) u8 inwin[256];
+};
 typedef QLayout<5, 5, 12> LayoutFull;     // = qlfc_coder.cuh: 205 KB, one stream per SM
 typedef QLayout<4, 2, 10> LayoutDiet;     // 110 KB, two streams per SM
+typedef QLayout<4, 1, 10> LayoutEncDiet;  // 106 KB + the encoder's pipe state (5.6 KB): two six-warp encoders per SM
 static_assert(LayoutFull::R_END == R_END && LayoutFull::S16_COUNT == S16_COUNT && LayoutFull::O_S16 == O3_S16, "LayoutFull must reproduce qlfc_coder.cuh");
 static_assert(LayoutFull::R_RM_STATE == R_RM_STATE && LayoutFull::R_UM_CHAR == R_UM_CHAR && LayoutFull::C_CHAR_VAL == C_CHAR_VAL, "LayoutFull must reproduce qlfc_coder.cuh");
+static_assert(sizeof(CoderSmemT<LayoutFull>) == sizeof(CoderSmem) && offsetof(CoderSmemT<LayoutFull>, tag_state) == offsetof(CoderSmem, tag_state) &&
+              offsetof(CoderSmemT<LayoutFull>, rankHist) == offsetof(CoderSmem, rankHist) && offsetof(CoderSmemT<LayoutFull>, inwin) == offsetof(CoderSmem, inwin),
+              "CoderSmemT<LayoutFull> must be CoderSmem");
 static_assert(LayoutDiet::BYTES <= 113 * 1024, "two diet decoders must fit one SM (227 KB, 1 KB reserved per CTA)");
 static_assert(LayoutDiet::O_S16 == O3_S16 && (LayoutDiet::O_WIN & 15u) == 0 && (LayoutDiet::O_MTF & 3u) == 0, "alignment of the shared-memory image");
 
@@ -377,6 +392,19 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
 
 
 #ifndef QD3_HOST
+// coder_smem_init (qlfc_coder.cuh) for any layout: same statements, sizes from LY
+template <class LY> __device__ __forceinline__ void coder_smem_init_t(CoderSmemT<LY> &S, const QTables *__restrict__ g)
+{
+    const u32 lane = threadIdx.x & 31;
+    const uint4 *src = (const uint4 *)g; uint4 *dst = (uint4 *)S.rank_state;      // rank_state and run_state are contiguous
+    for (u32 i = lane; i < sizeof(QTables) / 16; i += 32) dst[i] = src[i];
+    u32 *w = (u32 *)S.s16;
+    for (u32 i = lane; i < LY::S16_COUNT / 2; i += 32) w[i] = 0x08000800u;        // every counter starts at 2048
+    u32 *t = (u32 *)S.tag_state;
+    for (u32 i = lane; i < (2 * LY::SLOTS * 2 + 512 + 288) / 4; i += 32) t[i] = 0; // tags, histories, mtf
+    __syncwarp();
+}
+
 template <class LY> __device__ __forceinline__ void qd6_smem_init(u8 *raw, const QTables *__restrict__ g)
 {
     const u32 lane = threadIdx.x & 31;

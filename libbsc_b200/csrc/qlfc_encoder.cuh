@@ -87,12 +87,12 @@ __device__ __forceinline__ void enc_fill_params(EncPipe &P, u32 lane)
 // rare counter `key` through this kind's direct-mapped write-back cache): returns the counter's value
 // BEFORE this lane's decision and applies the move (v*M + Kc) >> 12.  Lanes that share a counter -- or
 // a cache slot -- are served in lane (= stream) order, one per round.
-template <int KIND>   // 0 by state, 1 by symbol, 2 shared (never cached)
-__device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool cached, u32 key, int M, int Kc, short *__restrict__ cold, u32 lane, u32 &misses QE_DIAG_ROUNDS_PARAM)
+template <class LY, int KIND>   // 0 by state, 1 by symbol, 2 shared (never cached)
+__device__ __forceinline__ int enc_resolve(CoderSmemT<LY> &S, bool act, u32 x, bool cached, u32 key, int M, int Kc, short *__restrict__ cold, u32 lane, u32 &misses QE_DIAG_ROUNDS_PARAM)
 {
     u16 *tags = KIND == 0 ? S.tag_state : S.tag_char;
-    const u32 vbase = KIND == 0 ? C_STATE_VAL : C_CHAR_VAL;
-    if (KIND != 2 && cached) x = vbase + cache_slot(key);
+    const u32 vbase = KIND == 0 ? LY::C_STATE_VAL : LY::C_CHAR_VAL;
+    if (KIND != 2 && cached) x = vbase + LY::cache_slot(key);
     const u32 m = __match_any_sync(0xffffffffu, act ? x : (0x80000000u | lane));
     const u32 below = m & lanemask_lt();
     const u32 occ = __popc(below);
@@ -109,9 +109,9 @@ __device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool c
         if (act && occ == 0) {
             if (KIND != 2 && cached) {
                 const u32 slot = x - vbase, t = tags[slot];
-                if (t != cache_tag(key)) {
-                    if (t) cold[cache_unslot(slot, t)] = (short)S.s16[x];
-                    S.s16[x] = (u16)cold[key]; tags[slot] = (u16)cache_tag(key); ++misses;
+                if (t != LY::cache_tag(key)) {
+                    if (t) cold[LY::cache_unslot(slot, t)] = (short)S.s16[x];
+                    S.s16[x] = (u16)cold[key]; tags[slot] = (u16)LY::cache_tag(key); ++misses;
                 }
             }
             v = S.s16[x];
@@ -129,9 +129,9 @@ __device__ __forceinline__ int enc_resolve(CoderSmem &S, bool act, u32 x, bool c
         if (act && occ == round) {
             if (KIND != 2 && cached) {
                 const u32 slot = x - vbase, t = tags[slot];
-                if (t != cache_tag(key)) {
-                    if (t) cold[cache_unslot(slot, t)] = (short)S.s16[x];
-                    S.s16[x] = (u16)cold[key]; tags[slot] = (u16)cache_tag(key); ++misses;
+                if (t != LY::cache_tag(key)) {
+                    if (t) cold[LY::cache_unslot(slot, t)] = (short)S.s16[x];
+                    S.s16[x] = (u16)cold[key]; tags[slot] = (u16)LY::cache_tag(key); ++misses;
                 }
             }
             v = S.s16[x];
@@ -150,18 +150,20 @@ __device__ __forceinline__ u32 enc_window(u32 prev_rev, u32 cur_rev, u32 lane) {
 //          = rin * (bit ? -p : p) + (bit ? range_s : 0),                    rin = range_s >> 12 = sh ? range << 4 : range >> 12
 // The multiplier and the addend mask come from the record (off the chain); the dependent chain through `range` shrinks from
 // six instructions per record (ISETP, shift, shift, IMAD, IADD, SEL -- cuobjdump of q_encode5) to about four.
-template <bool RANGE3> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
+// LY: layout of the counter file (qlfc_decoder6.cuh): LayoutFull = qlfc_coder.cuh (one stream per SM); an encoder diet layout keeps
+// fewer mantissa rows resident so that two encoders fit one SM (BSCB200_QENC=6/7, not yet run on a GPU).
+template <class LY, bool RANGE3> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                     SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
                                                     const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
-    CoderSmem &S = *reinterpret_cast<CoderSmem *>(q_smem_raw);
-    EncPipe &P = *reinterpret_cast<EncPipe *>(q_smem_raw + ((sizeof(CoderSmem) + 15) & ~(size_t)15));
+    CoderSmemT<LY> &S = *reinterpret_cast<CoderSmemT<LY> *>(q_smem_raw);
+    EncPipe &P = *reinterpret_cast<EncPipe *>(q_smem_raw + ((sizeof(CoderSmemT<LY>) + 15) & ~(size_t)15));
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 sid = sb_list ? sb_list[blockIdx.x] : blockIdx.x;
     SubBlock &sb = sbs[sid];
 
-    if (warp == 0) coder_smem_init(S, tables);
+    if (warp == 0) coder_smem_init_t<LY>(S, tables);
     if (warp == 1) {
         enc_fill_params(P, lane);
         for (int i = lane; i < 512; i += 32) (&P.hist2[0][0])[i] = 0;
@@ -499,9 +501,9 @@ template <bool RANGE3> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode
                 const u32 k = d - 1; const bool isT = d == 0;
                 K = isT ? K_RANK_T : K_RANK_E;
                 bit = isT ? (v_ != 1) : (k + 1 < r_er);
-                is = isT ? R_RT_STATE + st : R_RE_STATE + st * 8 + k;
-                ic = isT ? R_RT_CHAR + c : R_RE_CHAR + c * 8 + k;
-                ig = isT ? R_RT_SHARED : R_RE_SHARED + k;
+                is = isT ? LY::R_RT_STATE + st : LY::R_RE_STATE + st * 8 + k;
+                ic = isT ? LY::R_RT_CHAR + c : LY::R_RE_CHAR + c * 8 + k;
+                ig = isT ? LY::R_RT_SHARED : LY::R_RE_SHARED + k;
                 runflag = isT;
             } else if (warp == 1) {     // rank: mantissa tree of depth e (or the escape tree of depth maxRank+1)
                 const u32 e_m = r_esc ? maxRank + 1u : r_er, v = r_esc ? (v_ | (1u << e_m)) : v_;
@@ -510,8 +512,8 @@ template <bool RANGE3> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode
                 const u32 rowoff = (1u << r_er) - 2u + node;
                 K = r_esc ? K_RANK_P : K_RANK_M;
                 bit = (v >> bp) & 1u;
-                cached = r_esc || r_er > M_MAXE;
-                is = R_RM_STATE + st * M_ROW + rowoff; ic = R_RM_CHAR + c * M_ROW + rowoff; ig = R_WIDE_SHARED + bank * 256 + node;
+                cached = r_esc || r_er > LY::MAXE_R;
+                is = LY::R_RM_STATE + st * LY::ROW_R + rowoff; ic = LY::R_RM_CHAR + c * LY::ROW_R + rowoff; ig = LY::R_WIDE_SHARED + bank * 256 + node;
                 cs = wide_idx(bank, st, node); cc = wide_idx(bank, c, node);
                 runflag = r_esc && d == 0;
             } else if (warp == 2) {     // run length: first bit (d = 0) and unary exponent (d = 1..eu)
@@ -519,28 +521,28 @@ template <bool RANGE3> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode
                 K = isT ? K_RUN_T : K_RUN_E;
                 bit = isT ? (v_ != 1) : (k + 1 < r_eu);
                 cached = !isT && k >= UE_RES;
-                is = isT ? R_UT_STATE + st : R_UE_STATE + st * UE_RES + k;
-                ic = isT ? R_UT_CHAR + c : R_UE_CHAR + c * UE_RES + k;
-                ig = isT ? R_UT_SHARED : R_UE_SHARED + k;
+                is = isT ? LY::R_UT_STATE + st : LY::R_UE_STATE + st * UE_RES + k;
+                ic = isT ? LY::R_UT_CHAR + c : LY::R_UE_CHAR + c * UE_RES + k;
+                ig = isT ? LY::R_UT_SHARED : LY::R_UE_SHARED + k;
                 cs = ue_idx(st, k); cc = ue_idx(c, k);
             } else {                    // run length: mantissa (tree for exponents <= 5, linear contexts above; qlfc.cpp:1119)
                 const u32 bp = r_eu - 1 - (d < r_eu ? d : 0);
-                const bool tree = r_eu <= M_MAXE;
+                const bool tree = r_eu <= 5u;                                   // the FORMAT's rule (qlfc.cpp:1119), not a residency question
                 const u32 node = tree ? (v_ >> (bp + 1)) : 1u + d;
                 const u32 rowoff = (1u << r_eu) - 2u + node;
                 K = K_RUN_M;
                 bit = (v_ >> bp) & 1u;
-                cached = !tree;
-                is = R_UM_STATE + st * M_ROW + rowoff; ic = R_UM_CHAR + c * M_ROW + rowoff; ig = R_NARROW_SHARED + r_eu * 32 + node;
+                cached = LY::MAXE_U >= 5u ? !tree : r_eu > LY::MAXE_U;          // full layout: exactly the tree rows are resident
+                is = LY::R_UM_STATE + st * LY::ROW_U + rowoff; ic = LY::R_UM_CHAR + c * LY::ROW_U + rowoff; ig = LY::R_NARROW_SHARED + r_eu * 32 + node;
                 cs = narrow_idx(r_eu, st, node); cc = narrow_idx(r_eu, c, node);
             }
             cached = cached && act;
             if (__any_sync(0xffffffffu, cached)) n_cached += 2u * (u32)__popc(__ballot_sync(0xffffffffu, cached));
             const int4 *q = reinterpret_cast<const int4 *>(P.prm[K][bit & 1u]);
             const int4 qa = q[0], qb = q[1]; const int qg = P.prm[K][bit & 1u][8];
-            const int vs = enc_resolve<0>(S, act, is, cached, cs, qa.w, qb.x, cold_s, lane, misses QE_DIAG_ROUNDS(0));
-            const int vc = enc_resolve<1>(S, act, ic, cached, cc, qb.y, qb.z, cold_c, lane, misses QE_DIAG_ROUNDS(1));
-            const int vg = enc_resolve<2>(S, act, ig, false, 0, qb.w, qg, nullptr, lane, misses QE_DIAG_ROUNDS(2));
+            const int vs = enc_resolve<LY, 0>(S, act, is, cached, cs, qa.w, qb.x, cold_s, lane, misses QE_DIAG_ROUNDS(0));
+            const int vc = enc_resolve<LY, 1>(S, act, ic, cached, cc, qb.y, qb.z, cold_c, lane, misses QE_DIAG_ROUNDS(1));
+            const int vg = enc_resolve<LY, 2>(S, act, ig, false, 0, qb.w, qg, nullptr, lane, misses QE_DIAG_ROUNDS(2));
             const u32 p = (u32)((vc * qa.x + vs * qa.y + vg * qa.z) >> 5);
             if (act) P.ring[(base_off + rp + d) & (QE_RING - 1)] = p | (bit ? QE_BIT : 0u) | (runflag ? QE_RUN : 0u);
         }

@@ -2,7 +2,7 @@
 """tools/cmp_sass.py OLD.o NEW.o -- are the kernels of two builds of csrc/qlfc.cu the same machine code?
 Used at the end of round 1 (no GPU minutes left) to show that the GPU-verified kernels were not touched by later host-side
 and experimental additions: every kernel of the verified commit must have byte-identical SASS text in the new object
-(the static encoder became a template on the way: q_encode5 is matched with q_encode5<false>)."""
+(the static encoder became a template on the way: q_encode5 is matched with q_encode5<LayoutFull, false>)."""
 import re, subprocess, sys
 def funcs(obj):
     out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
@@ -20,7 +20,7 @@ def key(n):   # strip the per-TU hash of the anonymous namespace and template sp
 ka = {key(k): k for k in a}; kb = {key(k): k for k in b}
 for k in sorted(ka):
     # the encoder became a template: q_encode5 -> q_encode5<false>
-    cand = [k2 for k2 in kb if k2 == k or (("q_encode5" in k) and ("q_encode5ILb0" in k2))]
+    cand = [k2 for k2 in kb if k2 == k or (("q_encode5" in k) and ("q_encode5" in k2) and ("Lj5ELj5ELi12" in k2 or "q_encode5ILb0" in k2) and "Lb0" in k2)]
     if not cand: print("MISSING in new:", k); continue
     same = a[ka[k]] == b[kb[cand[0]]]
     print(("SAME  " if same else "DIFF  ") + "%5d instr  " % len(a[ka[k]]) + k[:110])

@@ -12,12 +12,18 @@ echo "== 2b. file-level front end (bsc1 container, multi-GPU scheduler) on the G
 BSCB200_TEST_CLI=1 timeout 200 python -m pytest tests/test_cli_container.py -m gpu -q 2>&1 | tail -3
 echo "== 3. decoder A/B on one 64 MiB block: 4 = default, 7 = tuned code + full layout, 6 = tuned code + diet layout (2 streams/SM)"
 timeout 200 python tools/dec_ab.py 64 4 7 6 2>&1 | tail -4
-echo "== 3b. encoder range warp with the one-multiply-add recurrence: parity + time"
-BSCB200_QENC=2 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "coder_compress or block_bytes or k3" 2>&1 | tail -3
-BSCB200_QENC=2 timeout 100 python tools/dec_ab.py 64 4 2>&1 | tail -2
+echo "== 3b. encoder variants: 2 = one-multiply-add range recurrence, 6 = diet counter file (two encoders per SM), 7 = both: parity + time"
+for v in 2 6 7; do
+  BSCB200_QENC=$v timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "coder_compress or block_bytes or k3" 2>&1 | tail -1
+  BSCB200_QENC=$v timeout 100 python tools/dec_ab.py 64 4 2>&1 | tail -2
+done
 echo "== 4. parity of the diet decoder as the default decoder"
 BSCB200_QDEC=6 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
 echo "== 5. does co-residency pay?  36 blocks per GPU (18 compression contexts of 4.6 GiB, 36 decode-only contexts of 1.4 GiB): default decoder vs diet decoder"
 timeout 300 python bench.py --blocks 36 --workers 18 --decode-workers 36 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench36_gen4.json 2> gpurun_out/r2_bench36_gen4.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench36_gen4.json'));print('gen4 36 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
 BSCB200_QDEC=6 timeout 300 python bench.py --blocks 36 --workers 18 --decode-workers 36 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench36_gen6.json 2> gpurun_out/r2_bench36_gen6.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench36_gen6.json'));print('gen6 36 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
 } 2>&1 | tee gpurun_out/r2_first_call.log
+{
+echo "== 6. everything two-per-SM: 32 blocks in flight in both directions (32 contexts x 4.6 GiB), diet decoder + diet encoder with RANGE3"
+BSCB200_QDEC=6 BSCB200_QENC=7 timeout 300 python bench.py --blocks 32 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench32_diet.json 2> gpurun_out/r2_bench32_diet.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench32_diet.json'));print('diet both, 32 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
+} 2>&1 | tee -a gpurun_out/r2_first_call.log
