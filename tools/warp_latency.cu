@@ -27,6 +27,20 @@ template <int WHAT> __global__ void k(unsigned *out, long long *cyc, unsigned se
         if (WHAT == 7) { if ((v & 31) == (unsigned)(r & 31)) v = v * 3 + 1; __syncwarp(); }
         if (WHAT == 8) { v = __reduce_add_sync(0xffffffffu, v) + lane; }
     }
+    // ---- issue rate of a LONE warp (round 2: does "one instruction per 4-5 cycles whatever the dependency structure" hold?) ----
+    // N independent multiply-add chains in one instruction stream: cycles per INSTRUCTION = t / (REPS * N)
+    if (WHAT >= 100) {
+        unsigned a0 = v, a1 = v + 1, a2 = v + 2, a3 = v + 3, a4 = v + 4, a5 = v + 5, a6 = v + 6, a7 = v + 7;
+        t0 = clock64();
+#pragma unroll 1
+        for (int r = 0; r < REPS; ++r) {
+            a0 = a0 * 4093u + 77u;
+            if (WHAT >= 102) { a1 = a1 * 4091u + 79u; }
+            if (WHAT >= 104) { a2 = a2 * 4089u + 81u; a3 = a3 * 4087u + 83u; }
+            if (WHAT >= 108) { a4 = a4 * 4085u + 85u; a5 = a5 * 4083u + 87u; a6 = a6 * 4081u + 89u; a7 = a7 * 4079u + 91u; }
+        }
+        acc = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    }
     long long t1 = clock64();
     out[lane] = v + acc;
     if (lane == 0) *cyc = t1 - t0;
@@ -58,5 +72,10 @@ int main()
     run<1>("__match_any_sync, 8 distinct values", 8);
     run<1>("__match_any_sync, 4 distinct values", 4);
     run<1>("__match_any_sync, 1 distinct value", 1);
+    // cycles per LOOP ITERATION below; divide by the number of chains for cycles per instruction
+    run<100>("lone warp, 1 IMAD chain  (per iteration)");
+    run<102>("lone warp, 2 independent IMAD chains");
+    run<104>("lone warp, 4 independent IMAD chains");
+    run<108>("lone warp, 8 independent IMAD chains");
     return 0;
 }
