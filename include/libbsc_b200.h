@@ -52,7 +52,8 @@ int bsc_init(int features);
 int bsc_init_full(int features, void *(*malloc_fn)(size_t), void *(*zero_malloc_fn)(size_t), void (*free_fn)(void *));
 
 /* libbsc/libbsc.h:118 ; libbsc.cpp:213-338.  output holds n + 28 bytes; input may equal output.
- * LZP (lzpHashSize/lzpMinLen != 0) is outside the replaced path: LIBBSC_NOT_SUPPORTED. */
+ * bsc_compress: LZP (lzpHashSize/lzpMinLen != 0) is outside the replaced path: LIBBSC_NOT_SUPPORTED.
+ * bsc_decompress: blocks with an LZP stage are accepted (the inverse stage runs on the host after the GPU stages). */
 int bsc_compress(const unsigned char *input, unsigned char *output, int n, int lzpHashSize, int lzpMinLen, int blockSorter, int coder, int features);
 /* libbsc/libbsc.h:128 ; libbsc.cpp:68-81 */
 int bsc_store(const unsigned char *input, unsigned char *output, int n, int features);
@@ -97,6 +98,7 @@ int bscb200_coder_decompress(const unsigned char *input, int inputSize, unsigned
 void              *bscb200_ctx_create(int device, void *cuda_stream);
 void               bscb200_ctx_destroy(void *ctx);
 int                bscb200_ctx_reserve(void *ctx, long long bytes);
+int                bscb200_lzp_decompress_host(const unsigned char *input, int n, unsigned char *output, int outputCapacity, int lzpHashSize, int lzpMinLen);   /* inverse of the reference LZP stage (libbsc/lzp/lzp.h), host only */
 int                bscb200_device_count(void);                    /* CUDA devices visible to the process */
 int                bscb200_set_device(int device);                /* bind the calling thread: all entry points use the current device */
 long long          bscb200_workspace_bytes(int n, int blockSorter);

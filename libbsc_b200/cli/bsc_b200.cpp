@@ -6,9 +6,10 @@
 //
 // Format: 'b','s','c',0x31 | int32 nBlocks | per block { int64 blockOffset, int8 recordSize,
 // int8 sortingContexts } + one libbsc block.  Archives are interchangeable with the stock `bsc` in both directions as long as
-// the host-side preprocessing of the reference is off (`bsc e ... -p`): this front end always writes recordSize = 1,
-// sortingContexts = FOLLOWING and LZP-free blocks, and refuses archives that need LZP, record reordering or reversed contexts
-// (those stages stay in the reference's host code, BASELINE.json north_star).
+// the host-side filters of the reference are off: this front end always writes recordSize = 1, sortingContexts = FOLLOWING and
+// LZP-free blocks (= `bsc e ... -p`); it READS blocks with an LZP stage as well (the library undoes LZP on the host), i.e. archives
+// made with the reference's default options, and refuses only record reordering (-r) and reversed contexts (-cp / -ca), which stay
+// in the reference's host code (BASELINE.json north_star).
 //
 // Scheduling: blocks are independent.  One worker thread per (GPU, slot): a worker binds to its GPU once, takes the
 // next block index, reads it with pread, calls bsc_compress / bsc_decompress (the library stages the block through pinned memory on
@@ -71,7 +72,7 @@ const char *error_text(int code)
 {
     switch (code) {
     case -2: return "not enough memory";
-    case -4: return "method not supported by this build (LZP / adaptive / fast coder / ST decoding stay outside the device path)";
+    case -4: return "method not supported by this build (see DESIGN.md 1: LZP on compression, ST decoding, gated coders)";
     case -5: return "unexpected end of block";
     case -6: return "the compressed data is corrupted";
     case -7: return "general GPU failure";
@@ -240,7 +241,7 @@ void usage()
             "  -e<algo>  entropy coder: -e1 static QLFC (default), -e0 fast, -e2 adaptive (experimental, see DESIGN.md)\n"
             "  -g<list>  GPUs to use, e.g. -g0,1,2,3 (default: all visible)\n"
             "  -j<n>     blocks in flight per GPU, default -j18 (one coder stream per SM: 18 x 8 = 144 of 148)\n"
-            "Archives are interchangeable with `bsc` when its preprocessing is off (`bsc e in out -p`).\n");
+            "Writes what `bsc e in out -p` writes; reads `bsc` archives made without -r / -c (LZP is undone on the host).\n");
     exit(0);
 }
 

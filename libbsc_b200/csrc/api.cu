@@ -11,6 +11,7 @@
 // (coder.h:56,66), bsc_adler32 (adler32.h).
 #include "common.cuh"
 #include "stages.cuh"
+#include "lzp_host.h"
 #include "../../include/libbsc_b200.h"
 
 #include <mutex>
@@ -217,7 +218,9 @@ int block_info_host(const unsigned char *h, int headerSize, int *pBlockSize, int
 }
 
 // bsc_decompress body once the 28-byte header `h` is on the host and the block is in HBM.
-int decompress_dev(Ctx *ctx, const unsigned char *h, const u8 *d_block, int inputSize, u8 *d_out, int outputSize, int features)
+// `lz_out` (host-pointer entry point only): blocks with an LZP stage (mode bits 8..23) are decoded up to the LZP stream, whose
+// length goes to *lz_out; the caller undoes LZP on the host (lzp_host.h) and checks length and Adler-32 of the data there.
+int decompress_dev(Ctx *ctx, const unsigned char *h, const u8 *d_block, int inputSize, u8 *d_out, int outputSize, int features, int *lz_out = nullptr)
 {
     int blockSize = 0, dataSize = 0;
     int info = block_info_host(h, inputSize, &blockSize, &dataSize);
@@ -231,7 +234,8 @@ int decompress_dev(Ctx *ctx, const unsigned char *h, const u8 *d_block, int inpu
         ctx->sync();
         return LIBBSC_NO_ERROR;
     }
-    if (mode != (mode & 0xff)) return LIBBSC_NOT_SUPPORTED;              // LZP stays on the host side of the boundary
+    const bool lzp = mode != (mode & 0xff);
+    if (lzp && !lz_out) return LIBBSC_NOT_SUPPORTED;                     // device-resident API: LZP stays on the host side of the boundary
     const int index = (int)get32(h + 12); const u32 adler_data = get32(h + 16);
     const int coder = (mode >> 5) & 7, sorter = mode & 0x1f;
     if (payload < 1) return LIBBSC_DATA_CORRUPT;
@@ -242,6 +246,7 @@ int decompress_dev(Ctx *ctx, const unsigned char *h, const u8 *d_block, int inpu
     if (sorter == 1) r = stage_bwt_decode(ctx, d_out, lzSize, index);
     else return LIBBSC_NOT_SUPPORTED;                                    // bsc_st_decode: SURVEY 8(f) next #2
     if (r < 0) return r;
+    if (lzp) { *lz_out = lzSize; return LIBBSC_NO_ERROR; }
     if (lzSize != dataSize) return LIBBSC_DATA_CORRUPT;
     return adler_data == stage_adler32(ctx, d_out, dataSize) ? LIBBSC_NO_ERROR : LIBBSC_DATA_CORRUPT;
 }
@@ -349,7 +354,18 @@ int bsc_decompress(const unsigned char *input, int inputSize, unsigned char *out
         u8 *d_out = ctx->arena.get<u8>((size_t)dataSize + 128);
         CUDA_TRY(cudaMemcpyAsync(d_blk, input, (size_t)blockSize, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(d_blk + blockSize, 0, 64, ctx->stream));
-        int r = decompress_dev(ctx, h, d_blk, blockSize, d_out, dataSize, features);
+        int lzSize = -1;
+        int r = decompress_dev(ctx, h, d_blk, blockSize, d_out, dataSize, features, &lzSize);
+        if (r == LIBBSC_NO_ERROR && lzSize >= 0) {                       // libbsc.cpp:599-613: undo the LZP stage on the host
+            const int mode = (int)get32(h + 8);
+            unsigned char *lz = (unsigned char *)bsc_malloc((size_t)lzSize + 1);
+            if (!lz) return LIBBSC_NOT_ENOUGH_MEMORY;
+            if (lzSize > 0) { CUDA_TRY(cudaMemcpyAsync(lz, d_out, (size_t)lzSize, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+            r = lzp_host::decompress(lz, lzSize, output, dataSize, (mode >> 16) & 0xff, (mode >> 8) & 0xff);
+            bsc_free(lz);
+            if (r < 0) return r;
+            return (r == dataSize && get32(h + 16) == host_adler32(output, (size_t)dataSize)) ? LIBBSC_NO_ERROR : LIBBSC_DATA_CORRUPT;
+        }
         if (r == LIBBSC_NO_ERROR && dataSize > 0) { CUDA_TRY(cudaMemcpyAsync(output, d_out, (size_t)dataSize, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
         return r;
     });
@@ -490,6 +506,13 @@ long long bscb200_workspace_bytes(int n, int blockSorter)
     size_t d = need_bwt_decode((size_t)n);
     return (long long)((s > d ? s : d) + need_coder((size_t)n) + (size_t)n + 8192);
 }
+// host-only: the inverse LZP stage by itself (what bsc_decompress runs after the GPU stages), for CPU tests against the reference
+int bscb200_lzp_decompress_host(const unsigned char *input, int n, unsigned char *output, int outputCapacity, int lzpHashSize, int lzpMinLen)
+{
+    if (!input || !output || n < 0 || outputCapacity < 0 || lzpHashSize < 10 || lzpHashSize > 28 || lzpMinLen < 4 || lzpMinLen > 255) return LIBBSC_BAD_PARAMETER;
+    return lzp_host::decompress(input, n, output, outputCapacity, lzpHashSize, lzpMinLen);
+}
+
 // Multi-GPU callers (libbsc_b200/cli/bsc_b200.cpp, one worker thread per GPU slot): every entry point works on the CURRENT device
 // of the calling thread, so a worker only has to bind itself once.  Plain wrappers, so that callers need no CUDA headers.
 int bscb200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }

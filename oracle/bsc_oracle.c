@@ -841,6 +841,68 @@ int orc_coder_decompress(const unsigned char *in, unsigned char *out, int coder)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* LZP decoder (the host-side preprocessing stage; only its inverse is restated: blocks made by   */
+/* the reference's default options can then be decoded).  lzp.cpp:564-674 (scalar tail loop =   */
+/* the definition), container lzp.cpp:813-887.                                                  */
+/* ------------------------------------------------------------------------------------------ */
+static int lzp_decode_block(const unsigned char *in, const unsigned char *inEnd, unsigned char *out, long outCap, int hashSize, int minLen)
+{
+    if (inEnd - in < 4) return ORC_UNEXPECTED_EOB;
+    int *lookup = calloc((size_t)1 << hashSize, sizeof(int));
+    if (!lookup) return ORC_NOT_ENOUGH_MEMORY;
+    const uint32_t mask = ((uint32_t)1 << hashSize) - 1;
+    long o = 0;
+    if (outCap < 4) { free(lookup); return ORC_DATA_CORRUPT; }
+    for (int i = 0; i < 4; ++i) out[o++] = *in++;
+    uint32_t ctx = (uint32_t)out[3] | ((uint32_t)out[2] << 8) | ((uint32_t)out[1] << 16) | ((uint32_t)out[0] << 24);
+    int bad = 0;
+    while (in < inEnd) {
+        const uint32_t idx = ((ctx >> 15) ^ ctx ^ (ctx >> 3)) & mask;
+        const int value = lookup[idx]; lookup[idx] = (int)o;
+        if (*in == 0xf2 && value > 0) {                              /* LIBBSC_LZP_MATCH_FLAG */
+            ++in;
+            if (in >= inEnd) { bad = 1; break; }
+            if (*in != 255) {
+                long len = minLen;
+                for (;;) { if (in >= inEnd) { bad = 1; break; } len += *in; if (*in++ != 254) break; }
+                if (bad || o + len > outCap) { bad = 1; break; }
+                for (long k = 0; k < len; ++k, ++o) out[o] = out[value + k];     /* forward copy: may overlap */
+                ctx = (uint32_t)out[o - 1] | ((uint32_t)out[o - 2] << 8) | ((uint32_t)out[o - 3] << 16) | ((uint32_t)out[o - 4] << 24);
+            } else {
+                ++in;
+                if (o >= outCap) { bad = 1; break; }
+                out[o++] = 0xf2; ctx = (ctx << 8) | 0xf2;
+            }
+        } else {
+            if (o >= outCap) { bad = 1; break; }
+            ctx = (ctx << 8) | (out[o++] = *in++);
+        }
+    }
+    free(lookup);
+    return bad ? ORC_DATA_CORRUPT : (int)o;
+}
+
+int orc_lzp_decompress(const unsigned char *in, unsigned char *out, int n, int outCap, int hashSize, int minLen)
+{
+    if (n < 1) return ORC_UNEXPECTED_EOB;
+    const int nBlocks = in[0];
+    if (nBlocks == 1) return lzp_decode_block(in + 1, in + n, out, outCap, hashSize, minLen);
+    if (nBlocks == 0 || n < 1 + 8 * nBlocks) return ORC_DATA_CORRUPT;
+    long inPtr = 1 + 8L * nBlocks, outPtr = 0;
+    for (int b = 0; b < nBlocks; ++b) {
+        const int outSize = (int)get32(in + 1 + 8 * b), inSize = (int)get32(in + 5 + 8 * b);
+        if (outSize < 0 || inSize < 0 || inPtr + inSize > n || outPtr + outSize > outCap) return ORC_DATA_CORRUPT;
+        int r;
+        if (inSize != outSize) r = lzp_decode_block(in + inPtr, in + inPtr + inSize, out + outPtr, outSize, hashSize, minLen);
+        else { r = inSize; memcpy(out + outPtr, in + inPtr, (size_t)inSize); }
+        if (r < 0) return r;
+        if (r != outSize) return ORC_DATA_CORRUPT;
+        inPtr += inSize; outPtr += outSize;
+    }
+    return (int)outPtr;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Block framing.  libbsc.cpp:68-81, 213-338, 340-418, 522-617.  LZP is not part of the path.   */
 /* ------------------------------------------------------------------------------------------ */
 int orc_store(const unsigned char *in, unsigned char *out, int n)
@@ -911,14 +973,22 @@ int orc_decompress(const unsigned char *in, int inSize, unsigned char *out, int 
     if (get32(in + 20) != orc_adler32(in + ORC_HEADER_SIZE, blockSize - ORC_HEADER_SIZE)) return ORC_DATA_CORRUPT;
     int mode = (int)get32(in + 8);
     if (mode == 0) { memcpy(out, in + ORC_HEADER_SIZE, (size_t)dataSize); return ORC_NO_ERROR; }
-    if (mode != (mode & 0xff)) return ORC_NOT_SUPPORTED;          /* LZP stays outside this oracle */
     int index = (int)get32(in + 12); uint32_t adler = get32(in + 16);
-    int coder = (mode >> 5) & 7, sorter = mode & 0x1f;
+    int coder = (mode >> 5) & 7, sorter = mode & 0x1f, lzpHash = (mode >> 16) & 0xff, lzpMin = (mode >> 8) & 0xff;
     int lzSize = orc_coder_decompress(in + ORC_HEADER_SIZE, out, coder);
     if (lzSize < 0) return lzSize;
     int r;
     if (sorter == 1) r = orc_bwt_decode(out, lzSize, index);
     else return ORC_NOT_SUPPORTED;                                /* bsc_st_decode: SURVEY 8(f) next #2 */
     if (r < 0) return r;
+    if (mode != (mode & 0xff)) {                                  /* libbsc.cpp:599-613: undo the LZP stage */
+        unsigned char *lz = malloc((size_t)lzSize + 1);
+        if (!lz) return ORC_NOT_ENOUGH_MEMORY;
+        memcpy(lz, out, (size_t)lzSize);
+        r = orc_lzp_decompress(lz, out, lzSize, dataSize, lzpHash, lzpMin);
+        free(lz);
+        if (r < 0) return r;
+        lzSize = r;
+    }
     return (lzSize == dataSize && adler == orc_adler32(out, dataSize)) ? ORC_NO_ERROR : ORC_DATA_CORRUPT;
 }

@@ -68,7 +68,10 @@ int orc_coder_compress(const unsigned char *in, unsigned char *out, int n, int c
 /* libbsc/coder/coder.cpp:273 bsc_coder_decompress */
 int orc_coder_decompress(const unsigned char *in, unsigned char *out, int coder);
 
-/* libbsc/libbsc/libbsc.cpp:68,213,340,522 (LZP disabled: lzpHashSize = lzpMinLen = 0 only) */
+/* libbsc/lzp/lzp.cpp:813 bsc_lzp_decompress (decoder only; writes at most outCap bytes) */
+int orc_lzp_decompress(const unsigned char *in, unsigned char *out, int n, int outCap, int hashSize, int minLen);
+
+/* libbsc/libbsc/libbsc.cpp:68,213,340,522 (orc_compress: lzpHashSize = lzpMinLen = 0 only; orc_decompress undoes LZP) */
 int orc_store(const unsigned char *in, unsigned char *out, int n);
 int orc_compress(const unsigned char *in, unsigned char *out, int n, int blockSorter, int coder, int features);
 int orc_block_info(const unsigned char *hdr, int hdrSize, int *pBlockSize, int *pDataSize);

@@ -151,6 +151,7 @@ class Port(_Api):
         self.f_dec_fast = s("qlfc_fast_decode_block", [vp, vp])
         self.f_enc_adapt = s("qlfc_adaptive_encode_block", [vp, vp, ci, ci])
         self.f_dec_adapt = s("qlfc_adaptive_decode_block", [vp, vp])
+        self.f_lzp_dec = s("lzp_decompress", [vp, vp, ci, ci, ci, ci])
         self.f_split = s("coder_split_blocks", [vp, ci, ci, vp, vp], None)
         self.f_cc = s("coder_compress", [vp, vp, ci, ci, ci])
         self.f_cd = s("coder_decompress", [vp, vp, ci])
@@ -194,6 +195,13 @@ class Port(_Api):
         out = np.empty(n + 64, dtype=np.uint8)
         f = {1: self.f_dec_block, 2: self.f_dec_adapt, 3: self.f_dec_fast}[coder]
         r = f(_ptr(s), _ptr(out))
+        return r, out[:max(r, 0)].copy()
+
+    def lzp_decompress(self, stream, out_cap, lzp_hash=15, lzp_min=128):
+        s = np.ascontiguousarray(stream, dtype=np.uint8)
+        out = np.full(out_cap + 64, 0xAA, dtype=np.uint8)
+        r = self.f_lzp_dec(_ptr(s), _ptr(out), s.size, out_cap, lzp_hash, lzp_min)
+        assert np.all(out[out_cap:] == 0xAA)
         return r, out[:max(r, 0)].copy()
 
     def split_blocks(self, data, nblocks):
@@ -306,6 +314,20 @@ class Ref(_Api):
 
     def _compress(self, data, out, sorter, coder, features):
         return self.f_comp(_ptr(data), _ptr(out), data.size, 0, 0, sorter, coder, features)
+
+    def compress_lzp(self, data, lzp_hash=15, lzp_min=128, sorter=1, coder=1, features=3):
+        """bsc_compress with the reference's LZP stage on (its default options)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.empty(data.size + 28 + 64, dtype=np.uint8)
+        r = self.f_comp(_ptr(data), _ptr(out), data.size, lzp_hash, lzp_min, sorter, coder, features)
+        return r, (out[:r].copy() if r > 0 else None)
+
+    def lzp_compress(self, data, lzp_hash=15, lzp_min=128, features=3):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.empty(data.size + 64, dtype=np.uint8)
+        f = self._sig("lzp_compress", [vp, vp, ci, ci, ci, ci])
+        r = f(_ptr(data), _ptr(out), data.size, lzp_hash, lzp_min, features)
+        return r, (out[:r].copy() if r > 0 else None)
 
     def _block_info(self, block, bs, ds):
         return self.f_info(_ptr(block), block.size, ctypes.cast(bs, vp), ctypes.cast(ds, vp), 0)

@@ -79,6 +79,17 @@ def test_reader_accepts_blocks_in_any_order(clis, gen):
     assert open(back, "rb").read() == open(path, "rb").read()
 
 
+def test_reader_accepts_reference_default_archives(clis, gen):
+    """`bsc e in out` (LZP on, parallel block loop): the container carries LZP blocks, the block API undoes them."""
+    d = clis
+    path = str(d / "dflt.bin")
+    np.tile(gen.text(8, 300000), 12).tofile(path)                       # repetitive: LZP finds matches
+    arch, back = str(d / "dflt.bsc"), str(d / "dflt.back")
+    _run(REFCLI, "e", path, arch, "-b1")
+    _run(TESTCLI, "d", arch, back, "-j3")
+    assert open(back, "rb").read() == open(path, "rb").read()
+
+
 def test_reader_refuses_host_side_preprocessing(clis, gen):
     d = clis
     path = str(d / "lzp.bin")

@@ -175,3 +175,17 @@ def test_k5_st6_skew_32mb(bsc, gen):
     assert i == 28690215 and gen.adler32(L) == 0x3141fea1
     z, blk = bsc.compress(a, sorter=6)
     assert z == 32294018 and gen.adler32(blk) == 0x8d12e56b
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BSCB200_TEST_LZP") != "1", reason="set BSCB200_TEST_LZP=1 (decoding of LZP blocks not yet run on a GPU)")
+def test_decompress_blocks_made_with_reference_default_options(bsc, gen, ref):
+    """bsc_decompress accepts blocks with an LZP stage (the reference's default lzpHashSize 15 / lzpMinLen 128): GPU stages, then
+    the inverse LZP stage on the host (csrc/lzp_host.h).  bsc_compress with LZP parameters stays LIBBSC_NOT_SUPPORTED."""
+    rep = np.tile(gen.text(3, 700), 900)
+    for a in (rep, np.tile(gen.text(2, 1 << 20), 5), gen.text(6, 200000)):
+        z, blk = ref.compress_lzp(a)
+        assert z > 0
+        q, u = bsc.decompress(blk)
+        assert q == 0 and np.array_equal(u, a)
+        bad = blk.copy(); bad[-5] ^= 1
+        assert bsc.decompress(bad)[0] == -6

@@ -143,6 +143,50 @@ def test_port_other_coders_match_reference(gen, port, ref, coder):
     assert port.decompress(b2)[0] == 0 and ref.decompress(b1)[0] == 0
 
 
+def test_port_undoes_reference_lzp(gen, port, ref):
+    """The LZP stage stays on the host (BASELINE.json north_star); only its DECODER is restated (lzp.cpp:564-674, 813-887), so
+    that blocks made with the reference's default options (`lzpHashSize` 15, `lzpMinLen` 128) can be decoded."""
+    rng = np.random.default_rng(1)
+    rep = np.tile(gen.text(3, 700), 900)                                          # long repeats: many LZP matches
+    mixed = np.concatenate([gen.text(4, 300000), rep[:400000], np.full(5000, 0xF2, np.uint8), gen.text(4, 300000), rng.integers(0, 256, 50000, dtype=np.uint8)])
+    for name, a in (("rep", rep), ("mixed", mixed), ("text5M", np.tile(gen.text(2, 1 << 20), 5)), ("flags", np.full(100000, 0xF2, np.uint8))):
+        for h, m in ((15, 128), (12, 4), (16, 32), (18, 255)):
+            r, s = ref.lzp_compress(a, h, m)
+            if r <= 0:
+                continue
+            n, out = port.lzp_decompress(s, a.size, h, m)
+            assert n == a.size and np.array_equal(out, a), (name, h, m)
+            assert port.lzp_decompress(s, a.size - 1, h, m)[0] < 0                 # never writes past the capacity
+        z, blk = ref.compress_lzp(a)                                              # the reference's default block
+        assert z > 0 and (int.from_bytes(bytes(blk[8:12]), "little") >> 8) != 0, name
+        q, u = port.decompress(blk)
+        assert q == 0 and np.array_equal(u, a), name
+
+
+def test_product_host_lzp_decoder_matches_reference(gen, ref):
+    """libbsc_b200's host-side inverse LZP stage (csrc/lzp_host.h, what bsc_decompress runs after the GPU stages) against the
+    reference's bsc_lzp_compress -- host-only code, so it is checked here without a GPU."""
+    import libbsc_b200
+    L = libbsc_b200.lib()
+    rng = np.random.default_rng(2)
+    rep = np.tile(gen.text(3, 700), 900)
+    mixed = np.concatenate([gen.text(4, 300000), rep[:400000], np.full(5000, 0xF2, np.uint8), rng.integers(0, 256, 50000, dtype=np.uint8)])
+    for name, a in (("rep", rep), ("mixed", mixed), ("text5M", np.tile(gen.text(2, 1 << 20), 5))):
+        for h, m in ((15, 128), (12, 4), (18, 255)):
+            r, s = ref.lzp_compress(a, h, m)
+            if r <= 0:
+                continue
+            out = np.full(a.size + 64, 0xAA, dtype=np.uint8)
+            n = L.bscb200_lzp_decompress_host(s.ctypes.data, s.size, out.ctypes.data, a.size, h, m)
+            assert n == a.size and np.array_equal(out[:a.size], a) and np.all(out[a.size:] == 0xAA), (name, h, m)
+            assert L.bscb200_lzp_decompress_host(s.ctypes.data, s.size, out.ctypes.data, a.size - 1, h, m) == -6
+            bad = s.copy(); bad[bad.size // 2] ^= 0x55
+            out2 = np.full(a.size + 64, 0xAA, dtype=np.uint8)
+            L.bscb200_lzp_decompress_host(bad.ctypes.data, bad.size, out2.ctypes.data, a.size, h, m)   # any result, but inside the capacity
+            assert np.all(out2[a.size:] == 0xAA)
+    assert L.bscb200_lzp_decompress_host(s.ctypes.data, s.size, out.ctypes.data, a.size, 9, 128) == -1
+
+
 def test_small_n_bwt_conventions(port, ref):
     for n in (0, 1, 2, 3, 7, 8, 15, 16, 17, 31, 33):
         a = (np.arange(n, dtype=np.uint8) * 7 + 3) % 5
