@@ -99,6 +99,7 @@ void              *bscb200_ctx_create(int device, void *cuda_stream);
 void               bscb200_ctx_destroy(void *ctx);
 int                bscb200_ctx_reserve(void *ctx, long long bytes);
 int                bscb200_lzp_decompress_host(const unsigned char *input, int n, unsigned char *output, int outputCapacity, int lzpHashSize, int lzpMinLen);   /* inverse of the reference LZP stage (libbsc/lzp/lzp.h), host only */
+int                bscb200_lzp_compress_host(const unsigned char *input, unsigned char *output, int n, int lzpHashSize, int lzpMinLen, int features);   /* the reference LZP stage forward (libbsc/lzp/lzp.h), host only */
 int                bscb200_device_count(void);                    /* CUDA devices visible to the process */
 int                bscb200_set_device(int device);                /* bind the calling thread: all entry points use the current device */
 long long          bscb200_workspace_bytes(int n, int blockSorter);

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "bscb200_ctx_destroy": ([vp], None),
     "bscb200_ctx_reserve": ([vp, ctypes.c_longlong], ci),
     "bscb200_lzp_decompress_host": ([vp, ci, vp, ci, ci, ci], ci),
+    "bscb200_lzp_compress_host": ([vp, vp, ci, ci, ci, ci], ci),
     "bscb200_device_count": ([], ci),
     "bscb200_set_device": ([ci], ci),
     "bscb200_workspace_bytes": ([ci, ci], ctypes.c_longlong),

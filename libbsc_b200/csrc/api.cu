@@ -154,14 +154,21 @@ int store_dev(Ctx *ctx, const u8 *d_in, int n, u8 *d_out, u32 adler_data)
 }
 
 // bsc_compress with LZP disabled, everything in HBM.  d_out must hold n + 28 bytes.
-int compress_dev(Ctx *ctx, const u8 *d_in, int n, u8 *d_out, int blockSorter, int coder, int features, bool inplace_rules)
+// `lz` (host-pointer bsc_compress with LZP parameters only): d_in holds the LZP stream of a block of lz->orig_n bytes whose Adler-32
+// is lz->adler_orig; the header describes the original block, and a block that does not shrink is reported as LIBBSC_NOT_COMPRESSIBLE
+// (the caller stores the ORIGINAL data, libbsc.cpp:315-318).
+struct LzpInfo { int orig_n; u32 adler_orig; int mode_bits; };
+
+int compress_dev(Ctx *ctx, const u8 *d_in, int n, u8 *d_out, int blockSorter, int coder, int features, bool inplace_rules, const LzpInfo *lz = nullptr)
 {
     if (!sorter_valid(blockSorter)) return LIBBSC_BAD_PARAMETER;
     if (coder < 1 || coder > 3) return LIBBSC_BAD_PARAMETER;
     if (n < 0 || n > 1073741824) return LIBBSC_BAD_PARAMETER;
-    int mode = blockSorter | (coder << 5);
-    const u32 adler_data = stage_adler32(ctx, d_in, n);
-    if (n <= LIBBSC_HEADER_SIZE) return store_dev(ctx, d_in, n, d_out, adler_data);
+    if (lz && n <= LIBBSC_HEADER_SIZE) blockSorter = 1;                  // libbsc.cpp:278-282: a tiny LZP stream is always BWT-sorted
+    int mode = blockSorter | (coder << 5) | (lz ? lz->mode_bits : 0);
+    const u32 adler_data = lz ? lz->adler_orig : stage_adler32(ctx, d_in, n);
+    if (!lz && n <= LIBBSC_HEADER_SIZE) return store_dev(ctx, d_in, n, d_out, adler_data);
+    const int orig_n = lz ? lz->orig_n : n;
 
     Arena &A = ctx->arena;
     const size_t mark = A.mark();
@@ -171,14 +178,14 @@ int compress_dev(Ctx *ctx, const u8 *d_in, int n, u8 *d_out, int blockSorter, in
     int indexes[256]; unsigned char num_indexes = 0; int index;
     if (blockSorter == 1) index = stage_bwt_encode(ctx, work, n, &num_indexes, indexes);
     else index = stage_st_encode(ctx, work, n, blockSorter);
-    if (n < 64 * 1024) num_indexes = 0;                   // libbsc.cpp:303
+    if (orig_n < 64 * 1024) num_indexes = 0;              // libbsc.cpp:303
     if (index < 0) { A.release(mark); return index; }
 
     int result = stage_coder_compress(ctx, work, d_out + LIBBSC_HEADER_SIZE, n, coder, features);
     A.release(mark);
     if (result == LIBBSC_NOT_SUPPORTED) return result;
-    if (result < 0 || result + 1 + 4 * num_indexes >= n) {
-        if (inplace_rules) return LIBBSC_NOT_COMPRESSIBLE;               // libbsc.cpp:188-191
+    if (result < 0 || result + 1 + 4 * num_indexes >= orig_n) {
+        if (inplace_rules || lz) return LIBBSC_NOT_COMPRESSIBLE;         // libbsc.cpp:188-191
         return store_dev(ctx, d_in, n, d_out, adler_data);               // libbsc.cpp:315-318
     }
     unsigned char *tail = (unsigned char *)(ctx->h_mail + 96);            // pinned, <= 4*255+1 bytes needs care: num_indexes <= 15 here
@@ -188,7 +195,7 @@ int compress_dev(Ctx *ctx, const u8 *d_in, int n, u8 *d_out, int blockSorter, in
     result += 1 + 4 * num_indexes;
     const u32 adler_payload = stage_adler32(ctx, d_out + LIBBSC_HEADER_SIZE, result);
     unsigned char *h = (unsigned char *)(ctx->h_mail + 64);
-    put32(h, (u32)(result + LIBBSC_HEADER_SIZE)); put32(h + 4, (u32)n); put32(h + 8, (u32)mode); put32(h + 12, (u32)index);
+    put32(h, (u32)(result + LIBBSC_HEADER_SIZE)); put32(h + 4, (u32)orig_n); put32(h + 8, (u32)mode); put32(h + 12, (u32)index);
     put32(h + 16, adler_data); put32(h + 20, adler_payload); put32(h + 24, host_adler32(h, 24));
     CUDA_TRY(cudaMemcpyAsync(d_out, h, LIBBSC_HEADER_SIZE, cudaMemcpyHostToDevice, ctx->stream));
     ctx->sync();
@@ -324,12 +331,36 @@ int bsc_compress(const unsigned char *input, unsigned char *output, int n, int l
     if (lzpMinLen != 0 || lzpHashSize != 0) {
         if (lzpMinLen < 4 || lzpMinLen > 255) return LIBBSC_BAD_PARAMETER;
         if (lzpHashSize < 10 || lzpHashSize > 28) return LIBBSC_BAD_PARAMETER;
-        return LIBBSC_NOT_SUPPORTED;                       // LZP is outside this library (stays in host libbsc)
+        // The LZP stage runs on the host (lzp_host.h: the reference's x86-64 variants `large` and `generic`).  Bit-exact against the
+        // reference on CPU, but the combined path has not run on a GPU yet: behind BSCB200_ENABLE_LZP=1 until then.
+        static const bool on = [] { const char *e = getenv("BSCB200_ENABLE_LZP"); return e && e[0] == '1'; }();
+        if (!on || !lzp_host::supported(lzpHashSize, lzpMinLen)) return LIBBSC_NOT_SUPPORTED;
     }
     const bool inplace = (input == output);
     if (n < 0 || n > (inplace ? 2146435072 : 1073741824)) return LIBBSC_BAD_PARAMETER;
     if (n > 1073741824) return LIBBSC_NOT_SUPPORTED;
     if (n <= LIBBSC_HEADER_SIZE) return bsc_store(input, output, n, features);
+    if (lzpMinLen != 0) {                                   // libbsc.cpp:264-276
+        unsigned char *lzbuf = (unsigned char *)bsc_malloc((size_t)n + 64);
+        if (!lzbuf) return LIBBSC_NOT_ENOUGH_MEMORY;
+        const int lzSize = lzp_host::compress(input, lzbuf, n, lzpHashSize, lzpMinLen, (features & LIBBSC_FEATURE_MULTITHREADING) != 0);
+        if (lzSize >= 0) {
+            const LzpInfo lz = {n, host_adler32(input, (size_t)n), (lzpMinLen << 8) | (lzpHashSize << 16)};
+            int r = with_ctx([&](Ctx *ctx) {
+                ctx->arena.reserve(2 * (size_t)n + 8192 + (blockSorter == 1 ? need_bwt_encode(n) : need_st_encode(n)) + need_coder(n));
+                u8 *d_in = ctx->arena.get<u8>((size_t)lzSize + 64);
+                u8 *d_out = ctx->arena.get<u8>((size_t)n + 4096) + 4;
+                if (lzSize > 0) CUDA_TRY(cudaMemcpyAsync(d_in, lzbuf, (size_t)lzSize, cudaMemcpyHostToDevice, ctx->stream));
+                int rr = compress_dev(ctx, d_in, lzSize, d_out, blockSorter, coder, features, inplace, &lz);
+                if (rr > 0) { CUDA_TRY(cudaMemcpyAsync(output, d_out, (size_t)rr, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+                return rr;
+            });
+            bsc_free(lzbuf);
+            if (r == LIBBSC_NOT_COMPRESSIBLE && !inplace) return bsc_store(input, output, n, features);
+            return r;
+        }
+        bsc_free(lzbuf);                                    // LZP did not shrink the block: continue without it (mode &= 0xff)
+    }
     return with_ctx([&](Ctx *ctx) {
         ctx->arena.reserve(2 * (size_t)n + 8192 + (blockSorter == 1 ? need_bwt_encode(n) : need_st_encode(n)) + need_coder(n));
         u8 *d_in = ctx->arena.get<u8>((size_t)n + 64);
@@ -511,6 +542,15 @@ int bscb200_lzp_decompress_host(const unsigned char *input, int n, unsigned char
 {
     if (!input || !output || n < 0 || outputCapacity < 0 || lzpHashSize < 10 || lzpHashSize > 28 || lzpMinLen < 4 || lzpMinLen > 255) return LIBBSC_BAD_PARAMETER;
     return lzp_host::decompress(input, n, output, outputCapacity, lzpHashSize, lzpMinLen);
+}
+
+// host-only: the forward LZP stage by itself (bsc_lzp_compress, lzp.h); LIBBSC_NOT_SUPPORTED for the parameter classes whose
+// reference variant is not restated (lzp_host.h)
+int bscb200_lzp_compress_host(const unsigned char *input, unsigned char *output, int n, int lzpHashSize, int lzpMinLen, int features)
+{
+    if (!input || !output || n < 0 || lzpHashSize < 10 || lzpHashSize > 28 || lzpMinLen < 4 || lzpMinLen > 255) return LIBBSC_BAD_PARAMETER;
+    if (!lzp_host::supported(lzpHashSize, lzpMinLen)) return LIBBSC_NOT_SUPPORTED;
+    return lzp_host::compress(input, output, n, lzpHashSize, lzpMinLen, (features & LIBBSC_FEATURE_MULTITHREADING) != 0);
 }
 
 // Multi-GPU callers (libbsc_b200/cli/bsc_b200.cpp, one worker thread per GPU slot): every entry point works on the CURRENT device

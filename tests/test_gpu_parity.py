@@ -189,3 +189,17 @@ def test_decompress_blocks_made_with_reference_default_options(bsc, gen, ref):
         assert q == 0 and np.array_equal(u, a)
         bad = blk.copy(); bad[-5] ^= 1
         assert bsc.decompress(bad)[0] == -6
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BSCB200_TEST_LZP") != "1" or __import__("os").environ.get("BSCB200_ENABLE_LZP") != "1",
+                    reason="set BSCB200_ENABLE_LZP=1 BSCB200_TEST_LZP=1 (bsc_compress with the host LZP stage not yet run on a GPU)")
+def test_compress_with_reference_default_options(bsc, gen, ref):
+    """bsc_compress(lzpHashSize 15, lzpMinLen 128) = the reference's default call: host LZP stage, then the GPU stages."""
+    rep = np.tile(gen.text(3, 700), 900)
+    for a in (rep, np.tile(gen.text(2, 1 << 20), 5), gen.text(6, 200000), np.full(3000, 65, np.uint8), gen.rand(1, 300000)):
+        for feats in (3, 1):
+            z2, b2 = ref.compress_lzp(a, 15, 128, 1, 1, feats)
+            z1, b1 = bsc.compress(a, 1, 1, feats, lzp_hash=15, lzp_min=128)
+            assert z1 == z2 and np.array_equal(b1, b2)
+        q, u = bsc.decompress(b1)
+        assert q == 0 and np.array_equal(u, a)

@@ -187,6 +187,31 @@ def test_product_host_lzp_decoder_matches_reference(gen, ref):
     assert L.bscb200_lzp_decompress_host(s.ctypes.data, s.size, out.ctypes.data, a.size, 9, 128) == -1
 
 
+def test_product_host_lzp_encoder_matches_reference(gen, ref):
+    """The forward LZP stage of libbsc_b200 (csrc/lzp_host.h: the reference's x86-64 variants `large` and `generic`, both chunk
+    container rules) reproduces bsc_lzp_compress byte for byte; the other variants answer LIBBSC_NOT_SUPPORTED."""
+    import libbsc_b200
+    L = libbsc_b200.lib()
+    rng = np.random.default_rng(2)
+    rep = np.tile(gen.text(3, 700), 900)
+    cases = {"rep": rep, "mixed": np.concatenate([gen.text(4, 300000), rep[:400000], np.full(5000, 0xF2, np.uint8), rng.integers(0, 256, 50000, dtype=np.uint8)]),
+             "text5M": np.tile(gen.text(2, 1 << 20), 5), "flags": np.full(100000, 0xF2, np.uint8), "small": np.tile(gen.text(5, 300), 100), "rand": gen.rand(1, 500000),
+             "nearrep": np.concatenate([gen.text(9, 200000)] * 3 + [gen.rand(2, 100000)] + [gen.text(9, 200000)] * 2)}
+    for name, a in cases.items():
+        for h, m in ((15, 128), (16, 64), (17, 17), (12, 255), (20, 128), (18, 4)):
+            for feats in (1, 3):
+                r1, s1 = ref.lzp_compress(a, h, m, feats)
+                out = np.full(a.size + 64, 0xAA, dtype=np.uint8)
+                r2 = L.bscb200_lzp_compress_host(a.ctypes.data, out.ctypes.data, a.size, h, m, feats)
+                assert r1 == r2, (name, h, m, feats, r1, r2)
+                assert r1 <= 0 or np.array_equal(out[:r2], s1), (name, h, m, feats)
+                assert np.all(out[a.size:] == 0xAA), "wrote past n bytes"
+    a = cases["rep"]
+    out = np.empty(a.size + 64, dtype=np.uint8)
+    assert L.bscb200_lzp_compress_host(a.ctypes.data, out.ctypes.data, a.size, 15, 8, 3) == -4     # `medium` variant: not restated
+    assert L.bscb200_lzp_compress_host(a.ctypes.data, out.ctypes.data, a.size, 9, 128, 3) == -1
+
+
 def test_small_n_bwt_conventions(port, ref):
     for n in (0, 1, 2, 3, 7, 8, 15, 16, 17, 31, 33):
         a = (np.arange(n, dtype=np.uint8) * 7 + 3) % 5
