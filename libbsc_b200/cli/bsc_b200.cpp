@@ -1,14 +1,13 @@
 // libbsc_b200/cli/bsc_b200.cpp -- file-level front end: the `bsc1` container of the reference CLI (bsc.cpp:50-57, 163-178,
 // 401-417, 470-600) around the block API of libbsc_b200, with a multi-GPU block scheduler.
 //
-//   bsc_b200 e <input> <archive> [-b<MiB>] [-m<0|3..8>] [-e<0|1|2>] [-g<dev[,dev...]>] [-j<blocks in flight per GPU>]
+//   bsc_b200 e <input> <archive> [-b<MiB>] [-m<0|3..8>] [-e<0|1|2>] [-l [-H<bits>] [-M<len>]] [-g<dev[,dev...]>] [-j<blocks in flight per GPU>]
 //   bsc_b200 d <archive> <output>              [-g...] [-j...]
 //
 // Format: 'b','s','c',0x31 | int32 nBlocks | per block { int64 blockOffset, int8 recordSize,
 // int8 sortingContexts } + one libbsc block.  Archives are interchangeable with the stock `bsc` in both directions as long as
-// the host-side filters of the reference are off: this front end always writes recordSize = 1, sortingContexts = FOLLOWING and
-// LZP-free blocks (= `bsc e ... -p`); it READS blocks with an LZP stage as well (the library undoes LZP on the host), i.e. archives
-// made with the reference's default options, and refuses only record reordering (-r) and reversed contexts (-cp / -ca), which stay
+// the host-side FILTERS of the reference are off: this front end always writes recordSize = 1 and sortingContexts = FOLLOWING; LZP
+// is off by default (= `bsc e ... -p`) and on with -l (= `bsc e ...` without -s / -r); it reads both kinds, and refuses only record reordering (-r) and reversed contexts (-cp / -ca), which stay
 // in the reference's host code (BASELINE.json north_star).
 //
 // Scheduling: blocks are independent.  One worker thread per (GPU, slot): a worker binds to its GPU once, takes the
@@ -58,6 +57,7 @@ enum { kFeatures = 1 | 2, kContextsFollowing = 1, kContextsPreceding = 2, kRecor
 
 struct Options {
     int block_bytes = 25 << 20, sorter = 1, coder = 1, slots = 18;
+    int lzp_hash = 0, lzp_min = 0;                                       // -l: the reference's LZP stage (host side of the library), off by default
     std::vector<int> devices;
 };
 
@@ -150,7 +150,7 @@ int compress_file(const char *in_name, const char *out_name, Options opt)
             pread_all(fin, in.data(), (size_t)n, (off_t)off, in_name);
             out.assign((size_t)n + LIBBSC_HEADER_SIZE + kRecordBytes, 0);
             put_record(out.data(), off, 1, kContextsFollowing);
-            const int r = bsc_compress(in.data(), out.data() + kRecordBytes, n, 0, 0, opt.sorter, opt.coder, kFeatures);   // stores incompressible blocks itself
+            const int r = bsc_compress(in.data(), out.data() + kRecordBytes, n, opt.lzp_hash, opt.lzp_min, opt.sorter, opt.coder, kFeatures);   // stores incompressible blocks itself
             if (r < LIBBSC_NO_ERROR) die("\nCompression failed: %s", error_text(r));
             out.resize((size_t)r + kRecordBytes);
             std::unique_lock<std::mutex> lk(mu);
@@ -239,6 +239,7 @@ void usage()
             "  -b<size>  block size in MiB, default -b25 (1..1024)\n"
             "  -m<algo>  block sorter: -m0 Burrows-Wheeler transform (default), -m3..-m8 sort transform of order n (encode only)\n"
             "  -e<algo>  entropy coder: -e1 static QLFC (default), -e0 fast, -e2 adaptive (experimental, see DESIGN.md)\n"
+            "  -l        LZP preprocessing on (host stage; -H<10..28> hash bits, -M<4..255> minimum match; bsc's defaults 15 / 128)\n"
             "  -g<list>  GPUs to use, e.g. -g0,1,2,3 (default: all visible)\n"
             "  -j<n>     blocks in flight per GPU, default -j18 (one coder stream per SM: 18 x 8 = 144 of 148)\n"
             "Writes what `bsc e in out -p` writes; reads `bsc` archives made without -r / -c (LZP is undone on the host).\n");
@@ -261,7 +262,10 @@ int main(int argc, char **argv)
         case 'e': if (v < 0 || v > 2) usage(); opt.coder = v == 0 ? 3 : v; break;
         case 'j': if (v < 1 || v > 64) usage(); opt.slots = v; break;
         case 'g': { opt.devices.clear(); for (const char *p = a + 2; *p; ) { opt.devices.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p == ',') ++p; } break; }
-        case 'p': break;                                                             // accepted for bsc compatibility: preprocessing is always off
+        case 'l': if (!opt.lzp_hash) { opt.lzp_hash = 15; opt.lzp_min = 128; } break;   // bsc's defaults (libbsc.h:78-79)
+        case 'H': if (v < 10 || v > 28) usage(); opt.lzp_hash = v; if (!opt.lzp_min) opt.lzp_min = 128; break;
+        case 'M': if (v < 4 || v > 255) usage(); opt.lzp_min = v; if (!opt.lzp_hash) opt.lzp_hash = 15; break;
+        case 'p': opt.lzp_hash = opt.lzp_min = 0; break;                             // bsc compatibility: all preprocessing off (the default here)
         default: usage();
         }
     }

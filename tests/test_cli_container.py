@@ -90,6 +90,18 @@ def test_reader_accepts_reference_default_archives(clis, gen):
     assert open(back, "rb").read() == open(path, "rb").read()
 
 
+def test_lzp_option_matches_reference_default(clis, gen):
+    """`bsc_b200 e -l` = `bsc e` (LZP 15 / 128 on, filters off); `-H` / `-M` as in bsc."""
+    d = clis
+    path = str(d / "l.bin")
+    np.tile(gen.text(8, 300000), 12).tofile(path)
+    for ours_opts, their_opts in ((["-l"], []), (["-l", "-H16", "-M64"], ["-H16", "-M64"]), (["-M200"], ["-M200"])):
+        ours, theirs = str(d / "l_ours.bsc"), str(d / "l_theirs.bsc")
+        _run(TESTCLI, "e", path, ours, "-b1", "-j3", *ours_opts)
+        _run(REFCLI, "e", path, theirs, "-b1", "-t", *their_opts)
+        assert open(ours, "rb").read() == open(theirs, "rb").read(), ours_opts
+
+
 def test_reader_refuses_host_side_preprocessing(clis, gen):
     d = clis
     path = str(d / "lzp.bin")
