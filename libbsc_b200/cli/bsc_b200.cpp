@@ -5,10 +5,11 @@
 //   bsc_b200 d <archive> <output>              [-g...] [-j...]
 //
 // Format: 'b','s','c',0x31 | int32 nBlocks | per block { int64 blockOffset, int8 recordSize,
-// int8 sortingContexts } + one libbsc block.  Archives are interchangeable with the stock `bsc` in both directions as long as
-// the host-side FILTERS of the reference are off: this front end always writes recordSize = 1 and sortingContexts = FOLLOWING; LZP
-// is off by default (= `bsc e ... -p`) and on with -l (= `bsc e ...` without -s / -r); it reads both kinds, and refuses only record reordering (-r) and reversed contexts (-cp / -ca), which stay
-// in the reference's host code (BASELINE.json north_star).
+// int8 sortingContexts } + one libbsc block.  This front end always WRITES recordSize = 1 and sortingContexts =
+// FOLLOWING (the reference's filters off), so the stock `bsc` reads everything it writes; LZP
+// is off by default (= `bsc e ... -p`) and on with -l (= `bsc e ...` without -s / -r).  It READS every bsc archive whose blocks the
+// library decodes: the inverses of the reference's filters (reversed contexts, record reordering) are applied after decoding;
+// the detectors that choose them on the compression side stay in the reference (BASELINE.json north_star: filters on the host).
 //
 // Scheduling: blocks are independent.  One worker thread per (GPU, slot): a worker binds to its GPU once, takes the
 // next block index, reads it with pread, calls bsc_compress / bsc_decompress (the library stages the block through pinned memory on
@@ -172,7 +173,19 @@ int compress_file(const char *in_name, const char *out_name, Options opt)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-struct BlockRef { long long file_pos, out_offset; int block_size, data_size; };
+struct BlockRef { long long file_pos, out_offset; int block_size, data_size, record_size, contexts; };
+
+// inverses of the reference's host-side filters, applied after the block is decoded (bsc.cpp:614-647):
+// reversed contexts (preprocessing.cpp:41-66) and record reordering (preprocessing.cpp:123-178: column-major back to records)
+void undo_filters(std::vector<unsigned char> &buf, int n, int record_size, int contexts, std::vector<unsigned char> &tmp)
+{
+    if (contexts == kContextsPreceding) std::reverse(buf.begin(), buf.begin() + n);
+    if (record_size > 1) {
+        tmp.assign(buf.begin(), buf.begin() + n);
+        const int rows = n / record_size;
+        for (int i = 0; i < rows; ++i) for (int j = 0; j < record_size; ++j) buf[(size_t)record_size * i + j] = tmp[(size_t)j * rows + i];
+    }
+}
 
 int decompress_file(const char *in_name, const char *out_name, Options opt)
 {
@@ -187,32 +200,32 @@ int decompress_file(const char *in_name, const char *out_name, Options opt)
     if (size < 8) die("This is not bsc archive!");
     pread_all(fin, head, 8, 0, in_name);
     if (memcmp(head, kSign, 4) != 0) die("This is not bsc archive or invalid compression method!");
-    int nBlocks; memcpy(&nBlocks, head + 4, 4);
-
+    // The block count in the header is only what the writer expected (segmentation, `bsc -s`, cuts blocks differently):
+    // like the reference (bsc.cpp:520-524) read records until the file ends.
     // pass 1 (sequential, headers only): where is every block and where does it go
     std::vector<BlockRef> blocks;
     long long pos = 8;
-    for (int b = 0; b < nBlocks; ++b) {
+    while (pos < size) {
         unsigned char rec[kRecordBytes + LIBBSC_HEADER_SIZE];
         if (pos + (long long)sizeof rec > size) die("Unexpected end of file: %s!", in_name);
         pread_all(fin, rec, sizeof rec, (off_t)pos, in_name);
         long long off = 0; for (int i = 0; i < 8; ++i) off |= (long long)rec[i] << (8 * i);
         const int recordSize = (signed char)rec[8], contexts = (signed char)rec[9];
         if (recordSize < 1 || (contexts != kContextsFollowing && contexts != kContextsPreceding)) die("This is not bsc archive or invalid compression method!");
-        if (recordSize != 1 || contexts != kContextsFollowing) die("This archive uses record reordering / reversed contexts (host-side filters of the reference): decode it with the stock bsc");
-        BlockRef r; r.file_pos = pos + kRecordBytes; r.out_offset = off;
+        BlockRef r; r.file_pos = pos + kRecordBytes; r.out_offset = off; r.record_size = recordSize; r.contexts = contexts;
         if (bsc_block_info(rec + kRecordBytes, LIBBSC_HEADER_SIZE, &r.block_size, &r.data_size, kFeatures) != LIBBSC_NO_ERROR) die("This is not bsc archive or invalid compression method!");
         if (r.file_pos + r.block_size > size) die("Unexpected end of file: %s!", in_name);
         blocks.push_back(r);
         pos = r.file_pos + r.block_size;
     }
 
+    const int nBlocks = (int)blocks.size();
     const double t0 = now();
     std::mutex mu; int next = 0; long long out_size = 0;
     const int W = std::max(1, std::min((int)opt.devices.size() * opt.slots, nBlocks));
     opt.slots = (W + (int)opt.devices.size() - 1) / (int)opt.devices.size();
     run_workers(opt, [&](int) {
-        std::vector<unsigned char> in, out;
+        std::vector<unsigned char> in, out, tmp;
         for (;;) {
             int b;
             { std::lock_guard<std::mutex> lk(mu); if (next >= nBlocks) return; b = next++; }
@@ -221,6 +234,7 @@ int decompress_file(const char *in_name, const char *out_name, Options opt)
             pread_all(fin, in.data(), in.size(), (off_t)r.file_pos, in_name);
             const int rc = bsc_decompress(in.data(), r.block_size, out.data(), r.data_size, kFeatures);
             if (rc < LIBBSC_NO_ERROR) die("\nDecompression failed: %s", error_text(rc));
+            undo_filters(out, r.data_size, r.record_size, r.contexts, tmp);
             pwrite_all(fout, out.data(), (size_t)r.data_size, (off_t)r.out_offset, out_name);
             std::lock_guard<std::mutex> lk(mu); out_size += r.data_size;
         }

@@ -102,14 +102,27 @@ def test_lzp_option_matches_reference_default(clis, gen):
         assert open(ours, "rb").read() == open(theirs, "rb").read(), ours_opts
 
 
-def test_reader_refuses_host_side_preprocessing(clis, gen):
+def test_reader_undoes_reference_filters(clis, gen):
+    """Archives made with the reference's host-side filters: reversed contexts (-cp), autodetected contexts (-ca), record
+    reordering (-r) and segmentation (-s).  The inverse filters are applied after the blocks are decoded."""
     d = clis
-    path = str(d / "lzp.bin")
-    gen.text(4, 1 << 20).tofile(path)
-    arch = str(d / "lzp.bsc")
-    _run(REFCLI, "e", path, arch, "-b1", "-t", "-cp")                   # reversed contexts: a host-side filter of the reference
-    p = subprocess.run([TESTCLI, "d", arch, str(d / "x")], capture_output=True, text=True)
-    assert p.returncode != 0 and "stock bsc" in p.stderr
+    rng = np.random.default_rng(8)
+    recs = np.zeros((300000, 4), dtype=np.uint8)                        # 4-byte records: slowly varying columns -> the detector picks recordSize 4
+    recs[:, 0] = np.arange(300000) & 255; recs[:, 1] = (np.arange(300000) >> 8) & 255; recs[:, 2] = 7; recs[:, 3] = rng.integers(0, 3, 300000)
+    files = {"text": gen.text(4, (1 << 20) + 77), "records": recs.reshape(-1), "mixed": np.concatenate([recs.reshape(-1)[:500000], gen.text(5, 600000)])}
+    seen_filter = False
+    for name, a in files.items():
+        path = str(d / (name + ".flt"))
+        a.tofile(path)
+        for opts in (["-cp"], ["-ca"], ["-r"], ["-r", "-ca", "-s"], ["-r", "-cp", "-l"]):
+            arch, back = str(d / "f.bsc"), str(d / "f.back")
+            _run(REFCLI, "e", path, arch, "-b1", "-t", *([] if "-l" in opts else ["-p"]), *[o for o in opts if o != "-l"])
+            raw = open(arch, "rb").read()
+            n_blocks = int.from_bytes(raw[4:8], "little")
+            seen_filter |= n_blocks > 0 and (raw[8 + 8] > 1 or raw[8 + 9] == 2)    # first record: recordSize, sortingContexts
+            _run(TESTCLI, "d", arch, back, "-j3")
+            assert open(back, "rb").read() == open(path, "rb").read(), (name, opts)
+    assert seen_filter
 
 
 @pytest.mark.gpu
