@@ -123,7 +123,8 @@ def test_error_codes(bsc, gen):
     a = gen.text(1, 1000)
     assert bsc.compress(a, sorter=2)[0] == -1
     assert bsc.compress(a, coder=0)[0] == -1
-    assert bsc.compress(a, lzp_hash=15, lzp_min=128)[0] == -4     # LZP is outside the replaced path
+    if __import__("os").environ.get("BSCB200_ENABLE_LZP") != "1":
+        assert bsc.compress(a, lzp_hash=15, lzp_min=128)[0] == -4     # the host LZP stage is gated until it has run on a GPU
     assert bsc.compress(a, lzp_hash=5, lzp_min=128)[0] == -1
     z, blk = bsc.compress(a)
     bad = blk.copy(); bad[40] ^= 1
