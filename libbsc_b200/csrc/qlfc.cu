@@ -560,13 +560,11 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             } else if (gen == 3) { if (prof) LAUNCH_DEC3(0, true); else LAUNCH_DEC3(0, false); }
             else if (gen == 4)   { if (prof) LAUNCH_DEC3(1, true); else LAUNCH_DEC3(1, false); }
             else if (gen == 5)   { if (prof) LAUNCH_DEC3(2, true); else LAUNCH_DEC3(2, false); }
-            else if (gen == 6) {
-                ensure_dyn_smem(q_decode6<LayoutDiet, false>, ctx->device, LayoutDiet::BYTES);
-                LAUNCH(ctx, (q_decode6<LayoutDiet, false>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list);
-            } else {
-                ensure_dyn_smem(q_decode6<LayoutFull, false>, ctx->device, LayoutFull::BYTES);
-                LAUNCH(ctx, (q_decode6<LayoutFull, false>), nlist, 32, LayoutFull::BYTES, d_in, d_sb, models, tables, d_out, d_list);
-            }
+#define LAUNCH_DEC6(LY, PROF) do { ensure_dyn_smem(q_decode6<LY, PROF>, ctx->device, LY::BYTES); \
+                LAUNCH(ctx, (q_decode6<LY, PROF>), nlist, 32, LY::BYTES, d_in, d_sb, models, tables, d_out, d_list); } while (0)
+            else if (gen == 6) { if (prof) LAUNCH_DEC6(LayoutDiet, true); else LAUNCH_DEC6(LayoutDiet, false); }
+            else               { if (prof) LAUNCH_DEC6(LayoutFull, true); else LAUNCH_DEC6(LayoutFull, false); }
+#undef LAUNCH_DEC6
 #undef LAUNCH_DEC3
         }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));

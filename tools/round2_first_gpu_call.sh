@@ -28,3 +28,4 @@ echo "== 6. everything two-per-SM: 32 blocks in flight in both directions (32 co
 BSCB200_QDEC=6 BSCB200_QENC=7 timeout 300 python bench.py --blocks 32 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench32_diet.json 2> gpurun_out/r2_bench32_diet.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench32_diet.json'));print('diet both, 32 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
 } 2>&1 | tee -a gpurun_out/r2_first_call.log
 echo "== 7. lone-warp issue rate (cost model of DESIGN.md 4.5)"; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/warp_latency tools/warp_latency.cu && gpurun_out/warp_latency | tee -a gpurun_out/r2_first_call.log
+echo "== 8. phase breakdown of the tuned decoder (cycles per run)"; for g in 7 6; do BSCB200_QDEC=$g BSCB200_QDEC_PROF=1 timeout 60 python tools/one_block.py 64 2>&1 | grep prof | tee -a gpurun_out/r2_first_call.log; done
