@@ -30,7 +30,11 @@ def _ptr(a):
 def build(force=False):
     """(Re)build liboracle.so, libbscgen.so and -- when /root/reference exists -- _ref/libbsc_ref.so."""
     # always through make: it rebuilds only what is stale (liboracle.so; oracle/_ref/* when /root/reference exists)
-    subprocess.check_call(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    try:
+        subprocess.check_call(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        if force or not os.path.exists(os.path.join(HERE, "liboracle.so")):
+            raise                                          # nothing usable: report the build failure
     gen = os.path.join(ROOT, "tools", "libbscgen.so")
     if force or not os.path.exists(gen):
         subprocess.check_call(["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-o", gen, os.path.join(ROOT, "tools", "bscgen.c")])
