@@ -73,7 +73,7 @@ const char *error_text(int code)
 {
     switch (code) {
     case -2: return "not enough memory";
-    case -4: return "method not supported by this build (see DESIGN.md 1: LZP on compression, ST decoding, gated coders)";
+    case -4: return "method not supported by this build (see DESIGN.md 1: ST decoding, gated coders and LZP)";
     case -5: return "unexpected end of block";
     case -6: return "the compressed data is corrupted";
     case -7: return "general GPU failure";

@@ -331,7 +331,7 @@ int bsc_compress(const unsigned char *input, unsigned char *output, int n, int l
     if (lzpMinLen != 0 || lzpHashSize != 0) {
         if (lzpMinLen < 4 || lzpMinLen > 255) return LIBBSC_BAD_PARAMETER;
         if (lzpHashSize < 10 || lzpHashSize > 28) return LIBBSC_BAD_PARAMETER;
-        // The LZP stage runs on the host (lzp_host.h: the reference's x86-64 variants `large` and `generic`).  Bit-exact against the
+        // The LZP stage runs on the host (lzp_host.h: all five x86-64 variants of the reference).  Bit-exact against the
         // reference on CPU, but the combined path has not run on a GPU yet: behind BSCB200_ENABLE_LZP=1 until then.
         static const bool on = [] { const char *e = getenv("BSCB200_ENABLE_LZP"); return e && e[0] == '1'; }();
         if (!on || !lzp_host::supported(lzpHashSize, lzpMinLen)) return LIBBSC_NOT_SUPPORTED;

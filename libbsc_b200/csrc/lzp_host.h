@@ -75,9 +75,9 @@ inline int decompress(const unsigned char *in, int n, unsigned char *out, int ca
 // ---- forward stage ------------------------------------------------------------------------------------------------------------
 // The reference picks one of five encoder variants by (hashSize, minLen) and platform (lzp.cpp:533-562), and they do NOT produce the
 // same bytes (different match verification and length counting), so "the reference's output" means the variant an x86-64 build
-// takes.  Restated here: `large` (hashSize <= 17, minLen > 16 -- includes the default 15 / 128) and `generic` (hashSize > 17).
-// The `small` / `small2x` / `medium` variants (hashSize <= 17 with minLen <= 16) are not: supported() is false for them.
-inline bool supported(int hash_bits, int min_len) { return hash_bits > 17 || min_len > 16; }
+// takes: `generic` for hashSize > 17, else `small` (minLen 4, 8), `small2x` (16), `medium` (5-7, 9-15), `large` (> 16, which includes
+// the default 15 / 128).  All of them are restated here.
+inline bool supported(int hash_bits, int min_len) { (void)hash_bits; (void)min_len; return true; }
 
 inline uint64_t load64(const unsigned char *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 inline uint32_t load32(const unsigned char *p) { uint32_t v; memcpy(&v, p, 4); return v; }
@@ -139,6 +139,41 @@ inline int encode_large(const unsigned char *in, const unsigned char *in_end, un
     return finish_literals(in, in_start, in_end, out, out_start, eob, seen, mask);
 }
 
+// lzp.cpp:55-147 small<T>, 149-241 small2x<T>, 243-335 medium<T>: one skeleton -- groups of four positions, a candidate is taken
+// when one or two machine words agree (no "too short" path: the words cover min_len), the length is then counted in 8-byte steps.
+//   word       4 or 8 bytes (T)
+//   second_at  offset of the second word that must agree, or -1 (small)
+//   guard      bytes kept clear at the end of the chunk: word (small) or 2 * word (small2x, medium)
+inline int encode_short(const unsigned char *in, const unsigned char *in_end, unsigned char *out, unsigned char *out_end, int *seen, uint32_t mask,
+                        int min_len, int word, int second_at, int guard)
+{
+    const unsigned char *in_start = in, *out_start = out, *eob = out_end - 8;
+    const unsigned char *scan_end = in_end - guard - 32;
+    auto same = [&](const unsigned char *a, const unsigned char *b) { return word == 8 ? load64(a) == load64(b) : load32(a) == load32(b); };
+    for (int i = 0; i < 4; ++i) *out++ = *in++;
+    while (in < scan_end && out < eob) {
+        int from = 0, good = -1, bad = -1;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t slot = hash_of(in + k) & mask;
+            from = seen[slot]; seen[slot] = (int)(in + k - in_start);
+            if (from > 0 && (second_at < 0 || same(in + k + second_at, in_start + from + second_at)) && same(in + k, in_start + from)) { good = k; break; }
+            if (from > 0 && in[k] == kMatchFlag) { bad = k; break; }
+        }
+        if (good < 0 && bad < 0) { memcpy(out, in, 4); in += 4; out += 4; continue; }
+        if (bad >= 0) { memcpy(out, in, (size_t)bad + 1); in += bad + 1; out += bad + 1; *out++ = 255; continue; }
+        memcpy(out, in, (size_t)good); in += good; out += good;
+        const unsigned char *ref = in_start + from;
+        long len = min_len;
+        for (; in + len < scan_end; len += 8) {
+            const uint64_t x = load64(in + len) ^ load64(ref + len);
+            if (x) { len += __builtin_ctzll(x) / 8; break; }
+        }
+        in += len;
+        put_length(out, eob, len - min_len);
+    }
+    return finish_literals(in, in_start, in_end, out, out_start, eob, seen, mask);
+}
+
 // lzp.cpp:441-531 bsc_lzp_encode_generic (the unaligned-access build)
 inline int encode_generic(const unsigned char *in, const unsigned char *in_end, unsigned char *out, unsigned char *out_end, int *seen, uint32_t mask, int min_len)
 {
@@ -173,7 +208,14 @@ inline int encode_chunk(const unsigned char *in, const unsigned char *in_end, un
     int *seen = (int *)calloc((size_t)1 << hash_bits, sizeof(int));
     if (!seen) return -2;
     const uint32_t mask = (uint32_t(1) << hash_bits) - 1u;
-    const int r = hash_bits <= 17 ? encode_large(in, in_end, out, out_end, seen, mask, min_len) : encode_generic(in, in_end, out, out_end, seen, mask, min_len);
+    int r;
+    if (hash_bits > 17)      r = encode_generic(in, in_end, out, out_end, seen, mask, min_len);
+    else if (min_len == 4)   r = encode_short(in, in_end, out, out_end, seen, mask, min_len, 4, -1, 4);            // small<unsigned int>
+    else if (min_len == 8)   r = encode_short(in, in_end, out, out_end, seen, mask, min_len, 8, -1, 8);            // small<unsigned long long>
+    else if (min_len == 16)  r = encode_short(in, in_end, out, out_end, seen, mask, min_len, 8, 8, 16);            // small2x<unsigned long long>
+    else if (min_len < 8)    r = encode_short(in, in_end, out, out_end, seen, mask, min_len, 4, min_len - 4, 8);   // medium<unsigned int>
+    else if (min_len < 16)   r = encode_short(in, in_end, out, out_end, seen, mask, min_len, 8, min_len - 8, 16);  // medium<unsigned long long>
+    else                     r = encode_large(in, in_end, out, out_end, seen, mask, min_len);
     free(seen);
     return r;
 }

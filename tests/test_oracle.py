@@ -188,8 +188,9 @@ def test_product_host_lzp_decoder_matches_reference(gen, ref):
 
 
 def test_product_host_lzp_encoder_matches_reference(gen, ref):
-    """The forward LZP stage of libbsc_b200 (csrc/lzp_host.h: the reference's x86-64 variants `large` and `generic`, both chunk
-    container rules) reproduces bsc_lzp_compress byte for byte; the other variants answer LIBBSC_NOT_SUPPORTED."""
+    """The forward LZP stage of libbsc_b200 (csrc/lzp_host.h: the all five variants an x86-64 reference build picks
+    from by (hashSize, minLen) -- small, small2x, medium, large, generic -- and both chunk container rules) reproduces
+    bsc_lzp_compress byte for byte."""
     import libbsc_b200
     L = libbsc_b200.lib()
     rng = np.random.default_rng(2)
@@ -198,7 +199,8 @@ def test_product_host_lzp_encoder_matches_reference(gen, ref):
              "text5M": np.tile(gen.text(2, 1 << 20), 5), "flags": np.full(100000, 0xF2, np.uint8), "small": np.tile(gen.text(5, 300), 100), "rand": gen.rand(1, 500000),
              "nearrep": np.concatenate([gen.text(9, 200000)] * 3 + [gen.rand(2, 100000)] + [gen.text(9, 200000)] * 2)}
     for name, a in cases.items():
-        for h, m in ((15, 128), (16, 64), (17, 17), (12, 255), (20, 128), (18, 4)):
+        for h, m in ((15, 128), (16, 64), (17, 17), (12, 255), (20, 128), (18, 4),
+                     (15, 4), (13, 8), (17, 16), (15, 6), (10, 12), (16, 9), (15, 15)):
             for feats in (1, 3):
                 r1, s1 = ref.lzp_compress(a, h, m, feats)
                 out = np.full(a.size + 64, 0xAA, dtype=np.uint8)
@@ -208,7 +210,6 @@ def test_product_host_lzp_encoder_matches_reference(gen, ref):
                 assert np.all(out[a.size:] == 0xAA), "wrote past n bytes"
     a = cases["rep"]
     out = np.empty(a.size + 64, dtype=np.uint8)
-    assert L.bscb200_lzp_compress_host(a.ctypes.data, out.ctypes.data, a.size, 15, 8, 3) == -4     # `medium` variant: not restated
     assert L.bscb200_lzp_compress_host(a.ctypes.data, out.ctypes.data, a.size, 9, 128, 3) == -1
 
 
