@@ -29,7 +29,7 @@ template <int WHAT> __global__ void k(unsigned *out, long long *cyc, unsigned se
     }
     // ---- issue rate of a LONE warp (round 2: does "one instruction per 4-5 cycles whatever the dependency structure" hold?) ----
     // N independent multiply-add chains in one instruction stream: cycles per INSTRUCTION = t / (REPS * N)
-    if (WHAT >= 100) {
+    if (WHAT >= 100 && WHAT < 110) {
         unsigned a0 = v, a1 = v + 1, a2 = v + 2, a3 = v + 3, a4 = v + 4, a5 = v + 5, a6 = v + 6, a7 = v + 7;
         t0 = clock64();
 #pragma unroll 1
@@ -40,6 +40,70 @@ template <int WHAT> __global__ void k(unsigned *out, long long *cyc, unsigned se
             if (WHAT >= 108) { a4 = a4 * 4085u + 85u; a5 = a5 * 4083u + 87u; a6 = a6 * 4081u + 89u; a7 = a7 * 4079u + 91u; }
         }
         acc = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    }
+    // ---- straight-line issue: 64 independent operations per iteration (branch amortised) ----
+    //   110: 64 IMAD (one pipe)   111: 32 IMAD + 32 LOP3 alternating (two pipes)
+    if (WHAT == 110 || WHAT == 111) {
+        unsigned a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = v + j;
+        t0 = clock64();
+#pragma unroll 1
+        for (int r = 0; r < REPS; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (WHAT == 110 || (j & 1) == 0) asm volatile("mad.lo.u32 %0, %0, %1, 77;" : "+r"(a[j]) : "r"(seed));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(seed), "r"(lane));
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += a[j];
+    }
+    // ---- control flow of a lone warp ----
+    //   120: 8 forward branches per iteration, ALWAYS taken (uniform, condition known long before): cost of a taken branch
+    //   121: the same branches, NEVER taken
+    //   122: one forward branch per iteration whose condition is computed right before it (multiply -> compare -> branch), taken
+    //   123: as 122 but the compare feeds a predicated instruction instead of a branch
+    if (WHAT == 120 || WHAT == 121) {
+        const unsigned flag = (WHAT == 120) ? (v | 1u) : (v & (unsigned)(distinct >> 20));   // per-lane runtime values (vector predicate, like the coder's): 120 -> non-zero, 121 -> 0
+        t0 = clock64();
+#pragma unroll 1
+        for (int r = 0; r < REPS; ++r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p bra.uni SKIP;\n\t"
+                             "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+                             "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+                             "SKIP:\n\tadd.u32 %0, %0, 1;\n\t}" : "+r"(v) : "r"(flag));
+        }
+    }
+    if (WHAT == 122 || WHAT == 123) {
+        unsigned w = seed | 0x80000000u;                                     // stays >= 2^31 >= thr: the compare below is always true, but ptxas cannot know
+        const unsigned thr = (unsigned)distinct;
+        t0 = clock64();
+#pragma unroll 1
+        for (int r = 0; r < REPS; ++r) {
+            if (WHAT == 122)
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tmad.lo.u32 %0, %0, 1, %1;\n\tshr.u32 t, %0, 12;\n\tsetp.ge.u32 p, t, %2;\n\t@p bra.uni SKIP;\n\t"
+                             "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+                             "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+                             "SKIP:\n\t}" : "+r"(w) : "r"(lane), "r"(thr));
+            else
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tmad.lo.u32 %0, %0, 1, %1;\n\tshr.u32 t, %0, 12;\n\tsetp.ge.u32 p, t, %2;\n\t@p add.u32 %0, %0, 2;\n\t}"
+                             : "+r"(w) : "r"(lane), "r"(thr));
+        }
+        acc += w;
+    }
+    // ---- 130: LDS.U16 pointer chase (the counter loads of the coder are 16-bit) ----
+    if (WHAT == 130) {
+        unsigned short *s16 = (unsigned short *)sm;
+        unsigned x = v & 1023u;
+        t0 = clock64();
+#pragma unroll 1
+        for (int r = 0; r < REPS; ++r) x = s16[x] & 1023u;
+        acc += x;
     }
     long long t1 = clock64();
     out[lane] = v + acc;
@@ -77,5 +141,12 @@ int main()
     run<102>("lone warp, 2 independent IMAD chains");
     run<104>("lone warp, 4 independent IMAD chains");
     run<108>("lone warp, 8 independent IMAD chains");
+    run<110>("lone warp, 64 independent IMAD, straight line (per iteration of 64)");
+    run<111>("lone warp, 32 IMAD + 32 LOP3 alternating   (per iteration of 64)");
+    run<120>("8 uniform forward branches, all TAKEN      (per iteration of 8)");
+    run<121>("8 uniform forward branches, none taken     (per iteration of 8 x 9 instr)");
+    run<122>("IMAD -> SHF -> ISETP -> taken BRA chain     (per iteration)");
+    run<123>("IMAD -> SHF -> ISETP -> predicated IADD     (per iteration)");
+    run<130>("LDS.U16 pointer chase (+ LOP3)");
     return 0;
 }
