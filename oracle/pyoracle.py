@@ -29,12 +29,16 @@ def _ptr(a):
 
 def build(force=False):
     """(Re)build liboracle.so, libbscgen.so and -- when /root/reference exists -- _ref/libbsc_ref.so."""
-    # always through make: it rebuilds only what is stale (liboracle.so; oracle/_ref/* when /root/reference exists)
-    try:
-        subprocess.check_call(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
-    except (OSError, subprocess.CalledProcessError):
-        if force or not os.path.exists(os.path.join(HERE, "liboracle.so")):
-            raise                                          # nothing usable: report the build failure
+    # Through make wherever the sources can change (the build container: /root/reference present), so that staleness is handled
+    # there.  On the GPU box the prebuilt files of the snapshot are used as they are: nothing is rebuilt on the strength of file
+    # times a copy may not have preserved, and the ranks of a torchrun launch never race to rewrite a library another rank loads.
+    have = os.path.exists(os.path.join(HERE, "liboracle.so"))
+    if force or not have or os.path.exists("/root/reference/libbsc/libbsc.h"):
+        try:
+            subprocess.check_call(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+        except (OSError, subprocess.CalledProcessError):
+            if force or not have:
+                raise                                      # nothing usable: report the build failure
     gen = os.path.join(ROOT, "tools", "libbscgen.so")
     if force or not os.path.exists(gen):
         subprocess.check_call(["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-o", gen, os.path.join(ROOT, "tools", "bscgen.c")])
