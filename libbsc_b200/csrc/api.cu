@@ -60,6 +60,7 @@ void ctx_delete(Ctx *c)
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->qlfc_tables) cudaFree(c->qlfc_tables);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->long_ev) cudaEventDestroy(c->long_ev);
     if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -102,6 +102,15 @@ struct Ctx {
     }
 
     void sync() { CUDA_TRY(cudaStreamSynchronize(stream)); }
+    // Wait for work that runs for 0.1 - 2 s (the coder kernels).  cudaStreamSynchronize spins; with one worker thread per block in
+    // flight (18 per GPU in bench.py, times 8 ranks on one host) the spinning threads would take the cores away from the threads
+    // that are launching the short kernels of other blocks.  A blocking-sync event lets the thread sleep instead.
+    cudaEvent_t  long_ev = nullptr;
+    void sync_long() {
+        if (!long_ev) CUDA_TRY(cudaEventCreateWithFlags(&long_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(long_ev, stream));
+        CUDA_TRY(cudaEventSynchronize(long_ev));
+    }
     // Read `words` u32 from the device mailbox (blocks the host on this stream only).
     void fetch_mail(int words) {
         CUDA_TRY(cudaMemcpyAsync(h_mail, d_mail, sizeof(u32) * words, cudaMemcpyDeviceToHost, stream));

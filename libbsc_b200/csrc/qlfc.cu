@@ -410,7 +410,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         LAUNCH_ENC_VARIANT(nBlocks, nullptr);
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->sync();
+    ctx->sync_long();                                    // the encoder runs for 0.01 - 0.7 s: sleep, do not spin
 
     if (getenv("BSCB200_QSTATS"))
         for (int b = 0; b < nBlocks; ++b) fprintf(stderr, "[qstats enc] sub %d: in %u runs %u out %d rare-accesses %u misses %u\n", b, h_sb[b].in_size, h_sb[b].run_end - h_sb[b].run_begin, h_sb[b].result, h_sb[b].stat_cached, h_sb[b].stat_miss);
@@ -569,7 +569,7 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    ctx->sync();
+    ctx->sync_long();                                    // the decoder runs for up to 2 s: sleep, do not spin
     if (getenv("BSCB200_QSTATS"))
         for (int b = 0; b < (nBlocks == 1 ? 1 : nBlocks); ++b) fprintf(stderr, "[qstats dec] sub %d: out %d rare-accesses %u misses %u\n", b, h_sb[b].result, h_sb[b].stat_cached, h_sb[b].stat_miss);
     int total = 0, err = 0;
