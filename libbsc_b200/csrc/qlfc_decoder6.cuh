@@ -37,7 +37,10 @@ template <u32 MAXE_R_, u32 MAXE_U_, int CLOG_> struct QLayout {
     static constexpr u32 C_STATE_VAL = R_END, C_CHAR_VAL = C_STATE_VAL + SLOTS, S16_COUNT = (C_CHAR_VAL + SLOTS + 1) & ~1u;
     // shared-memory image (byte offsets); the counters start where CoderSmem's do, so SM3::cnt / SM3::set apply
     static constexpr u32 O_RANK_STATE = 0, O_RUN_STATE = 32768, O_S16 = 40960, O_TAG_STATE = O_S16 + 2 * S16_COUNT, O_TAG_CHAR = O_TAG_STATE + 2 * SLOTS;
-    static constexpr u32 O_RANK_HIST = O_TAG_CHAR + 2 * SLOTS, O_RUN_HIST = O_RANK_HIST + 256, O_MTF = (O_RUN_HIST + 256 + 15u) & ~15u, O_WIN = O_MTF + 288, BYTES = O_WIN + 272;
+    static constexpr u32 O_RANK_HIST = O_TAG_CHAR + 2 * SLOTS, O_RUN_HIST = O_RANK_HIST + 256, O_MTF = (O_RUN_HIST + 256 + 15u) & ~15u, O_WIN = O_MTF + 288;
+    // decoder only: two staged rows [256] of the escape bank (state row, symbol row), addressed like counters
+    static constexpr u32 O_ROWS = O_WIN + 272, BYTES = O_ROWS + 1024;
+    static constexpr u32 R_ROW_STATE = (O_ROWS - O_S16) / 2u, R_ROW_CHAR = R_ROW_STATE + 256u;
     // cache slot of a cold index: classes as in qlfc_coder.cuh (0,1 rank banks, 2 run mantissa, 3 run exponent >= 8)
     static QD3_FN_MEMBER u32 cache_slot(u32 idx)
     {
@@ -84,6 +87,32 @@ template <class LY> QD3_FN u32 qd6_cache_get(const SM3 &sm, u32 val_base, u32 ta
     return val_base + slot;
 }
 
+
+// 16-byte accesses: a row of the escape bank in global memory <-> the staged copy in shared memory
+QD3_FN U4 qd6_ldg128(const short *p)
+{
+#ifdef QD3_HOST
+    U4 v; memcpy(&v, p, 16); return v;
+#else
+    const uint4 t = *(const uint4 *)p; U4 v; v.x = t.x; v.y = t.y; v.z = t.z; v.w = t.w; return v;
+#endif
+}
+QD3_FN void qd6_stg128(short *p, const U4 &v)
+{
+#ifdef QD3_HOST
+    memcpy(p, &v, 16);
+#else
+    *(uint4 *)p = make_uint4(v.x, v.y, v.z, v.w);
+#endif
+}
+QD3_FN void qd6_sts128(const SM3 &sm, u32 off, const U4 &v)
+{
+#ifdef QD3_HOST
+    memcpy(sm.b + off, &v, 16);
+#else
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(sm.b + off), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
+}
 
 // one decision with P(bit = 0) = p / 4096
 template <class LY> QD3_FN u32 qd6_step(const SM3 &sm, Rc3 &rc, u32 p)
@@ -218,6 +247,21 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
     { const int err = qd6_prologue<LY>(sm, rc, lr, in, in_limit, out_cap, n, maxRank); if (err) return err; }
 
     u32 ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0; int avgRank = 0;
+    // Escape mode (avgRank >= 32, high-entropy data): the 8 decisions of a rank walk one row [256] of the escape bank per
+    // (state) and one per (symbol) -- 2 x 64 K counters that fit no cache (measured through the write-back caches: 16 accesses
+    // and 7-10 misses per run on G_skew, a dependent global round trip each).  Both rows are contiguous 512 bytes in the cold
+    // arrays, so they are fetched whole -- lane l owns bytes [16 l, 16 l + 16) of a row, always, which makes the global
+    // traffic program-ordered per address --, at the end of the previous run (state and symbol are known there), staged in
+    // shared memory for the decisions and written back whole.  The escape bank never goes through the caches here.
+#ifdef QD3_HOST
+    U4 rowS_[32], rowC_[32];
+    for (u32 lane = 0; lane < 32; ++lane) rowS_[lane] = rowC_[lane] = U4{0, 0, 0, 0};
+#define QD6_ROW(x) x##_[lane]
+#else
+    U4 rowS_ = {0, 0, 0, 0}, rowC_ = {0, 0, 0, 0};
+#define QD6_ROW(x) x##_
+#endif
+    u32 rowS_at = 0, rowC_at = 0;                                               // cold index of the fetched rows
     // positions 0..31 of the MTF list live in the lanes (lane l holds position l; shared memory keeps 32..255), the front
     // and its successor also as uniform values: c = list[0], m1 = list[1]
     QD3_LANES { QD3_L(lr).mtfv = sm.ld8(LY::O_MTF + lane); }
@@ -275,13 +319,15 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
             }
         } else {
             rank = 0;
+            QD3_LANES { qd6_sts128(sm, LY::O_ROWS + 16u * lane, QD6_ROW(rowS)); qd6_sts128(sm, LY::O_ROWS + 512u + 16u * lane, QD6_ROW(rowC)); }
+            QD3_SYNC();
             for (int node = 1, bit = maxRank; bit >= 0; --bit) {
-                const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, wide_idx(8, st, (u32)node), st_miss);
-                const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, wide_idx(8, c, (u32)node), st_miss);
-                st_cached += 2;
-                b = qd6_dec3<LY, K_RANK_P>(sm, rc, mv, is, ic, LY::R_WIDE_SHARED + 8u * 256u + (u32)node);
+                b = qd6_dec3<LY, K_RANK_P>(sm, rc, mv, LY::R_ROW_STATE + (u32)node, LY::R_ROW_CHAR + (u32)node, LY::R_WIDE_SHARED + 8u * 256u + (u32)node);
                 node = 2 * node + (int)b; rank = 2u * rank + b;
             }
+            QD3_SYNC();
+            QD3_LANES { qd6_stg128(cold_s + rowS_at + 8u * lane, sm.ld128(LY::O_ROWS + 16u * lane)); qd6_stg128(cold_c + rowC_at + 8u * lane, sm.ld128(LY::O_ROWS + 512u + 16u * lane)); }
+            st_cached += 2;                                                      // statistics: row fetches
             sm.st8(LY::O_RANK_HIST + c, (u32)qd3_ilog2(rank));
         }
         rank &= 255u;
@@ -370,6 +416,10 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
         // first-decision counters of the next run (nothing writes the rank counters until then) and its run state for rank 1
         tS = sm.cnt(LY::R_RT_STATE + st); tC = sm.cnt(LY::R_RT_CHAR + c); tG = sm.cnt(LY::R_RT_SHARED);
         st2z = sm.ld8(LY::O_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));
+        if (avgRank >= 32) {                                                     // the next run decodes its rank in escape mode: fetch its two rows now
+            rowS_at = wide_idx(8, st, 0); rowC_at = wide_idx(8, c, 0);
+            QD3_LANES { QD6_ROW(rowS) = qd6_ldg128(cold_s + rowS_at + 8u * lane); QD6_ROW(rowC) = qd6_ldg128(cold_c + rowC_at + 8u * lane); }
+        }
 
         // run expansion: byte address A is always written by lane A mod 32
         if (run <= 32u && i + 32u <= n) { QD3_LANES { out[i + ((lane - i) & 31u)] = (u8)cur; } }
@@ -389,6 +439,7 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
 #endif
     return (int)n;
 }
+#undef QD6_ROW
 
 
 #ifndef QD3_HOST
