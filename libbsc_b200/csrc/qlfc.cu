@@ -489,7 +489,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
 // Decoder kernel selection (A/B measurements, profiles/r1h_decoder_ab.txt); default 4.  BSCB200_QDEC=2 q_decode2 (serial walk, two-sided branches),
 // 3 q_decode3<0> (speculative lane-parallel evaluation), 4 q_decode3<1> (serial walk on the branch-free plumbing),
 // 5 q_decode3<2> (serial walk with two-way speculation of the next decision's counters),
-// 6 q_decode6<LayoutDiet> (gen 4 with a 110 KB counter file: two streams per SM; not yet run on a GPU), 7 q_decode6<LayoutFull> (refactoring check).
+// 6 q_decode6<LayoutDiet> (tuned gen 4, rows instead of caches, 110 KB counter file: two streams per SM; not yet run on a GPU), 7 q_decode6<LayoutFull> (same code, full layout).
 static int decoder_generation()
 {
     static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 7) ? g : 4; }();

@@ -63,7 +63,8 @@ template <class LY> struct CoderSmemT {
     alignas(16) u8 inwin[256];
 };
 typedef QLayout<5, 5, 12> LayoutFull;     // = qlfc_coder.cuh: 205 KB, one stream per SM
-typedef QLayout<4, 2, 10> LayoutDiet;     // 110 KB, two streams per SM
+typedef QLayout<4, 3, 2> LayoutDiet;      // 110 KB, two DEcoder streams per SM: q_decode6 uses no caches (rows instead, see qd6_rows_in), so
+                                          // their 8 KB hold the run-mantissa exponent 3 (run lengths 8..15) instead
 typedef QLayout<4, 1, 10> LayoutEncDiet;  // 106 KB + the encoder's pipe state (5.6 KB): two six-warp encoders per SM
 static_assert(LayoutFull::R_END == R_END && LayoutFull::S16_COUNT == S16_COUNT && LayoutFull::O_S16 == O3_S16, "LayoutFull must reproduce qlfc_coder.cuh");
 static_assert(LayoutFull::R_RM_STATE == R_RM_STATE && LayoutFull::R_UM_CHAR == R_UM_CHAR && LayoutFull::C_CHAR_VAL == C_CHAR_VAL, "LayoutFull must reproduce qlfc_coder.cuh");
@@ -72,6 +73,8 @@ static_assert(sizeof(CoderSmemT<LayoutFull>) == sizeof(CoderSmem) && offsetof(Co
               "CoderSmemT<LayoutFull> must be CoderSmem");
 static_assert(LayoutDiet::BYTES <= 113 * 1024, "two diet decoders must fit one SM (227 KB, 1 KB reserved per CTA)");
 static_assert(LayoutDiet::O_S16 == O3_S16 && (LayoutDiet::O_WIN & 15u) == 0 && (LayoutDiet::O_MTF & 3u) == 0, "alignment of the shared-memory image");
+static_assert((LayoutDiet::O_ROWS & 15u) == 0 && (LayoutFull::O_ROWS & 15u) == 0 && (LayoutDiet::O_TAG_STATE & 3u) == 0, "staged rows are moved 16 bytes at a time");
+static_assert(LayoutFull::BYTES <= 232448, "one full decoder per SM");
 
 // Index (into the counter file) of rare counter `idx` through the direct-mapped write-back cache (uniform).
 template <class LY> QD3_FN u32 qd6_cache_get(const SM3 &sm, u32 val_base, u32 tags_off, short *__restrict__ cold, u32 idx, u32 &misses)
@@ -112,6 +115,42 @@ QD3_FN void qd6_sts128(const SM3 &sm, u32 off, const U4 &v)
 #else
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(sm.b + off), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 #endif
+}
+
+// Everything that is not resident (rank mantissa exponents > MAXE_R, the escape bank, run exponent indices >= UE_RES, run
+// mantissa exponents > MAXE_U) is used ROW-wise: the counters one run can touch in such a bank are one contiguous row per
+// (state) and one per (symbol) -- 2^e entries of a wide bank, 256 of the escape bank, 32 of a narrow bank or of the run exponent
+// file -- so the two rows are fetched with one coalesced access each (lane l always owns bytes [16 l, 16 l + 16) of a row, which
+// makes the global traffic program-ordered per address), staged in shared memory for the decisions and written back whole.
+// One global round trip per event, where the write-back caches of qlfc_coder.cuh cost one per MISS: measured with this source
+// on the host (first sub-blocks of BWT output, layout <4,2>): Python sources 0.99 cached accesses / 0.53 misses per run, an
+// x86-64 shared object 2.2 / 1.3, G_skew 16 / 9.7 -- against 0.11, 0.13 and 1.0 row events per run.
+template <class LY> QD3_FN void qd6_rows_in(const SM3 &sm, const short *__restrict__ cold_s, const short *__restrict__ cold_c, u32 rs_at, u32 rc_at, u32 nb)
+{
+#ifndef QD3_HOST
+    const u32 lane = threadIdx.x & 31u;
+#endif
+    QD3_LANES {
+        if (16u * lane < nb) {
+            qd6_sts128(sm, LY::O_ROWS + 16u * lane, qd6_ldg128(cold_s + rs_at + 8u * lane));
+            qd6_sts128(sm, LY::O_ROWS + 512u + 16u * lane, qd6_ldg128(cold_c + rc_at + 8u * lane));
+        }
+    }
+    QD3_SYNC();
+}
+template <class LY> QD3_FN void qd6_rows_out(const SM3 &sm, short *__restrict__ cold_s, short *__restrict__ cold_c, u32 rs_at, u32 rc_at, u32 nb)
+{
+#ifndef QD3_HOST
+    const u32 lane = threadIdx.x & 31u;
+#endif
+    QD3_SYNC();
+    QD3_LANES {
+        if (16u * lane < nb) {
+            qd6_stg128(cold_s + rs_at + 8u * lane, sm.ld128(LY::O_ROWS + 16u * lane));
+            qd6_stg128(cold_c + rc_at + 8u * lane, sm.ld128(LY::O_ROWS + 512u + 16u * lane));
+        }
+    }
+    QD3_SYNC();
 }
 
 // one decision with P(bit = 0) = p / 4096
@@ -308,13 +347,14 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
                         rank = r2 + b;
                     }
                 } else {
+                    const u32 rs = wide_idx(e, st, 0), rx = wide_idx(e, c, 0), nb = (2u << e) < 16u ? 16u : (2u << e);   // nodes 1 .. 2^e - 1 of the two rows
+                    qd6_rows_in<LY>(sm, cold_s, cold_c, rs, rx, nb);
                     for (int bit = (int)e - 1; bit >= 0; --bit) {
-                        const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, wide_idx(e, st, rank), st_miss);
-                        const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, wide_idx(e, c, rank), st_miss);
-                        st_cached += 2;
-                        b = qd6_dec3<LY, K_RANK_M>(sm, rc, mv, is, ic, LY::R_WIDE_SHARED + e * 256u + rank);
+                        b = qd6_dec3<LY, K_RANK_M>(sm, rc, mv, LY::R_ROW_STATE + rank, LY::R_ROW_CHAR + rank, LY::R_WIDE_SHARED + e * 256u + rank);
                         rank = 2u * rank + b;
                     }
+                    qd6_rows_out<LY>(sm, cold_s, cold_c, rs, rx, nb);
+                    st_cached += 2;
                 }
             }
         } else {
@@ -377,18 +417,18 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
         if (!b) sm.st8(LY::O_RUN_HIST + cur, (rhU + 2u) >> 2);
         else {
             u32 eu = 1;
+            bool ueRows = false;
             for (;;) {
                 const u32 k = eu - 1u;
                 if (k < UE_RES) b = qd6_dec3<LY, K_RUN_E>(sm, rc, mv, LY::R_UE_STATE + st2 * UE_RES + k, LY::R_UE_CHAR + cur * UE_RES + k, LY::R_UE_SHARED + k);
                 else {
-                    const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, ue_idx(st2, k), st_miss);
-                    const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, ue_idx(cur, k), st_miss);
-                    st_cached += 2;
-                    b = qd6_dec3<LY, K_RUN_E>(sm, rc, mv, is, ic, LY::R_UE_SHARED + k);
+                    if (!ueRows) { qd6_rows_in<LY>(sm, cold_s, cold_c, ue_idx(st2, 0), ue_idx(cur, 0), 64u); ueRows = true; st_cached += 2; }   // run length >= 2^UE_RES
+                    b = qd6_dec3<LY, K_RUN_E>(sm, rc, mv, LY::R_ROW_STATE + k, LY::R_ROW_CHAR + k, LY::R_UE_SHARED + k);
                 }
                 if (!b) break;
                 if (++eu >= 31u) break;                                          // corrupt-input guard
             }
+            if (ueRows) qd6_rows_out<LY>(sm, cold_s, cold_c, ue_idx(st2, 0), ue_idx(cur, 0), 64u);
             sm.st8(LY::O_RUN_HIST + cur, ((rhU + 3u * eu + 3u) >> 2) & 255u);
             if (eu <= LY::MAXE_U) {
                 const u32 bs = LY::R_UM_STATE + st2 * LY::ROW_U + (1u << eu) - 2u, bc = LY::R_UM_CHAR + cur * LY::ROW_U + (1u << eu) - 2u, bg = LY::R_NARROW_SHARED + eu * 32u;
@@ -397,13 +437,14 @@ template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const
                     run = 2u * run + b; node = 2u * node + b;
                 }
             } else {
+                const u32 rs = narrow_idx(eu, st2, 0), rx = narrow_idx(eu, cur, 0);
+                qd6_rows_in<LY>(sm, cold_s, cold_c, rs, rx, 64u);
                 for (u32 node = 1, bit = eu; bit > 0; --bit) {
-                    const u32 is = qd6_cache_get<LY>(sm, LY::C_STATE_VAL, LY::O_TAG_STATE, cold_s, narrow_idx(eu, st2, node), st_miss);
-                    const u32 ic = qd6_cache_get<LY>(sm, LY::C_CHAR_VAL, LY::O_TAG_CHAR, cold_c, narrow_idx(eu, cur, node), st_miss);
-                    st_cached += 2;
-                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, mv, is, ic, LY::R_NARROW_SHARED + eu * 32u + node);
+                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, mv, LY::R_ROW_STATE + node, LY::R_ROW_CHAR + node, LY::R_NARROW_SHARED + eu * 32u + node);
                     run = 2u * run + b; node = eu <= 5u ? 2u * node + b : node + 1u;   // qlfc.cpp:1119: tree contexts up to 5 bits, linear above
                 }
+                qd6_rows_out<LY>(sm, cold_s, cold_c, rs, rx, 64u);
+                st_cached += 2;
             }
         }
         QD3_T(5);

@@ -169,13 +169,13 @@ def test_layout_templated_decoder_host_emulation(gen, checker, port):
             rare[layout] += stats[0]
         covered += 1
     assert covered >= 8
-    assert rare[1] > rare[0]                                                      # the diet layout really sends more decisions through the caches
+    assert rare[1] > rare[0]                                                      # the diet layout really has more row events (stats[0] = 2 per event)
 
 
 def test_escape_mode_rows_instead_of_cache_misses(gen, checker):
     """High-entropy streams (avgRank >= 32) code every rank bit in the escape bank: 2 x 64 K counters per stream.  q_decode6 fetches
-    the two 512-byte rows a run needs (state row, symbol row) whole instead of sending 16 accesses per run through the write-back
-    caches (7-10 misses per run, measured with this emulation before the change).  Checked here: bit-exact, exactly two row
+    the two 512-byte rows a run needs (state row, symbol row) whole instead of sending 16 accesses per run through write-back
+    caches (7-10 misses per run, measured with this emulation before the change); it uses rows for every non-resident bank.  Checked here: bit-exact, exactly two row
     fetches per escape-mode run, and (almost) no cache miss on such a stream."""
     lib = _hostlib()
     lib.qdec6_host_decode.restype = ctypes.c_int
