@@ -43,7 +43,7 @@ template <int WHAT> __global__ void k(unsigned *out, long long *cyc, unsigned se
     }
     // ---- straight-line issue: 64 independent operations per iteration (branch amortised) ----
     //   110: 64 IMAD (one pipe)   111: 32 IMAD + 32 LOP3 alternating (two pipes)
-    if (WHAT == 110 || WHAT == 111) {
+    if (WHAT == 110 || WHAT == 111 || WHAT == 112) {     // 112: as 110 but 2048 instructions (32 KB) of straight-line code per iteration
         unsigned a[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = v + j;
@@ -51,10 +51,10 @@ template <int WHAT> __global__ void k(unsigned *out, long long *cyc, unsigned se
 #pragma unroll 1
         for (int r = 0; r < REPS; ++r) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < (WHAT == 112 ? 256 : 8); ++u)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (WHAT == 110 || (j & 1) == 0) asm volatile("mad.lo.u32 %0, %0, %1, 77;" : "+r"(a[j]) : "r"(seed));
+                    if (WHAT == 110 || WHAT == 112 || (j & 1) == 0) asm volatile("mad.lo.u32 %0, %0, %1, 77;" : "+r"(a[j]) : "r"(seed));
                     else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(seed), "r"(lane));
                 }
         }
@@ -77,6 +77,34 @@ template <int WHAT> __global__ void k(unsigned *out, long long *cyc, unsigned se
                              "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
                              "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
                              "SKIP:\n\tadd.u32 %0, %0, 1;\n\t}" : "+r"(v) : "r"(flag));
+        }
+    }
+    //   124 / 125 / 126: the instruction-fetch question.  NB branches per iteration, all taken, each jumping over SKIP dead multiply-adds, so
+    //   that the loop's code footprint is NB x (SKIP + 3) x 16 bytes: 124 = 32 x 16 (9.5 KB), 125 = 32 x 64 (34 KB), 126 = 64 x 64 (68 KB),
+    //   against 120 (8 x 8, 1.5 KB).  If a taken branch costs the same in all four, instruction fetch is not what limits a lone warp whose
+    //   hot path does not fit the L0 instruction cache; if it grows with the footprint, it is.
+    if (WHAT >= 124 && WHAT <= 126) {
+        constexpr int NB = WHAT == 126 ? 64 : 32, SK = WHAT == 124 ? 16 : 64;
+        const unsigned flag = v | 1u;
+        t0 = clock64();
+#pragma unroll 1
+        for (int r = 0; r < REPS; ++r) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (SK == 16)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p bra.uni SKIP;\n\t"
+                                 "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+                                 "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+                                 "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+                                 "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+                                 "SKIP:\n\tadd.u32 %0, %0, 1;\n\t}" : "+r"(v) : "r"(flag));
+                else
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p bra.uni SKIP;\n\t"
+#define M4 "mad.lo.u32 %0, %0, 4093, 77;\n\tmad.lo.u32 %0, %0, 4091, 79;\n\tmad.lo.u32 %0, %0, 4089, 81;\n\tmad.lo.u32 %0, %0, 4087, 83;\n\t"
+#define M16 M4 M4 M4 M4
+                                 M16 M16 M16 M16
+                                 "SKIP:\n\tadd.u32 %0, %0, 1;\n\t}" : "+r"(v) : "r"(flag));
+            }
         }
     }
     if (WHAT == 122 || WHAT == 123) {
@@ -143,8 +171,12 @@ int main()
     run<108>("lone warp, 8 independent IMAD chains");
     run<110>("lone warp, 64 independent IMAD, straight line (per iteration of 64)");
     run<111>("lone warp, 32 IMAD + 32 LOP3 alternating   (per iteration of 64)");
+    run<112>("lone warp, 2048 independent IMAD, 32 KB of straight-line code (per iteration of 2048)");
     run<120>("8 uniform forward branches, all TAKEN      (per iteration of 8)");
     run<121>("8 uniform forward branches, none taken     (per iteration of 8 x 9 instr)");
+    run<124>("32 taken forward branches, footprint 9.5 KB (per iteration of 32)");
+    run<125>("32 taken forward branches, footprint 34 KB  (per iteration of 32)");
+    run<126>("64 taken forward branches, footprint 68 KB  (per iteration of 64)");
     run<122>("IMAD -> SHF -> ISETP -> taken BRA chain     (per iteration)");
     run<123>("IMAD -> SHF -> ISETP -> predicated IADD     (per iteration)");
     run<130>("LDS.U16 pointer chase (+ LOP3)");
