@@ -489,10 +489,11 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
 // Decoder kernel selection (A/B measurements, profiles/r1h_decoder_ab.txt); default 4.  BSCB200_QDEC=2 q_decode2 (serial walk, two-sided branches),
 // 3 q_decode3<0> (speculative lane-parallel evaluation), 4 q_decode3<1> (serial walk on the branch-free plumbing),
 // 5 q_decode3<2> (serial walk with two-way speculation of the next decision's counters),
-// 6 q_decode6<LayoutDiet> (tuned gen 4, rows instead of caches, 110 KB counter file: two streams per SM; not yet run on a GPU), 7 q_decode6<LayoutFull> (same code, full layout).
+// 6 q_decode6<LayoutDiet> (tuned gen 4, rows instead of caches, 110 KB counter file: two streams per SM; not yet run on a GPU), 7 q_decode6<LayoutFull> (same code, full layout),
+// 8 / 9 q_decode8<LayoutFull / LayoutDiet>: the statements of 7 / 6 with every decision loop kept rolled (small instruction footprint).
 static int decoder_generation()
 {
-    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 7) ? g : 4; }();
+    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 9) ? g : 4; }();
     return gen;
 }
 
@@ -562,8 +563,13 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             else if (gen == 5)   { if (prof) LAUNCH_DEC3(2, true); else LAUNCH_DEC3(2, false); }
 #define LAUNCH_DEC6(LY, PROF) do { ensure_dyn_smem(q_decode6<LY, PROF>, ctx->device, LY::BYTES); \
                 LAUNCH(ctx, (q_decode6<LY, PROF>), nlist, 32, LY::BYTES, d_in, d_sb, models, tables, d_out, d_list); } while (0)
+#define LAUNCH_DEC8(LY, PROF) do { ensure_dyn_smem(q_decode8<LY, PROF>, ctx->device, LY::BYTES); \
+                LAUNCH(ctx, (q_decode8<LY, PROF>), nlist, 32, LY::BYTES, d_in, d_sb, models, tables, d_out, d_list); } while (0)
             else if (gen == 6) { if (prof) LAUNCH_DEC6(LayoutDiet, true); else LAUNCH_DEC6(LayoutDiet, false); }
-            else               { if (prof) LAUNCH_DEC6(LayoutFull, true); else LAUNCH_DEC6(LayoutFull, false); }
+            else if (gen == 7) { if (prof) LAUNCH_DEC6(LayoutFull, true); else LAUNCH_DEC6(LayoutFull, false); }
+            else if (gen == 8) { if (prof) LAUNCH_DEC8(LayoutFull, true); else LAUNCH_DEC8(LayoutFull, false); }
+            else               { if (prof) LAUNCH_DEC8(LayoutDiet, true); else LAUNCH_DEC8(LayoutDiet, false); }
+#undef LAUNCH_DEC8
 #undef LAUNCH_DEC6
 #undef LAUNCH_DEC3
         }

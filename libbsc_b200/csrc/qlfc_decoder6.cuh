@@ -274,213 +274,20 @@ template <class LY> QD3_FN int qd6_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PA
 }
 
 
-template <class LY, bool PROF> QD3_FN int qd6_decode_stream(const SM3 &sm, const u8 *__restrict__ in, u32 in_limit, u8 *__restrict__ out, u32 out_cap,
-                                    short *__restrict__ cold_s, short *__restrict__ cold_c, const int *__restrict__ moves, u32 &st_cached, u32 &st_miss)
-{
-    QD3_LREGS;
-    Qd6Mv mv; qd6_load_moves(mv, moves);
-#ifndef QD3_HOST
-    const u32 lane = threadIdx.x & 31u;
-#endif
-    Rc3 rc; u32 n; int maxRank;
-    { const int err = qd6_prologue<LY>(sm, rc, lr, in, in_limit, out_cap, n, maxRank); if (err) return err; }
-
-    u32 ctxRank0 = 0, ctxRank4 = 0, ctxRun = 0; int avgRank = 0;
-    // Escape mode (avgRank >= 32, high-entropy data): the 8 decisions of a rank walk one row [256] of the escape bank per
-    // (state) and one per (symbol) -- 2 x 64 K counters that fit no cache (measured through the write-back caches: 16 accesses
-    // and 7-10 misses per run on G_skew, a dependent global round trip each).  Both rows are contiguous 512 bytes in the cold
-    // arrays, so they are fetched whole -- lane l owns bytes [16 l, 16 l + 16) of a row, always, which makes the global
-    // traffic program-ordered per address --, at the end of the previous run (state and symbol are known there), staged in
-    // shared memory for the decisions and written back whole.  The escape bank never goes through the caches here.
+#define QD6_STREAM qd6_decode_stream
+#define QD6_ROLL
+#include "qlfc_decoder6_stream.inc"
+#undef QD6_STREAM
+#undef QD6_ROLL
+#define QD6_STREAM qd6_decode_stream_compact
 #ifdef QD3_HOST
-    U4 rowS_[32], rowC_[32];
-    for (u32 lane = 0; lane < 32; ++lane) rowS_[lane] = rowC_[lane] = U4{0, 0, 0, 0};
-#define QD6_ROW(x) x##_[lane]
+#define QD6_ROLL
 #else
-    U4 rowS_ = {0, 0, 0, 0}, rowC_ = {0, 0, 0, 0};
-#define QD6_ROW(x) x##_
+#define QD6_ROLL _Pragma("unroll 1")
 #endif
-    u32 rowS_at = 0, rowC_at = 0;                                               // cold index of the fetched rows
-    // positions 0..31 of the MTF list live in the lanes (lane l holds position l; shared memory keeps 32..255), the front
-    // and its successor also as uniform values: c = list[0], m1 = list[1]
-    QD3_LANES { QD3_L(lr).mtfv = sm.ld8(LY::O_MTF + lane); }
-    u32 c = sm.ld8(LY::O_MTF), m1 = sm.ld8(LY::O_MTF + 1);
-    u32 rhU = sm.ld8(LY::O_RUN_HIST + c);
-    u32 st = sm.ld8(LY::O_RANK_STATE + ((ctxRun << 11) | (ctxRank4 << 3) | sm.ld8(LY::O_RANK_HIST + c)));
-    int tS = sm.cnt(LY::R_RT_STATE + st), tC = sm.cnt(LY::R_RT_CHAR + c), tG = sm.cnt(LY::R_RT_SHARED);
-    u32 st2z = sm.ld8(LY::O_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));       // run state if rank == 1
-
-    long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = 0; u32 prof_runs = 0;
-    (void)prof_t; (void)prof_last; (void)prof_runs;
-#ifndef QD3_HOST
-    if (PROF) prof_last = clock64();
-#endif
-    for (u32 i = 0; i < n; ) {
-        u32 rank = 1, b;
-        const u32 rhq = rhU < 7 ? rhU : 7;
-        const bool plain = avgRank < 32;
-        if (rc.pos - rc.wbase > QD3_RUN_ROOM) QD6_REFILL();
-        // first-decision counters of the run length, should the rank turn out to be 1 (the rank decisions never touch them)
-        const int uS0 = sm.cnt(LY::R_UT_STATE + st2z), uC0 = sm.cnt(LY::R_UT_CHAR + c), uG0 = sm.cnt(LY::R_UT_SHARED);
-        QD3_T(0);
-        if (plain) {
-            b = qd6_dec3v<LY, K_RANK_T>(sm, rc, mv, LY::R_RT_STATE + st, LY::R_RT_CHAR + c, LY::R_RT_SHARED, tS, tC, tG);
-            if (!b) sm.st8(LY::O_RANK_HIST + c, 0);
-            else {
-                u32 e = 1;
-                {   // exponent decisions e-1 = 0, 1, ...: consecutive counters, addresses advance by 2 bytes
-                    u32 aS = sm.at(LY::O_S16 + 2u * (LY::R_RE_STATE + st * 8)), aC = sm.at(LY::O_S16 + 2u * (LY::R_RE_CHAR + c * 8)), aG = sm.at(LY::O_S16 + 2u * LY::R_RE_SHARED);
-                    while ((int)e != maxRank) {
-                        b = qd6_dec3a<LY, K_RANK_E>(sm, rc, mv, aS, aC, aG);
-                        if (!b) break;
-                        if (++e >= 7) break;                                  // e <= maxRank <= 7 in valid streams
-                        aS += 2u; aC += 2u; aG += 2u;
-                    }
-                }
-                sm.st8(LY::O_RANK_HIST + c, e);
-                if (e <= LY::MAXE_R) {
-                    const u32 bs = LY::R_RM_STATE + st * LY::ROW_R + (1u << e) - 2u, bc = LY::R_RM_CHAR + c * LY::ROW_R + (1u << e) - 2u, bg = LY::R_WIDE_SHARED + e * 256;
-                    const u32 aS = sm.at(LY::O_S16 + 2u * bs), aC = sm.at(LY::O_S16 + 2u * bc), aG = sm.at(LY::O_S16 + 2u * bg);
-                    for (int bit = (int)e - 1; bit >= 0; --bit) {
-                        const u32 r2 = 2u * rank;
-                        b = qd6_dec3a<LY, K_RANK_M>(sm, rc, mv, aS + r2, aC + r2, aG + r2);
-                        rank = r2 + b;
-                    }
-                } else {
-                    const u32 rs = wide_idx(e, st, 0), rx = wide_idx(e, c, 0), nb = (2u << e) < 16u ? 16u : (2u << e);   // nodes 1 .. 2^e - 1 of the two rows
-                    qd6_rows_in<LY>(sm, cold_s, cold_c, rs, rx, nb);
-                    for (int bit = (int)e - 1; bit >= 0; --bit) {
-                        b = qd6_dec3<LY, K_RANK_M>(sm, rc, mv, LY::R_ROW_STATE + rank, LY::R_ROW_CHAR + rank, LY::R_WIDE_SHARED + e * 256u + rank);
-                        rank = 2u * rank + b;
-                    }
-                    qd6_rows_out<LY>(sm, cold_s, cold_c, rs, rx, nb);
-                    st_cached += 2;
-                }
-            }
-        } else {
-            rank = 0;
-            QD3_LANES { qd6_sts128(sm, LY::O_ROWS + 16u * lane, QD6_ROW(rowS)); qd6_sts128(sm, LY::O_ROWS + 512u + 16u * lane, QD6_ROW(rowC)); }
-            QD3_SYNC();
-            for (int node = 1, bit = maxRank; bit >= 0; --bit) {
-                b = qd6_dec3<LY, K_RANK_P>(sm, rc, mv, LY::R_ROW_STATE + (u32)node, LY::R_ROW_CHAR + (u32)node, LY::R_WIDE_SHARED + 8u * 256u + (u32)node);
-                node = 2 * node + (int)b; rank = 2u * rank + b;
-            }
-            QD3_SYNC();
-            QD3_LANES { qd6_stg128(cold_s + rowS_at + 8u * lane, sm.ld128(LY::O_ROWS + 16u * lane)); qd6_stg128(cold_c + rowC_at + 8u * lane, sm.ld128(LY::O_ROWS + 512u + 16u * lane)); }
-            st_cached += 2;                                                      // statistics: row fetches
-            sm.st8(LY::O_RANK_HIST + c, (u32)qd3_ilog2(rank));
-        }
-        rank &= 255u;
-        QD3_T(1);
-
-        // push c `rank` places back (qlfc.cpp:1830-1860): positions 0..rank-1 take their successor, position rank takes c.
-        // One shuffle for the lanes' part; shared memory only moves for rank >= 32 (0.2 % of the runs on text).
-        const u32 cur = c;
-        if (rank != 0) {
-#ifdef QD3_HOST
-            for (u32 lane = 0; lane < 32; ++lane) lr[lane].tmp = lr[lane < 31 ? lane + 1 : lane].mtfv;
-#else
-            lr.tmp = __shfl_down_sync(0xffffffffu, lr.mtfv, 1);
-#endif
-            if (rank >= 32u) {
-                QD3_LANES { if (lane == 31u) QD3_L(lr).tmp = sm.ld8(LY::O_MTF + 32u); }
-                QD3_SYNC();
-                for (u32 basep = 32; basep < rank; basep += 32) {
-                    QD3_LANES { QD3_L(lr).used8 = sm.ld8(LY::O_MTF + basep + lane + 1u); }               // used8 is free after the header
-                    QD3_SYNC();
-                    QD3_LANES { if (basep + lane < rank) sm.st8(LY::O_MTF + basep + lane, QD3_L(lr).used8); }
-                    QD3_SYNC();
-                }
-                sm.st8(LY::O_MTF + rank, cur);
-                QD3_SYNC();
-            }
-            QD3_LANES { Qd3Lane &r = QD3_L(lr); r.mtfv = lane < rank ? r.tmp : (lane == rank ? cur : r.mtfv); }
-            c = m1;                                                            // the new front is the old second entry
-            m1 = QF_BCAST(mtfv, 1);
-        }
-        // (c, m1) now describe the NEXT run; `cur` is this run's symbol
-        const u32 rhRn = sm.ld8(LY::O_RANK_HIST + c), rhUn = sm.ld8(LY::O_RUN_HIST + c);
-        avgRank = (avgRank * 124 + (int)rank * 4) >> 7;
-        const u32 rank0 = rank - 1u;
-        u32 st2 = st2z, run = 1;
-        QD3_T(4);
-        if (rank0 == 0) b = qd6_dec3v<LY, K_RUN_T>(sm, rc, mv, LY::R_UT_STATE + st2z, LY::R_UT_CHAR + cur, LY::R_UT_SHARED, uS0, uC0, uG0);
-        else {
-            st2 = sm.ld8(LY::O_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7u ? rank0 : 7u) << 3) | rhq));
-            b = qd6_dec3<LY, K_RUN_T>(sm, rc, mv, LY::R_UT_STATE + st2, LY::R_UT_CHAR + cur, LY::R_UT_SHARED);
-        }
-        // both candidates for the next run's rank state (its ctxRun gets one more bit: run < 3)
-        const u32 ctxRank4n = ((ctxRank4 << 2) | (rank0 < 3u ? rank0 : 3u)) & 0xffu;
-        const u32 ctxRunN = (ctxRun << 1) & 0xfu;
-        const u32 stA = sm.ld8(LY::O_RANK_STATE + (((ctxRunN | 1u) << 11) | (ctxRank4n << 3) | rhRn)), stB = sm.ld8(LY::O_RANK_STATE + ((ctxRunN << 11) | (ctxRank4n << 3) | rhRn));
-        QD3_T(2);
-        if (!b) sm.st8(LY::O_RUN_HIST + cur, (rhU + 2u) >> 2);
-        else {
-            u32 eu = 1;
-            bool ueRows = false;
-            for (;;) {
-                const u32 k = eu - 1u;
-                if (k < UE_RES) b = qd6_dec3<LY, K_RUN_E>(sm, rc, mv, LY::R_UE_STATE + st2 * UE_RES + k, LY::R_UE_CHAR + cur * UE_RES + k, LY::R_UE_SHARED + k);
-                else {
-                    if (!ueRows) { qd6_rows_in<LY>(sm, cold_s, cold_c, ue_idx(st2, 0), ue_idx(cur, 0), 64u); ueRows = true; st_cached += 2; }   // run length >= 2^UE_RES
-                    b = qd6_dec3<LY, K_RUN_E>(sm, rc, mv, LY::R_ROW_STATE + k, LY::R_ROW_CHAR + k, LY::R_UE_SHARED + k);
-                }
-                if (!b) break;
-                if (++eu >= 31u) break;                                          // corrupt-input guard
-            }
-            if (ueRows) qd6_rows_out<LY>(sm, cold_s, cold_c, ue_idx(st2, 0), ue_idx(cur, 0), 64u);
-            sm.st8(LY::O_RUN_HIST + cur, ((rhU + 3u * eu + 3u) >> 2) & 255u);
-            if (eu <= LY::MAXE_U) {
-                const u32 bs = LY::R_UM_STATE + st2 * LY::ROW_U + (1u << eu) - 2u, bc = LY::R_UM_CHAR + cur * LY::ROW_U + (1u << eu) - 2u, bg = LY::R_NARROW_SHARED + eu * 32u;
-                for (u32 node = 1, bit = eu; bit > 0; --bit) {
-                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, mv, bs + node, bc + node, bg + node);
-                    run = 2u * run + b; node = 2u * node + b;
-                }
-            } else {
-                const u32 rs = narrow_idx(eu, st2, 0), rx = narrow_idx(eu, cur, 0);
-                qd6_rows_in<LY>(sm, cold_s, cold_c, rs, rx, 64u);
-                for (u32 node = 1, bit = eu; bit > 0; --bit) {
-                    b = qd6_dec3<LY, K_RUN_M>(sm, rc, mv, LY::R_ROW_STATE + node, LY::R_ROW_CHAR + node, LY::R_NARROW_SHARED + eu * 32u + node);
-                    run = 2u * run + b; node = eu <= 5u ? 2u * node + b : node + 1u;   // qlfc.cpp:1119: tree contexts up to 5 bits, linear above
-                }
-                qd6_rows_out<LY>(sm, cold_s, cold_c, rs, rx, 64u);
-                st_cached += 2;
-            }
-        }
-        QD3_T(5);
-        const bool shortRun = run < 3u;
-        ctxRank0 = ((ctxRank0 << 1) | (rank0 == 0u ? 1u : 0u)) & 0x7u;
-        ctxRank4 = ctxRank4n;
-        ctxRun   = ctxRunN | (shortRun ? 1u : 0u);
-        st = shortRun ? stA : stB;
-        rhU = rank != 0 ? rhUn : sm.ld8(LY::O_RUN_HIST + c);                         // rank 0 (corrupt input only): same symbol again
-        // first-decision counters of the next run (nothing writes the rank counters until then) and its run state for rank 1
-        tS = sm.cnt(LY::R_RT_STATE + st); tC = sm.cnt(LY::R_RT_CHAR + c); tG = sm.cnt(LY::R_RT_SHARED);
-        st2z = sm.ld8(LY::O_RUN_STATE + ((ctxRank0 << 10) | (ctxRun << 6) | (rhU < 7 ? rhU : 7)));
-        if (avgRank >= 32) {                                                     // the next run decodes its rank in escape mode: fetch its two rows now
-            rowS_at = wide_idx(8, st, 0); rowC_at = wide_idx(8, c, 0);
-            QD3_LANES { QD6_ROW(rowS) = qd6_ldg128(cold_s + rowS_at + 8u * lane); QD6_ROW(rowC) = qd6_ldg128(cold_c + rowC_at + 8u * lane); }
-        }
-
-        // run expansion: byte address A is always written by lane A mod 32
-        if (run <= 32u && i + 32u <= n) { QD3_LANES { out[i + ((lane - i) & 31u)] = (u8)cur; } }
-        else {
-            if (run > n - i) run = n - i;                                        // never write past n
-            QD3_LANES { for (u32 k = (lane - i) & 31u; k < run; k += 32) out[i + k] = (u8)cur; }
-        }
-        i += run;
-        QD3_T(6);
-        if (PROF) ++prof_runs;
-    }
-#ifndef QD3_HOST
-    if (PROF && blockIdx.x == 0 && threadIdx.x == 0)
-        printf("[qdec6 prof] runs %u; cycles/run: top %.1f rank %.1f runbit %.1f mtf+hist %.1f run>1 %.1f tail %.1f\n", prof_runs,
-               (double)prof_t[0] / prof_runs, (double)prof_t[1] / prof_runs, (double)prof_t[2] / prof_runs, (double)prof_t[4] / prof_runs,
-               (double)prof_t[5] / prof_runs, (double)prof_t[6] / prof_runs);
-#endif
-    return (int)n;
-}
-#undef QD6_ROW
+#include "qlfc_decoder6_stream.inc"
+#undef QD6_STREAM
+#undef QD6_ROLL
 
 
 #ifndef QD3_HOST
@@ -521,6 +328,22 @@ template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode6(c
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 st_cached = 0, st_miss = 0;
     const int r = qd6_decode_stream<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), st_cached, st_miss);
+    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
+}
+
+// the same decoder with every decision loop kept as one copy (qlfc_decoder6_stream.inc): small code footprint for the lone warp
+template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode8(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
+                                                                              const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+{
+    extern __shared__ __align__(16) u8 q_smem_raw[];
+    qd6_smem_init<LY>(q_smem_raw, tables);
+    SM3 sm; sm.b = (u32)__cvta_generic_to_shared(q_smem_raw);
+    asm volatile("" : "+r"(sm.b) :: "memory");
+    const u32 sid = sb_list[blockIdx.x];
+    SubBlock &sb = sbs[sid];
+    short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
+    u32 st_cached = 0, st_miss = 0;
+    const int r = qd6_decode_stream_compact<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), st_cached, st_miss);
     if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
 #endif

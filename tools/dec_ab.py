@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """tools/dec_ab.py -- A/B timing of the QLFC coder kernels on ONE block (CUDA events around every launch); the encoder variant
 is taken from the environment (BSCB200_QENC=2: one-multiply-add range recurrence).
-    python tools/dec_ab.py [MiB] [gen ...]      gen: 2 q_decode2, 3 speculative q_decode3<0>, 4 serial q_decode3<1> (default), 5 q_decode3<2>, 6 q_decode6<LayoutDiet>, 7 q_decode6<LayoutFull>
+    python tools/dec_ab.py [MiB] [gen ...]      gen: 2 q_decode2, 3 speculative q_decode3<0>, 4 serial q_decode3<1> (default), 5 q_decode3<2>, 6 q_decode6<LayoutDiet>, 7 q_decode6<LayoutFull>,
+                                                8 / 9 q_decode8<LayoutFull / LayoutDiet> (decision loops kept rolled)
 Each generation runs in its own process (the selection is read once from BSCB200_QDEC)."""
 import os
 import subprocess
