@@ -227,6 +227,19 @@ template <class LY, int K> QD3_FN u32 qd6_dec3v(const SM3 &sm, Rc3 &rc, const Qd
     return b;
 }
 
+// the same multipliers as compile-time constants, for the cold functions of q_decode8 (no 24-register argument)
+QD3_FN Qd6Mv qd6_const_moves()
+{
+    Qd6Mv mv;
+#define QD6_CM(h, K) mv.m[h][0][0] = 4096 - bscb_param(K, 4); mv.m[h][0][1] = 4096 - bscb_param(K, 6); mv.m[h][1][0] = 4096 - bscb_param(K, 8); \
+                     mv.m[h][1][1] = 4096 - bscb_param(K, 10); mv.m[h][2][0] = 4096 - bscb_param(K, 12); mv.m[h][2][1] = 4096 - bscb_param(K, 14);
+    QD6_CM(0, K_RANK_T) QD6_CM(1, K_RANK_E) QD6_CM(2, K_RANK_M) QD6_CM(3, K_RUN_T)
+#undef QD6_CM
+    return mv;
+}
+// what a cold decision function hands back: the range-coder registers it advanced and its result
+struct Qd6Cold { u32 code, range, pos, nx, val; };
+
 // (re)load the input window at rc.pos: 8 bytes per lane + 16 more by lanes 0..15
 #define QD6_REFILL() do { rc.wbase = rc.pos; QD3_SYNC(); \
         QD3_LANES { for (u32 k_ = 0; k_ < 8; ++k_) { const u32 w_ = lane * 8u + k_, o_ = rc.wbase + w_; sm.st8(LY::O_WIN + w_, o_ < rc.limit ? rc.in[o_] : 0u); } \
@@ -275,19 +288,28 @@ template <class LY> QD3_FN int qd6_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PA
 
 
 #define QD6_STREAM qd6_decode_stream
+#define QD6_SUFFIX _i
 #define QD6_ROLL
+#define QD6_COLD QD3_FN
 #include "qlfc_decoder6_stream.inc"
 #undef QD6_STREAM
+#undef QD6_SUFFIX
 #undef QD6_ROLL
+#undef QD6_COLD
 #define QD6_STREAM qd6_decode_stream_compact
+#define QD6_SUFFIX _c
 #ifdef QD3_HOST
 #define QD6_ROLL
+#define QD6_COLD static inline
 #else
 #define QD6_ROLL _Pragma("unroll 1")
+#define QD6_COLD __device__ __noinline__
 #endif
 #include "qlfc_decoder6_stream.inc"
 #undef QD6_STREAM
+#undef QD6_SUFFIX
 #undef QD6_ROLL
+#undef QD6_COLD
 
 
 #ifndef QD3_HOST

@@ -106,7 +106,7 @@ extern "C" int qfast_host_encode(const unsigned *run_pos, const unsigned char *r
 }
 
 // ---- layout-templated serial decoder (libbsc_b200/csrc/qlfc_decoder6.cuh): layout 0 = full (205 KB), 1 = diet (101 KB) ------------
-template <class LY> static int qdec6_run(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
+template <class LY, bool COMPACT = false> static int qdec6_run(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
 {
     u8 *smem = (u8 *)calloc(1, LY::BYTES);
     short *cold = (short *)malloc(sizeof(short) * 2 * (size_t)COLD_PAD);
@@ -118,14 +118,20 @@ template <class LY> static int qdec6_run(const unsigned char *in, unsigned in_si
     SM3 sm; sm.b = smem;
     u32 st_cached = 0, st_miss = 0;
     int moves[QD6_MOVES]; qd6_fill_moves(moves);
-    const int r = qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss);
+    const int r = COMPACT ? qd6_decode_stream_compact<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss)
+                          : qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss);
     if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
     free(smem); free(cold);
     return r;
 }
 extern "C" int qdec6_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats, int layout)
 {
-    return layout == 0 ? qdec6_run<LayoutFull>(in, in_size, out, out_cap, stats) : qdec6_run<LayoutDiet>(in, in_size, out, out_cap, stats);
+    switch (layout) {                                                   // 2, 3: the q_decode8 instantiation (same statements; on the host the pragmas and attributes are void)
+    case 0: return qdec6_run<LayoutFull>(in, in_size, out, out_cap, stats);
+    case 1: return qdec6_run<LayoutDiet>(in, in_size, out, out_cap, stats);
+    case 2: return qdec6_run<LayoutFull, true>(in, in_size, out, out_cap, stats);
+    default: return qdec6_run<LayoutDiet, true>(in, in_size, out, out_cap, stats);
+    }
 }
 extern "C" unsigned qdec6_smem_bytes(int layout) { return layout == 0 ? LayoutFull::BYTES : LayoutDiet::BYTES; }
 
