@@ -298,6 +298,7 @@ template <class LY> QD3_FN int qd6_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PA
 #undef QD6_COLD
 #define QD6_STREAM qd6_decode_stream_compact
 #define QD6_SUFFIX _c
+#define QD6_ONE_RUN_T 1
 #ifdef QD3_HOST
 #define QD6_ROLL
 #define QD6_COLD static inline
@@ -310,6 +311,7 @@ template <class LY> QD3_FN int qd6_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PA
 #undef QD6_SUFFIX
 #undef QD6_ROLL
 #undef QD6_COLD
+#undef QD6_ONE_RUN_T
 
 
 #ifndef QD3_HOST
