@@ -32,8 +32,8 @@ echo "== 6. everything two-per-SM: 32 blocks in flight in both directions (32 co
 BSCB200_QDEC=6 BSCB200_QENC=7 timeout 300 python bench.py --blocks 32 --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/r2_bench32_diet.json 2> gpurun_out/r2_bench32_diet.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench32_diet.json'));print('diet both, 32 blocks', d['value'], d['compress_MBps'], d['decompress_MBps'])"
 } 2>&1 | tee -a gpurun_out/r2_first_call.log
 echo "== 8. phase breakdown of the tuned decoder (cycles per run)"; for g in 7 8 6; do BSCB200_QDEC=$g BSCB200_QDEC_PROF=1 timeout 60 python tools/one_block.py 64 2>&1 | grep prof | tee -a gpurun_out/r2_first_call.log; done
-echo "== 9. where does a lone decoder warp wait?  ncu --set full on a SMALL block (4 MiB: the coder kernel runs ~0.1 s, 40 replays fit) for the default and the rolled decoder"
+echo "== 9. where do the coder warps wait (encoder + decoder)?  ncu --set full on a SMALL block (4 MiB: the coder kernel runs ~0.1 s, 40 replays fit) for the default and the rolled decoder"
 for g in 4 8; do
-  BSCB200_QDEC=$g timeout 280 ncu --set full --clock-control none --import-source on -k regex:q_decode -c 1 -f -o gpurun_out/r2_qdec_gen$g python tools/one_block.py 4 > gpurun_out/r2_ncu_gen$g.log 2>&1
+  BSCB200_QDEC=$g timeout 280 ncu --set full --clock-control none --import-source on -k "regex:q_(de|en)code" -c 2 -f -o gpurun_out/r2_qdec_gen$g python tools/one_block.py 4 > gpurun_out/r2_ncu_gen$g.log 2>&1
   ncu -i gpurun_out/r2_qdec_gen$g.ncu-rep --page details --csv 2>/dev/null | grep -i -E "stall|no instruction|issued|ipc|branch" | cut -c1-200 | head -40 | tee -a gpurun_out/r2_first_call.log
 done
