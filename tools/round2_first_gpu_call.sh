@@ -12,6 +12,7 @@ echo "== 2b. file-level front end (bsc1 container, multi-GPU scheduler) on the G
 BSCB200_TEST_CLI=1 BSCB200_TEST_LZP=1 BSCB200_ENABLE_LZP=1 timeout 300 python -m pytest tests/test_cli_container.py tests/test_gpu_parity.py -m gpu -q -k "cli or reference_default" 2>&1 | tail -3
 echo "== 0. lone-warp microbenchmarks FIRST (seconds): issue rate, branch cost against code footprint (cases 120, 124-126), LDS.U16"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/warp_latency tools/warp_latency.cu && timeout 60 gpurun_out/warp_latency
+python tools/fetch_verdict.py gpurun_out/r2_first_call.log 2>&1 | tail -20
 echo "== 3. decoder A/B on one 64 MiB block: 4 = default, 7 = tuned code + full layout, 6 = tuned code + diet layout (2 streams/SM), 8 / 9 = 7 / 6 with rolled decision loops (small code footprint)"
 timeout 300 python tools/dec_ab.py 64 4 7 8 6 9 2>&1 | tail -6
 echo "== 3a. parity of the decoder variants on the small-input suite"
