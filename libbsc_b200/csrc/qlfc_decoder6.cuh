@@ -24,6 +24,7 @@
 
 template <u32 MAXE_R_, u32 MAXE_U_, int CLOG_> struct QLayout {
     static constexpr u32 MAXE_R = MAXE_R_, MAXE_U = MAXE_U_;                 // resident mantissa exponents (rank, run length)
+    static constexpr bool BR = false;                                        // renormalisation of the range decoder as a rarely taken branch (q_decode8)
     static constexpr u32 ROW_R = (2u << MAXE_R_) - 2u, ROW_U = (2u << MAXE_U_) - 2u;   // compact row: exponent e at offsets 2^e-2 .. 2^(e+1)-3
     // counter file, indices in u16 units (same order as qlfc_coder.cuh)
     static constexpr u32 R_RT_SHARED = 0, R_RT_STATE = 2, R_RT_CHAR = R_RT_STATE + 256;
@@ -62,6 +63,7 @@ template <class LY> struct CoderSmemT {
     u8    mtf[256 + 32];
     alignas(16) u8 inwin[256];
 };
+template <class LY_> struct WithBranchRenorm : LY_ { static constexpr bool BR = true; };   // same image, other range-decoder step (qd6_step)
 typedef QLayout<5, 5, 12> LayoutFull;     // = qlfc_coder.cuh: 205 KB, one stream per SM
 typedef QLayout<4, 3, 2> LayoutDiet;      // 110 KB, two DEcoder streams per SM: q_decode6 uses no caches (rows instead, see qd6_rows_in), so
                                           // their 8 KB hold the run-mantissa exponent 3 (run lengths 8..15) instead
@@ -153,9 +155,36 @@ template <class LY> QD3_FN void qd6_rows_out(const SM3 &sm, short *__restrict__ 
     QD3_SYNC();
 }
 
+// The 16-bit renormalisation (rangecoder.h:213-219) as a function of its own: q_decode8 calls it from a rarely taken branch (once per
+// 16 coded bits) instead of carrying seven always-executed instructions and a shared-memory load in every decision.
+struct Qd6Norm { u32 code, pos; };
+#ifdef QD3_HOST
+static inline
+#else
+__device__ __noinline__
+#endif
+Qd6Norm qd6_renorm_cold(const SM3 sm, u32 win_off, u32 code, u32 pos, u32 wbase)
+{
+    Qd6Norm r;
+    r.code = (code << 16) | sm.ld16(win_off + (pos - wbase));
+    r.pos = pos + 2u;
+    return r;
+}
+
 // one decision with P(bit = 0) = p / 4096
 template <class LY> QD3_FN u32 qd6_step(const SM3 &sm, Rc3 &rc, u32 p)
 {
+    if (LY::BR) {
+        if (rc.range < 0x10000u) {
+            const Qd6Norm t = qd6_renorm_cold(sm, LY::O_WIN, rc.code, rc.pos, rc.wbase);
+            rc.code = t.code; rc.pos = t.pos; rc.range <<= 16;
+        }
+        const u32 r = (rc.range >> 12) * p;
+        const bool bit = rc.code >= r;
+        rc.code -= bit ? r : 0u;
+        rc.range = bit ? rc.range - r : r;
+        return bit ? 1u : 0u;
+    }
     const bool need = rc.range < 0x10000u;
     rc.code = need ? (rc.code << 16) | rc.nx : rc.code;
     rc.range = need ? rc.range << 16 : rc.range;
@@ -367,7 +396,7 @@ template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode8(c
     SubBlock &sb = sbs[sid];
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 st_cached = 0, st_miss = 0;
-    const int r = qd6_decode_stream_compact<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), st_cached, st_miss);
+    const int r = qd6_decode_stream_compact<WithBranchRenorm<LY>, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), st_cached, st_miss);
     if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
 #endif

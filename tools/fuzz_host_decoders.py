@@ -5,10 +5,10 @@
         -o /tmp/asan/libqdec3_host.so tools/qdec3_host.cpp
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python tools/fuzz_host_decoders.py
 
-Feeds random garbage, bit-flipped, truncated and garbage-tailed streams to every decoder variant (q_decode3<0..2>, q_decode6 with
+Feeds random garbage, bit-flipped, truncated and garbage-tailed streams to every decoder variant (q_decode3<0..2>, q_decode6 and q_decode8 with
 both layouts, the fast and the adaptive decoder).  A decoder may return anything, but it must not touch memory outside its
 shared-memory image, its cold-counter arrays and its output slice, and must terminate: on the GPU an out-of-bounds access is a
-sticky fault that takes the whole process down.  Round 1: 2100 cases, no sanitizer report."""
+sticky fault that takes the whole process down.  Round 1: 2700 cases, no sanitizer report."""
 import ctypes, sys, numpy as np
 sys.path.insert(0,'/root/repo')
 from oracle import pyoracle
@@ -31,7 +31,7 @@ def run(fn,stream,cap,*extra):
     out=np.empty(cap+64,np.uint8)
     return fn(s.ctypes.data,s.size,out.ctypes.data,cap,None,*extra)
 decs=[("d3m0",lib.qdec3_host_decode,(0,),1),("d3m1",lib.qdec3_host_decode,(1,),1),("d3m2",lib.qdec3_host_decode,(2,),1),
-      ("d6full",lib.qdec6_host_decode,(0,),1),("d6diet",lib.qdec6_host_decode,(1,),1),("fast",lib.qfast_host_decode,(),3),("adapt",lib.qadapt_host_decode,(),2)]
+      ("d6full",lib.qdec6_host_decode,(0,),1),("d6diet",lib.qdec6_host_decode,(1,),1),("d8full",lib.qdec6_host_decode,(2,),1),("d8diet",lib.qdec6_host_decode,(3,),1),("fast",lib.qfast_host_decode,(),3),("adapt",lib.qadapt_host_decode,(),2)]
 count=0
 for it in range(300):
     for name,fn,extra,coder in decs:

@@ -118,7 +118,7 @@ template <class LY, bool COMPACT = false> static int qdec6_run(const unsigned ch
     SM3 sm; sm.b = smem;
     u32 st_cached = 0, st_miss = 0;
     int moves[QD6_MOVES]; qd6_fill_moves(moves);
-    const int r = COMPACT ? qd6_decode_stream_compact<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss)
+    const int r = COMPACT ? qd6_decode_stream_compact<WithBranchRenorm<LY>, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss)
                           : qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss);
     if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
     free(smem); free(cold);
