@@ -106,7 +106,11 @@ def run_reference(args, rank, world):
     from oracle import pyoracle
     if rank != 0:
         return
-    info = reference_timing(args, steps=args.steps, warmup=args.warmup)
+    # Same workload as the GPU arm (world x blocks-per-GPU blocks of the same size), bounded to ONE block per host thread:
+    # the reference's throughput saturates there (one block per OpenMP thread, bsc.cpp:184-199), more blocks only lengthen the step.
+    threads = len(os.sched_getaffinity(0))
+    sample = max(1, min(world * args.blocks, threads))
+    info = reference_timing(args, steps=args.steps, warmup=args.warmup, sample_blocks=sample)
     line = {"metric": METRIC, "value": info["value"], "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "impl": "reference",
@@ -140,8 +144,10 @@ def reference_timing(args, steps, warmup, sample_blocks=None):
 
 def _reference_native(drv_path, blocks, steps, warmup, sorter):
     vp, ci = ctypes.c_void_p, ctypes.c_int
+    os.environ.pop("OMP_NUM_THREADS", None)                  # torchrun exports OMP_NUM_THREADS=1 to its ranks; the baseline uses the whole host
     d = ctypes.CDLL(drv_path)
     d.refdrv_init()
+    d.refdrv_set_threads(len(os.sched_getaffinity(0)))
     d.refdrv_set_nested(1 if os.environ.get("BSCB200_REF_NESTED") == "1" else 0)   # stock CLI behaviour by default (see oracle/ref_driver.c)
     nb = len(blocks)
     PP = ctypes.c_void_p * nb

@@ -70,7 +70,7 @@ int bsc_bwt_decode(unsigned char *T, int n, int index, unsigned char num_indexes
 /* libbsc/st/st.h:47,57,68 ; libbsc/st/st.cpp:990-1012 (k = 3..8; st.cu:334 for 7, 8).  In place on T. */
 int bsc_st_init(int features);
 int bsc_st_encode(unsigned char *T, int n, int k, int features);
-int bsc_st_decode(unsigned char *T, int n, int k, int index, int features);   /* LIBBSC_NOT_SUPPORTED: see DESIGN.md 1 (stateful serial walk, stays on the host) */
+int bsc_st_decode(unsigned char *T, int n, int k, int index, int features);   /* st.h:68 ; st.cpp:1491-1527 (csrc/st_decode.cu) */
 
 /* libbsc/coder/coder.h:45,56,66 ; libbsc/coder/coder.cpp:244-347.  output of compress holds n + 4096 bytes. */
 int bsc_coder_init(int features);
@@ -103,7 +103,8 @@ int                bscb200_lzp_compress_host(const unsigned char *input, unsigne
 int                bscb200_device_count(void);                    /* CUDA devices visible to the process */
 int                bscb200_set_device(int device);                /* bind the calling thread: all entry points use the current device */
 long long          bscb200_workspace_bytes(int n, int blockSorter);
-long long          bscb200_workspace_bytes_decode(int n);         /* a context that only decompresses */
+long long          bscb200_workspace_bytes_decode(int n);         /* a context that only decompresses BWT blocks */
+long long          bscb200_workspace_bytes_decode_sorter(int n, int blockSorter);   /* ... blocks of the given sorter (ST-k: ~41 n) */
 unsigned long long bscb200_ctx_kernel_launches(void *ctx);
 unsigned long long bscb200_total_kernel_launches(void);
 /* per-kernel CUDA-event timing of everything launched through ctx (bench.py's roofline leg) */
@@ -118,6 +119,7 @@ int bscb200_decompress_device(void *ctx, const unsigned char *d_input, int input
 int bscb200_bwt_encode_device(void *ctx, unsigned char *d_T, int n, unsigned char *num_indexes /* host */, int *indexes /* host */);
 int bscb200_bwt_decode_device(void *ctx, unsigned char *d_T, int n, int index);
 int bscb200_st_encode_device(void *ctx, unsigned char *d_T, int n, int k);
+int bscb200_st_decode_device(void *ctx, unsigned char *d_T, int n, int k, int index);
 int bscb200_coder_compress_device(void *ctx, const unsigned char *d_in, unsigned char *d_out /* n+4096 */, int n, int coder, int features);
 int bscb200_coder_decompress_device(void *ctx, const unsigned char *d_in, int inputSize, unsigned char *d_out, int outputCapacity, int coder, int features);
 unsigned int bscb200_adler32_device(void *ctx, const unsigned char *d_p, int n);

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "bscb200_set_device": ([ci], ci),
     "bscb200_workspace_bytes": ([ci, ci], ctypes.c_longlong),
     "bscb200_workspace_bytes_decode": ([ci], ctypes.c_longlong),
+    "bscb200_workspace_bytes_decode_sorter": ([ci, ci], ctypes.c_longlong),
     "bscb200_ctx_kernel_launches": ([vp], ctypes.c_ulonglong),
     "bscb200_total_kernel_launches": ([], ctypes.c_ulonglong),
     "bscb200_ctx_set_profile": ([vp, ci], None),
@@ -64,6 +65,7 @@ _SIGNATURES = {
     "bscb200_bwt_encode_device": ([vp, vp, ci, vp, vp], ci),
     "bscb200_bwt_decode_device": ([vp, vp, ci, ci], ci),
     "bscb200_st_encode_device": ([vp, vp, ci, ci], ci),
+    "bscb200_st_decode_device": ([vp, vp, ci, ci, ci], ci),
     "bscb200_coder_compress_device": ([vp, vp, vp, ci, ci, ci], ci),
     "bscb200_coder_decompress_device": ([vp, vp, ci, vp, ci, ci, ci], ci),
     "bscb200_adler32_device": ([vp, vp, ci], ctypes.c_uint32),
@@ -127,6 +129,11 @@ class Bsc:
         T[:n] = data
         r = self.lib.bsc_st_encode(T.ctypes.data, n, k, self.features)
         return r, T[:n].copy()
+
+    def st_decode(self, L, k, index):
+        T = np.array(L, dtype=np.uint8, copy=True)
+        r = self.lib.bsc_st_decode(T.ctypes.data, T.size, k, index, self.features)
+        return r, T
 
     def coder_compress(self, L, coder=1, features=3):
         L = np.ascontiguousarray(L, dtype=np.uint8)
@@ -231,6 +238,9 @@ class DeviceCtx:
 
     def st_encode(self, d_T, n, k):
         return self.lib.bscb200_st_encode_device(self.handle, d_T, n, k)
+
+    def st_decode(self, d_T, n, k, index):
+        return self.lib.bscb200_st_decode_device(self.handle, d_T, n, k, index)
 
     def coder_compress(self, d_in, d_out, n, coder=1, features=3):
         return self.lib.bscb200_coder_compress_device(self.handle, d_in, d_out, n, coder, features)

@@ -112,6 +112,7 @@ template <class F> int guarded(Ctx *c, F body)
 size_t need_bwt_encode(size_t n) { return 58 * n + (64u << 20); }
 size_t need_bwt_decode(size_t n) { return 8 * n + (16u << 20); }
 size_t need_st_encode(size_t n)  { return 30 * n + (16u << 20); }
+size_t need_st_decode(size_t n)  { return 41 * n + (16u << 20); }
 size_t need_coder(size_t n)      { return 12 * n + (64u << 20); }
 
 unsigned int host_adler32(const unsigned char *p, size_t n)
@@ -238,9 +239,12 @@ int decompress_dev(Ctx *ctx, const unsigned char *h, const u8 *d_block, int inpu
     if (get32(h + 20) != stage_adler32(ctx, d_block + LIBBSC_HEADER_SIZE, payload)) return LIBBSC_DATA_CORRUPT;
     const int mode = (int)get32(h + 8);
     if (mode == 0) {
+        // A stored block carries exactly dataSize payload bytes (bsc_store, libbsc.cpp:68-81).  The reference copies dataSize bytes
+        // whatever blockSize says (libbsc.cpp:550-555); here a header that promises more data than the block holds is corrupt.
+        if (payload != dataSize) return LIBBSC_DATA_CORRUPT;
         if (dataSize > 0) CUDA_TRY(cudaMemcpyAsync(d_out, d_block + LIBBSC_HEADER_SIZE, (size_t)dataSize, cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->sync();
-        return LIBBSC_NO_ERROR;
+        return get32(h + 16) == get32(h + 20) ? LIBBSC_NO_ERROR : LIBBSC_DATA_CORRUPT;   // same bytes, same checksum
     }
     const bool lzp = mode != (mode & 0xff);
     if (lzp && !lz_out) return LIBBSC_NOT_SUPPORTED;                     // device-resident API: LZP stays on the host side of the boundary
@@ -252,7 +256,7 @@ int decompress_dev(Ctx *ctx, const unsigned char *h, const u8 *d_block, int inpu
     if (lzSize < 0) return lzSize;
     int r;
     if (sorter == 1) r = stage_bwt_decode(ctx, d_out, lzSize, index);
-    else return LIBBSC_NOT_SUPPORTED;                                    // bsc_st_decode: SURVEY 8(f) next #2
+    else r = stage_st_decode(ctx, d_out, lzSize, sorter, index);         // libbsc.cpp:584-589
     if (r < 0) return r;
     if (lzp) { *lz_out = lzSize; return LIBBSC_NO_ERROR; }
     if (lzSize != dataSize) return LIBBSC_DATA_CORRUPT;
@@ -381,7 +385,9 @@ int bsc_decompress(const unsigned char *input, int inputSize, unsigned char *out
     if (inputSize < blockSize || outputSize < dataSize) return LIBBSC_UNEXPECTED_EOB;
     unsigned char h[LIBBSC_HEADER_SIZE]; memcpy(h, input, LIBBSC_HEADER_SIZE);
     return with_ctx([&](Ctx *ctx) {
-        ctx->arena.reserve((size_t)blockSize + (size_t)dataSize + 8192 + need_bwt_decode((size_t)dataSize) + need_coder((size_t)dataSize));
+        const int sorter = (int)(get32(h + 8) & 0x1f);
+        const size_t inverse = sorter > 1 ? need_st_decode((size_t)dataSize) : need_bwt_decode((size_t)dataSize);
+        ctx->arena.reserve((size_t)blockSize + (size_t)dataSize + 8192 + (inverse > need_coder((size_t)dataSize) ? inverse : need_coder((size_t)dataSize)) + need_coder((size_t)dataSize));
         u8 *d_blk = ctx->arena.get<u8>((size_t)blockSize + 128) + 4;
         u8 *d_out = ctx->arena.get<u8>((size_t)dataSize + 128);
         CUDA_TRY(cudaMemcpyAsync(d_blk, input, (size_t)blockSize, cudaMemcpyHostToDevice, ctx->stream));
@@ -450,8 +456,19 @@ int bsc_st_encode(unsigned char *T, int n, int k, int features)
 
 int bsc_st_decode(unsigned char *T, int n, int k, int index, int features)
 {
-    (void)T; (void)n; (void)k; (void)index; (void)features;
-    return LIBBSC_NOT_SUPPORTED;
+    (void)features;
+    if (T == nullptr || n < 0) return LIBBSC_BAD_PARAMETER;       // st.cpp:1493-1496
+    if (index < 0 || index >= n) return LIBBSC_BAD_PARAMETER;
+    if (k < 3 || k > 8) return LIBBSC_BAD_PARAMETER;
+    if (n <= 1) return LIBBSC_NO_ERROR;
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve((size_t)n + 4096 + need_st_decode(n));
+        u8 *d = ctx->arena.get<u8>((size_t)n + 64);
+        CUDA_TRY(cudaMemcpyAsync(d, T, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        int r = stage_st_decode(ctx, d, n, k, index);
+        if (r == 0) { CUDA_TRY(cudaMemcpyAsync(T, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
 }
 
 int bsc_coder_compress(const unsigned char *input, unsigned char *output, int n, int coder, int features)
@@ -535,7 +552,7 @@ int bscb200_ctx_reserve(void *ctx, long long bytes)
 long long bscb200_workspace_bytes(int n, int blockSorter)
 {
     size_t s = (blockSorter == 1 ? need_bwt_encode((size_t)n) : need_st_encode((size_t)n));
-    size_t d = need_bwt_decode((size_t)n);
+    size_t d = blockSorter == 1 ? need_bwt_decode((size_t)n) : need_st_decode((size_t)n);
     return (long long)((s > d ? s : d) + need_coder((size_t)n) + (size_t)n + 8192);
 }
 // host-only: the inverse LZP stage by itself (what bsc_decompress runs after the GPU stages), for CPU tests against the reference
@@ -561,6 +578,12 @@ int bscb200_set_device(int device) { return cudaSetDevice(device) == cudaSuccess
 
 // workspace of a context that only ever DEcompresses blocks of n bytes (inverse BWT + coder stage: ~21 n instead of ~71 n)
 long long bscb200_workspace_bytes_decode(int n) { return (long long)(need_bwt_decode((size_t)n) + need_coder((size_t)n) + (size_t)n + 8192); }
+// ... of blocks that may carry any sorter (the inverse ST needs ~41 n)
+long long bscb200_workspace_bytes_decode_sorter(int n, int blockSorter)
+{
+    const size_t inv = blockSorter > 1 ? need_st_decode((size_t)n) : need_bwt_decode((size_t)n);
+    return (long long)(inv + need_coder((size_t)n) + (size_t)n + 8192);
+}
 unsigned long long bscb200_ctx_kernel_launches(void *ctx) { return ((Ctx *)ctx)->kernels_launched; }
 
 int bscb200_compress_device(void *ctx, const unsigned char *d_input, unsigned char *d_output, int n, int blockSorter, int coder, int features)
@@ -576,7 +599,7 @@ int bscb200_decompress_device(void *ctx, const unsigned char *d_input, int input
         unsigned char h[LIBBSC_HEADER_SIZE];
         CUDA_TRY(cudaMemcpyAsync(c->h_mail + 64, d_input, LIBBSC_HEADER_SIZE, cudaMemcpyDeviceToHost, c->stream));
         c->sync(); memcpy(h, c->h_mail + 64, LIBBSC_HEADER_SIZE);
-        c->arena.reset(); c->arena.reserve((size_t)bscb200_workspace_bytes_decode(outputSize));   // no-op for a context that already compressed
+        c->arena.reset(); c->arena.reserve((size_t)bscb200_workspace_bytes_decode_sorter(outputSize, (int)(get32(h + 8) & 0x1f)));   // no-op for a context that already compressed
         return decompress_dev(c, h, d_input, inputSize, d_output, outputSize, features);
     });
 }
@@ -594,6 +617,11 @@ int bscb200_st_encode_device(void *ctx, unsigned char *d_T, int n, int k)
 {
     Ctx *c = (Ctx *)ctx;
     return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_st_encode((size_t)n)); return stage_st_encode(c, d_T, n, k); });
+}
+int bscb200_st_decode_device(void *ctx, unsigned char *d_T, int n, int k, int index)
+{
+    Ctx *c = (Ctx *)ctx;
+    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_st_decode((size_t)n)); int r = stage_st_decode(c, d_T, n, k, index); c->sync(); return r; });
 }
 int bscb200_coder_compress_device(void *ctx, const unsigned char *d_in, unsigned char *d_out, int n, int coder, int features)
 {

@@ -9,6 +9,8 @@ int stage_bwt_encode(Ctx *ctx, u8 *d_T, int n, unsigned char *num_indexes, int *
 int stage_bwt_decode(Ctx *ctx, u8 *d_T, int n, int index);
 // Sort transform of order k in place (bsc_st_encode, st.cpp:990; k = 3..8).
 int stage_st_encode(Ctx *ctx, u8 *d_T, int n, int k);
+// Inverse sort transform in place (bsc_st_decode, st.cpp:1491; k = 3..8, index = row of rotation 0).
+int stage_st_decode(Ctx *ctx, u8 *d_T, int n, int k, int index);
 // Coder container (bsc_coder_compress, coder.cpp:244).  d_out must hold n + 4096 bytes.
 int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n, int coder, int features);
 // bsc_coder_decompress (coder.cpp:273).  `in_size` bounds the readable input (device padded by >= 64 bytes);

@@ -179,6 +179,49 @@ int orc_st_encode(unsigned char *T, int n, int k)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Inverse sort transform.  st.cpp:1491-1527 (context boundaries 1014-1093, walk 1095-1130).     */
+/*   Rows with equal k-byte context (a k-group) stand in text order.  Walking the text backwards */
+/*   from a row with L = c lands in the k-group that LF (stable counting sort of L) maps it to,  */
+/*   and the rows of every k-group are consumed from the last one to the first one.             */
+/*   Group boundaries by induction on the context order r: row LF[i] starts an (r+1)-group iff   */
+/*   row i is the first one carrying its symbol inside its r-group.                              */
+/* ------------------------------------------------------------------------------------------ */
+int orc_st_decode(unsigned char *T, int n, int k, int index)
+{
+    if (T == NULL || n < 0) return ORC_BAD_PARAMETER;
+    if (index < 0 || index >= n) return ORC_BAD_PARAMETER;
+    if (k < 3 || k > 8) return ORC_BAD_PARAMETER;
+    if (n <= 1) return ORC_NO_ERROR;
+    uint32_t *lf = malloc(sizeof(uint32_t) * (size_t)n), *grp = malloc(sizeof(uint32_t) * (size_t)n), *via = malloc(sizeof(uint32_t) * (size_t)n);
+    uint32_t *top = malloc(sizeof(uint32_t) * (size_t)n);
+    unsigned char *out = malloc((size_t)n), *bucket = calloc((size_t)n, 1);
+    if (!lf || !grp || !via || !top || !out || !bucket) { free(lf); free(grp); free(via); free(top); free(out); free(bucket); return ORC_NOT_ENOUGH_MEMORY; }
+    uint32_t cnt[257]; memset(cnt, 0, sizeof cnt);
+    for (int i = 0; i < n; ++i) cnt[T[i] + 1]++;
+    for (int c = 0; c < 256; ++c) { if (cnt[c + 1]) bucket[cnt[c]] = 1; cnt[c + 1] += cnt[c]; }
+    for (int i = 0; i < n; ++i) lf[i] = cnt[T[i]]++;
+    for (int r = 1; r <= k; ++r) {                       /* grp[j] = first row of j's r-group */
+        uint32_t g = 0;
+        for (int j = 0; j < n; ++j) {
+            if (bucket[j] || (r > 1 && via[j] != via[j - 1])) g = (uint32_t)j;
+            grp[j] = g;
+        }
+        if (r < k) { for (int j = 0; j < n; ++j) top[lf[j]] = grp[j]; uint32_t *t = via; via = top; top = t; }
+    }
+    for (int j = 0; j < n; ++j) top[grp[j]] = (uint32_t)j; /* last row of every k-group */
+    uint32_t p = (uint32_t)index;
+    for (int i = n - 1; i >= 0; --i) {
+        out[i] = T[p];
+        uint32_t g = grp[lf[p]];
+        p = top[g]; top[g] = p - 1;                      /* may wrap below the group on the very last step only */
+        if (p >= (uint32_t)n) p = 0;                     /* corrupt input guard */
+    }
+    memcpy(T, out, (size_t)n);
+    free(lf); free(grp); free(via); free(top); free(out); free(bucket);
+    return ORC_NO_ERROR;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* QLFC stage 1: backward move-to-front ranks, one per run.  qlfc.cpp:398-455.                  */
 /* ------------------------------------------------------------------------------------------ */
 int orc_qlfc_transform(const unsigned char *in, int n, unsigned char *ranks, unsigned char mtf[256])
@@ -979,7 +1022,7 @@ int orc_decompress(const unsigned char *in, int inSize, unsigned char *out, int 
     if (lzSize < 0) return lzSize;
     int r;
     if (sorter == 1) r = orc_bwt_decode(out, lzSize, index);
-    else return ORC_NOT_SUPPORTED;                                /* bsc_st_decode: SURVEY 8(f) next #2 */
+    else r = orc_st_decode(out, lzSize, sorter, index);           /* libbsc.cpp:584-589 */
     if (r < 0) return r;
     if (mode != (mode & 0xff)) {                                  /* libbsc.cpp:599-613: undo the LZP stage */
         unsigned char *lz = malloc((size_t)lzSize + 1);

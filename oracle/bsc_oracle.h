@@ -42,6 +42,8 @@ int orc_bwt_decode(unsigned char *T, int n, int index);
 
 /* libbsc/st/st.cpp:990 bsc_st_encode ; k = 3..8 (7,8 defined by st.cu:99-163) */
 int orc_st_encode(unsigned char *T, int n, int k);
+/* libbsc/st/st.cpp:1491 bsc_st_decode */
+int orc_st_decode(unsigned char *T, int n, int k, int index);
 
 /* libbsc/coder/qlfc/qlfc.cpp:398-455 bsc_qlfc_transform (scalar variant).
  * ranks[0..R) in forward run order, returns R. */

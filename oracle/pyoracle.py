@@ -152,6 +152,7 @@ class Port(_Api):
         self.f_bwt_enc = s("bwt_encode", [vp, ci, vp, vp])
         self.f_bwt_dec = s("bwt_decode", [vp, ci, ci])
         self.f_st_enc = s("st_encode", [vp, ci, ci])
+        self.f_st_dec = s("st_decode", [vp, ci, ci, ci])
         self.f_transform = s("qlfc_transform", [vp, ci, vp, vp])
         self.f_enc_block = s("qlfc_static_encode_block", [vp, vp, ci, ci])
         self.f_dec_block = s("qlfc_static_decode_block", [vp, vp])
@@ -180,6 +181,11 @@ class Port(_Api):
 
     def _st_encode(self, T, n, k):
         return self.f_st_enc(_ptr(T), n, k)
+
+    def st_decode(self, L, k, index):
+        T = np.array(L, dtype=np.uint8, copy=True)
+        r = self.f_st_dec(_ptr(T), T.size, k, index)
+        return r, T
 
     def transform(self, data):
         data = np.ascontiguousarray(data, dtype=np.uint8)

@@ -43,6 +43,9 @@ static int cli_features(int nBlocks, int *threads_out)
 
 int refdrv_init(void) { return bsc_init(FEATURE_FASTMODE | FEATURE_MULTITHREADING); }
 int refdrv_max_threads(void) { return omp_get_max_threads(); }
+/* The launcher's environment must not decide the baseline: torchrun exports OMP_NUM_THREADS=1 to its ranks, which made
+ * rank 0 run 18 x 64 MiB blocks on one thread (round 1, SCALE N = 2/4/8: rc 124).  bench.py passes the host's thread count. */
+void refdrv_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 /* compress nBlocks independent blocks; out[b] must hold size[b] + 28 bytes; outSize[b] = result */
 int refdrv_compress(const unsigned char *const *in, const int *size, int nBlocks, unsigned char *const *out, int *outSize, int sorter, int coder)

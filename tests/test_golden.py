@@ -33,6 +33,8 @@ def _check_impl(impl, gen, coders, st_ks, sorters):
             i, Ls = _index_and_bytes(_load(name, "st%d" % k))
             i1, L1 = impl.st_encode(a, k)
             assert i1 == i and np.array_equal(L1, Ls), (name, k)
+            d, T = impl.st_decode(Ls, k, i)
+            assert d == 0 and np.array_equal(T, a), (name, k)
         for c in coders:
             gold = _load(name, "coder%d" % c)
             z, s = impl.coder_compress(L, c, 3)
@@ -46,9 +48,8 @@ def _check_impl(impl, gen, coders, st_ks, sorters):
                 blk = _load(name, "block.m%de%d" % (sorter, c))
                 z, b = impl.compress(a, sorter, c, 3)
                 assert z == blk.size and np.array_equal(b[:z], blk), (name, sorter, c)
-                if sorter == 1:
-                    q, u = impl.decompress(blk)
-                    assert q == 0 and np.array_equal(u, a), (name, c)
+                q, u = impl.decompress(blk)
+                assert q == 0 and np.array_equal(u, a), (name, sorter, c)
 
 
 def test_fixtures_present():

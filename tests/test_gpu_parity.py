@@ -55,6 +55,49 @@ def test_st_tiny_sizes(bsc, port):
             assert i1 == i2 and np.array_equal(L1, L2), (n, k)
 
 
+def test_st_decode_matches_oracle(bsc, gen, port, checker):
+    """bsc_st_decode (st.cpp:1491): inverse of every order on every input class, against the input and against the oracle's inverse."""
+    for name, a in small_inputs(gen):
+        for k in (3, 4, 5, 6, 7, 8):
+            i, L = port.st_encode(a, k) if k > 6 else checker.st_encode(a, k)
+            r, T = bsc.st_decode(L, k, i)
+            assert r == 0 and np.array_equal(T, a), (name, k)
+            r2, T2 = checker.st_decode(L, k, i)
+            assert r2 == 0 and np.array_equal(T, T2), (name, k)
+    for n in (2, 3, 4, 5, 7, 8, 9, 16, 17):
+        a = ((np.arange(n) * 5 + 1) % 3).astype(np.uint8)
+        for k in (3, 6, 8):
+            i, L = port.st_encode(a, k)
+            r, T = bsc.st_decode(L, k, i)
+            assert r == 0 and np.array_equal(T, a), (n, k)
+    a = gen.text(1, 100)
+    assert bsc.st_decode(a, 6, 100)[0] == -1 and bsc.st_decode(a, 6, -1)[0] == -1 and bsc.st_decode(a, 2, 0)[0] == -1 and bsc.st_decode(a, 9, 0)[0] == -1
+
+
+def test_st_decode_corrupt_input_terminates(bsc, gen):
+    """An L / index pair that no text produces must come back (garbage, like the reference) without hanging or faulting."""
+    rng = np.random.default_rng(5)
+    for n in (1000, 70000, 1 << 20):
+        L = rng.integers(0, 7, n, dtype=np.uint8)
+        for k in (3, 6):
+            r, T = bsc.st_decode(L, k, int(rng.integers(0, n)))
+            assert r == 0 and T.size == n
+
+
+def test_st_blocks_round_trip_all_orders(bsc, gen, checker):
+    """-m3..8 archives: our blocks through our decoder and the reference's, the reference's (k <= 6 on its CPU build) through ours."""
+    for name, a in small_inputs(gen):
+        for sorter in (3, 4, 5, 6, 7, 8):
+            z, blk = bsc.compress(a, sorter, 1, 3)
+            q, u = bsc.decompress(blk)
+            assert q == 0 and np.array_equal(u, a), (name, sorter)
+            q, u = checker.decompress(blk)
+            assert q == 0 and np.array_equal(u, a), (name, sorter)
+            if sorter <= 6:
+                z2, b2 = checker.compress(a, sorter, 1, 3)
+                assert z == z2 and np.array_equal(blk, b2), (name, sorter)
+
+
 def test_bwt_encode_matches_oracle(bsc, gen, checker):
     for name, a in small_inputs(gen):
         r2, L2, x2 = checker.bwt_encode(a)
@@ -176,6 +219,10 @@ def test_k5_st6_skew_32mb(bsc, gen):
     assert i == 28690215 and gen.adler32(L) == 0x3141fea1
     z, blk = bsc.compress(a, sorter=6)
     assert z == 32294018 and gen.adler32(blk) == 0x8d12e56b
+    r, T = bsc.st_decode(L, 6, i)                                 # BASELINE config 5, decode side
+    assert r == 0 and np.array_equal(T, a)
+    q, u = bsc.decompress(blk)
+    assert q == 0 and np.array_equal(u, a)
 
 
 @pytest.mark.skipif(__import__("os").environ.get("BSCB200_TEST_LZP") != "1", reason="set BSCB200_TEST_LZP=1 (decoding of LZP blocks not yet run on a GPU)")

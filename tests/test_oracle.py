@@ -83,6 +83,14 @@ def test_port_matches_reference_stages(gen, port, ref):
             x1, y1 = port.st_encode(a, k)
             x2, y2 = ref.st_encode(a, k)
             assert x1 == x2 and np.array_equal(y1, y2), (name, k)
+            d1, t1 = port.st_decode(y2, k, x2)            # inverse ST: port and reference both give the input back
+            d2, t2 = ref.st_decode(y2, k, x2)
+            assert d1 == 0 and d2 == 0 and np.array_equal(t1, a) and np.array_equal(t2, a), (name, k)
+        for k in (7, 8):                                  # forward k = 7, 8 exists only in the reference's CUDA build; its inverse is on the CPU
+            x1, y1 = port.st_encode(a, k)
+            d2, t2 = ref.st_decode(y1, k, x1)
+            d1, t1 = port.st_decode(y1, k, x1)
+            assert d1 == 0 and d2 == 0 and np.array_equal(t1, a) and np.array_equal(t2, a), (name, k)
 
 
 def test_port_matches_reference_blocks(gen, port, ref):
@@ -91,9 +99,10 @@ def test_port_matches_reference_blocks(gen, port, ref):
             z1, b1 = port.compress(a, sorter, 1, 3)
             z2, b2 = ref.compress(a, sorter, 1, 3)
             assert z1 == z2 and np.array_equal(b1, b2), (name, sorter)
-        z, b = ref.compress(a, 1, 1, 3)
-        q, u = port.decompress(b)
-        assert q == 0 and np.array_equal(u, a), name
+        for sorter in (1, 4, 6):
+            z, b = ref.compress(a, sorter, 1, 3)
+            q, u = port.decompress(b)
+            assert q == 0 and np.array_equal(u, a), (name, sorter)
 
 
 def test_port_transform_and_split(gen, port, ref):
