@@ -102,9 +102,9 @@ int                bscb200_lzp_decompress_host(const unsigned char *input, int n
 int                bscb200_lzp_compress_host(const unsigned char *input, unsigned char *output, int n, int lzpHashSize, int lzpMinLen, int features);   /* the reference LZP stage forward (libbsc/lzp/lzp.h), host only */
 int                bscb200_device_count(void);                    /* CUDA devices visible to the process */
 int                bscb200_set_device(int device);                /* bind the calling thread: all entry points use the current device */
-long long          bscb200_workspace_bytes(int n, int blockSorter);
-long long          bscb200_workspace_bytes_decode(int n);         /* a context that only decompresses BWT blocks */
-long long          bscb200_workspace_bytes_decode_sorter(int n, int blockSorter);   /* ... blocks of the given sorter (ST-k: ~41 n) */
+long long          bscb200_workspace_bytes(int n, int blockSorter);   /* per-context workspace (~13 n + 64 MB): staged block + coder stage */
+long long          bscb200_workspace_bytes_decode(int n);         /* the same (kept for callers of the round-1 ABI) */
+long long          bscb200_scratch_bytes(int n, int blockSorter);  /* one device-wide sort slab (~58 n for BWT); BSCB200_SORT_SLABS of them per GPU (default 3) */
 unsigned long long bscb200_ctx_kernel_launches(void *ctx);
 unsigned long long bscb200_total_kernel_launches(void);
 /* per-kernel CUDA-event timing of everything launched through ctx (bench.py's roofline leg) */

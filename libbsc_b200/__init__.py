@@ -54,7 +54,7 @@ _SIGNATURES = {
     "bscb200_set_device": ([ci], ci),
     "bscb200_workspace_bytes": ([ci, ci], ctypes.c_longlong),
     "bscb200_workspace_bytes_decode": ([ci], ctypes.c_longlong),
-    "bscb200_workspace_bytes_decode_sorter": ([ci, ci], ctypes.c_longlong),
+    "bscb200_scratch_bytes": ([ci, ci], ctypes.c_longlong),
     "bscb200_ctx_kernel_launches": ([vp], ctypes.c_ulonglong),
     "bscb200_total_kernel_launches": ([], ctypes.c_ulonglong),
     "bscb200_ctx_set_profile": ([vp, ci], None),

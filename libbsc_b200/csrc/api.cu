@@ -14,6 +14,8 @@
 #include "lzp_host.h"
 #include "../../include/libbsc_b200.h"
 
+#include <condition_variable>
+#include <new>
 #include <mutex>
 #include <vector>
 #include <sys/mman.h>
@@ -85,27 +87,99 @@ void ctx_release(Ctx *c)
     g_pool[c->device].push_back(c);
 }
 
+// ---- scratch pool: a few large slabs per device for the sort stages, shared by every context of that device -----------------
+// BSCB200_SORT_SLABS (default 3) bounds how many exist; a sort waits (host side) for a free one.  Handing a slab from one stream to
+// another is ordered by an event recorded at release and waited for at acquisition, so no host synchronisation is needed.
+struct ScratchPool { std::mutex m; std::condition_variable cv; std::vector<Scratch *> free_list; int created = 0; };
+ScratchPool g_scratch[MAX_DEVICES];
+int scratch_limit()
+{
+    static const int v = [] { const char *e = getenv("BSCB200_SORT_SLABS"); int k = e ? atoi(e) : 0; return k >= 1 && k <= 64 ? k : 3; }();
+    return v;
+}
+
+Scratch *scratch_acquire(Ctx *c, size_t bytes)
+{
+    ScratchPool &P = g_scratch[c->device];
+    Scratch *s = nullptr;
+    {
+        std::unique_lock<std::mutex> lk(P.m);
+        for (;;) {
+            if (!P.free_list.empty()) { s = P.free_list.back(); P.free_list.pop_back(); break; }
+            if (P.created < scratch_limit()) { P.created++; break; }         // make a new one outside the lock
+            P.cv.wait(lk);
+        }
+    }
+    try {
+        if (!s) { s = new Scratch(); CUDA_TRY(cudaEventCreateWithFlags(&s->idle, cudaEventDisableTiming)); }
+        if (s->idle_valid) CUDA_TRY(cudaStreamWaitEvent(c->stream, s->idle, 0));
+        if (s->arena.cap < bytes) {
+            if (s->idle_valid) CUDA_TRY(cudaEventSynchronize(s->idle));         // the slab is about to be freed: its last user must be done
+            s->arena.reset(); s->arena.reserve(bytes);
+        }
+    } catch (...) {
+        std::lock_guard<std::mutex> lk(P.m);
+        if (s) { P.free_list.push_back(s); } else { P.created--; }
+        P.cv.notify_one();
+        throw;
+    }
+    s->arena.reset();
+    return s;
+}
+
+void scratch_release(Ctx *c, Scratch *s)
+{
+    if (!s) return;
+    s->idle_valid = cudaEventRecord(s->idle, c->stream) == cudaSuccess;
+    if (!s->idle_valid) { cudaGetLastError(); cudaStreamSynchronize(c->stream); cudaGetLastError(); }
+    ScratchPool &P = g_scratch[c->device];
+    { std::lock_guard<std::mutex> lk(P.m); P.free_list.push_back(s); }
+    P.cv.notify_one();
+}
+
+// holds a scratch slab for the duration of one sort stage
+struct ScratchLease {
+    Ctx *c;
+    ScratchLease(Ctx *ctx, size_t bytes) : c(ctx) { c->scratch = scratch_acquire(c, bytes); }
+    ~ScratchLease() { Scratch *s = c->scratch; c->scratch = nullptr; scratch_release(c, s); }
+    ScratchLease(const ScratchLease &) = delete; ScratchLease &operator=(const ScratchLease &) = delete;
+};
+
 int map_failure(const CudaFail &f)
 {
     cudaGetLastError();
     return f.err == cudaErrorMemoryAllocation ? LIBBSC_GPU_NOT_ENOUGH_MEMORY : LIBBSC_GPU_ERROR;
 }
 
-// run `body(ctx)` on a pooled context, translating CUDA failures into libbsc error codes
+// run `body(ctx)` on a pooled context, translating CUDA failures into libbsc error codes.  Nothing may unwind through the
+// extern "C" boundary, and a context that failed mid-stage is destroyed instead of pooled (its device mailbox may hold partial
+// Adler-32 sums that the next block would inherit).
 template <class F> int with_ctx(F body)
 {
     Ctx *c = ctx_acquire();
     if (!c) return LIBBSC_GPU_NOT_SUPPORTED;
-    int r;
-    try { r = body(c); }
-    catch (const CudaFail &f) { r = map_failure(f); cudaStreamSynchronize(c->stream); cudaGetLastError(); }
-    ctx_release(c);
+    int r; bool broken = true;
+    try { r = body(c); broken = false; }
+    catch (const CudaFail &f) { r = map_failure(f); }
+    catch (const std::bad_alloc &) { r = LIBBSC_NOT_ENOUGH_MEMORY; }
+    catch (...) { r = LIBBSC_GPU_ERROR; }
+    if (broken) {
+        cudaStreamSynchronize(c->stream); cudaGetLastError();
+        { std::lock_guard<std::mutex> lk(g_pool_mutex); g_launches_retired += c->kernels_launched; }
+        ctx_delete(c);
+    } else ctx_release(c);
     return r;
 }
 template <class F> int guarded(Ctx *c, F body)
 {
+    int r;
     try { return body(); }
-    catch (const CudaFail &f) { int r = map_failure(f); cudaStreamSynchronize(c->stream); cudaGetLastError(); c->arena.reset(); return r; }
+    catch (const CudaFail &f) { r = map_failure(f); }
+    catch (const std::bad_alloc &) { r = LIBBSC_NOT_ENOUGH_MEMORY; }
+    catch (...) { r = LIBBSC_GPU_ERROR; }
+    cudaStreamSynchronize(c->stream); cudaGetLastError(); c->arena.reset();
+    cudaMemsetAsync(c->d_mail, 0, 1024, c->stream); cudaStreamSynchronize(c->stream); cudaGetLastError();   // adler32.cu expects zeroed accumulators
+    return r;
 }
 
 // arena sizes (bytes) generous enough for each stage at block length n
@@ -178,8 +252,11 @@ int compress_dev(Ctx *ctx, const u8 *d_in, int n, u8 *d_out, int blockSorter, in
     CUDA_TRY(cudaMemcpyAsync(work, d_in, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
 
     int indexes[256]; unsigned char num_indexes = 0; int index;
-    if (blockSorter == 1) index = stage_bwt_encode(ctx, work, n, &num_indexes, indexes);
-    else index = stage_st_encode(ctx, work, n, blockSorter);
+    {
+        ScratchLease lease(ctx, blockSorter == 1 ? need_bwt_encode(n) : need_st_encode(n));      // the sort's ~58 n live in a shared slab
+        if (blockSorter == 1) index = stage_bwt_encode(ctx, work, n, &num_indexes, indexes);
+        else index = stage_st_encode(ctx, work, n, blockSorter);
+    }
     if (orig_n < 64 * 1024) num_indexes = 0;              // libbsc.cpp:303
     if (index < 0) { A.release(mark); return index; }
 
@@ -256,7 +333,7 @@ int decompress_dev(Ctx *ctx, const unsigned char *h, const u8 *d_block, int inpu
     if (lzSize < 0) return lzSize;
     int r;
     if (sorter == 1) r = stage_bwt_decode(ctx, d_out, lzSize, index);
-    else r = stage_st_decode(ctx, d_out, lzSize, sorter, index);         // libbsc.cpp:584-589
+    else { ScratchLease lease(ctx, need_st_decode((size_t)lzSize)); r = stage_st_decode(ctx, d_out, lzSize, sorter, index); }   // libbsc.cpp:584-589
     if (r < 0) return r;
     if (lzp) { *lz_out = lzSize; return LIBBSC_NO_ERROR; }
     if (lzSize != dataSize) return LIBBSC_DATA_CORRUPT;
@@ -336,10 +413,8 @@ int bsc_compress(const unsigned char *input, unsigned char *output, int n, int l
     if (lzpMinLen != 0 || lzpHashSize != 0) {
         if (lzpMinLen < 4 || lzpMinLen > 255) return LIBBSC_BAD_PARAMETER;
         if (lzpHashSize < 10 || lzpHashSize > 28) return LIBBSC_BAD_PARAMETER;
-        // The LZP stage runs on the host (lzp_host.h: all five x86-64 variants of the reference).  Bit-exact against the
-        // reference on CPU, but the combined path has not run on a GPU yet: behind BSCB200_ENABLE_LZP=1 until then.
-        static const bool on = [] { const char *e = getenv("BSCB200_ENABLE_LZP"); return e && e[0] == '1'; }();
-        if (!on || !lzp_host::supported(lzpHashSize, lzpMinLen)) return LIBBSC_NOT_SUPPORTED;
+        // The LZP stage runs on the host (lzp_host.h: all five x86-64 variants of the reference; north star: libbsc/lzp stays on the host).
+        if (!lzp_host::supported(lzpHashSize, lzpMinLen)) return LIBBSC_NOT_SUPPORTED;
     }
     const bool inplace = (input == output);
     if (n < 0 || n > (inplace ? 2146435072 : 1073741824)) return LIBBSC_BAD_PARAMETER;
@@ -352,7 +427,7 @@ int bsc_compress(const unsigned char *input, unsigned char *output, int n, int l
         if (lzSize >= 0) {
             const LzpInfo lz = {n, host_adler32(input, (size_t)n), (lzpMinLen << 8) | (lzpHashSize << 16)};
             int r = with_ctx([&](Ctx *ctx) {
-                ctx->arena.reserve(2 * (size_t)n + 8192 + (blockSorter == 1 ? need_bwt_encode(n) : need_st_encode(n)) + need_coder(n));
+                ctx->arena.reserve(3 * (size_t)n + 16384 + need_coder(n));
                 u8 *d_in = ctx->arena.get<u8>((size_t)lzSize + 64);
                 u8 *d_out = ctx->arena.get<u8>((size_t)n + 4096) + 4;
                 if (lzSize > 0) CUDA_TRY(cudaMemcpyAsync(d_in, lzbuf, (size_t)lzSize, cudaMemcpyHostToDevice, ctx->stream));
@@ -367,7 +442,7 @@ int bsc_compress(const unsigned char *input, unsigned char *output, int n, int l
         bsc_free(lzbuf);                                    // LZP did not shrink the block: continue without it (mode &= 0xff)
     }
     return with_ctx([&](Ctx *ctx) {
-        ctx->arena.reserve(2 * (size_t)n + 8192 + (blockSorter == 1 ? need_bwt_encode(n) : need_st_encode(n)) + need_coder(n));
+        ctx->arena.reserve(3 * (size_t)n + 16384 + need_coder(n));
         u8 *d_in = ctx->arena.get<u8>((size_t)n + 64);
         u8 *d_out = ctx->arena.get<u8>((size_t)n + 4096) + 4;      // payload (offset 28) lands 16-byte aligned
         CUDA_TRY(cudaMemcpyAsync(d_in, input, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -385,9 +460,7 @@ int bsc_decompress(const unsigned char *input, int inputSize, unsigned char *out
     if (inputSize < blockSize || outputSize < dataSize) return LIBBSC_UNEXPECTED_EOB;
     unsigned char h[LIBBSC_HEADER_SIZE]; memcpy(h, input, LIBBSC_HEADER_SIZE);
     return with_ctx([&](Ctx *ctx) {
-        const int sorter = (int)(get32(h + 8) & 0x1f);
-        const size_t inverse = sorter > 1 ? need_st_decode((size_t)dataSize) : need_bwt_decode((size_t)dataSize);
-        ctx->arena.reserve((size_t)blockSize + (size_t)dataSize + 8192 + (inverse > need_coder((size_t)dataSize) ? inverse : need_coder((size_t)dataSize)) + need_coder((size_t)dataSize));
+        ctx->arena.reserve((size_t)blockSize + (size_t)dataSize + 8192 + need_coder((size_t)dataSize));      // coder stage, then the inverse BWT in the same space
         u8 *d_blk = ctx->arena.get<u8>((size_t)blockSize + 128) + 4;
         u8 *d_out = ctx->arena.get<u8>((size_t)dataSize + 128);
         CUDA_TRY(cudaMemcpyAsync(d_blk, input, (size_t)blockSize, cudaMemcpyHostToDevice, ctx->stream));
@@ -414,9 +487,10 @@ int bsc_bwt_encode(unsigned char *T, int n, unsigned char *num_indexes, int *ind
     (void)features;
     if (T == nullptr || n < 0) return LIBBSC_BAD_PARAMETER;
     return with_ctx([&](Ctx *ctx) {
-        ctx->arena.reserve((size_t)n + 4096 + need_bwt_encode(n));
+        ctx->arena.reserve((size_t)n + 4096);
         u8 *d = ctx->arena.get<u8>((size_t)n + 64);
         if (n > 0) CUDA_TRY(cudaMemcpyAsync(d, T, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        ScratchLease lease(ctx, need_bwt_encode(n));
         int r = stage_bwt_encode(ctx, d, n, num_indexes, indexes);
         if (r >= 0 && n > 0) { CUDA_TRY(cudaMemcpyAsync(T, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
         return r;
@@ -445,9 +519,10 @@ int bsc_st_encode(unsigned char *T, int n, int k, int features)
     if (k < 3 || k > 8) return LIBBSC_BAD_PARAMETER;
     if (n <= 1) return 0;
     return with_ctx([&](Ctx *ctx) {
-        ctx->arena.reserve((size_t)n + 4096 + need_st_encode(n));
+        ctx->arena.reserve((size_t)n + 4096);
         u8 *d = ctx->arena.get<u8>((size_t)n + 64);
         CUDA_TRY(cudaMemcpyAsync(d, T, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        ScratchLease lease(ctx, need_st_encode(n));
         int r = stage_st_encode(ctx, d, n, k);
         if (r >= 0) { CUDA_TRY(cudaMemcpyAsync(T, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
         return r;
@@ -462,9 +537,10 @@ int bsc_st_decode(unsigned char *T, int n, int k, int index, int features)
     if (k < 3 || k > 8) return LIBBSC_BAD_PARAMETER;
     if (n <= 1) return LIBBSC_NO_ERROR;
     return with_ctx([&](Ctx *ctx) {
-        ctx->arena.reserve((size_t)n + 4096 + need_st_decode(n));
+        ctx->arena.reserve((size_t)n + 4096);
         u8 *d = ctx->arena.get<u8>((size_t)n + 64);
         CUDA_TRY(cudaMemcpyAsync(d, T, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        ScratchLease lease(ctx, need_st_decode(n));
         int r = stage_st_decode(ctx, d, n, k, index);
         if (r == 0) { CUDA_TRY(cudaMemcpyAsync(T, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
         return r;
@@ -549,11 +625,18 @@ int bscb200_ctx_reserve(void *ctx, long long bytes)
     Ctx *c = (Ctx *)ctx;
     return guarded(c, [&]() { CUDA_TRY(cudaSetDevice(c->device)); c->arena.reset(); c->arena.reserve((size_t)bytes); return 0; });
 }
+// Per-context workspace: the staged block + the coder stage (the inverse BWT reuses the coder's space).  The sort stages work in
+// the device-wide scratch slabs (scratch pool above), which is what lets dozens of blocks be in flight per GPU.
 long long bscb200_workspace_bytes(int n, int blockSorter)
 {
+    (void)blockSorter;
+    return (long long)(need_coder((size_t)n) + (size_t)n + 8192);
+}
+long long bscb200_scratch_bytes(int n, int blockSorter)     /* size of one shared sort slab for blocks of n bytes */
+{
     size_t s = (blockSorter == 1 ? need_bwt_encode((size_t)n) : need_st_encode((size_t)n));
-    size_t d = blockSorter == 1 ? need_bwt_decode((size_t)n) : need_st_decode((size_t)n);
-    return (long long)((s > d ? s : d) + need_coder((size_t)n) + (size_t)n + 8192);
+    size_t d = blockSorter == 1 ? 0 : need_st_decode((size_t)n);
+    return (long long)(s > d ? s : d);
 }
 // host-only: the inverse LZP stage by itself (what bsc_decompress runs after the GPU stages), for CPU tests against the reference
 int bscb200_lzp_decompress_host(const unsigned char *input, int n, unsigned char *output, int outputCapacity, int lzpHashSize, int lzpMinLen)
@@ -577,13 +660,7 @@ int bscb200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cud
 int bscb200_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? LIBBSC_NO_ERROR : LIBBSC_GPU_ERROR; }
 
 // workspace of a context that only ever DEcompresses blocks of n bytes (inverse BWT + coder stage: ~21 n instead of ~71 n)
-long long bscb200_workspace_bytes_decode(int n) { return (long long)(need_bwt_decode((size_t)n) + need_coder((size_t)n) + (size_t)n + 8192); }
-// ... of blocks that may carry any sorter (the inverse ST needs ~41 n)
-long long bscb200_workspace_bytes_decode_sorter(int n, int blockSorter)
-{
-    const size_t inv = blockSorter > 1 ? need_st_decode((size_t)n) : need_bwt_decode((size_t)n);
-    return (long long)(inv + need_coder((size_t)n) + (size_t)n + 8192);
-}
+long long bscb200_workspace_bytes_decode(int n) { return bscb200_workspace_bytes(n, 1); }
 unsigned long long bscb200_ctx_kernel_launches(void *ctx) { return ((Ctx *)ctx)->kernels_launched; }
 
 int bscb200_compress_device(void *ctx, const unsigned char *d_input, unsigned char *d_output, int n, int blockSorter, int coder, int features)
@@ -599,14 +676,14 @@ int bscb200_decompress_device(void *ctx, const unsigned char *d_input, int input
         unsigned char h[LIBBSC_HEADER_SIZE];
         CUDA_TRY(cudaMemcpyAsync(c->h_mail + 64, d_input, LIBBSC_HEADER_SIZE, cudaMemcpyDeviceToHost, c->stream));
         c->sync(); memcpy(h, c->h_mail + 64, LIBBSC_HEADER_SIZE);
-        c->arena.reset(); c->arena.reserve((size_t)bscb200_workspace_bytes_decode_sorter(outputSize, (int)(get32(h + 8) & 0x1f)));   // no-op for a context that already compressed
+        c->arena.reset(); c->arena.reserve((size_t)bscb200_workspace_bytes_decode(outputSize));   // no-op for a context that already compressed
         return decompress_dev(c, h, d_input, inputSize, d_output, outputSize, features);
     });
 }
 int bscb200_bwt_encode_device(void *ctx, unsigned char *d_T, int n, unsigned char *num_indexes, int *indexes)
 {
     Ctx *c = (Ctx *)ctx;
-    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_bwt_encode((size_t)n)); return stage_bwt_encode(c, d_T, n, num_indexes, indexes); });
+    return guarded(c, [&]() { c->arena.reset(); ScratchLease lease(c, need_bwt_encode((size_t)n)); return stage_bwt_encode(c, d_T, n, num_indexes, indexes); });
 }
 int bscb200_bwt_decode_device(void *ctx, unsigned char *d_T, int n, int index)
 {
@@ -616,12 +693,12 @@ int bscb200_bwt_decode_device(void *ctx, unsigned char *d_T, int n, int index)
 int bscb200_st_encode_device(void *ctx, unsigned char *d_T, int n, int k)
 {
     Ctx *c = (Ctx *)ctx;
-    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_st_encode((size_t)n)); return stage_st_encode(c, d_T, n, k); });
+    return guarded(c, [&]() { c->arena.reset(); ScratchLease lease(c, need_st_encode((size_t)n)); return stage_st_encode(c, d_T, n, k); });
 }
 int bscb200_st_decode_device(void *ctx, unsigned char *d_T, int n, int k, int index)
 {
     Ctx *c = (Ctx *)ctx;
-    return guarded(c, [&]() { c->arena.reset(); c->arena.reserve(need_st_decode((size_t)n)); int r = stage_st_decode(c, d_T, n, k, index); c->sync(); return r; });
+    return guarded(c, [&]() { c->arena.reset(); ScratchLease lease(c, need_st_decode((size_t)n)); int r = stage_st_decode(c, d_T, n, k, index); c->sync(); return r; });
 }
 int bscb200_coder_compress_device(void *ctx, const unsigned char *d_in, unsigned char *d_out, int n, int coder, int features)
 {

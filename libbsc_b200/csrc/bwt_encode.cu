@@ -229,7 +229,7 @@ int stage_bwt_encode(Ctx *ctx, u8 *d_T, int n_, unsigned char *num_indexes, int 
     if (n_ <= 1) return n_;                              // libsais.c:6845-6850
     const u32 n = (u32)n_;
 
-    Arena &A = ctx->arena;
+    Arena &A = ctx->sort_arena();
     const size_t mark = A.mark();
     u8  *Tp      = A.get<u8>((size_t)n + 32);
     u64 *k[2]    = { A.get<u64>(n), A.get<u64>(n) };

@@ -80,11 +80,22 @@ struct Arena {
 // one timed kernel launch (profiling mode only): CUDA events on the launching stream
 struct ProfRec { const char *name; cudaEvent_t a, b; double bytes; };
 
+// A large scratch slab for the SORT stages (forward BWT ~58 n, ST-k ~30 n, inverse ST ~41 n), shared by all contexts of a device:
+// a sort holds it for some tens of milliseconds of a block whose coder stage runs for seconds, so a handful of slabs serve any
+// number of blocks in flight (api.cu: scratch pool).  `idle` is recorded on the last user's stream when it hands the slab back.
+struct Scratch {
+    Arena       arena;
+    cudaEvent_t idle = nullptr;
+    bool        idle_valid = false;
+};
+
 struct Ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
     bool         owns_stream = false;
-    Arena        arena;
+    Arena        arena;                 // per-block state: staged block, coder stage, inverse BWT
+    Scratch     *scratch = nullptr;     // held only while a sort stage runs (ScratchLease in api.cu); sort stages fall back to `arena`
+    Arena       &sort_arena() { return scratch ? scratch->arena : arena; }
     u32         *h_mail = nullptr;      // pinned host mailbox (64 words) for small D2H read-backs
     u32         *d_mail = nullptr;      // device mailbox (64 words)
     u8          *h_stage = nullptr;     // pinned staging for host<->device block copies

@@ -9,17 +9,16 @@
 // Device decomposition of the encoder:
 //   q_split      sub-block boundaries of the container (coder.cpp:70-109), one CTA.
 //   q_run_*      parallel run detection over the whole block: run start positions + symbols.
-//   q_ranks      stage 1 of QLFC (backward move-to-front rank per run), one warp per sub-block,
-//                the 256-entry recency list packed 8 symbols per lane and updated with
-//                byte-SIMD compares; also emits the MTF-order table.
-//   q_encode     stage 2: context model + binary range coder.  The format fixes <= 8 independent
+//   q_rank_*     stage 1 of QLFC (backward move-to-front rank per run) as tiled parallel ranks (qlfc_ranks.cuh);
+//                also emits the MTF-order table.
+//   q_encode5    stage 2: context model + binary range coder.  The format fixes <= 8 independent
 //                streams per block and each stream is a serial recurrence (adaptive counters +
-//                range/low), so this kernel runs one warp per sub-block in lock-step (all lanes
-//                execute the same decisions; lanes are used for prefetch/broadcast of run
-//                records).  Throughput comes from running many blocks' streams concurrently.
-//   q_decode     inverse of both stages, one warp per sub-block, warp-wide run expansion.
+//                range/low): a six-warp pipeline per stream (qlfc_encoder.cuh), two streams per SM.
+//                Throughput comes from running many blocks' streams concurrently.
+//   q_decode6    inverse of both stages, one lock-step warp per stream (qlfc_decoder6.cuh), two per SM.
 #include "common.cuh"
 #include "stages.cuh"
+#include <algorithm>
 #include "qlfc_tables.inc"
 #include "qlfc_tables2.inc"
 
@@ -168,65 +167,6 @@ __global__ void q_run_bounds(u32 *run_pos, u32 R, u32 n, const u32 *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// QLFC stage 1 (qlfc.cpp:200-255 / 398-455): backward MTF rank per run.  One warp per sub-block.
-// Lane l keeps the list positions of symbols 8l..8l+7 as bytes of (lo, hi).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) q_ranks(const u8 *__restrict__ run_sym, u8 *__restrict__ run_rank, SubBlock *__restrict__ sbs, u8 *__restrict__ mtf_out)
-{
-    SubBlock &sb = sbs[blockIdx.x];
-    const u32 lane = threadIdx.x;
-    const u32 rb = sb.run_begin, re = sb.run_end;
-    // initial order: identity, except symbols 0 and 1 swapped when the last byte is 0 (qlfc.cpp:405-408)
-    u32 lo = (8 * lane) | ((8 * lane + 1) << 8) | ((8 * lane + 2) << 16) | ((8 * lane + 3) << 24);
-    u32 hi = (8 * lane + 4) | ((8 * lane + 5) << 8) | ((8 * lane + 6) << 16) | ((8 * lane + 7) << 24);
-    if (re > rb && run_sym[re - 1] == 0 && lane == 0) lo = (lo & 0xffff0000u) | 0x0001u;   // pos[0]=1, pos[1]=0
-    u32 seen = 0, nsym = 0;
-
-    for (u32 hiR = re; hiR > rb; ) {
-        u32 cnt = min(32u, hiR - rb);
-        // lane j handles run (hiR-1-j)
-        u32 mysym = lane < cnt ? run_sym[hiR - 1 - lane] : 0, myrank = 0;
-        for (u32 j = 0; j < cnt; ++j) {
-            u32 c = __shfl_sync(0xffffffffu, mysym, j);
-            u32 word = (c & 4) ? hi : lo;
-            u32 wsel = __shfl_sync(0xffffffffu, word, c >> 3);
-            u32 sm = __shfl_sync(0xffffffffu, seen, c >> 3);
-            u32 r = (wsel >> ((c & 3) * 8)) & 255u;
-            u32 r4 = r * 0x01010101u;
-            lo = __vsub4(lo, __vcmpltu4(lo, r4));        // positions < r move one place back
-            hi = __vsub4(hi, __vcmpltu4(hi, r4));
-            if (lane == (c >> 3)) {
-                u32 clr = ~(255u << ((c & 3) * 8));
-                if (c & 4) hi &= clr; else lo &= clr;    // c goes to the front
-                seen |= 1u << (c & 7);
-            }
-            u32 out = r;
-            if (!((sm >> (c & 7)) & 1u)) out = nsym++;   // last occurrence: ordinal from the end
-            if (lane == j) myrank = out;
-        }
-        if (lane < cnt) run_rank[hiR - 1 - lane] = (u8)myrank;
-        hiR -= cnt;
-    }
-    __syncwarp();
-    if (lane == 0 && re > rb) run_rank[re - 1] = 1;       // qlfc.cpp:249
-
-    // MTF-order table: mtf[pos[c]] = c, then duplicate-terminate after the used symbols
-    __shared__ u8 s_mtf[256];
-    __shared__ u8 s_seen[256];
-    for (int k = 0; k < 8; ++k) {
-        u32 c = 8 * lane + k, p = ((k & 4 ? hi : lo) >> ((k & 3) * 8)) & 255u;
-        s_mtf[p] = (u8)c; s_seen[c] = (seen >> k) & 1u;
-    }
-    __syncwarp();
-    if (lane == 0) {
-        for (int d = 1; d < 256; ++d) if (!s_seen[s_mtf[d]]) { s_mtf[d] = s_mtf[d - 1]; break; }
-        sb.nsym = nsym;
-    }
-    __syncwarp();
-    for (int k = 0; k < 8; ++k) mtf_out[blockIdx.x * 256 + 8 * lane + k] = s_mtf[8 * lane + k];
-}
-
-// ---------------------------------------------------------------------------------------------
 // model helpers
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) q_model_init(short *__restrict__ models, size_t total_shorts)
@@ -255,8 +195,7 @@ struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 
 #include "qlfc_ranks.cuh"
 #include "qlfc_coder.cuh"
-#include "qlfc_decoder.cuh"
-#include "qlfc_decoder3.cuh"
+#include "qlfc_lanes.cuh"
 #include "qlfc_fast.cuh"
 #include "qlfc_decoder6.cuh"
 #include "qlfc_adaptive.cuh"
@@ -300,30 +239,14 @@ static const QTables *get_tables(Ctx *ctx)
     return (const QTables *)ctx->qlfc_tables;
 }
 
-// Coder ids (libbsc.h:60-62): 1 static, 2 adaptive, 3 fast.  The kernels of the adaptive and the fast coder (qlfc_adaptive.cuh,
-// qlfc_fast.cuh) are bit-exact in host emulation but have not run on a GPU yet, so they stay behind BSCB200_ENABLE_ADAPTIVE=1 /
-// BSCB200_ENABLE_FAST=1 until the parity tests have seen them.
-static int coder_gate(int coder)
-{
-    if (coder == 1) return LIBBSC_NO_ERROR;
-    if (coder == 2) { static const bool on = [] { const char *e = getenv("BSCB200_ENABLE_ADAPTIVE"); return e && e[0] == '1'; }(); return on ? LIBBSC_NO_ERROR : LIBBSC_NOT_SUPPORTED; }
-    if (coder == 3) { static const bool on = [] { const char *e = getenv("BSCB200_ENABLE_FAST"); return e && e[0] == '1'; }(); return on ? LIBBSC_NO_ERROR : LIBBSC_NOT_SUPPORTED; }
-    return LIBBSC_BAD_PARAMETER;
-}
+// Coder ids (libbsc.h:60-62): 1 static, 2 adaptive, 3 fast -- all three run on the device (parity on the B200: profiles/r2a_call_a.log).
+static int coder_gate(int coder) { return (coder >= 1 && coder <= 3) ? LIBBSC_NO_ERROR : LIBBSC_BAD_PARAMETER; }
 static_assert(QF_COLD <= 2 * (size_t)COLD_PAD, "the fast coder's cold counters must fit the per-stream model allocation");
 
 static void init_models(Ctx *ctx, short *models, int count)
 {
     size_t total = (size_t)count * MODEL_SHORTS_PAD;
     LAUNCH(ctx, q_model_init, ceil_div(total, 256 * 8), 256, 0, models, total);
-}
-
-// BSCB200_QENC: static-encoder variants for A/B measurements (qlfc_encoder.cuh): 2 = one-multiply-add range recurrence (RANGE3),
-// 6 = diet counter file (two encoders per SM), 7 = both; default: the GPU-verified kernel.
-static int encoder_variant()
-{
-    static const int v = [] { const char *e = getenv("BSCB200_QENC"); return e ? atoi(e) : 0; }();
-    return v;
 }
 
 int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder, int features)
@@ -377,6 +300,14 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         h_sb[b].tile_base = total_tiles; h_sb[b].tiles = ceil_div(h_sb[b].run_end - h_sb[b].run_begin, RK_TILE); total_tiles += h_sb[b].tiles;
     }
     CUDA_TRY(cudaMemcpyAsync(d_sb, h_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyHostToDevice, ctx->stream));
+    // Longest stream first: the format's sub-blocks differ 3.5x in length (coder.cpp:70-109 cuts at data-dependent places), a
+    // coder CTA runs for as long as its stream has runs, and CTAs start in blockIdx order -- so the order decides how long the
+    // last SM of the launch stays busy while the others idle (or pick up another block's streams).
+    u32 *enc_order = ctx->h_mail + 224;                     // pinned
+    u32 *d_order = A.get<u32>(Q_MAX_SUB);
+    for (int b = 0; b < nBlocks; ++b) enc_order[b] = (u32)b;
+    std::stable_sort(enc_order, enc_order + nBlocks, [&](u32 x, u32 y) { return h_sb[x].run_end - h_sb[x].run_begin > h_sb[y].run_end - h_sb[y].run_begin; });
+    CUDA_TRY(cudaMemcpyAsync(d_order, enc_order, sizeof(u32) * Q_MAX_SUB, cudaMemcpyHostToDevice, ctx->stream));
     // 3. ranks, 4. encode
     {
         u32 *first_tab = A.get<u32>((size_t)total_tiles * 256), *next_tab = A.get<u32>((size_t)total_tiles * 256);
@@ -385,29 +316,26 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         PROF_BYTES(ctx, 2.0 * R);
         LAUNCH(ctx, q_rank_tile, ceil_div(total_tiles, 4), 128, 0, run_sym, run_rank, d_sb, (u32)nBlocks, total_tiles, next_tab);
     }
-    static_assert(((sizeof(CoderSmem) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448, "encoder working set must fit the 227 KB of one SM");
-    static_assert(((sizeof(CoderSmemT<LayoutEncDiet>) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448 / 2 - 1024, "two diet encoders must fit one SM");
-    // static encoder variants (A/B): BSCB200_QENC = 2 RANGE3, 6 diet layout, 7 diet layout + RANGE3; anything else: the default
-#define LAUNCH_ENC(LY, R3, GRID, LIST) do { const size_t sm_ = ((sizeof(CoderSmemT<LY>) + 15) & ~(size_t)15) + sizeof(EncPipe); \
-        ensure_dyn_smem(q_encode5<LY, R3>, ctx->device, sm_); \
-        LAUNCH(ctx, (q_encode5<LY, R3>), (GRID), QE_THREADS, sm_, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)(LIST)); } while (0)
-#define LAUNCH_ENC_VARIANT(GRID, LIST) do { switch (encoder_variant()) { \
-        case 2: LAUNCH_ENC(LayoutFull, true, GRID, LIST); break; case 6: LAUNCH_ENC(LayoutEncDiet, false, GRID, LIST); break; \
-        case 7: LAUNCH_ENC(LayoutEncDiet, true, GRID, LIST); break; default: LAUNCH_ENC(LayoutFull, false, GRID, LIST); } } while (0)
+    // The counter file of the static coder is the "diet" layout (qlfc_decoder6.cuh: 106 KB + 5.6 KB of pipe state for the encoder,
+    // 110 KB for the decoder), so that TWO coder CTAs share an SM: a coder CTA keeps one scheduler a third busy (ncu: 0.27-0.35
+    // issue slots per cycle, profiles/r2a_ncu_coder_kernels_4MiB.txt), and a second stream on the SM costs the first one ~15 %.
+    static_assert(((sizeof(CoderSmemT<LayoutEncDiet>) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448 / 2 - 1024, "two encoders must fit one SM");
+    const size_t enc_smem = ((sizeof(CoderSmemT<LayoutEncDiet>) + 15) & ~(size_t)15) + sizeof(EncPipe);
     if (fast) {
         LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
         ensure_dyn_smem(q_fast_encode, ctx->device, sizeof(FastSmem));
         PROF_BYTES(ctx, (double)n);
-        LAUNCH(ctx, q_fast_encode, nBlocks, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)nullptr);
+        LAUNCH(ctx, q_fast_encode, nBlocks, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)d_order);
     } else if (coder == 2) {
         init_models(ctx, models, nBlocks);
         ensure_dyn_smem(q_adaptive_encode, ctx->device, QA_BYTES);
         PROF_BYTES(ctx, (double)n);
-        LAUNCH(ctx, q_adaptive_encode, nBlocks, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)nullptr);
+        LAUNCH(ctx, q_adaptive_encode, nBlocks, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order);
     } else {
         init_models(ctx, models, nBlocks);
         PROF_BYTES(ctx, (double)n);                      // + c written; the launch is latency-, not bandwidth-bound
-        LAUNCH_ENC_VARIANT(nBlocks, nullptr);
+        ensure_dyn_smem(q_encode5<LayoutEncDiet>, ctx->device, enc_smem);
+        LAUNCH(ctx, (q_encode5<LayoutEncDiet>), nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order);
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync_long();                                    // the encoder runs for 0.01 - 0.7 s: sleep, do not spin
@@ -454,7 +382,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                     LAUNCH(ctx, q_adaptive_encode, 1, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 } else {
                     init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                    LAUNCH_ENC_VARIANT(1, d_list);
+                    LAUNCH(ctx, (q_encode5<LayoutEncDiet>), 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 }
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
@@ -484,17 +412,6 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     }
     A.release(mark);
     return result;
-}
-
-// Decoder kernel selection (A/B measurements, profiles/r1h_decoder_ab.txt); default 4.  BSCB200_QDEC=2 q_decode2 (serial walk, two-sided branches),
-// 3 q_decode3<0> (speculative lane-parallel evaluation), 4 q_decode3<1> (serial walk on the branch-free plumbing),
-// 5 q_decode3<2> (serial walk with two-way speculation of the next decision's counters),
-// 6 q_decode6<LayoutDiet> (tuned gen 4, rows instead of caches, 110 KB counter file: two streams per SM; not yet run on a GPU), 7 q_decode6<LayoutFull> (same code, full layout),
-// 8 / 9 q_decode8<LayoutFull / LayoutDiet>: the statements of 7 / 6 with every decision loop kept rolled (small instruction footprint).
-static int decoder_generation()
-{
-    static const int gen = [] { const char *e = getenv("BSCB200_QDEC"); const int g = e ? atoi(e) : 0; return (g >= 2 && g <= 9) ? g : 4; }();
-    return gen;
 }
 
 int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int out_cap, int coder, int features)
@@ -531,6 +448,8 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             inPtr += packed; outPtr += rawSize;
         }
     }
+    // longest stream first (see stage_coder_compress); the packed size is the best proxy for the number of decisions
+    std::stable_sort(list, list + nlist, [&](u32 x, u32 y) { return h_sb[x].out_cap > h_sb[y].out_cap; });
     if (nlist > 0) {
         SubBlock *d_sb = A.get<SubBlock>(Q_MAX_SUB);
         u32 *d_list = A.get<u32>(Q_MAX_SUB);
@@ -552,26 +471,11 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             init_models(ctx, models, nlist);
             PROF_BYTES(ctx, (double)in_size + (double)out_cap);
             static const bool prof = getenv("BSCB200_QDEC_PROF") != nullptr;          // per-phase cycle counts (diagnostic)
-            const int gen = decoder_generation();
-#define LAUNCH_DEC3(MODE, PROF) do { ensure_dyn_smem(q_decode3<MODE, PROF>, ctx->device, sizeof(Dec3Smem)); \
-                LAUNCH(ctx, (q_decode3<MODE, PROF>), nlist, 32, sizeof(Dec3Smem), d_in, d_sb, models, tables, d_out, d_list); } while (0)
-            if (gen == 2) {
-                ensure_dyn_smem(q_decode2, ctx->device, sizeof(CoderSmem));
-                LAUNCH(ctx, q_decode2, nlist, 32, sizeof(CoderSmem), d_in, d_sb, models, tables, d_out, d_list);
-            } else if (gen == 3) { if (prof) LAUNCH_DEC3(0, true); else LAUNCH_DEC3(0, false); }
-            else if (gen == 4)   { if (prof) LAUNCH_DEC3(1, true); else LAUNCH_DEC3(1, false); }
-            else if (gen == 5)   { if (prof) LAUNCH_DEC3(2, true); else LAUNCH_DEC3(2, false); }
-#define LAUNCH_DEC6(LY, PROF) do { ensure_dyn_smem(q_decode6<LY, PROF>, ctx->device, LY::BYTES); \
-                LAUNCH(ctx, (q_decode6<LY, PROF>), nlist, 32, LY::BYTES, d_in, d_sb, models, tables, d_out, d_list); } while (0)
-#define LAUNCH_DEC8(LY, PROF) do { ensure_dyn_smem(q_decode8<LY, PROF>, ctx->device, LY::BYTES); \
-                LAUNCH(ctx, (q_decode8<LY, PROF>), nlist, 32, LY::BYTES, d_in, d_sb, models, tables, d_out, d_list); } while (0)
-            else if (gen == 6) { if (prof) LAUNCH_DEC6(LayoutDiet, true); else LAUNCH_DEC6(LayoutDiet, false); }
-            else if (gen == 7) { if (prof) LAUNCH_DEC6(LayoutFull, true); else LAUNCH_DEC6(LayoutFull, false); }
-            else if (gen == 8) { if (prof) LAUNCH_DEC8(LayoutFull, true); else LAUNCH_DEC8(LayoutFull, false); }
-            else               { if (prof) LAUNCH_DEC8(LayoutDiet, true); else LAUNCH_DEC8(LayoutDiet, false); }
-#undef LAUNCH_DEC8
-#undef LAUNCH_DEC6
-#undef LAUNCH_DEC3
+            static_assert(LayoutDiet::BYTES <= 232448 / 2 - 1024, "two decoder streams must fit one SM");
+            if (prof) { ensure_dyn_smem(q_decode6<LayoutDiet, true>, ctx->device, LayoutDiet::BYTES);
+                        LAUNCH(ctx, (q_decode6<LayoutDiet, true>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
+            else      { ensure_dyn_smem(q_decode6<LayoutDiet, false>, ctx->device, LayoutDiet::BYTES);
+                        LAUNCH(ctx, (q_decode6<LayoutDiet, false>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
         }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }

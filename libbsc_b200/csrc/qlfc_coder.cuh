@@ -17,7 +17,7 @@
 //     exponents 6-7, the escape bank, run exponents >= 6 and run-exponent indices >= 8; the
 //     1.7 M counters behind them live in HBM                                    24 KB
 //
-// The decoder (qlfc_decoder.cuh) is one lock-step warp per stream; the encoder (qlfc_encoder.cuh) is a
+// The decoder (qlfc_decoder6.cuh) is one lock-step warp per stream; the encoder (qlfc_encoder.cuh) is a
 // six-warp pipeline per stream.
 #pragma once
 

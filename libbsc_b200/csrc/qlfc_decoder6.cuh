@@ -1,25 +1,21 @@
-// libbsc_b200/csrc/qlfc_decoder6.cuh -- the serial QLFC static decoder (q_decode3<1>, qlfc_decoder3.cuh) with the LAYOUT of
-// the counter file as a template parameter, so that the same code runs with a shared-memory footprint small enough for
-// TWO streams per SM.  Included by qlfc.cu after qlfc_decoder3.cuh; also compiled for the host (tools/qdec3_host.cpp).
+// libbsc_b200/csrc/qlfc_decoder6.cuh -- the QLFC static DECODER (qlfc.cpp:1672-1927): one lock-step warp per stream, with the LAYOUT
+// of the counter file as a template parameter so that it fits TWO streams per SM.  Included by qlfc.cu after qlfc_lanes.cuh; also
+// compiled for the host (tools/qdec3_host.cpp), where the 32 lanes are emulated and the output is compared with reference streams.
 //
-// Why: every measurement of round 1 says the coder kernels are bound by what one lone warp can issue,
-// and an SM has four schedulers.  q_decode3 needs 205 KB of shared memory per stream = one stream per SM.  The "diet"
-// layout keeps resident only what is hot:
+// Why two per SM: the decoder is a serial recurrence (the context of every decision depends on the previous decisions); ncu on the
+// B200 (profiles/r2a_ncu_coder_kernels_4MiB.txt) shows one warp issuing 0.35 instructions per cycle on ONE of the SM's four
+// schedulers -- 2.88 cycles per instruction, of which 1.32 are fixed-latency dependency waits -- so a second stream on the same SM
+// is almost free (measured: 15 % slower per stream, profiles/r2b_call_b.log).  The "diet" layout keeps resident only what is hot:
 //     state tables 40 KB | first-bit / exponent / shared counters 25 KB | rank mantissa trees for exponents 1..4 (30 nodes
-//     per state / symbol) 30 KB | run mantissa trees for exponents 1..2 (6 nodes) 6 KB | two 1 K-entry write-back caches 8 KB
-// = 110 KB, i.e. two CTAs per SM.  Rank exponent 5 and run exponents 3..5 now go through the caches (same cold index space
-// in HBM as before).  Measured in host emulation on the bench data (64 MiB G_text block, sub-blocks 0 and 4): 0.00 / 0.20
-// cached accesses per run and 0.000 / 0.046 misses per run; the smaller QLayout<3, 2, 11> (102 KB) would take 1.8 / 0.9
-// accesses and 0.26 / 0.14 misses per run.  QLayout<5, 5, 12> is exactly the layout of qlfc_coder.cuh and is instantiated
-// too: it must behave like q_decode3<1> (a refactoring check for the A/B).
-// Besides the layout, three instruction-count measures (the cost model of DESIGN.md 4.5: a lone warp retires one instruction
-// per 4-5 cycles, so instructions are what counts): the multipliers of the hot counter moves live in registers (loaded from
-// a table, see q_move6), and the exponent / mantissa loops address their counters through absolute shared-memory
-// addresses that advance with the node; positions 0..31 of the MTF list live in the lanes (one shuffle per run instead of
-// shared-memory traffic and three warp barriers for every rank > 3, i.e. 58 % of the runs on text).  SASS of the rank-mantissa loop: 53 instructions per decision in q_decode3<1>,
-// 28-42 here (cuobjdump, r1h).
-// STATUS: bit-exact in host emulation with both layouts (tests/test_qdec3_host.py); not yet run on a GPU.  To profit from it
-// more than 148 streams have to be in flight (>= 19 blocks of >= 16 MiB per GPU): BSCB200_QDEC=6 selects it.
+//     per state / symbol) 30 KB | run mantissa trees for exponents 1..3 | staged rows
+// = 110 KB.  Everything else (rank exponent 5, the escape bank, long runs) is used ROW-wise from HBM: the counters one run can
+// touch in such a bank are one contiguous row per state and one per symbol, fetched with one coalesced access each, staged in
+// 1 KB of shared memory for the decisions and written back whole (qd6_rows_in / qd6_rows_out).
+// Instruction-count measures (a lone warp's time is its instruction count): the multipliers of the hot counter moves live in
+// registers (q_move6), the exponent / mantissa loops address their counters through absolute shared-memory addresses that advance
+// with the node, positions 0..31 of the MTF list live in the lanes (one shuffle per run instead of shared-memory traffic and
+// three warp barriers for every rank > 3, i.e. 58 % of the runs on text).
+// QLayout<5, 5, 12> (LayoutFull, 205 KB) is the layout of qlfc_coder.cuh; the adaptive coder derives its own from it.
 #pragma once
 
 template <u32 MAXE_R_, u32 MAXE_U_, int CLOG_> struct QLayout {
@@ -325,22 +321,6 @@ template <class LY> QD3_FN int qd6_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PA
 #undef QD6_SUFFIX
 #undef QD6_ROLL
 #undef QD6_COLD
-#define QD6_STREAM qd6_decode_stream_compact
-#define QD6_SUFFIX _c
-#define QD6_ONE_RUN_T 1
-#ifdef QD3_HOST
-#define QD6_ROLL
-#define QD6_COLD static inline
-#else
-#define QD6_ROLL _Pragma("unroll 1")
-#define QD6_COLD __device__ __noinline__
-#endif
-#include "qlfc_decoder6_stream.inc"
-#undef QD6_STREAM
-#undef QD6_SUFFIX
-#undef QD6_ROLL
-#undef QD6_COLD
-#undef QD6_ONE_RUN_T
 
 
 #ifndef QD3_HOST
@@ -384,19 +364,4 @@ template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode6(c
     if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
 }
 
-// the same decoder with every decision loop kept as one copy (qlfc_decoder6_stream.inc): small code footprint for the lone warp
-template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode8(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
-                                                                              const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
-{
-    extern __shared__ __align__(16) u8 q_smem_raw[];
-    qd6_smem_init<LY>(q_smem_raw, tables);
-    SM3 sm; sm.b = (u32)__cvta_generic_to_shared(q_smem_raw);
-    asm volatile("" : "+r"(sm.b) :: "memory");
-    const u32 sid = sb_list[blockIdx.x];
-    SubBlock &sb = sbs[sid];
-    short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
-    u32 st_cached = 0, st_miss = 0;
-    const int r = qd6_decode_stream_compact<WithBranchRenorm<LY>, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), st_cached, st_miss);
-    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
-}
 #endif

@@ -145,14 +145,10 @@ __device__ __forceinline__ int enc_resolve(CoderSmemT<LY> &S, bool act, u32 x, b
 // bits [32-lane, ...) of (prev:cur): the flags of the runs before this lane's run, most recent in bit 0
 __device__ __forceinline__ u32 enc_window(u32 prev_rev, u32 cur_rev, u32 lane) { return (u32)((((u64)prev_rev << 32) | cur_rev) >> (32u - lane)); }
 
-// RANGE3 (BSCB200_QENC=2, not yet run on a GPU): the range recurrence of the range warp as ONE multiply-add per record.
-//   range' = bit ? range_s - (range_s >> 12) * p : (range_s >> 12) * p      with range_s = range renormalised
-//          = rin * (bit ? -p : p) + (bit ? range_s : 0),                    rin = range_s >> 12 = sh ? range << 4 : range >> 12
-// The multiplier and the addend mask come from the record (off the chain); the dependent chain through `range` shrinks from
-// six instructions per record (ISETP, shift, shift, IMAD, IADD, SEL -- cuobjdump of q_encode5) to about four.
-// LY: layout of the counter file (qlfc_decoder6.cuh): LayoutFull = qlfc_coder.cuh (one stream per SM); an encoder diet layout keeps
-// fewer mantissa rows resident so that two encoders fit one SM (BSCB200_QENC=6/7, not yet run on a GPU).
-template <class LY, bool RANGE3> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
+// LY: layout of the counter file (qlfc_decoder6.cuh).  The product instantiates LayoutEncDiet: fewer mantissa rows resident, 106 KB
+// + 5.6 KB of pipe state, so that two six-warp encoders share an SM (same time per stream as the 205 KB layout when alone: 682 ms
+// per 64 MiB block, profiles/r2a_call_a.log).  (A one-multiply-add form of the range recurrence was tried in round 2: 707 vs 682 ms.)
+template <class LY> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                     SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
                                                     const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
 {
@@ -208,18 +204,10 @@ template <class LY, bool RANGE3> __global__ void __launch_bounds__(QE_THREADS, 1
                         const u32 rec = recs[k];
                         const bool sh = range < 0x10000u;
                         const bool bit = rec & QE_BIT;
-                        if (RANGE3) {
-                            const u32 p = rec & 0x1fffu, mul = bit ? 0u - p : p, keep = bit ? 0xffffffffu : 0u;
-                            const u32 rin = sh ? range << 4 : range >> 12;
-                            const u32 rs = sh ? range << 16 : range;
-                            recs[k] = (rin * p) & keep;                        // the addend of `low` (off the chain)
-                            range = rin * mul + (rs & keep);
-                        } else {
-                            if (sh) range <<= 16;
-                            const u32 r = (range >> 12) * (rec & 0x1fffu);
-                            range = bit ? range - r : r;
-                            recs[k] = bit ? r : 0u;
-                        }
+                        if (sh) range <<= 16;
+                        const u32 r = (range >> 12) * (rec & 0x1fffu);
+                        range = bit ? range - r : r;
+                        recs[k] = bit ? r : 0u;
                         f |= (sh ? 1u << k : 0u) | ((rec & QE_RUN) ? 16u << k : 0u);
                     }
                     *reinterpret_cast<uint4 *>(&P.ring[slot]) = make_uint4(recs[0], recs[1], recs[2], recs[3]);

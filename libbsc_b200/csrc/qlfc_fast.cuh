@@ -1,7 +1,7 @@
 // libbsc_b200/csrc/qlfc_fast.cuh -- the FAST QLFC coder (coder id 3, `-e0`): encoder qlfc.cpp:1135-1336, decoder 1933-2127,
 // model qlfc_model.h:243-259 (QlfcStatisticalModel2), start values qlfc_model.cpp:73-74, counter moves predictor.h:63-71,
 // range coder rangecoder.h:145-177 / 213-240 with the precision template (13 bits for ranks, 11 for run lengths).
-// Included by qlfc.cu after qlfc_decoder3.cuh (uses SM3, Rc3 and the QD3_* dual-compile macros); ALSO compiled for the
+// Included by qlfc.cu after qlfc_lanes.cuh (uses SM3, Rc3 and the QD3_* dual-compile macros); ALSO compiled for the
 // host by tools/qdec3_host.cpp, which runs this very source with 32 emulated lanes against the oracle on the CPU
 // (tests/test_qdec3_host.py).
 //

@@ -230,7 +230,7 @@ int stage_st_decode(Ctx *ctx, u8 *d_T, int n_, int k, int index_)
     if (k < 3 || k > 8) return LIBBSC_BAD_PARAMETER;
     if (n_ <= 1) return LIBBSC_NO_ERROR;
     const u32 n = (u32)n_, index = (u32)index_;
-    Arena &A = ctx->arena;
+    Arena &A = ctx->sort_arena();
     const size_t mark = A.mark();
 
     const u32 lf_tiles = ceil_div(n, LF_TILE), sr_tiles = ceil_div(n, SR_TILE), nb = ceil_div(n, 256);

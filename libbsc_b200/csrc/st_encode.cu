@@ -59,7 +59,7 @@ int stage_st_encode(Ctx *ctx, u8 *d_T, int n_, int k)
     if (k < 3 || k > 8) return LIBBSC_BAD_PARAMETER;
     if (n_ <= 1) return 0;
     const u32 n = (u32)n_;
-    Arena &A = ctx->arena;
+    Arena &A = ctx->sort_arena();
     const size_t mark = A.mark();
     u8  *Tw   = A.get<u8>((size_t)n + 64);
     u64 *kb[2] = { A.get<u64>(n), A.get<u64>(n) };

@@ -1,4 +1,5 @@
 #!/bin/bash
+# Run at commit 4a20aea (BSCB200_QDEC / BSCB200_QENC selected kernel generations that have since been removed); kept as the record of how profiles/r2a_call_a.log was produced.
 # tools/r2_call_a.sh -- round 2, first GPU call: never-GPU-verified code first (coders 2/3, CLI, LZP, decoder generations), then stall-reason ncu.
 mkdir -p gpurun_out
 {

@@ -1,4 +1,5 @@
 #!/bin/bash
+# Run at commit 4a20aea; kept as the record of how profiles/r2b_call_b.log was produced.
 # tools/r2_call_b.sh -- round 2, second GPU call: inverse ST (new), reference CUDA path timing, co-residency / oversubscription benches.
 mkdir -p gpurun_out
 {

@@ -44,4 +44,7 @@ def checker():
 def bsc():
     """The product: CUDA library through its host-pointer C ABI.  No fallback."""
     import libbsc_b200
+    L = libbsc_b200.lib()                                  # a missing / unloadable library is an ERROR, never a skip
+    if L.bsc_init(3) == -8:                                # LIBBSC_GPU_NOT_SUPPORTED: no CUDA device on this machine
+        pytest.skip("no CUDA device (gpu-marked tests run on the B200 box)")
     return libbsc_b200.Bsc(features=3)

@@ -4,7 +4,7 @@ CPU part: the same CLI source is built against the UNMODIFIED reference library 
 GPU) and its archives are compared with the reference's own CLI (oracle/_ref/bsc, built by oracle/Makefile from
 /root/reference/bsc.cpp): byte-identical containers when both write blocks in order (`bsc -t`), and each side decodes the
 other's archives.  That pins the container logic, option handling and the in-order writer without a GPU.
-GPU part (BSCB200_TEST_CLI=1, tools/round2_first_gpu_call.sh): the product binary libbsc_b200/bsc_b200 round-trips a file and
+GPU part: the product binary libbsc_b200/bsc_b200 round-trips a file and
 produces the bytes of the reference CLI."""
 import os
 import subprocess
@@ -126,7 +126,6 @@ def test_reader_undoes_reference_filters(clis, gen):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("BSCB200_TEST_CLI") != "1", reason="set BSCB200_TEST_CLI=1 (product CLI not yet run on a GPU)")
 def test_product_cli_round_trip_on_gpu(gen, tmp_path):
     path, arch, back = str(tmp_path / "in.bin"), str(tmp_path / "a.bsc"), str(tmp_path / "back.bin")
     gen.text(2, 40 << 20).tofile(path)

@@ -62,5 +62,4 @@ def test_oracle_port_reproduces_reference_fixtures(gen, port):
 
 @pytest.mark.gpu
 def test_cuda_path_reproduces_reference_fixtures(gen, bsc):
-    coders = (1,) + ((2,) if os.environ.get("BSCB200_ENABLE_ADAPTIVE") == "1" else ()) + ((3,) if os.environ.get("BSCB200_ENABLE_FAST") == "1" else ())
-    _check_impl(bsc, gen, coders=coders, st_ks=(3, 4, 5, 6), sorters=(1, 6))
+    _check_impl(bsc, gen, coders=(1, 2, 3), st_ks=(3, 4, 5, 6), sorters=(1, 6))

@@ -1,25 +1,10 @@
 """GPU parity tests of the ADAPTIVE (coder id 2, csrc/qlfc_adaptive.cuh) and FAST (coder id 3, csrc/qlfc_fast.cuh) QLFC coders
-through the C ABI.
-
-Their kernels are bit-exact in host emulation (tests/test_qdec3_host.py) but were written after round 1's GPU budget was
-spent, so the product keeps them behind BSCB200_ENABLE_ADAPTIVE=1 / BSCB200_ENABLE_FAST=1 and these tests only run with
-the variables set:
-
-    BSCB200_ENABLE_ADAPTIVE=1 BSCB200_ENABLE_FAST=1 python -m pytest tests/test_gpu_other_coders.py -m gpu -q
-
-Without them the library must answer LIBBSC_NOT_SUPPORTED (-4) -- never different bytes."""
-import os
-
+through the C ABI: byte-identical streams, containers and blocks against the reference, and decoding of the
+reference's streams.  Both coders first passed here on the B200 in round 2 (profiles/r2a_call_a.log); they are ungated since."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-GATE = {2: "BSCB200_ENABLE_ADAPTIVE", 3: "BSCB200_ENABLE_FAST"}
-
-
-def _enabled(coder):
-    return os.environ.get(GATE[coder]) == "1"
-
 
 def _inputs(gen):
     rng = np.random.default_rng(11)
@@ -36,18 +21,7 @@ def _inputs(gen):
 
 
 @pytest.mark.parametrize("coder", [2, 3])
-def test_coder_is_gated_off_by_default(bsc, gen, coder):
-    if _enabled(coder):
-        pytest.skip("coder %d enabled" % coder)
-    L = gen.text(1, 100000)
-    assert bsc.coder_compress(L, coder, 3)[0] == -4
-    assert bsc.compress(L, coder=coder)[0] == -4
-
-
-@pytest.mark.parametrize("coder", [2, 3])
 def test_coder_matches_oracle(bsc, gen, checker, coder):
-    if not _enabled(coder):
-        pytest.skip("set %s=1 (kernels not yet verified on a GPU)" % GATE[coder])
     for name, a in _inputs(gen):
         _, L, _ = checker.bwt_encode(a)
         for feats in (3, 1):

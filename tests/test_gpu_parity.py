@@ -166,8 +166,6 @@ def test_error_codes(bsc, gen):
     a = gen.text(1, 1000)
     assert bsc.compress(a, sorter=2)[0] == -1
     assert bsc.compress(a, coder=0)[0] == -1
-    if __import__("os").environ.get("BSCB200_ENABLE_LZP") != "1":
-        assert bsc.compress(a, lzp_hash=15, lzp_min=128)[0] == -4     # the host LZP stage is gated until it has run on a GPU
     assert bsc.compress(a, lzp_hash=5, lzp_min=128)[0] == -1
     z, blk = bsc.compress(a)
     bad = blk.copy(); bad[40] ^= 1
@@ -225,10 +223,9 @@ def test_k5_st6_skew_32mb(bsc, gen):
     assert q == 0 and np.array_equal(u, a)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BSCB200_TEST_LZP") != "1", reason="set BSCB200_TEST_LZP=1 (decoding of LZP blocks not yet run on a GPU)")
 def test_decompress_blocks_made_with_reference_default_options(bsc, gen, ref):
     """bsc_decompress accepts blocks with an LZP stage (the reference's default lzpHashSize 15 / lzpMinLen 128): GPU stages, then
-    the inverse LZP stage on the host (csrc/lzp_host.h).  bsc_compress with LZP parameters stays LIBBSC_NOT_SUPPORTED."""
+    the inverse LZP stage on the host (csrc/lzp_host.h)."""
     rep = np.tile(gen.text(3, 700), 900)
     for a in (rep, np.tile(gen.text(2, 1 << 20), 5), gen.text(6, 200000)):
         z, blk = ref.compress_lzp(a)
@@ -239,8 +236,6 @@ def test_decompress_blocks_made_with_reference_default_options(bsc, gen, ref):
         assert bsc.decompress(bad)[0] == -6
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BSCB200_TEST_LZP") != "1" or __import__("os").environ.get("BSCB200_ENABLE_LZP") != "1",
-                    reason="set BSCB200_ENABLE_LZP=1 BSCB200_TEST_LZP=1 (bsc_compress with the host LZP stage not yet run on a GPU)")
 def test_compress_with_reference_default_options(bsc, gen, ref):
     """bsc_compress(lzpHashSize 15, lzpMinLen 128) = the reference's default call: host LZP stage, then the GPU stages."""
     rep = np.tile(gen.text(3, 700), 900)

@@ -1,8 +1,7 @@
-"""Host emulation of the CUDA QLFC decoder (libbsc_b200/csrc/qlfc_decoder3.cuh compiled with QD3_HOST by
-tools/qdec3_host.cpp: the same source, the 32 lanes run one after the other) against the oracle, on the CPU.
-This pins the LANE LOGIC of the speculative decoder (who evaluates which candidate context, which lane owns
-which counter move, the pair-prefetching mantissa walk, the branch-free range-coder step) bit-for-bit; the
-GPU parity tests (tests/test_gpu_parity.py) then only have to confirm that the device executes it the same way."""
+"""Host emulation of the single-warp CUDA QLFC coders (libbsc_b200/csrc/qlfc_decoder6.cuh, qlfc_fast.cuh, qlfc_adaptive.cuh compiled
+with QD3_HOST by tools/qdec3_host.cpp: the same source, the 32 lanes run one after the other) against the oracle, on the CPU.
+This pins the LANE LOGIC (which lane owns which MTF slot / row bytes, the staged rows, the branch-free range-coder step)
+bit-for-bit; the GPU parity tests (tests/test_gpu_parity.py) then only have to confirm that the device executes it the same way."""
 import ctypes
 import os
 import subprocess
@@ -13,7 +12,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tools", "qdec3_host.cpp")
 LIB = os.path.join(ROOT, "tools", "bin", "libqdec3_host.so")
-DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_decoder3.cuh", "qlfc_decoder6.cuh", "qlfc_decoder6_stream.inc", "qlfc_fast.cuh", "qlfc_adaptive.cuh", "qlfc_tables2.inc", "qlfc_coder.cuh", "qlfc_tables.inc")]
+DEPS = [SRC] + [os.path.join(ROOT, "libbsc_b200", "csrc", f) for f in ("qlfc_lanes.cuh", "qlfc_decoder6.cuh", "qlfc_decoder6_stream.inc", "qlfc_fast.cuh", "qlfc_adaptive.cuh", "qlfc_tables2.inc", "qlfc_coder.cuh", "qlfc_tables.inc")]
 
 
 def _hostlib():
@@ -26,14 +25,14 @@ def _hostlib():
 @pytest.fixture(scope="module")
 def qdec3():
     lib = _hostlib()
-    lib.qdec3_host_decode.restype = ctypes.c_int
-    lib.qdec3_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int]
+    lib.qdec6_host_decode.restype = ctypes.c_int
+    lib.qdec6_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int]
 
     def decode(stream, n, mode):
         stream = np.ascontiguousarray(stream, dtype=np.uint8)
         out = np.full(n + 64, 0xAA, dtype=np.uint8)
         stats = (ctypes.c_uint * 2)()
-        r = lib.qdec3_host_decode(stream.ctypes.data, stream.size, out.ctypes.data, n, stats, mode)
+        r = lib.qdec6_host_decode(stream.ctypes.data, stream.size, out.ctypes.data, n, stats, mode)
         assert np.all(out[n:] == 0xAA), "wrote past the output slice"
         return r, out[:n], (stats[0], stats[1])
     return decode
@@ -66,7 +65,7 @@ def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
             r, s = enc.encode_block(a)
             if r <= 0:
                 continue                                              # not compressible: the container stores it raw
-            for mode in (0, 1, 2):                                    # speculative, serial, pipelined serial
+            for mode in (1, 0):                                       # the product's diet layout, the full layout
                 n, out, stats = qdec3(s, a.size, mode)
                 assert n == a.size, (name, mode, n)
                 assert np.array_equal(out, a), (name, mode)
@@ -77,7 +76,7 @@ def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
 def test_host_emulation_rejects_oversized_stream(qdec3, gen, checker):
     a = checker.bwt_encode(gen.text(2, 100000))[1]
     r, s = checker.encode_block(a)
-    for mode in (0, 1, 2):
+    for mode in (1, 0):
         n, _, _ = qdec3(s, a.size - 1, mode)                          # declared length exceeds the slice
         assert n == -6
 
@@ -160,7 +159,7 @@ def test_layout_templated_decoder_host_emulation(gen, checker, port):
         r, s = checker.encode_block(a)
         if r <= 0:
             continue
-        for layout in (0, 1, 2, 3):                                               # 2, 3: the q_decode8 instantiation of the same source (rolled loops, cold functions)
+        for layout in (0, 1):
             out = np.full(a.size + 64, 0xAA, dtype=np.uint8)
             stats = (ctypes.c_uint * 2)()
             s_ = np.ascontiguousarray(s)

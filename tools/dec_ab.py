@@ -1,9 +1,8 @@
 #!/usr/bin/env python3
-"""tools/dec_ab.py -- A/B timing of the QLFC coder kernels on ONE block (CUDA events around every launch); the encoder variant
-is taken from the environment (BSCB200_QENC=2: one-multiply-add range recurrence).
-    python tools/dec_ab.py [MiB] [gen ...]      gen: 2 q_decode2, 3 speculative q_decode3<0>, 4 serial q_decode3<1> (default), 5 q_decode3<2>, 6 q_decode6<LayoutDiet>, 7 q_decode6<LayoutFull>,
-                                                8 / 9 q_decode8<LayoutFull / LayoutDiet> (decision loops kept rolled)
-Each generation runs in its own process (the selection is read once from BSCB200_QDEC)."""
+"""tools/dec_ab.py -- timing of the QLFC coder kernels on ONE block (CUDA events around every launch), round trip checked.
+    python tools/dec_ab.py [MiB]
+(Round 2's A/B of the decoder generations and encoder variants used this script with BSCB200_QDEC / BSCB200_QENC at commit 4a20aea:
+profiles/r2a_call_a.log; the losers are gone and so are the switches.)"""
 import os
 import subprocess
 import sys
@@ -35,12 +34,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         assert torch.equal(back[:n], src)
     for name, (cnt, ms, by) in ctx.profile_report().items():
         if name.startswith(("q_decode", "q_encode")):
-            print("QDEC=%s QENC=%s  %-10s  %d launch(es)  %.1f ms  (%d MiB block, round trip bit-exact, %d bytes)" %
-                  (os.environ.get("BSCB200_QDEC", "default"), os.environ.get("BSCB200_QENC", "default"), name, cnt, ms, mib, size), flush=True)
+            print("%-10s  %d launch(es)  %.1f ms  (%d MiB block, round trip bit-exact, %d bytes)" % (name, cnt, ms, mib, size), flush=True)
     sys.exit(0)
 
 mib = sys.argv[1] if len(sys.argv) > 1 else "64"
-gens = sys.argv[2:] or ["2", "4", "7", "6"]
-for g in gens:
-    env = dict(os.environ, BSCB200_QDEC=g)
-    subprocess.run([sys.executable, os.path.abspath(__file__), "--child", mib], env=env, check=False)
+subprocess.run([sys.executable, os.path.abspath(__file__), "--child", mib], check=False)

@@ -1,4 +1,4 @@
-// tools/qdec3_host.cpp -- compiles libbsc_b200/csrc/qlfc_decoder3.cuh FOR THE HOST (QD3_HOST): the decoder's
+// tools/qdec3_host.cpp -- compiles the single-warp QLFC coders of libbsc_b200/csrc FOR THE HOST (QD3_HOST): the decoder's
 // lane-parallel phases run as loops over 32 emulated lanes, the shared-memory counter file is a plain byte
 // array.  Test infrastructure only (tests/test_qdec3_host.py compares it with the oracle on the CPU); the
 // product never links or loads this file -- it checks the LOGIC of the CUDA decoder where there is no GPU.
@@ -37,32 +37,10 @@ struct SubBlock { u32 in_start, in_size, run_begin, run_end, out_off, out_cap; i
 struct QTables { u8 rank_state[32768]; u8 run_state[8192]; };
 #include "../libbsc_b200/csrc/qlfc_coder.cuh"
 #define QD3_HOST 1
-#include "../libbsc_b200/csrc/qlfc_decoder3.cuh"
+#include "../libbsc_b200/csrc/qlfc_lanes.cuh"
 #include "../libbsc_b200/csrc/qlfc_fast.cuh"
 #include "../libbsc_b200/csrc/qlfc_decoder6.cuh"
 #include "../libbsc_b200/csrc/qlfc_adaptive.cuh"
-}
-
-// Decodes one QLFC static stream (what bsc_qlfc_static_decode_block reads) of `in_size` bytes into out[0..out_cap).
-// mode 0: the speculative decoder, mode 1: the serial decoder, mode 2: the pipelined serial decoder
-extern "C" int qdec3_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats, int mode)
-{
-    u8 *smem = (u8 *)calloc(1, sizeof(Dec3Smem));
-    short *cold = (short *)malloc(sizeof(short) * 2 * (size_t)COLD_PAD);
-    if (!smem || !cold) { free(smem); free(cold); return LIBBSC_NOT_ENOUGH_MEMORY; }
-    Dec3Smem *D = (Dec3Smem *)smem;
-    memcpy(D->cs.rank_state, bscb_rank_state_tab, 32768);
-    memcpy(D->cs.run_state, bscb_run_state_tab, 8192);
-    for (u32 i = 0; i < S16_COUNT; ++i) D->cs.s16[i] = 2048;
-    for (size_t i = 0; i < 2 * (size_t)COLD_PAD; ++i) cold[i] = 2048;
-    SM3 sm; sm.b = smem;
-    u32 st_cached = 0, st_miss = 0;
-    const int r = mode == 0 ? qd3_decode_stream<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss)
-                : mode == 1 ? qd3_decode_stream_serial<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss)
-                            : qd3_decode_stream_pipe<false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, st_cached, st_miss);
-    if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
-    free(smem); free(cold);
-    return r;
 }
 
 // ---- fast coder (coder id 3), libbsc_b200/csrc/qlfc_fast.cuh ---------------------------------------------------------
@@ -106,7 +84,7 @@ extern "C" int qfast_host_encode(const unsigned *run_pos, const unsigned char *r
 }
 
 // ---- layout-templated serial decoder (libbsc_b200/csrc/qlfc_decoder6.cuh): layout 0 = full (205 KB), 1 = diet (101 KB) ------------
-template <class LY, bool COMPACT = false> static int qdec6_run(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
+template <class LY> static int qdec6_run(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
 {
     u8 *smem = (u8 *)calloc(1, LY::BYTES);
     short *cold = (short *)malloc(sizeof(short) * 2 * (size_t)COLD_PAD);
@@ -118,20 +96,15 @@ template <class LY, bool COMPACT = false> static int qdec6_run(const unsigned ch
     SM3 sm; sm.b = smem;
     u32 st_cached = 0, st_miss = 0;
     int moves[QD6_MOVES]; qd6_fill_moves(moves);
-    const int r = COMPACT ? qd6_decode_stream_compact<WithBranchRenorm<LY>, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss)
-                          : qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss);
+    const int r = qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss);
     if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
     free(smem); free(cold);
     return r;
 }
 extern "C" int qdec6_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats, int layout)
 {
-    switch (layout) {                                                   // 2, 3: the q_decode8 instantiation (same statements; on the host the pragmas and attributes are void)
-    case 0: return qdec6_run<LayoutFull>(in, in_size, out, out_cap, stats);
-    case 1: return qdec6_run<LayoutDiet>(in, in_size, out, out_cap, stats);
-    case 2: return qdec6_run<LayoutFull, true>(in, in_size, out, out_cap, stats);
-    default: return qdec6_run<LayoutDiet, true>(in, in_size, out, out_cap, stats);
-    }
+    return layout == 0 ? qdec6_run<LayoutFull>(in, in_size, out, out_cap, stats)         // 0: the full layout (what the adaptive coder derives from)
+                       : qdec6_run<LayoutDiet>(in, in_size, out, out_cap, stats);        // 1: the product's layout
 }
 extern "C" unsigned qdec6_smem_bytes(int layout) { return layout == 0 ? LayoutFull::BYTES : LayoutDiet::BYTES; }
 

@@ -33,11 +33,13 @@ B = libbsc_b200.Bsc(features=3)
 L = B.lib
 
 
-def timed(fn, reps):
+def timed(call, prep, reps):
+    """prep() restores the in-place buffer (untimed); call() is ONE C entry point on preallocated, already touched buffers"""
     ts = []
     out = None
     for _ in range(reps + 1):                            # first call warms allocations / module load
-        t0 = time.perf_counter(); out = fn(); ts.append(time.perf_counter() - t0)
+        prep()
+        t0 = time.perf_counter(); out = call(); ts.append(time.perf_counter() - t0)
     ts = ts[1:]
     return out, min(ts) * 1e3, float(np.median(ts)) * 1e3
 
@@ -70,57 +72,82 @@ def ours_kernel_ms(stage, data, **kw):
     return best
 
 
+# ---- single-call mode for kernel-only sums under ncu:  TRC_SIDE=ref|ours TRC_STAGE=bwt_encode|bwt_decode|st6_encode  ncu --metrics
+# gpu__time_duration.sum --csv ... python tools/time_ref_cuda.py   (one call of one entry point of one library; tools/ncu_launch_sum.py adds up)
+if os.environ.get("TRC_SIDE"):
+    side, stage = os.environ["TRC_SIDE"], os.environ.get("TRC_STAGE", "bwt_encode")
+    lib_, feat_ = (R, FEAT) if side == "ref" else (L, 3)
+    for f_, a_ in (("bsc_bwt_encode", [vp, ci, vp, vp, ci]), ("bsc_bwt_decode", [vp, ci, ci, ctypes.c_ubyte, vp, ci]), ("bsc_st_encode", [vp, ci, ci, ci])):
+        getattr(lib_, f_).argtypes = a_
+    ni_ = ctypes.c_ubyte(0); idx_ = (ci * 256)()
+    if stage.startswith("bwt"):
+        a_ = gen.text(2, 64 << 20); buf_ = np.empty(a_.size + 64, dtype=np.uint8); buf_[:a_.size] = a_
+        if stage == "bwt_decode":                        # the forward transform comes from the CPU reference (no kernels in the list)
+            chk_ = pyoracle.best(); r_, L_, _ = chk_.bwt_encode(a_); buf_[:a_.size] = L_
+            q_ = lib_.bsc_bwt_decode(buf_.ctypes.data, a_.size, r_, 0, None, feat_)
+            assert q_ == 0 and np.array_equal(buf_[:a_.size], a_)
+        else:
+            r_ = lib_.bsc_bwt_encode(buf_.ctypes.data, a_.size, ctypes.byref(ni_), idx_, feat_)
+            assert r_ == 10745360
+    else:
+        a_ = gen.skew(3, 32 << 20); buf_ = np.empty(a_.size + 64, dtype=np.uint8); buf_[:a_.size] = a_
+        r_ = lib_.bsc_st_encode(buf_.ctypes.data, a_.size, 6, feat_)
+        assert r_ == 28690215
+    print("single call done:", side, stage)
+    sys.exit(0)
+
 rows = []
 text = gen.text(2, 64 << 20)
 skew = gen.skew(3, 32 << 20)
+ni = ctypes.c_ubyte(0); idx = (ci * 256)()
+bufR = np.empty(text.size + 64, dtype=np.uint8); bufO = np.empty(text.size + 64, dtype=np.uint8)
+L.bsc_bwt_encode.argtypes = [vp, ci, vp, vp, ci]
+L.bsc_bwt_decode.argtypes = [vp, ci, ci, ctypes.c_ubyte, vp, ci]
+L.bsc_st_encode.argtypes = [vp, ci, ci, ci]
+L.bsc_st_decode.argtypes = [vp, ci, ci, ci, ci]
+R.bsc_st_decode.argtypes = [vp, ci, ci, ci, ci]
+
+
+def load(buf, src):
+    def f():
+        buf[:src.size] = src
+    return f
+
 
 # ---- forward BWT, 64 MiB text (a3: libcubwt_bwt_aux through bsc_bwt_encode) ----
-def ref_bwt_enc():
-    T = text.copy(); ni = ctypes.c_ubyte(0); idx = (ci * 256)()
-    r = R.bsc_bwt_encode(T.ctypes.data, T.size, ctypes.byref(ni), idx, FEAT)
-    return r, T
-(r_ref, L_ref), rb, rm = timed(ref_bwt_enc, reps)
-(r_our, L_our, _), ob, om = timed(lambda: B.bwt_encode(text), reps)
-assert r_ref == r_our and np.array_equal(L_ref, L_our), "forward BWT differs from the reference's CUDA path"
+n = text.size
+r_ref, rb, rm = timed(lambda: R.bsc_bwt_encode(bufR.ctypes.data, n, ctypes.byref(ni), idx, FEAT), load(bufR, text), reps)
+r_our, ob, om = timed(lambda: L.bsc_bwt_encode(bufO.ctypes.data, n, ctypes.byref(ni), idx, 3), load(bufO, text), reps)
+assert r_ref == r_our and np.array_equal(bufR[:n], bufO[:n]), "forward BWT differs from the reference's CUDA path"
+L_ref = bufR[:n].copy()
 rows.append({"stage": "bsc_bwt_encode 64 MiB G_text", "ref_cuda_ms_best": rb, "ref_cuda_ms_median": rm, "ours_ms_best": ob, "ours_ms_median": om,
              "ours_kernels_only_ms": ours_kernel_ms("bwt_encode", text), "bit_identical": True})
 
 # ---- inverse BWT (a6: libcubwt_unbwt through bsc_bwt_decode) ----
-def ref_bwt_dec():
-    T = L_ref.copy()
-    r = R.bsc_bwt_decode(T.ctypes.data, T.size, r_ref, 0, None, FEAT)
-    return r, T
-(q_ref, T_ref), rb, rm = timed(ref_bwt_dec, reps)
-(q_our, T_our), ob, om = timed(lambda: B.bwt_decode(L_ref, r_ref), reps)
-assert q_ref == 0 and q_our == 0 and np.array_equal(T_ref, text) and np.array_equal(T_our, text)
+q_ref, rb, rm = timed(lambda: R.bsc_bwt_decode(bufR.ctypes.data, n, r_ref, 0, None, FEAT), load(bufR, L_ref), reps)
+q_our, ob, om = timed(lambda: L.bsc_bwt_decode(bufO.ctypes.data, n, r_ref, 0, None, 3), load(bufO, L_ref), reps)
+assert q_ref == 0 and q_our == 0 and np.array_equal(bufR[:n], text) and np.array_equal(bufO[:n], text)
 rows.append({"stage": "bsc_bwt_decode 64 MiB G_text", "ref_cuda_ms_best": rb, "ref_cuda_ms_median": rm, "ours_ms_best": ob, "ours_ms_median": om,
              "ours_kernels_only_ms": ours_kernel_ms("bwt_decode", L_ref, index=r_ref), "bit_identical": True})
 
 # ---- forward ST (a8: bsc_st_encode_cuda, k = 5..8) on 32 MiB skew ----
+n = skew.size
 st_out = {}
 for k in (5, 6, 7, 8):
-    def ref_st():
-        T = np.empty(skew.size + 64, dtype=np.uint8); T[:skew.size] = skew
-        r = R.bsc_st_encode(T.ctypes.data, skew.size, k, FEAT)
-        return r, T[:skew.size]
-    (i_ref, S_ref), rb, rm = timed(ref_st, reps)
-    (i_our, S_our), ob, om = timed(lambda: B.st_encode(skew, k), reps)
-    assert i_ref == i_our and np.array_equal(S_ref, S_our), "ST%d differs from the reference's CUDA path" % k
-    st_out[k] = (i_our, S_our.copy())
+    i_ref, rb, rm = timed(lambda: R.bsc_st_encode(bufR.ctypes.data, n, k, FEAT), load(bufR, skew), reps)
+    i_our, ob, om = timed(lambda: L.bsc_st_encode(bufO.ctypes.data, n, k, 3), load(bufO, skew), reps)
+    assert i_ref == i_our and np.array_equal(bufR[:n], bufO[:n]), "ST%d differs from the reference's CUDA path" % k
+    st_out[k] = (i_our, bufO[:n].copy())
     rows.append({"stage": "bsc_st_encode k=%d 32 MiB G_skew" % k, "ref_cuda_ms_best": rb, "ref_cuda_ms_median": rm, "ours_ms_best": ob, "ours_ms_median": om,
                  "ours_kernels_only_ms": ours_kernel_ms("st_encode", skew, k=k, sorter=k), "bit_identical": True})
 
 # ---- inverse ST: the reference has no GPU path (st.cpp:1491, CPU only) ----
-if hasattr(B, "st_decode"):
-    R.bsc_st_decode.argtypes = [vp, ci, ci, ci, ci]
-    i6, S6 = st_out[6]
-    def ref_unst():
-        T = S6.copy(); r = R.bsc_st_decode(T.ctypes.data, T.size, 6, i6, FEAT); return r, T
-    (q_ref, U_ref), rb, rm = timed(ref_unst, 1)
-    (q_our, U_our), ob, om = timed(lambda: B.st_decode(S6, 6, i6), reps)
-    assert q_ref == 0 and q_our == 0 and np.array_equal(U_ref, skew) and np.array_equal(U_our, skew)
-    rows.append({"stage": "bsc_st_decode k=6 32 MiB G_skew (reference: CPU, OpenMP)", "ref_cuda_ms_best": rb, "ref_cuda_ms_median": rm, "ours_ms_best": ob, "ours_ms_median": om,
-                 "ours_kernels_only_ms": ours_kernel_ms("st_decode", S6, k=6, index=i6, sorter=6), "bit_identical": True})
+i6, S6 = st_out[6]
+q_ref, rb, rm = timed(lambda: R.bsc_st_decode(bufR.ctypes.data, n, 6, i6, FEAT), load(bufR, S6), 1)
+q_our, ob, om = timed(lambda: L.bsc_st_decode(bufO.ctypes.data, n, 6, i6, 3), load(bufO, S6), reps)
+assert q_ref == 0 and q_our == 0 and np.array_equal(bufR[:n], skew) and np.array_equal(bufO[:n], skew)
+rows.append({"stage": "bsc_st_decode k=6 32 MiB G_skew (reference: CPU, OpenMP)", "ref_cuda_ms_best": rb, "ref_cuda_ms_median": rm, "ours_ms_best": ob, "ours_ms_median": om,
+             "ours_kernels_only_ms": ours_kernel_ms("st_decode", S6, k=6, index=i6, sorter=6), "bit_identical": True})
 
 for r in rows:
     r["speedup_best"] = round(r["ref_cuda_ms_best"] / r["ours_ms_best"], 2)
