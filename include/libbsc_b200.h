@@ -77,6 +77,15 @@ int bsc_coder_init(int features);
 int bsc_coder_compress(const unsigned char *input, unsigned char *output, int n, int coder, int features);
 int bsc_coder_decompress(const unsigned char *input, unsigned char *output, int coder, int features);
 int bsc_qlfc_init(int features);                                              /* libbsc/coder/qlfc/qlfc.h:45 */
+/* libbsc/coder/qlfc/qlfc.h:55-99 ; qlfc.cpp:2138-2226: ONE QLFC stream (what the container holds per sub-block).  encode: fails
+ * with LIBBSC_NOT_COMPRESSIBLE when the stream would come within 16 bytes of outputSize (rangecoder.h:118-127).  decode: size-less
+ * like the reference's; the stream is taken to end at most n + 16 bytes after `input` (n = the size coded in the stream). */
+int bsc_qlfc_static_encode_block(const unsigned char *input, unsigned char *output, int inputSize, int outputSize);
+int bsc_qlfc_adaptive_encode_block(const unsigned char *input, unsigned char *output, int inputSize, int outputSize);
+int bsc_qlfc_fast_encode_block(const unsigned char *input, unsigned char *output, int inputSize, int outputSize);
+int bsc_qlfc_static_decode_block(const unsigned char *input, unsigned char *output);
+int bsc_qlfc_adaptive_decode_block(const unsigned char *input, unsigned char *output);
+int bsc_qlfc_fast_decode_block(const unsigned char *input, unsigned char *output);
 
 /* libbsc/adler32/adler32.h ; adler32.cpp:83 */
 unsigned int bsc_adler32(const unsigned char *T, int n, int features);
@@ -101,6 +110,8 @@ int                bscb200_ctx_reserve(void *ctx, long long bytes);
 int                bscb200_lzp_decompress_host(const unsigned char *input, int n, unsigned char *output, int outputCapacity, int lzpHashSize, int lzpMinLen);   /* inverse of the reference LZP stage (libbsc/lzp/lzp.h), host only */
 int                bscb200_lzp_compress_host(const unsigned char *input, unsigned char *output, int n, int lzpHashSize, int lzpMinLen, int features);   /* the reference LZP stage forward (libbsc/lzp/lzp.h), host only */
 int                bscb200_device_count(void);                    /* CUDA devices visible to the process */
+long long          bscb200_device_free_bytes(void);               /* free HBM on the current device, -1 on error */
+void               bscb200_release_pools(void);                   /* free the pooled contexts and sort slabs of every device (no call in flight) */
 int                bscb200_set_device(int device);                /* bind the calling thread: all entry points use the current device */
 long long          bscb200_workspace_bytes(int n, int blockSorter);   /* per-context workspace (~13 n + 64 MB): staged block + coder stage */
 long long          bscb200_workspace_bytes_decode(int n);         /* the same (kept for callers of the round-1 ABI) */

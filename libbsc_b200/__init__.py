@@ -38,6 +38,12 @@ _SIGNATURES = {
     "bsc_coder_compress": ([vp, vp, ci, ci, ci], ci),
     "bsc_coder_decompress": ([vp, vp, ci, ci], ci),
     "bsc_qlfc_init": ([ci], ci),
+    "bsc_qlfc_static_encode_block": ([vp, vp, ci, ci], ci),
+    "bsc_qlfc_adaptive_encode_block": ([vp, vp, ci, ci], ci),
+    "bsc_qlfc_fast_encode_block": ([vp, vp, ci, ci], ci),
+    "bsc_qlfc_static_decode_block": ([vp, vp], ci),
+    "bsc_qlfc_adaptive_decode_block": ([vp, vp], ci),
+    "bsc_qlfc_fast_decode_block": ([vp, vp], ci),
     "bsc_adler32": ([vp, ci, ci], ctypes.c_uint32),
     "bsc_platform_init": ([ci, vp, vp, vp], ci),
     "bsc_malloc": ([ctypes.c_size_t], vp),
@@ -52,6 +58,8 @@ _SIGNATURES = {
     "bscb200_lzp_compress_host": ([vp, vp, ci, ci, ci, ci], ci),
     "bscb200_device_count": ([], ci),
     "bscb200_set_device": ([ci], ci),
+    "bscb200_device_free_bytes": ([], ctypes.c_longlong),
+    "bscb200_release_pools": ([], None),
     "bscb200_workspace_bytes": ([ci, ci], ctypes.c_longlong),
     "bscb200_workspace_bytes_decode": ([ci], ctypes.c_longlong),
     "bscb200_scratch_bytes": ([ci, ci], ctypes.c_longlong),
@@ -134,6 +142,22 @@ class Bsc:
         T = np.array(L, dtype=np.uint8, copy=True)
         r = self.lib.bsc_st_decode(T.ctypes.data, T.size, k, index, self.features)
         return r, T
+
+    _QLFC = {1: "static", 2: "adaptive", 3: "fast"}
+
+    def encode_block(self, data, out_size=None, coder=1):
+        """bsc_qlfc_<coder>_encode_block: one QLFC stream (same method as oracle/pyoracle.py)"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        cap = data.size if out_size is None else out_size
+        out = np.empty(max(cap, data.size) + 64, dtype=np.uint8)
+        r = getattr(self.lib, "bsc_qlfc_%s_encode_block" % self._QLFC[coder])(data.ctypes.data, out.ctypes.data, data.size, cap)
+        return r, out[:max(r, 0)].copy()
+
+    def decode_block(self, stream, n, coder=1):
+        stream = np.concatenate([np.ascontiguousarray(stream, dtype=np.uint8), np.zeros(n + 64, dtype=np.uint8)])   # size-less ABI: n + 16 readable bytes
+        out = np.empty(n + 64, dtype=np.uint8)
+        r = getattr(self.lib, "bsc_qlfc_%s_decode_block" % self._QLFC[coder])(stream.ctypes.data, out.ctypes.data)
+        return r, out[:max(r, 0)].copy()
 
     def coder_compress(self, L, coder=1, features=3):
         L = np.ascontiguousarray(L, dtype=np.uint8)

@@ -43,6 +43,10 @@ int bsc_block_info(const unsigned char *blockHeader, int headerSize, int *pBlock
 int bsc_decompress(const unsigned char *input, int inputSize, unsigned char *output, int outputSize, int features);
 }
 static int bscb200_device_count(void) { return 1; }
+static long long bscb200_device_free_bytes(void) { return -1; }
+static long long bscb200_workspace_bytes(int, int) { return 0; }
+static long long bscb200_scratch_bytes(int, int) { return 0; }
+static void bscb200_release_pools(void) {}
 static int bscb200_set_device(int) { return 0; }
 #define LIBBSC_HEADER_SIZE 28
 #define LIBBSC_NO_ERROR 0
@@ -57,7 +61,7 @@ const unsigned char kSign[4] = {'b', 's', 'c', 0x31};
 enum { kFeatures = 1 | 2, kContextsFollowing = 1, kContextsPreceding = 2, kRecordBytes = 10 };
 
 struct Options {
-    int block_bytes = 25 << 20, sorter = 1, coder = 1, slots = 18;
+    int block_bytes = 25 << 20, sorter = 1, coder = 1, slots = 40;
     int lzp_hash = 0, lzp_min = 0;                                       // -l: the reference's LZP stage (host side of the library), off by default
     std::vector<int> devices;
 };
@@ -100,6 +104,23 @@ void put_record(unsigned char *rec, long long offset, int recordSize, int contex
     rec[8] = (unsigned char)recordSize; rec[9] = (unsigned char)contexts;
 }
 
+// Blocks in flight per GPU, bounded by its free memory: a context holds the staged block + the coder stage (~15 n + 64 MB); three sort
+// slabs (~58 n each for BWT) are shared by all of them.  At -b1024 that is one or two blocks, at -b25 the full -j.
+int fit_slots(const Options &opt, int want)
+{
+    int slots = want;
+    for (int dev : opt.devices) {
+        if (bscb200_set_device(dev) != 0) die("cannot select GPU");
+        const long long fr = bscb200_device_free_bytes();
+        if (fr < 0) continue;
+        const long long per = 2LL * opt.block_bytes + bscb200_workspace_bytes(opt.block_bytes, opt.sorter) + (64LL << 20);
+        const long long avail = fr - fr / 10 - 3 * bscb200_scratch_bytes(opt.block_bytes, opt.sorter);
+        const int fit = per > 0 ? (int)std::max(1LL, avail / per) : want;
+        slots = std::min(slots, fit);
+    }
+    return std::max(1, slots);
+}
+
 // worker w of W runs on devices[w % devices.size()]
 template <class F> void run_workers(const Options &opt, F body)
 {
@@ -133,6 +154,7 @@ int compress_file(const char *in_name, const char *out_name, Options opt)
     std::mutex mu; std::condition_variable cv;
     int next = 0, next_to_write = 0;
     std::map<int, std::vector<unsigned char>> done;                                   // finished blocks waiting for their turn
+    opt.slots = fit_slots(opt, opt.slots);
     const int W = std::max(1, std::min((int)opt.devices.size() * opt.slots, nBlocks));
     opt.slots = (W + (int)opt.devices.size() - 1) / (int)opt.devices.size();
 
@@ -222,6 +244,7 @@ int decompress_file(const char *in_name, const char *out_name, Options opt)
     const int nBlocks = (int)blocks.size();
     const double t0 = now();
     std::mutex mu; int next = 0; long long out_size = 0;
+    { int big = 0; for (const BlockRef &r : blocks) big = std::max(big, r.data_size); Options o2 = opt; o2.block_bytes = big; o2.sorter = 6; opt.slots = fit_slots(o2, opt.slots); }
     const int W = std::max(1, std::min((int)opt.devices.size() * opt.slots, nBlocks));
     opt.slots = (W + (int)opt.devices.size() - 1) / (int)opt.devices.size();
     run_workers(opt, [&](int) {
@@ -255,7 +278,7 @@ void usage()
             "  -e<algo>  entropy coder: -e1 static QLFC (default), -e0 fast, -e2 adaptive (experimental, see DESIGN.md)\n"
             "  -l        LZP preprocessing on (host stage; -H<10..28> hash bits, -M<4..255> minimum match; bsc's defaults 15 / 128)\n"
             "  -g<list>  GPUs to use, e.g. -g0,1,2,3 (default: all visible)\n"
-            "  -j<n>     blocks in flight per GPU, default -j18 (one coder stream per SM: 18 x 8 = 144 of 148)\n"
+            "  -j<n>     blocks in flight per GPU, default -j40, fewer when HBM is short (8 coder streams per block, two per SM)\n"
             "Writes what `bsc e in out -p` writes; reads `bsc` archives made without -r / -c (LZP is undone on the host).\n");
     exit(0);
 }
@@ -287,5 +310,7 @@ int main(int argc, char **argv)
     if (opt.devices.empty()) die("no usable GPU (libbsc_b200 has no CPU path)");
     const int rc = bsc_init(kFeatures);
     if (rc != LIBBSC_NO_ERROR) die("Initialisation failed: %s", error_text(rc));
-    return argv[1][0] == 'e' ? compress_file(argv[2], argv[3], opt) : decompress_file(argv[2], argv[3], opt);
+    const int rc2 = argv[1][0] == 'e' ? compress_file(argv[2], argv[3], opt) : decompress_file(argv[2], argv[3], opt);
+    bscb200_release_pools();
+    return rc2;
 }

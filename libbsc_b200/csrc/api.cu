@@ -62,7 +62,6 @@ void ctx_delete(Ctx *c)
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->qlfc_tables) cudaFree(c->qlfc_tables);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-    if (c->long_ev) cudaEventDestroy(c->long_ev);
     if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -579,27 +578,34 @@ int bscb200_coder_decompress(const unsigned char *input, int inputSize, unsigned
     });
 }
 
-// libbsc's own signature carries no sizes (coder.h:66).  They are recovered from the container:
-// the sub-block table for nBlocks > 1; for a single sub-block the uncompressed size n is the first
-// 32 range-coded bits of the stream (qlfc.cpp:852) and the stream is shorter than n.
+// The uncompressed size n of a QLFC stream = its first 32 range-coded bits, each with p = 1/2 (qlfc.cpp:852; rangecoder.h:203-240).
+// Needs 14 readable bytes.  Returns -1 for n > 2^31 - 1.
+static long long qlfc_stream_size(const unsigned char *p)
+{
+    unsigned int code = ((unsigned)p[2] | ((unsigned)p[3] << 8)) << 16 | ((unsigned)p[4] | ((unsigned)p[5] << 8));
+    unsigned int range = 0xffffffffu, nn = 0; int pos = 6;
+    for (int b = 0; b < 32; ++b) {
+        if (range < 0x10000u) { range <<= 16; code = (code << 16) | ((unsigned)p[pos] | ((unsigned)p[pos + 1] << 8)); pos += 2; }
+        unsigned int r = (range >> 12) * 2048u;
+        if (code >= r) { code -= r; range -= r; nn = (nn << 1) | 1u; } else { range = r; nn <<= 1; }
+    }
+    return nn > 0x7fffffffu ? -1 : (long long)nn;
+}
+
+// libbsc's own signature carries no sizes (coder.h:66).  They are recovered from the container: the sub-block table for
+// nBlocks > 1; for a single sub-block the uncompressed size n is coded in the stream and the stream itself is shorter than n
+// (bsc_coder_compress stores a sub-block raw otherwise).  CALLER CONTRACT for the size-less ABI: the n + 17 bytes after `input`
+// are either part of the stream or unmapped -- they are copied to the device as far as they are mapped (never read by the decoder
+// beyond the stream's end).  Integrators that know their sizes should call bscb200_coder_decompress.
 int bsc_coder_decompress(const unsigned char *input, unsigned char *output, int coder, int features)
 {
     if (coder < 1 || coder > 3) return LIBBSC_BAD_PARAMETER;
     int nBlocks = input[0];
     long long inSize = 0, outSize = 0;
     if (nBlocks == 1) {
-        // decode the 32 equiprobable bits of n on the host (rangecoder.h:203-240 with p = 2048)
-        const unsigned char *p = input + 1;
-        unsigned int code = ((unsigned)p[2] | ((unsigned)p[3] << 8)) << 16 | ((unsigned)p[4] | ((unsigned)p[5] << 8));
-        unsigned int range = 0xffffffffu, nn = 0; int pos = 6;
-        for (int b = 0; b < 32; ++b) {
-            if (range < 0x10000u) { range <<= 16; code = (code << 16) | ((unsigned)p[pos] | ((unsigned)p[pos + 1] << 8)); pos += 2; }
-            unsigned int r = (range >> 12) * 2048u;
-            if (code >= r) { code -= r; range -= r; nn = (nn << 1) | 1u; } else { range = r; nn <<= 1; }
-        }
-        if (nn > 0x7fffffffu) return LIBBSC_DATA_CORRUPT;
-        outSize = nn;
-        inSize = (long long)readable_prefix(input, (size_t)nn + 1 + 16);  // the stream is < n bytes; never touch unmapped pages
+        outSize = qlfc_stream_size(input + 1);
+        if (outSize < 0) return LIBBSC_DATA_CORRUPT;
+        inSize = (long long)readable_prefix(input, (size_t)outSize + 1 + 16);
     } else {
         if (nBlocks == 0 || nBlocks > 8) return LIBBSC_DATA_CORRUPT;
         inSize = 1 + 8 * nBlocks;
@@ -608,6 +614,47 @@ int bsc_coder_decompress(const unsigned char *input, unsigned char *output, int 
     if (inSize > 0x7fffffffLL || outSize > 0x7fffffffLL) return LIBBSC_DATA_CORRUPT;
     return bscb200_coder_decompress(input, (int)inSize, output, (int)outSize, coder, features);
 }
+
+// ---- one QLFC stream at a time (libbsc/coder/qlfc/qlfc.h:55-99; qlfc.cpp:2138-2226) ------------------------------------------
+static int qlfc_encode_block(int coder, const unsigned char *input, unsigned char *output, int inputSize, int outputSize)
+{
+    if (inputSize <= 0 || outputSize < 0) return LIBBSC_BAD_PARAMETER;
+    return with_ctx([&](Ctx *ctx) {
+        const size_t room = (size_t)(outputSize > inputSize ? outputSize : inputSize);
+        ctx->arena.reserve(2 * room + (size_t)inputSize + 16384 + need_coder(room));
+        u8 *d_in = ctx->arena.get<u8>((size_t)inputSize + 64);
+        u8 *d_out = ctx->arena.get<u8>(room + 4096);
+        CUDA_TRY(cudaMemcpyAsync(d_in, input, (size_t)inputSize, cudaMemcpyHostToDevice, ctx->stream));
+        int r = stage_coder_compress(ctx, d_in, d_out, inputSize, coder, 0, outputSize);
+        if (r > 0) { CUDA_TRY(cudaMemcpyAsync(output, d_out, (size_t)r, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+// Size-less like the reference's: n comes from the stream; the stream is taken to be at most n + 16 bytes long (what
+// bsc_qlfc_*_encode_block produces with outputSize <= inputSize; same caller contract as bsc_coder_decompress above).
+static int qlfc_decode_block(int coder, const unsigned char *input, unsigned char *output)
+{
+    const long long n = qlfc_stream_size(input);
+    if (n < 0) return LIBBSC_DATA_CORRUPT;
+    const int inSize = (int)readable_prefix(input, (size_t)n + 16);
+    if (inSize < 14) return LIBBSC_UNEXPECTED_EOB;
+    return with_ctx([&](Ctx *ctx) {
+        ctx->arena.reserve((size_t)inSize + (size_t)n + 16384 + need_coder((size_t)n));
+        u8 *d_in = ctx->arena.get<u8>((size_t)inSize + 128);
+        u8 *d_out = ctx->arena.get<u8>((size_t)n + 128);
+        CUDA_TRY(cudaMemcpyAsync(d_in, input, (size_t)inSize, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(d_in + inSize, 0, 64, ctx->stream));
+        int r = stage_coder_decompress(ctx, d_in, inSize, d_out, (int)n, coder, 0, true);
+        if (r > 0) { CUDA_TRY(cudaMemcpyAsync(output, d_out, (size_t)r, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+        return r;
+    });
+}
+int bsc_qlfc_static_encode_block(const unsigned char *input, unsigned char *output, int inputSize, int outputSize) { return qlfc_encode_block(1, input, output, inputSize, outputSize); }
+int bsc_qlfc_adaptive_encode_block(const unsigned char *input, unsigned char *output, int inputSize, int outputSize) { return qlfc_encode_block(2, input, output, inputSize, outputSize); }
+int bsc_qlfc_fast_encode_block(const unsigned char *input, unsigned char *output, int inputSize, int outputSize) { return qlfc_encode_block(3, input, output, inputSize, outputSize); }
+int bsc_qlfc_static_decode_block(const unsigned char *input, unsigned char *output) { return qlfc_decode_block(1, input, output); }
+int bsc_qlfc_adaptive_decode_block(const unsigned char *input, unsigned char *output) { return qlfc_decode_block(2, input, output); }
+int bsc_qlfc_fast_decode_block(const unsigned char *input, unsigned char *output) { return qlfc_decode_block(3, input, output); }
 
 // ---- extensions: explicit contexts and device-resident operation ------------------------------
 void *bscb200_ctx_create(int device, void *cuda_stream)
@@ -656,6 +703,23 @@ int bscb200_lzp_compress_host(const unsigned char *input, unsigned char *output,
 
 // Multi-GPU callers (libbsc_b200/cli/bsc_b200.cpp, one worker thread per GPU slot): every entry point works on the CURRENT device
 // of the calling thread, so a worker only has to bind itself once.  Plain wrappers, so that callers need no CUDA headers.
+// free HBM on the current device (callers size their number of blocks in flight with it: libbsc_b200/cli/bsc_b200.cpp)
+long long bscb200_device_free_bytes(void) { size_t f = 0, t = 0; if (cudaMemGetInfo(&f, &t) != cudaSuccess) { cudaGetLastError(); return -1; } return (long long)f; }
+// Frees everything the library caches on every device: pooled contexts (bsc_* host-pointer entry points) and the sort slabs.  Only when no
+// call is in flight.  Contexts made with bscb200_ctx_create belong to their owner.
+void bscb200_release_pools(void)
+{
+    int cur = 0; cudaGetDevice(&cur);
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        std::vector<Ctx *> ctxs; std::vector<Scratch *> slabs;
+        { std::lock_guard<std::mutex> lk(g_pool_mutex); ctxs.swap(g_pool[d]); for (Ctx *c : ctxs) g_launches_retired += c->kernels_launched; }
+        { std::lock_guard<std::mutex> lk(g_scratch[d].m); slabs.swap(g_scratch[d].free_list); g_scratch[d].created -= (int)slabs.size(); }
+        for (Ctx *c : ctxs) ctx_delete(c);
+        if (!slabs.empty()) cudaSetDevice(d);
+        for (Scratch *s : slabs) { if (s->idle_valid) cudaEventSynchronize(s->idle); s->arena.destroy(); if (s->idle) cudaEventDestroy(s->idle); delete s; }
+    }
+    cudaSetDevice(cur); cudaGetLastError();
+}
 int bscb200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 int bscb200_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? LIBBSC_NO_ERROR : LIBBSC_GPU_ERROR; }
 

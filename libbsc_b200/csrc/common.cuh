@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 typedef uint8_t  u8;
 typedef uint16_t u16;
@@ -113,14 +114,20 @@ struct Ctx {
     }
 
     void sync() { CUDA_TRY(cudaStreamSynchronize(stream)); }
-    // Wait for work that runs for 0.1 - 2 s (the coder kernels).  cudaStreamSynchronize spins; with one worker thread per block in
-    // flight (18 per GPU in bench.py, times 8 ranks on one host) the spinning threads would take the cores away from the threads
-    // that are launching the short kernels of other blocks.  A blocking-sync event lets the thread sleep instead.
-    cudaEvent_t  long_ev = nullptr;
-    void sync_long() {
-        if (!long_ev) CUDA_TRY(cudaEventCreateWithFlags(&long_ev, cudaEventBlockingSync | cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(long_ev, stream));
-        CUDA_TRY(cudaEventSynchronize(long_ev));
+    // Wait for a kernel that runs for 0.01 - 2 s (the coder kernels) WITHOUT putting anything behind it on the stream.  A process has
+    // at most 32 hardware work queues per GPU (CUDA_DEVICE_MAX_CONNECTIONS), so with 40+ blocks in flight two streams share a queue;
+    // an event record or a copy enqueued behind the 2 s kernel of one of them holds the queue's head until that kernel ENDS, and the
+    // other stream's work waits behind it -- measured: 48 and 64 blocks in flight ran as waves of 32 (profiles/r2c_call_c.log).
+    // cudaStreamQuery enqueues nothing, and the sleeping poll leaves the host cores to the threads that launch other blocks' kernels.
+    void wait_long() {
+        unsigned us = 20;
+        for (;;) {
+            cudaError_t e = cudaStreamQuery(stream);
+            if (e == cudaSuccess) return;
+            if (e != cudaErrorNotReady) { cudaGetLastError(); throw CudaFail{e, __FILE__, __LINE__}; }
+            struct timespec ts = {0, (long)us * 1000L}; nanosleep(&ts, nullptr);
+            if (us < 500) us += us / 2;
+        }
     }
     // Read `words` u32 from the device mailbox (blocks the host on this stream only).
     void fetch_mail(int words) {
@@ -159,13 +166,65 @@ template <typename F> static inline void ensure_dyn_smem(F *kernel, int device, 
         if (p_) { CUDA_TRY(cudaEventRecord(eb_, c_->stream)); c_->prof.push_back(ProfRec{#kernel, ea_, eb_, c_->next_bytes}); } \
         c_->next_bytes = 0; c_->kernels_launched++; } while (0)
 
+// A launch that the host waits for (Ctx::wait_long) before anything else goes onto the stream: the closing profile event is recorded
+// after the wait, not behind the kernel.
+#define LAUNCH_LONG(ctx, kernel, grid, block, smem, ...) do { \
+        Ctx *c_ = (ctx); cudaEvent_t ea_ = nullptr, eb_ = nullptr; const bool p_ = c_->profile; const double nb_ = c_->next_bytes; \
+        if (p_) { ea_ = c_->ev(); eb_ = c_->ev(); CUDA_TRY(cudaEventRecord(ea_, c_->stream)); } \
+        kernel<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__); KERNEL_CHECK(); \
+        c_->next_bytes = 0; c_->kernels_launched++; \
+        c_->wait_long(); \
+        if (p_) { CUDA_TRY(cudaEventRecord(eb_, c_->stream)); c_->prof.push_back(ProfRec{#kernel, ea_, eb_, nb_}); } } while (0)
+
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ u32 lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
+// Lanes of the warp that hold the same `bits`-bit digit as this lane (all 32 lanes must call it).  One ballot per digit bit instead of
+// __match_any_sync, which on this chip costs 85 / 217 / 393 cycles for 4 / 16 / 32 distinct values in the warp (profiles/r2a_call_a.log:
+// it iterates over the distinct values), while the ballots are independent of each other and of the data.
+__device__ __forceinline__ u32 warp_peers(u32 d, int bits)
+{
+    u32 m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        if (b < bits) {                                  // warp-uniform
+            const u32 bit = (d >> b) & 1u, v = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? v : ~v;
+        }
+    }
+    return m;
+}
+
 // relaxed, device-scope single-word accesses for decoupled look-back descriptors
 __device__ __forceinline__ u64 ld_relaxed(const u64 *p) { u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_relaxed(u64 *p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier in shared memory -----------------------------------
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// one arrival + the number of bytes the bulk copies issued next will deliver
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile("{\n\t.reg .pred P1;\n\tMBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra MBAR_DONE;\n\tbra MBAR_WAIT;\n\tMBAR_DONE:\n\t}"
+                 :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes (complete_tx) on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// orders earlier generic-proxy accesses to shared memory (ld/st.shared of all threads, after a barrier) before later async-proxy writes (TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // streaming 128-bit loads that do not pollute L1 (inputs that are read exactly once)
 __device__ __forceinline__ uint4 ld_stream_v4(const void *p) {

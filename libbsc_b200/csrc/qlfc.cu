@@ -249,13 +249,15 @@ static void init_models(Ctx *ctx, short *models, int count)
     LAUNCH(ctx, q_model_init, ceil_div(total, 256 * 8), 256, 0, models, total);
 }
 
-int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder, int features)
+int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder, int features, int bare_out_size)
 {
     { const int g = coder_gate(coder); if (g != LIBBSC_NO_ERROR) return g; }
     const bool fast = coder == 3;
     if (n_ <= 0) return LIBBSC_BAD_PARAMETER;
     const u32 n = (u32)n_;
-    const int nBlocks = coder_num_blocks(n_);
+    // bare_out_size >= 0: ONE stream without the container byte, output capacity as given (bsc_qlfc_*_encode_block, qlfc.h:55-77)
+    const bool bare = bare_out_size >= 0;
+    const int nBlocks = bare ? 1 : coder_num_blocks(n_);
     const QTables *tables = get_tables(ctx);
     Arena &A = ctx->arena;
     const size_t mark = A.mark();
@@ -266,7 +268,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     u32 *tile_cnt = A.get<u32>(run_tiles + 1);
     u8 *mtf = A.get<u8>(256 * Q_MAX_SUB);
     short *models = A.get<short>((size_t)nBlocks * MODEL_SHORTS_PAD);
-    u8 *tmp = A.get<u8>((size_t)n + (4096 + 256) * Q_MAX_SUB);
+    u8 *tmp = A.get<u8>((size_t)(bare && (u32)bare_out_size > n ? (u32)bare_out_size : n) + (4096 + 256) * Q_MAX_SUB);
 
     // 1. split
     if (nBlocks > 1) LAUNCH(ctx, q_split, 1, 1024, 0, d_in, n, (u32)nBlocks, d_start, d_size);
@@ -295,7 +297,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     u32 total_tiles = 0;
     for (u32 b = 0, off = 0; b < (u32)nBlocks; ++b) {
         h_sb[b].out_off = off; off += (u32)align_up((size_t)h_size[b] + 4096, 256);   // 16-bit stores need even offsets
-        h_sb[b].out_cap = (nBlocks == 1) ? n - 1 : h_size[b];
+        h_sb[b].out_cap = bare ? (u32)bare_out_size : (nBlocks == 1) ? n - 1 : h_size[b];
         h_sb[b].result = 0; h_sb[b].nsym = 0; h_sb[b].stat_cached = 0; h_sb[b].stat_miss = 0;
         h_sb[b].tile_base = total_tiles; h_sb[b].tiles = ceil_div(h_sb[b].run_end - h_sb[b].run_begin, RK_TILE); total_tiles += h_sb[b].tiles;
     }
@@ -325,24 +327,30 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
         ensure_dyn_smem(q_fast_encode, ctx->device, sizeof(FastSmem));
         PROF_BYTES(ctx, (double)n);
-        LAUNCH(ctx, q_fast_encode, nBlocks, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)d_order);
+        LAUNCH_LONG(ctx, q_fast_encode, nBlocks, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)d_order);
     } else if (coder == 2) {
         init_models(ctx, models, nBlocks);
         ensure_dyn_smem(q_adaptive_encode, ctx->device, QA_BYTES);
         PROF_BYTES(ctx, (double)n);
-        LAUNCH(ctx, q_adaptive_encode, nBlocks, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order);
+        LAUNCH_LONG(ctx, q_adaptive_encode, nBlocks, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order);
     } else {
         init_models(ctx, models, nBlocks);
         PROF_BYTES(ctx, (double)n);                      // + c written; the launch is latency-, not bandwidth-bound
         ensure_dyn_smem(q_encode5<LayoutEncDiet>, ctx->device, enc_smem);
-        LAUNCH(ctx, (q_encode5<LayoutEncDiet>), nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order);
+        LAUNCH_LONG(ctx, (q_encode5<LayoutEncDiet>), nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order);
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->sync_long();                                    // the encoder runs for 0.01 - 0.7 s: sleep, do not spin
+    ctx->sync();                                         // short: the encoder (0.01 - 0.7 s) was waited for by LAUNCH_LONG
 
     if (getenv("BSCB200_QSTATS"))
         for (int b = 0; b < nBlocks; ++b) fprintf(stderr, "[qstats enc] sub %d: in %u runs %u out %d rare-accesses %u misses %u\n", b, h_sb[b].in_size, h_sb[b].run_end - h_sb[b].run_begin, h_sb[b].result, h_sb[b].stat_cached, h_sb[b].stat_miss);
     int result;
+    if (bare) {
+        result = h_sb[0].result;
+        if (result > 0) { CUDA_TRY(cudaMemcpyAsync(d_out, tmp + h_sb[0].out_off, (size_t)result, cudaMemcpyDeviceToDevice, ctx->stream)); ctx->sync(); }
+        A.release(mark);
+        return result;
+    }
     if (nBlocks == 1) {                                   // coder.cpp:113-119
         result = h_sb[0].result;
         if (result >= 0) {
@@ -376,13 +384,13 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                 ctx->sync();
                 if (fast) {                                // q_fast_encode indexes the cold counters by sub-block id
                     LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
-                    LAUNCH(ctx, q_fast_encode, 1, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)d_list);
+                    LAUNCH_LONG(ctx, q_fast_encode, 1, 32, sizeof(FastSmem), run_pos, run_sym, run_rank, d_sb, mtf, models, tmp, (const u32 *)d_list);
                 } else if (coder == 2) {
                     init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                    LAUNCH(ctx, q_adaptive_encode, 1, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
+                    LAUNCH_LONG(ctx, q_adaptive_encode, 1, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 } else {
                     init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                    LAUNCH(ctx, (q_encode5<LayoutEncDiet>), 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
+                    LAUNCH_LONG(ctx, (q_encode5<LayoutEncDiet>), 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 }
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
@@ -414,7 +422,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     return result;
 }
 
-int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int out_cap, int coder, int features)
+int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int out_cap, int coder, int features, bool bare)
 {
     (void)features;
     { const int g = coder_gate(coder); if (g != LIBBSC_NO_ERROR) return g; }
@@ -430,11 +438,11 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
         ctx->sync();
         memcpy(hdr, ctx->h_mail + 32, (size_t)want);
     }
-    const int nBlocks = hdr[0];
+    const int nBlocks = bare ? 1 : hdr[0];               // bare: ONE stream without the container byte (bsc_qlfc_*_decode_block, qlfc.h:79-99)
     SubBlock *h_sb = (SubBlock *)(ctx->h_mail + 128); u32 *list = ctx->h_mail + 232; int nlist = 0;   // pinned (see stage_coder_compress)
     memset(h_sb, 0, sizeof(SubBlock) * Q_MAX_SUB); memset(list, 0, sizeof(u32) * Q_MAX_SUB);
     if (nBlocks == 1) {
-        h_sb[0].in_start = 0; h_sb[0].in_size = (u32)out_cap; h_sb[0].out_off = 1; h_sb[0].out_cap = (u32)(in_size - 1);
+        h_sb[0].in_start = 0; h_sb[0].in_size = (u32)out_cap; h_sb[0].out_off = bare ? 0 : 1; h_sb[0].out_cap = (u32)(in_size - (bare ? 0 : 1));
         list[nlist++] = 0;
     } else {
         if (nBlocks == 0 || nBlocks > Q_MAX_SUB || in_size < 1 + 8 * nBlocks) { A.release(mark); return LIBBSC_DATA_CORRUPT; }
@@ -461,25 +469,25 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nlist);
             ensure_dyn_smem(q_fast_decode, ctx->device, sizeof(FastSmem));
             PROF_BYTES(ctx, (double)in_size + (double)out_cap);
-            LAUNCH(ctx, q_fast_decode, nlist, 32, sizeof(FastSmem), d_in, d_sb, models, d_out, (const u32 *)d_list);
+            LAUNCH_LONG(ctx, q_fast_decode, nlist, 32, sizeof(FastSmem), d_in, d_sb, models, d_out, (const u32 *)d_list);
         } else if (coder == 2) {
             init_models(ctx, models, nlist);
             ensure_dyn_smem(q_adaptive_decode, ctx->device, QA_BYTES);
             PROF_BYTES(ctx, (double)in_size + (double)out_cap);
-            LAUNCH(ctx, q_adaptive_decode, nlist, 32, QA_BYTES, d_in, d_sb, models, tables, d_out, (const u32 *)d_list);
+            LAUNCH_LONG(ctx, q_adaptive_decode, nlist, 32, QA_BYTES, d_in, d_sb, models, tables, d_out, (const u32 *)d_list);
         } else {
             init_models(ctx, models, nlist);
             PROF_BYTES(ctx, (double)in_size + (double)out_cap);
             static const bool prof = getenv("BSCB200_QDEC_PROF") != nullptr;          // per-phase cycle counts (diagnostic)
             static_assert(LayoutDiet::BYTES <= 232448 / 2 - 1024, "two decoder streams must fit one SM");
             if (prof) { ensure_dyn_smem(q_decode6<LayoutDiet, true>, ctx->device, LayoutDiet::BYTES);
-                        LAUNCH(ctx, (q_decode6<LayoutDiet, true>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
+                        LAUNCH_LONG(ctx, (q_decode6<LayoutDiet, true>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
             else      { ensure_dyn_smem(q_decode6<LayoutDiet, false>, ctx->device, LayoutDiet::BYTES);
-                        LAUNCH(ctx, (q_decode6<LayoutDiet, false>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
+                        LAUNCH_LONG(ctx, (q_decode6<LayoutDiet, false>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
         }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    ctx->sync_long();                                    // the decoder runs for up to 2 s: sleep, do not spin
+    ctx->sync();                                         // short: the decoder (up to 2 s) was waited for by LAUNCH_LONG
     if (getenv("BSCB200_QSTATS"))
         for (int b = 0; b < (nBlocks == 1 ? 1 : nBlocks); ++b) fprintf(stderr, "[qstats dec] sub %d: out %d rare-accesses %u misses %u\n", b, h_sb[b].result, h_sb[b].stat_cached, h_sb[b].stat_miss);
     int total = 0, err = 0;

@@ -6,7 +6,7 @@
 //
 //   rs_hist1      : 256-bin histogram of the FIRST digit only (one read of the source keys).
 //   rs_onesweep   : per digit pass, ONE read + ONE write of every (key,value): each CTA scans the
-//                   digit histogram into global bases, ranks a tile with warp match-any multisplit,
+//                   digit histogram into global bases, ranks a tile with a warp multisplit (peer masks from ballots),
 //                   obtains its per-digit global offsets by decoupled look-back over the preceding
 //                   tiles (single pass, no separate upsweep), reorders the tile in shared memory and
 //                   stores digit-contiguous, fully coalesced runs.  While storing, it accumulates
@@ -80,10 +80,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist1(Src src, u32 n, int shift
     sh[threadIdx.x] = 0;
     __syncthreads();
     const u32 stride = gridDim.x * RS_THREADS, dmask = (1u << bits) - 1u;
-    for (u32 i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
-        const u32 d = (u32)(src.key(i) >> shift) & dmask;
-        const u32 m = __match_any_sync(__activemask(), d);           // warp-aggregate: text digits are skewed
-        if ((m & lanemask_lt()) == 0) atomicAdd(&sh[d], __popc(m));
+    for (u32 i0 = blockIdx.x * RS_THREADS; i0 < n; i0 += stride) {       // whole warps stay in the loop (warp_peers is warp-collective)
+        const u32 i = i0 + threadIdx.x;
+        const u32 d = i < n ? ((u32)(src.key(i) >> shift) & dmask) : 256u;    // 256: "no item", a class of its own (bit 8)
+        const u32 m = warp_peers(d, 9);                              // warp-aggregate: text digits are skewed
+        if (i < n && (m & lanemask_lt()) == 0) atomicAdd(&sh[d], __popc(m));
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
@@ -158,7 +159,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         u32 d = (u32)(keys[i] >> shift) & dmask;
-        u32 m = __match_any_sync(0xffffffffu, d);
+        u32 m = warp_peers(d, bits);
         u32 leader = __ffs(m) - 1;
         u32 pre = 0;
         if (lane == leader) { pre = S.whist[warp][d]; S.whist[warp][d] = pre + __popc(m); }
@@ -229,7 +230,141 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
     }
 }
 
+// ---- one digit pass over MATERIALISED keys: persistent CTAs, tiles staged by TMA, two stages ------------------------------------
+// Every pass but the first reads (key, value) arrays.  Here a CTA keeps taking tiles (ordered tile ids from an atomic counter, as
+// the look-back needs) and the NEXT tile's 32 KB of keys + 16 KB of values are already on their way into the other shared-memory
+// stage -- one elected thread issues two cp.async.bulk (TMA, SASS UBLKCP) that complete on the stage's mbarrier -- while the
+// current tile is ranked, reordered in place in its stage and stored.  No load instruction sits between the tile and the ranking,
+// the registers hold only the current tile, and HBM reads run a full tile ahead of the compute.
+template <typename K, bool HAS_VAL> struct RsSmemTma {
+    alignas(128) K   keys[2][RS_TILE];
+    alignas(128) u32 vals[2][HAS_VAL ? RS_TILE : 4];
+    u32 whist[RS_WARPS][256];
+    u32 dstart[256];
+    u32 gbase[256];
+    u32 nexthist[256];
+    u32 scan_tmp[RS_WARPS];
+    u32 tile[2];
+    alignas(8) u64 full[2];                              // mbarriers: "stage s holds its tile"
+};
+
+template <typename K, bool HAS_VAL>
+__global__ void __launch_bounds__(RS_THREADS, 2)
+rs_onesweep_tma(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, u32 tiles, int shift, int bits,
+                const u32 *__restrict__ hist_in, u32 *__restrict__ hist_next, int shift2, int bits2, u32 *tile_counter, u64 *lookback)
+{
+    extern __shared__ __align__(128) unsigned char rs_smem_raw[];
+    RsSmemTma<K, HAS_VAL> &S = *reinterpret_cast<RsSmemTma<K, HAS_VAL> *>(rs_smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 dmask = (1u << bits) - 1u, dmask2 = (1u << bits2) - 1u;
+
+    // stage s <- tile t (thread 0 only): expect the bytes, then the two bulk copies; sizes rounded up to 16 (the arrays are padded)
+    auto fill = [&](u32 s, u32 t) {
+        const u32 base = t * RS_TILE, valid = min((u32)RS_TILE, n - base);
+        const u32 kb = (valid * (u32)sizeof(K) + 15u) & ~15u, vb = HAS_VAL ? ((valid * 4u + 15u) & ~15u) : 0u;
+        mbar_arrive_expect_tx(&S.full[s], kb + vb);
+        bulk_copy_g2s(S.keys[s], kin + base, kb, &S.full[s]);
+        if (HAS_VAL) bulk_copy_g2s(S.vals[s], vin + base, vb, &S.full[s]);
+    };
+
+    if (tid == 0) { mbar_init(&S.full[0], 1); mbar_init(&S.full[1], 1); mbar_init_fence(); }
+    S.nexthist[tid] = 0;
+    const u32 gdigit_base = rs_block_excl_scan(hist_in[tid], S.scan_tmp, lane, warp);   // contains __syncthreads: the barriers are initialised
+    if (tid == 0) {
+        for (u32 s = 0; s < 2; ++s) { const u32 t = atomicAdd(tile_counter, 1u); S.tile[s] = t; if (t < tiles) fill(s, t); }
+    }
+    u32 parity0 = 0, parity1 = 0;
+    const u32 wbase = warp * (32 * RS_ITEMS) + lane;     // warp-striped: item i of this lane = wbase + 32*i
+
+    for (u32 s = 0; ; s ^= 1) {
+        __syncthreads();                                 // tile[s] is visible; every read of the previous tile's stage is done
+        const u32 tile = S.tile[s];
+        if (tile >= tiles) break;                        // ids grow with time: the other stage has no tile either
+        const u32 base = tile * RS_TILE, valid = min((u32)RS_TILE, n - base);
+        for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&S.whist[0][0])[i] = 0;
+        if (s == 0) { mbar_wait(&S.full[0], parity0); parity0 ^= 1; } else { mbar_wait(&S.full[1], parity1); parity1 ^= 1; }
+
+        K keys[RS_ITEMS]; u32 vals[RS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const u32 off = wbase + 32 * i;
+            keys[i] = off < valid ? S.keys[s][off] : rs_all_ones<K>();
+            if (HAS_VAL) vals[i] = S.vals[s][off];
+        }
+        __syncthreads();                                 // the tile lives in registers: its stage can take the reordered tile; whist is zero
+
+        u32 pos[RS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const u32 d = (u32)(keys[i] >> shift) & dmask;
+            const u32 m = warp_peers(d, bits);
+            const u32 leader = __ffs(m) - 1;
+            u32 pre = 0;
+            if (lane == leader) { pre = S.whist[warp][d]; S.whist[warp][d] = pre + __popc(m); }
+            pre = __shfl_sync(0xffffffffu, pre, leader);
+            pos[i] = pre + __popc(m & lanemask_lt());
+            __syncwarp();
+        }
+        __syncthreads();
+        {
+            const u32 d = tid;
+            u32 run = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) { u32 t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
+            const u32 count = run;
+            const u32 excl = rs_block_excl_scan(count, S.scan_tmp, lane, warp);
+            S.dstart[d] = excl;
+            u64 *mine = lookback + (size_t)tile * 256 + d;
+            u32 gexcl = 0;
+            if (tile == 0) {
+                st_relaxed(mine, RS_FLAG_PREFIX | (u64)count);
+            } else {
+                st_relaxed(mine, RS_FLAG_AGG | (u64)count);
+                for (u32 t = tile; t-- > 0; ) {
+                    const u64 *theirs = lookback + (size_t)t * 256 + d;
+                    u64 v;
+                    do { v = ld_relaxed(theirs); } while ((v & RS_FLAG_MASK) == 0);
+                    gexcl += (u32)v;
+                    if ((v & RS_FLAG_MASK) == RS_FLAG_PREFIX) break;
+                }
+                st_relaxed(mine, RS_FLAG_PREFIX | (u64)(gexcl + count));
+            }
+            S.gbase[d] = gdigit_base + gexcl - excl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const u32 d = (u32)(keys[i] >> shift) & dmask;
+            const u32 q = pos[i] + S.dstart[d] + S.whist[warp][d];
+            S.keys[s][q] = keys[i];
+            if (HAS_VAL) S.vals[s][q] = vals[i];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (u32 j = tid; j < valid; j += RS_THREADS) {
+            const K k = S.keys[s][j];
+            const u32 g = S.gbase[(u32)(k >> shift) & dmask] + j;
+            kout[g] = k;
+            if (HAS_VAL) vout[g] = S.vals[s][j];
+            if (hist_next) atomicAdd(&S.nexthist[(u32)(k >> shift2) & dmask2], 1u);
+        }
+        __syncthreads();                                 // stage s has been read for the last time
+        if (tid == 0) {
+            const u32 t = atomicAdd(tile_counter, 1u);
+            S.tile[s] = t;
+            if (t < tiles) { fence_proxy_async_smem(); fill(s, t); }
+        }
+    }
+    if (hist_next) {
+        const u32 c = S.nexthist[tid];                   // all atomics on it precede the loop's final barrier
+        if (c) atomicAdd(&hist_next[tid], c);
+    }
+}
+
 // ---- host driver ---------------------------------------------------------------------------
+// BSCB200_SORT_TMA=0: every pass through rs_onesweep (A/B of the TMA-staged kernel, tools/sort_ab.sh)
+static inline bool rs_use_tma() { static const bool on = [] { const char *e = getenv("BSCB200_SORT_TMA"); return !(e && e[0] == '0'); }(); return on; }
+
 // Scratch needed by one sort (histograms, tile counters, look-back descriptors).
 static inline size_t rs_scratch_bytes(u32 n, int npasses)
 {
@@ -258,6 +393,8 @@ static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32
     const size_t smem = sizeof(RsSmem<K, HAS_VAL>);
     ensure_dyn_smem(rs_onesweep<K, HAS_VAL, FirstSrc>, ctx->device, smem);
     ensure_dyn_smem(rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>, ctx->device, smem);
+    const size_t smem_tma = sizeof(RsSmemTma<K, HAS_VAL>);
+    ensure_dyn_smem(rs_onesweep_tma<K, HAS_VAL>, ctx->device, smem_tma);
 
     for (int p = 0; p < passes.count; ++p) {
         int dst = p & 1;
@@ -269,10 +406,14 @@ static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32
         if (p == 0) {
             LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, FirstSrc>), tiles, RS_THREADS, smem,
                    first, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, hnext, s2, b2, counters + p, lb);
-        } else {
+        } else if (!rs_use_tma()) {
             SrcArray<K, HAS_VAL> src{k[dst ^ 1], v[dst ^ 1]};
             LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>), tiles, RS_THREADS, smem,
                    src, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, hnext, s2, b2, counters + p, lb);
+        } else {
+            const u32 grid = min(tiles, (u32)(B200_SMS * 2));                // persistent: two CTAs per SM, each loops over tiles
+            LAUNCH(ctx, (rs_onesweep_tma<K, HAS_VAL>), grid, RS_THREADS, smem_tma,
+                   (const K *)k[dst ^ 1], (const u32 *)v[dst ^ 1], k[dst], v[dst], n, tiles, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, hnext, s2, b2, counters + p, lb);
         }
     }
     return (passes.count - 1) & 1;

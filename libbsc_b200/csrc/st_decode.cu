@@ -283,7 +283,7 @@ int stage_st_decode(Ctx *ctx, u8 *d_T, int n_, int k, int index_)
     LAUNCH(ctx, st_heads, nb, 256, 0, pair, gk, dynf, tgt, n, index, rec);
     u32 *posh = LF, *posE = tmpk;                            // both free from here on
     CUDA_TRY(cudaMemsetAsync(posE, 0, sizeof(u32) * (size_t)n, ctx->stream));
-    LAUNCH(ctx, st_serial, 1, 32, 0, rec, top, n, index, posh, small + 9);
+    LAUNCH_LONG(ctx, st_serial, 1, 32, 0, rec, top, n, index, posh, small + 9);   // up to seconds on text (one step per list): nothing queued behind it
     LAUNCH(ctx, st_place, nb, 256, 0, pair, gk, dynf, posh, n, index, posE);
     PROF_BYTES(ctx, 14.0 * n);
     LAUNCH(ctx, st_emit, nb, 256, 0, pair, posE, Lp, n, d_T);

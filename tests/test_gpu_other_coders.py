@@ -39,3 +39,21 @@ def test_coder_matches_oracle(bsc, gen, checker, coder):
         assert z1 == z2 and np.array_equal(b1, b2), name
         q, u = bsc.decompress(b2)
         assert q == 0 and np.array_equal(u, a), name
+
+
+@pytest.mark.parametrize("coder", [1, 2, 3])
+def test_qlfc_block_entry_points(bsc, gen, checker, coder):
+    """bsc_qlfc_{static,adaptive,fast}_{encode,decode}_block (qlfc.h:55-99): one stream at a time, byte-identical to the reference, both the
+    default capacity (= inputSize) and a clipped one (the EOB rule of rangecoder.h:118-127 decides compressible / not compressible)."""
+    rng = np.random.default_rng(3)
+    for name, a in (("bwt text 300k", checker.bwt_encode(gen.text(7, 300000))[1]), ("bwt text 2M", checker.bwt_encode(gen.text(2, 2 << 20))[1]),
+                    ("skew 200k", gen.skew(3, 200000)), ("alpha4", rng.integers(0, 4, 50000, dtype=np.uint8)), ("allsame", np.full(3000, 65, dtype=np.uint8)),
+                    ("rand 70k", gen.rand(1, 70000)), ("tiny", gen.text(1, 40))):
+        for cap in (None, a.size // 3, a.size // 2):
+            r2, s2 = checker.encode_block(a, cap, coder)
+            r1, s1 = bsc.encode_block(a, cap, coder)
+            assert r1 == r2, (name, cap, r1, r2)
+            if r2 > 0:
+                assert np.array_equal(s1, s2), (name, cap)
+                n, out = bsc.decode_block(s2, a.size, coder)
+                assert n == a.size and np.array_equal(out, a), (name, cap)

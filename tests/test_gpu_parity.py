@@ -162,6 +162,54 @@ def test_block_bytes_and_cross_decoding(bsc, gen, checker):
         assert q == 0 and np.array_equal(u, a), name
 
 
+def test_inplace_compress_and_decompress(bsc, gen, ref):
+    """The CLI's calls (bsc.cpp:354, 594): bsc_compress(buf, buf, ...) and bsc_decompress(buf, size, buf, n) on ONE buffer.  In place,
+    an incompressible block answers LIBBSC_NOT_COMPRESSIBLE instead of being stored (libbsc.cpp:188-191)."""
+    import ctypes
+    L = bsc.lib
+    for a, sorter in ((gen.text(2, 1 << 20), 1), (gen.text(5, 300000), 1), (gen.skew(3, 1 << 20), 6), (gen.text(9, 70000), 4)):
+        n = a.size
+        buf = np.zeros(n + 28 + 64, dtype=np.uint8); buf[:n] = a
+        r = L.bsc_compress(buf.ctypes.data, buf.ctypes.data, n, 0, 0, sorter, 1, 3)
+        rbuf = np.zeros(n + 28 + 64, dtype=np.uint8); rbuf[:n] = a
+        r2 = ref.lib.bsc_compress(ctypes.c_void_p(rbuf.ctypes.data), ctypes.c_void_p(rbuf.ctypes.data), n, 0, 0, sorter, 1, 3)
+        assert r == r2 and r > 0 and np.array_equal(buf[:r], rbuf[:r]), (sorter, r, r2)
+        q = L.bsc_decompress(buf.ctypes.data, r, buf.ctypes.data, n, 3)
+        assert q == 0 and np.array_equal(buf[:n], a), sorter
+    a = gen.rand(1, 300000)
+    buf = np.zeros(a.size + 28 + 64, dtype=np.uint8); buf[:a.size] = a
+    assert L.bsc_compress(buf.ctypes.data, buf.ctypes.data, a.size, 0, 0, 1, 1, 3) == -3
+    assert np.array_equal(buf[:a.size], a)                           # the input is left alone
+
+
+def test_degenerate_blocks_at_full_size(bsc, gen, checker):
+    """64 MiB all-zero, period-7, period-8 (a power of two: LF keeps row residues) and two-symbol blocks: every suffix stays in an unsorted
+    group for ~23 doubling rounds, and the inverse walks arithmetic progressions of rows.  Bounded in time, bit-exact against the reference."""
+    import time
+    n = 64 << 20
+    rng = np.random.default_rng(17)
+    cases = {"zeros": np.zeros(n, dtype=np.uint8),
+             "period7": np.tile(np.frombuffer(b"abcabcd", dtype=np.uint8), n // 7 + 1)[:n],
+             "period8": np.tile(np.frombuffer(b"abcdefgh", dtype=np.uint8), n // 8),
+             "two-symbol runs": np.repeat(rng.integers(0, 2, n // 4096, dtype=np.uint8), 4096)}
+    for name, a in cases.items():
+        t0 = time.time()
+        r, L, aux = bsc.bwt_encode(a)
+        t1 = time.time()
+        r2, L2, aux2 = checker.bwt_encode(a)
+        assert r == r2 and aux == aux2 and np.array_equal(L, L2), name
+        t2 = time.time()
+        q, T = bsc.bwt_decode(L2, r2)
+        t3 = time.time()
+        assert q == 0 and np.array_equal(T, a), name
+        z, blk = bsc.compress(a)
+        z2, blk2 = checker.compress(a, 1, 1, 3)
+        assert z == z2 and np.array_equal(blk, blk2), name
+        q, u = bsc.decompress(blk2)
+        assert q == 0 and np.array_equal(u, a), name
+        assert t1 - t0 < 30 and t3 - t2 < 30, (name, t1 - t0, t3 - t2)
+
+
 def test_error_codes(bsc, gen):
     a = gen.text(1, 1000)
     assert bsc.compress(a, sorter=2)[0] == -1
