@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--sorter", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the extra keys for BASELINE configs C2 / C3-strong / C4 / C5")
     return ap.parse_args()
 
 
@@ -224,6 +225,99 @@ class Pipeline:
             raise errs[0]
 
 
+def extra_configs(args, rank, local_rank, world, L, gen, torch, dist, dev):
+    """The other BASELINE.json configurations as extra keys of the same line (not the headline): C2 (100 MB text, 25 MB blocks, one GPU),
+    C3 as written (1 GiB text = 16 blocks of 64 MiB shared by ALL ranks: strong scaling), C4 (stage-only bsc_bwt_decode of C3's blocks),
+    C5 (256 MiB high-entropy binary, 32 MiB blocks, ST6, both directions).  Host-pointer entry points, pinned buffers, blocks b -> rank
+    b mod world, device-timed max over ranks; one warm pass, then `reps` timed passes."""
+    from libbsc_b200 import blocks as blk
+    reps = 2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_pass(nb, task):
+        if nb == 0:
+            barrier(); barrier()
+            ms = 0.0
+        else:
+            pipe = Pipeline(nb, nb, task)
+            pipe.run(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); pipe.run(reps); torch.cuda.synchronize(); e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            barrier()
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0])
+        return ms
+
+    def round_trip(data, bb, sorter, ranks):
+        """compress+decompress of data cut into blocks of bb bytes, block b on rank b mod ranks (ranks beyond `ranks` idle)"""
+        parts = blk.split_blocks(data.size, bb)                      # CLI-style cut (bsc.cpp:163-178)
+        nblk = len(parts)
+        mine = blk.assign(nblk, ranks, rank) if rank < ranks else []  # block b -> rank b mod N
+        h_in = [torch.from_numpy(data[parts[b][0]:parts[b][0] + parts[b][1]]).pin_memory() for b in mine]
+        h_cmp = [torch.empty(t.numel() + 28 + 64, dtype=torch.uint8).pin_memory() for t in h_in]
+        h_back = [torch.zeros(t.numel() + 64, dtype=torch.uint8).pin_memory() for t in h_in]
+        hsize = [0] * len(mine)
+
+        def comp(w, i):
+            torch.cuda.set_device(local_rank)
+            r = L.bsc_compress(h_in[i].data_ptr(), h_cmp[i].data_ptr(), h_in[i].numel(), 0, 0, sorter, 1, 3)
+            assert r > 0, r
+            hsize[i] = r
+
+        def decomp(w, i):
+            torch.cuda.set_device(local_rank)
+            assert L.bsc_decompress(h_cmp[i].data_ptr(), hsize[i], h_back[i].data_ptr(), h_in[i].numel(), 3) == 0
+
+        def both(w, i):
+            comp(w, i); decomp(w, i)
+        ms_b = timed_pass(len(mine), both)
+        ms_c = timed_pass(len(mine), comp)
+        ms_d = timed_pass(len(mine), decomp)
+        for a, b in zip(h_in, h_back):
+            assert torch.equal(a, b[:a.numel()]), "extra config: round trip mismatch"
+        mb = data.size / 1e6
+        sizes = blk.gather_sizes(dist, mine, hsize, nblk, device=dev)  # what the file container needs: every block's compressed size, on every rank
+        return {"value": mb / (ms_b / 1e3), "unit": "MB/s", "compress_MBps": mb / (ms_c / 1e3), "decompress_MBps": mb / (ms_d / 1e3), "blocks": nblk,
+                "block_bytes": bb, "gpus": min(ranks, world), "compressed_bytes": int(sum(sizes))}, (mine, h_in)
+
+    out = {}
+    text = gen.text(2, 1 << 30)
+    c2, _ = round_trip(text[:104857600], 26214400, 1, 1)
+    out["C2_text_100MB_b25_1gpu"] = dict(c2, workload="G_text(2) first 104857600 bytes, 4 blocks of 26214400, BWT + QLFC static, one GPU, host buffers")
+    c3, (mine, h_in) = round_trip(text, 64 << 20, 1, world)
+    out["C3_text_1GiB_b64_strong"] = dict(c3, workload="G_text(2, 1 GiB) = 16 blocks of 64 MiB over all %d GPU(s) (block b -> rank b mod N): STRONG scaling, host buffers" % world, scaling="strong")
+    # C4: the inverse-BWT stage alone on the L of every C3 block (bsc_bwt_decode, host pointers)
+    Ls, idx = [], []
+    for t in h_in:
+        buf = t.clone().pin_memory()
+        r = L.bsc_bwt_encode(buf.data_ptr(), buf.numel(), None, None, 3)
+        assert r > 0
+        Ls.append(buf); idx.append(r)
+    work = [t.clone().pin_memory() for t in Ls]
+
+    def unbwt(w, i):
+        torch.cuda.set_device(local_rank)
+        work[i].copy_(Ls[i])
+        assert L.bsc_bwt_decode(work[i].data_ptr(), work[i].numel(), idx[i], 0, None, 3) == 0
+    ms = timed_pass(len(mine), unbwt)
+    for a, b in zip(h_in, work):
+        assert torch.equal(a, b)
+    out["C4_bwt_decode_stage_b64"] = {"value": text.size / 1e6 / (ms / 1e3), "unit": "MB/s", "blocks": 16, "gpus": world,
+                                      "workload": "bsc_bwt_decode alone on the BWT of each C3 block, host buffers (H2D + kernels + D2H + one host memcpy per block inside the time)"}
+    del text, Ls, work, h_in
+    skew = gen.skew(3, 256 << 20)
+    c5, _ = round_trip(skew, 32 << 20, 6, world)
+    out["C5_skew_256MiB_b32_st6"] = dict(c5, workload="G_skew(3, 256 MiB) = 8 blocks of 32 MiB over %d GPU(s), ST6 + QLFC static (-m6), both directions, host buffers" % world, scaling="strong")
+    return out
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import libbsc_b200
@@ -372,6 +466,11 @@ def run_b200(args, rank, local_rank, world):
         e2e = {"value": total_mb / (ms_e / 1e3), "unit": "MB/s", "h2d_bytes_per_step": nb * bb + hbytes, "d2h_bytes_per_step": hbytes + nb * bb,
                "ms_per_step": ms_e, "host_memory": "pinned", "pageable": {"value": total_mb / (ms_p / 1e3), "unit": "MB/s", "steps": 1}}
 
+    extras = None
+    if args.extras:
+        torch.cuda.empty_cache()
+        extras = extra_configs(args, rank, local_rank, world, L, gen, torch, dist, dev)
+
     if rank != 0:
         return
 
@@ -441,7 +540,7 @@ def run_b200(args, rank, local_rank, world):
             "compress_MBps": total_mb / (ms_c / 1e3), "decompress_MBps": total_mb / (ms_d / 1e3), "phase_note": "each direction alone, one drained pass over the batch",
             "compressed_bytes_rank0": comp_bytes, "ratio": comp_bytes / float(nb * bb),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue, "roofline_hbm_kernel": roofline_hbm,
-            "kernels": table, "kernels_standalone": alone_table, "cpu_baseline": cpu}
+            "other_configs": extras, "kernels": table, "kernels_standalone": alone_table, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
 

@@ -12,14 +12,17 @@
 //                warp match-any multisplit ranks the bytes, per-symbol decoupled look-back gives
 //                the tile's global offsets in the same pass              (reads n, writes 4n)
 //   unbwt_walk   K ~ n/64 start rows (one per 64-row window, jittered); one thread per segment chases LF until it
-//                reaches another start row.  Pass 1 records (length, successor); a device-side
-//                pointer-jumping list ranking (no host round trip, cf. libcubwt.cu:3077-3086)
-//                turns that into each segment's text offset; pass 2 walks again and writes the
-//                bytes straight to their final place.  This stage is sector/latency bound (one
-//                dependent 4-byte gather per output byte), not stream-bandwidth bound.
+//                reaches another start row -- ONCE: the bytes it meets are staged in 64-byte slabs (node k = segment k's first
+//                slab; a segment longer than 64 bytes takes further nodes from an atomic counter and links them), so the
+//                pointer chase, which is sector/latency bound (one dependent 4-byte gather per output byte), is never repeated
+//                (round 1 walked twice: 1.2 + 2.3 ms per 64 MiB; the reference stages too, libcubwt.cu:2744-2906)
+//   lr_jump      device-side pointer-jumping list ranking over the nodes (list_rank.cuh; no host round trip, cf.
+//                libcubwt.cu:3077-3086): bytes from the start of every node to the end of the walk
+//   unbwt_place  every staged byte goes to its final place (coalesced reads, contiguous reversed writes)
 #include "common.cuh"
 #include "stages.cuh"
 #include "lf_map.cuh"
+#include "list_rank.cuh"
 
 namespace {
 
@@ -35,37 +38,47 @@ __device__ __forceinline__ u32 mark_row(u32 w, u32 n)
 }
 __device__ __forceinline__ bool is_mark(u32 row, u32 n) { return mark_row(row >> 6, n) == row; }
 
-// One thread per segment.  EMIT = false: record length and successor.  EMIT = true: write the bytes.
-template <bool EMIT>
-__global__ void __launch_bounds__(256) unbwt_walk(const u32 *__restrict__ LF, const u8 *__restrict__ L, u32 n, u32 index, u32 K,
-                                                  u32 *__restrict__ seg_len, u32 *__restrict__ seg_next, const u32 *__restrict__ seg_dist, u8 *__restrict__ out)
+#define UW_SLAB 64u                                     // bytes per node
+
+// One thread per segment k (start row mark_row(k)); node ids: k for the first slab, K + (atomic counter) for the others.
+// pair[node] = (next node | bytes in this node << 32) for lr_jump; the node whose walk reaches row `index` ends the text's list.
+__global__ void __launch_bounds__(256) unbwt_walk(const u32 *__restrict__ LF, const u8 *__restrict__ L, u32 n, u32 index, u32 K, u32 max_nodes,
+                                                  u32 *node_counter, u64 *__restrict__ pair, u8 *__restrict__ node_len, u32 *__restrict__ stage)
 {
     u32 k = blockIdx.x * 256 + threadIdx.x;
     if (k >= K) return;
-    u32 row = mark_row(k, n), len = 0, next = K;         // K = sentinel "end of text"
-    long long o = 0;
-    if (EMIT) { o = (long long)seg_dist[k] - 1; if (o >= (long long)n) o = (long long)n - 1; }
-    while (row != index) {
-        if (EMIT) { if (o >= 0) out[o] = L[row < index ? row : row - 1]; --o; }
-        ++len;
+    u32 row = mark_row(k, n), node = k, j = 0, w = 0, extra = 0;
+    u32 *slab = stage + (size_t)node * (UW_SLAB / 4);
+    u64 link;
+    for (;;) {
+        if (row == index) { link = (u64)node | ((u64)(j | LR_DONE) << 32); break; }                    // the walk ends in front of the '$' row
+        w = (w >> 8) | ((u32)L[row < index ? row : row - 1] << 24);                                      // byte j of the node, little-endian packing
+        if ((++j & 3u) == 0) slab[(j >> 2) - 1] = w;
         row = __ldg(LF + row);
-        if (is_mark(row, n)) { next = row >> 6; break; }
-        if (len > n) break;                              // cannot happen for a permutation; corrupt-input guard
+        if (is_mark(row, n)) { link = (u64)(row >> 6) | ((u64)j << 32); break; }                        // the next segment starts here
+        if (j == UW_SLAB) {                                                                             // slab full: link a fresh node and go on
+            const u32 fresh = K + atomicAdd(node_counter, 1u);
+            if (fresh >= max_nodes || ++extra > n / UW_SLAB + 1) { link = (u64)node | ((u64)(j | LR_DONE) << 32); break; }   // corrupt input: LF is not a permutation
+            pair[node] = (u64)fresh | ((u64)j << 32); node_len[node] = (u8)j;
+            node = fresh; j = 0; slab = stage + (size_t)node * (UW_SLAB / 4);
+        }
     }
-    if (!EMIT) { seg_len[k] = len; seg_next[k] = next; }
+    if (j & 3u) slab[j >> 2] = w >> (8u * (4u - (j & 3u)));
+    pair[node] = link; node_len[node] = (u8)j;
 }
 
-// Wyllie pointer jumping: dist[k] = number of bytes from the start of segment k to the end.
-__global__ void __launch_bounds__(256) unbwt_jump(const u32 *__restrict__ dist_in, const u32 *__restrict__ next_in, u32 *__restrict__ dist_out, u32 *__restrict__ next_out, u32 K)
+// Byte j (walk order) of node i is text position D(i) - 1 - j, D(i) = bytes from the start of node i to the end of the walk.
+__global__ void __launch_bounds__(256) unbwt_place(const u64 *__restrict__ pair, const u8 *__restrict__ node_len, const u8 *__restrict__ stage, const u32 *__restrict__ node_counter,
+                                                   u32 K, u32 n, u8 *__restrict__ out)
 {
-    u32 k = blockIdx.x * 256 + threadIdx.x;
-    if (k > K) return;                                   // node K is the sentinel (dist 0, next K)
-    u32 nx = next_in[k];
-    dist_out[k] = dist_in[k] + dist_in[nx];
-    next_out[k] = next_in[nx];
+    const u64 t = (u64)blockIdx.x * 256 + threadIdx.x;
+    const u32 node = (u32)(t / UW_SLAB), j = (u32)(t % UW_SLAB);
+    if (node >= K + min(*node_counter, n / UW_SLAB + 1u)) return;
+    if (j >= node_len[node]) return;
+    const u32 D = (u32)(pair[node] >> 32) & ~LR_DONE;
+    const u64 pos = (u64)D - 1 - j;
+    if (D > j && pos < n) out[pos] = stage[t];
 }
-
-__global__ void unbwt_init_sentinel(u32 *dist, u32 *next, u32 K) { dist[K] = 0; next[K] = K; }
 
 }  // namespace
 
@@ -78,34 +91,33 @@ int stage_bwt_decode(Ctx *ctx, u8 *d_T, int n_, int index_)
     const size_t mark = A.mark();
 
     const u32 tiles = ceil_div(n, LF_TILE);
-    u8  *Lp   = A.get<u8>((size_t)n + 64);
-    u32 *LF   = A.get<u32>((size_t)n + 2);
-    u32 *hist = A.get<u32>(256 + 64);
-    u64 *lb   = A.get<u64>((size_t)tiles * 256);
     const u32 K = ceil_div((u64)n + 1, 64);                  // one segment per window of 64 rows (mark_row)
-    u32 *dist[2] = { A.get<u32>((size_t)K + 1), A.get<u32>((size_t)K + 1) };
-    u32 *next[2] = { A.get<u32>((size_t)K + 1), A.get<u32>((size_t)K + 1) };
+    const u32 max_nodes = K + n / UW_SLAB + 2;               // every further node of a segment holds 64 bytes of text
+    u8  *Lp    = A.get<u8>((size_t)n + 64);
+    u32 *LF    = A.get<u32>((size_t)n + 2);
+    u32 *hist  = A.get<u32>(256 + 64 + 64);                  // [0..255] counts / bases, [256] tile counter, [320] node counter, [321..] jump flags
+    u64 *lb    = A.get<u64>((size_t)tiles * 256);
+    u64 *pair  = A.get<u64>((size_t)max_nodes);
+    u8  *nlen  = A.get<u8>((size_t)max_nodes);
+    u32 *stage = A.get<u32>((size_t)max_nodes * (UW_SLAB / 4));
 
     CUDA_TRY(cudaMemcpyAsync(Lp, d_T, n, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(Lp + n, 0, 64, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(u32) * (256 + 64), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(u32) * (256 + 64 + 64), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lb, 0, sizeof(u64) * (size_t)tiles * 256, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(nlen, 0, (size_t)max_nodes, ctx->stream));                                  // unused nodes: empty ...
+    CUDA_TRY(cudaMemsetAsync(pair, 0xff, sizeof(u64) * (size_t)max_nodes, ctx->stream));                 // ... and LR_DONE, so the ranking skips them
 
     LAUNCH(ctx, unbwt_hist, min(ceil_div(n, 256 * 64), (u32)(B200_SMS * 8)), 256, 0, Lp, n, hist);
     LAUNCH(ctx, unbwt_scan256, 1, 32, 0, hist);
     PROF_BYTES(ctx, 5.0 * n);
     LAUNCH(ctx, unbwt_lf<true>, tiles, LF_THREADS, 0, Lp, n, index, hist, hist + 256, lb, LF);
 
-    PROF_BYTES(ctx, 4.0 * n);
-    LAUNCH(ctx, unbwt_walk<false>, ceil_div(K, 256), 256, 0, LF, Lp, n, index, K, dist[0], next[0], (const u32 *)nullptr, (u8 *)nullptr);
-    LAUNCH(ctx, unbwt_init_sentinel, 1, 1, 0, dist[0], next[0], K);
-    int cur = 0;
-    for (u32 span = 1; span < K + 1; span <<= 1) {
-        LAUNCH(ctx, unbwt_jump, ceil_div(K + 1, 256), 256, 0, dist[cur], next[cur], dist[cur ^ 1], next[cur ^ 1], K);
-        cur ^= 1;
-    }
-    PROF_BYTES(ctx, 6.0 * n);
-    LAUNCH(ctx, unbwt_walk<true>, ceil_div(K, 256), 256, 0, LF, Lp, n, index, K, (u32 *)nullptr, (u32 *)nullptr, dist[cur], d_T);
+    PROF_BYTES(ctx, 6.0 * n);                                // 4 n of LF gathered, n of L gathered, n staged
+    LAUNCH(ctx, unbwt_walk, ceil_div(K, 256), 256, 0, LF, Lp, n, index, K, max_nodes, hist + 320, pair, nlen, stage);
+    lr_rank(ctx, pair, max_nodes, max_nodes, hist + 321);
+    PROF_BYTES(ctx, 2.0 * n);
+    LAUNCH(ctx, unbwt_place, ceil_div((u64)max_nodes * UW_SLAB, 256), 256, 0, pair, nlen, (const u8 *)stage, hist + 320, K, n, d_T);
     A.release(mark);
     return LIBBSC_NO_ERROR;
 }

@@ -114,19 +114,28 @@ struct Ctx {
     }
 
     void sync() { CUDA_TRY(cudaStreamSynchronize(stream)); }
-    // Wait for a kernel that runs for 0.01 - 2 s (the coder kernels) WITHOUT putting anything behind it on the stream.  A process has
-    // at most 32 hardware work queues per GPU (CUDA_DEVICE_MAX_CONNECTIONS), so with 40+ blocks in flight two streams share a queue;
-    // an event record or a copy enqueued behind the 2 s kernel of one of them holds the queue's head until that kernel ENDS, and the
-    // other stream's work waits behind it -- measured: 48 and 64 blocks in flight ran as waves of 32 (profiles/r2c_call_c.log).
-    // cudaStreamQuery enqueues nothing, and the sleeping poll leaves the host cores to the threads that launch other blocks' kernels.
-    void wait_long() {
-        unsigned us = 20;
-        for (;;) {
-            cudaError_t e = cudaStreamQuery(stream);
-            if (e == cudaSuccess) return;
-            if (e != cudaErrorNotReady) { cudaGetLastError(); throw CudaFail{e, __FILE__, __LINE__}; }
+    // Wait for a kernel that runs for 0.01 - 2 s (the coder kernels) WITHOUT putting anything behind it on the stream and without
+    // driver calls.  A process has at most 32 hardware work queues per GPU (CUDA_DEVICE_MAX_CONNECTIONS), so with 40+ blocks in
+    // flight two streams share a queue; an event record or a copy enqueued behind the 2 s kernel of one of them holds the queue's head
+    // until that kernel ENDS and the other stream's work waits behind it -- measured: 48 and 64 blocks in flight ran as waves of 32
+    // (profiles/r2c_call_c.log).  Polling cudaStreamQuery from 48 threads instead made the launch-heavy sort stages of the other
+    // blocks four times slower (driver lock; profiles/r2d_call_d.log).  So the kernel itself reports: its last CTA writes a sequence
+    // number into this context's pinned mailbox (signal_done below) and the host thread sleeps on that word.
+    u32 done_seq = 0;
+    struct DoneSignalArgs { u32 *ctr; u32 *host_flag; u32 seq; };
+    DoneSignalArgs next_signal() { ++done_seq; return DoneSignalArgs{d_mail + 128, h_mail + 250, done_seq}; }
+    void wait_signal() {
+        volatile u32 *flag = (volatile u32 *)(h_mail + 250);
+        unsigned us = 20, slept = 0;
+        while (*flag != done_seq) {
             struct timespec ts = {0, (long)us * 1000L}; nanosleep(&ts, nullptr);
-            if (us < 500) us += us / 2;
+            slept += us; if (us < 400) us += us / 2;
+            if (slept > 200000) {                            // every 0.2 s: has the stream died (launch failure, kernel fault)?
+                slept = 0;
+                cudaError_t e = cudaStreamQuery(stream);
+                if (e == cudaSuccess) { if (*flag != done_seq) { cudaGetLastError(); throw CudaFail{cudaErrorUnknown, __FILE__, __LINE__}; } break; }
+                if (e != cudaErrorNotReady) { cudaGetLastError(); throw CudaFail{e, __FILE__, __LINE__}; }
+            }
         }
     }
     // Read `words` u32 from the device mailbox (blocks the host on this stream only).
@@ -166,23 +175,39 @@ template <typename F> static inline void ensure_dyn_smem(F *kernel, int device, 
         if (p_) { CUDA_TRY(cudaEventRecord(eb_, c_->stream)); c_->prof.push_back(ProfRec{#kernel, ea_, eb_, c_->next_bytes}); } \
         c_->next_bytes = 0; c_->kernels_launched++; } while (0)
 
-// A launch that the host waits for (Ctx::wait_long) before anything else goes onto the stream: the closing profile event is recorded
-// after the wait, not behind the kernel.
+// A launch that the host waits for before anything else goes onto the stream (Ctx::wait_signal): the kernel takes a DoneSignal as its
+// LAST parameter and calls signal_done once per CTA; the closing profile event is recorded after the wait, not behind the kernel.
 #define LAUNCH_LONG(ctx, kernel, grid, block, smem, ...) do { \
         Ctx *c_ = (ctx); cudaEvent_t ea_ = nullptr, eb_ = nullptr; const bool p_ = c_->profile; const double nb_ = c_->next_bytes; \
         if (p_) { ea_ = c_->ev(); eb_ = c_->ev(); CUDA_TRY(cudaEventRecord(ea_, c_->stream)); } \
-        kernel<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__); KERNEL_CHECK(); \
+        const Ctx::DoneSignalArgs sg_ = c_->next_signal(); \
+        kernel<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__, DoneSignal{sg_.ctr, sg_.host_flag, sg_.seq}); KERNEL_CHECK(); \
         c_->next_bytes = 0; c_->kernels_launched++; \
-        c_->wait_long(); \
+        c_->wait_signal(); \
         if (p_) { CUDA_TRY(cudaEventRecord(eb_, c_->stream)); c_->prof.push_back(ProfRec{#kernel, ea_, eb_, nb_}); } } while (0)
 
-// ---- small device helpers ------------------------------------------------------------------
+// ---- small device helpers// ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+
+// Completion report of a long kernel (LAUNCH_LONG): ONE thread per CTA calls it after the CTA's results are in global memory; the
+// last CTA of the grid re-arms the counter and writes `seq` into the context's pinned host mailbox.
+struct DoneSignal { u32 *ctr; u32 *host_flag; u32 seq; };
+__device__ __forceinline__ void signal_done(const DoneSignal &s)
+{
+    __threadfence();
+    if (atomicAdd(s.ctr, 1u) == gridDim.x * gridDim.y - 1u) {
+        *s.ctr = 0;
+        __threadfence_system();
+        *(volatile u32 *)s.host_flag = s.seq;
+    }
+}
 __device__ __forceinline__ u32 lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
-// Lanes of the warp that hold the same `bits`-bit digit as this lane (all 32 lanes must call it).  One ballot per digit bit instead of
-// __match_any_sync, which on this chip costs 85 / 217 / 393 cycles for 4 / 16 / 32 distinct values in the warp (profiles/r2a_call_a.log:
-// it iterates over the distinct values), while the ballots are independent of each other and of the data.
+// Lanes of the warp that hold the same `bits`-bit digit as this lane, from one ballot per digit bit (all 32 lanes must call it).
+// A/B on the B200 against __match_any_sync (profiles/r2d_call_d.log): as a DEPENDENT operation match.any costs 85 / 217 / 393 cycles for
+// 4 / 16 / 32 distinct values, but its THROUGHPUT with many warps in flight is better than 8 ballots + 8 selects -- rs_onesweep 2712 ->
+// 2490 GB/s, unbwt_lf 1032 -> 870 GB/s with ballots -- so the multisplits keep match.any; the grid-stride histogram (one item per
+// thread and iteration, little else to overlap with) gained 18 % from the ballots and keeps them.
 __device__ __forceinline__ u32 warp_peers(u32 d, int bits)
 {
     u32 m = 0xffffffffu;

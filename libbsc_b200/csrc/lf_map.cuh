@@ -2,7 +2,7 @@
 // inverse BWT (bwt_decode.cu) and the inverse sort transform (st_decode.cu).
 //
 //   unbwt_hist   256-bin histogram of L                                   (reads n)
-//   unbwt_lf     per 4 KB tile a warp multisplit (ballot peer masks) ranks the bytes, per-symbol decoupled look-back gives
+//   unbwt_lf     per 4 KB tile a warp match-any multisplit ranks the bytes, per-symbol decoupled look-back gives
 //                the tile's global offsets in the same pass              (reads n, writes 4n)
 #pragma once
 #include "common.cuh"
@@ -85,7 +85,7 @@ unbwt_lf(const u8 *__restrict__ L, u32 n, u32 index, const u32 *__restrict__ cba
         bool ok = off < valid;
         u32 d = ok ? bytes[off] : 256u;                  // 256 = "no item" (never matches a symbol)
         sym[i] = d;
-        u32 m = warp_peers(d, 9);                        // 9 bits: 256 = "no item" is a class of its own
+        u32 m = __match_any_sync(0xffffffffu, d);
         u32 leader = __ffs(m) - 1, pre = 0;
         if (ok && lane == leader) { pre = whist[warp][d]; whist[warp][d] = pre + __popc(m); }
         pre = __shfl_sync(0xffffffffu, pre, leader);

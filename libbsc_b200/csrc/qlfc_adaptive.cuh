@@ -316,7 +316,7 @@ __device__ __forceinline__ void qa_smem_init(u8 *raw, const QTables *__restrict_
 }
 
 __global__ void __launch_bounds__(32, 1) q_adaptive_decode(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
-                                                           const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+                                                           const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list, DoneSignal done)
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
     qa_smem_init(q_smem_raw, tables);
@@ -327,12 +327,13 @@ __global__ void __launch_bounds__(32, 1) q_adaptive_decode(const u8 *__restrict_
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 st_cached = 0, st_miss = 0;
     const int r = qa_decode_stream(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, st_cached, st_miss);
-    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
+    __syncwarp();                                        // every lane's output stores precede lane 0's report
+    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; signal_done(done); }
 }
 
 __global__ void __launch_bounds__(32, 1) q_adaptive_encode(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                            SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
-                                                           const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+                                                           const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list, DoneSignal done)
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
     qa_smem_init(q_smem_raw, tables);
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(32, 1) q_adaptive_encode(const u32 *__restrict
     u32 st_cached = 0, st_miss = 0;
     const int r = qa_encode_stream(sm, run_pos, run_sym, run_rank, sb.run_begin, sb.run_end, sb.in_size, mtf_all + sid * 256, out_all + sb.out_off, sb.out_cap,
                                    cold_s, cold_c, st_cached, st_miss);
-    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
+    __syncwarp();                                        // every lane's output stores precede lane 0's report
+    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; signal_done(done); }
 }
 #endif

@@ -350,7 +350,7 @@ template <class LY> __device__ __forceinline__ void qd6_smem_init(u8 *raw, const
 }
 
 template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode6(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
-                                                                              const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)   // the moves table (QD6_MOVES ints) follows the QTables
+                                                                              const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list, DoneSignal done)   // the moves table (QD6_MOVES ints) follows the QTables
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
     qd6_smem_init<LY>(q_smem_raw, tables);
@@ -361,7 +361,8 @@ template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode6(c
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 st_cached = 0, st_miss = 0;
     const int r = qd6_decode_stream<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), st_cached, st_miss);
-    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
+    __syncwarp();                                        // every lane's output stores precede lane 0's report
+    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; signal_done(done); }
 }
 
 #endif

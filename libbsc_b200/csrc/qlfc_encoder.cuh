@@ -150,7 +150,7 @@ __device__ __forceinline__ u32 enc_window(u32 prev_rev, u32 cur_rev, u32 lane) {
 // per 64 MiB block, profiles/r2a_call_a.log).  (A one-multiply-add form of the range recurrence was tried in round 2: 707 vs 682 ms.)
 template <class LY> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                     SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
-                                                    const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+                                                    const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list, DoneSignal done)
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
     CoderSmemT<LY> &S = *reinterpret_cast<CoderSmemT<LY> *>(q_smem_raw);
@@ -307,7 +307,8 @@ template <class LY> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(c
             if (result == 0 && P.fail == 2) result = LIBBSC_GPU_ERROR;
             if (result == 0) result = (int)rc.finish();
         }
-        if (lane == 0) { if (result < 0 && P.fail == 0) P.fail = 1; sb.result = result; }
+        __syncwarp();
+        if (lane == 0) { if (result < 0 && P.fail == 0) P.fail = 1; sb.result = result; signal_done(done); }   // the stream's bytes are all written by this (LOW) warp
         return;
     }
 

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) q_fast_model_init(short *__restrict__ col
 }
 
 __global__ void __launch_bounds__(32, 1) q_fast_decode(const u8 *__restrict__ in_all, SubBlock *__restrict__ sbs, short *__restrict__ cold_all,
-                                                       u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+                                                       u8 *__restrict__ out_all, const u32 *__restrict__ sb_list, DoneSignal done)
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
     qf_smem_init(*reinterpret_cast<FastSmem *>(q_smem_raw));
@@ -353,12 +353,13 @@ __global__ void __launch_bounds__(32, 1) q_fast_decode(const u8 *__restrict__ in
     SubBlock &sb = sbs[sid];
     u32 st_cached = 0, st_miss = 0;
     const int r = qf_decode_stream(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_all + (size_t)blockIdx.x * QF_COLD, st_cached, st_miss);
-    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
+    __syncwarp();                                        // every lane's output stores precede lane 0's report
+    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; signal_done(done); }
 }
 
 __global__ void __launch_bounds__(32, 1) q_fast_encode(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                        SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
-                                                       u8 *__restrict__ out_all, const u32 *__restrict__ sb_list)
+                                                       u8 *__restrict__ out_all, const u32 *__restrict__ sb_list, DoneSignal done)
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
     qf_smem_init(*reinterpret_cast<FastSmem *>(q_smem_raw));
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(32, 1) q_fast_encode(const u32 *__restrict__ r
     u32 st_cached = 0, st_miss = 0;
     const int r = qf_encode_stream(sm, run_pos, run_sym, run_rank, sb.run_begin, sb.run_end, sb.in_size, mtf_all + sid * 256, out_all + sb.out_off, sb.out_cap,
                                    cold_all + (size_t)sid * QF_COLD, st_cached, st_miss);
-    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; }
+    __syncwarp();                                        // every lane's output stores precede lane 0's report
+    if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; signal_done(done); }
 }
 #endif

@@ -6,7 +6,7 @@
 //
 //   rs_hist1      : 256-bin histogram of the FIRST digit only (one read of the source keys).
 //   rs_onesweep   : per digit pass, ONE read + ONE write of every (key,value): each CTA scans the
-//                   digit histogram into global bases, ranks a tile with a warp multisplit (peer masks from ballots),
+//                   digit histogram into global bases, ranks a tile with warp match-any multisplit,
 //                   obtains its per-digit global offsets by decoupled look-back over the preceding
 //                   tiles (single pass, no separate upsweep), reorders the tile in shared memory and
 //                   stores digit-contiguous, fully coalesced runs.  While storing, it accumulates
@@ -159,7 +159,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         u32 d = (u32)(keys[i] >> shift) & dmask;
-        u32 m = warp_peers(d, bits);
+        u32 m = __match_any_sync(0xffffffffu, d);
         u32 leader = __ffs(m) - 1;
         u32 pre = 0;
         if (lane == leader) { pre = S.whist[warp][d]; S.whist[warp][d] = pre + __popc(m); }
@@ -297,7 +297,7 @@ rs_onesweep_tma(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const u32 d = (u32)(keys[i] >> shift) & dmask;
-            const u32 m = warp_peers(d, bits);
+            const u32 m = __match_any_sync(0xffffffffu, d);
             const u32 leader = __ffs(m) - 1;
             u32 pre = 0;
             if (lane == leader) { pre = S.whist[warp][d]; S.whist[warp][d] = pre + __popc(m); }

@@ -23,7 +23,7 @@
 //                  pass per order: decoupled look-back max-scan (group start per row) + scatter through LF
 //   st_groups      last row (= stack top) of every k-group, dynamic flag (sources from more than one k-group)
 //   st_link        per row: static successor, or list end + the dynamic group it pops from
-//   st_jump x log  in-place Wyllie pointer jumping on 64-bit (successor, distance) pairs -> list end + distance per row;
+//   lr_jump x log  in-place Wyllie pointer jumping on 64-bit (successor, distance) pairs (list_rank.cuh) -> list end + distance per row;
 //                  rounds after convergence return at once (device-side flag, no host round trip)
 //   st_heads       per list head: list length and the dynamic group its end pops from
 //   st_serial      the part that is inherently serial: one lane pops list heads, one step per LIST (not per byte) -- n/4 steps
@@ -33,12 +33,13 @@
 #include "common.cuh"
 #include "stages.cuh"
 #include "lf_map.cuh"
+#include "list_rank.cuh"
 
 #define SR_THREADS 256
 #define SR_ITEMS   8
 #define SR_TILE    (SR_THREADS * SR_ITEMS)
 
-#define ST_DONE   0x80000000u
+#define ST_DONE   LR_DONE
 #define ST_NONE   0xffffffffu
 
 namespace {
@@ -152,24 +153,6 @@ __global__ void __launch_bounds__(256) st_link(const u32 *__restrict__ LF, const
     pair[i] = end ? ((u64)i | ((u64)ST_DONE << 32)) : ((u64)nx | (1ull << 32));
 }
 
-// One round of pointer jumping, in place: any 64-bit snapshot of pair[j] is a valid (successor, distance) statement, so reading a
-// pair that another thread has already advanced in this round only speeds convergence up.
-__global__ void __launch_bounds__(256) st_jump(u64 *pair, u32 n, u32 *flags, int round)
-{
-    if (round > 0 && flags[round - 1] == 0) return;     // converged in an earlier round
-    u32 i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const u64 p = ld_relaxed(pair + i);
-    const u32 d = (u32)(p >> 32);
-    if (d & ST_DONE) return;
-    const u32 nx = (u32)p;
-    const u64 q = ld_relaxed(pair + nx);
-    const u32 qd = (u32)(q >> 32);
-    const u32 nd = (d + (qd & ~ST_DONE)) | (qd & ST_DONE);
-    st_relaxed(pair + i, (u64)(u32)q | ((u64)nd << 32));
-    if (!(qd & ST_DONE)) flags[round] = 1;
-}
-
 // rec[h] = (list length | dynamic group its end pops from << 32) for every list head h (rows of dynamic groups + rotation 0)
 __global__ void __launch_bounds__(256) st_heads(const u64 *__restrict__ pair, const u32 *__restrict__ gk, const u8 *__restrict__ dynf, const u32 *__restrict__ tgt,
                                                 u32 n, u32 index, u64 *__restrict__ rec)
@@ -183,7 +166,7 @@ __global__ void __launch_bounds__(256) st_heads(const u64 *__restrict__ pair, co
 }
 
 // The serial part: list after list, backwards through the text.  posh[h] = text offset of the END of list h (its lowest offset).
-__global__ void st_serial(const u64 *__restrict__ rec, u32 *top, u32 n, u32 index, u32 *__restrict__ posh, u32 *status)
+__global__ void st_serial(const u64 *__restrict__ rec, u32 *top, u32 n, u32 index, u32 *__restrict__ posh, u32 *status, DoneSignal done)
 {
     if (threadIdx.x != 0) return;
     long long cur = n;
@@ -201,6 +184,7 @@ __global__ void st_serial(const u64 *__restrict__ rec, u32 *top, u32 n, u32 inde
         h = t;
     }
     status[0] = cur == 0 ? 0u : 1u;                      // 1: the lists do not tile the text (corrupt input)
+    signal_done(done);
 }
 
 __global__ void __launch_bounds__(256) st_place(const u64 *__restrict__ pair, const u32 *__restrict__ gk, const u8 *__restrict__ dynf, const u32 *__restrict__ posh,
@@ -278,8 +262,7 @@ int stage_st_decode(Ctx *ctx, u8 *d_T, int n_, int k, int index_)
     LAUNCH(ctx, st_special, 1, 1, 0, gk, LF, index, small + 8);
     PROF_BYTES(ctx, 25.0 * n);
     LAUNCH(ctx, st_link, nb, 256, 0, LF, gk, dynf, top, small + 8, n, index, pair, tgt);
-    int rounds = 1; while ((1ull << rounds) < (u64)n) ++rounds;
-    for (int r = 0; r <= rounds; ++r) LAUNCH(ctx, st_jump, nb, 256, 0, pair, n, small + 16, r);
+    lr_rank(ctx, pair, n, n, small + 16);
     LAUNCH(ctx, st_heads, nb, 256, 0, pair, gk, dynf, tgt, n, index, rec);
     u32 *posh = LF, *posE = tmpk;                            // both free from here on
     CUDA_TRY(cudaMemsetAsync(posE, 0, sizeof(u32) * (size_t)n, ctx->stream));
