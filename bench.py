@@ -55,6 +55,7 @@ def parse_args():
                                                          "streams keep the 296 coder slots of a B200 (two per SM) full while the others sort")
     ap.add_argument("--sorter", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="phased", choices=["phased", "pipeline"], help="order of the work inside the timed steps (see class Steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the extra keys for BASELINE configs C2 / C3-strong / C4 / C5")
     return ap.parse_args()
@@ -377,7 +378,23 @@ def run_b200(args, rank, local_rank, world):
         e1.record(); e1.synchronize()
         return e0.elapsed_time(e1)
 
-    pipe = Pipeline(nb, workers, dev_task)
+    def phase(fn):
+        return lambda w, i: (torch.cuda.set_device(local_rank), fn(w, i))
+
+    class Steps:
+        """--mode pipeline: compress -> decompress per block, all blocks and steps as one flow.  --mode phased: per step every block is
+        compressed, then every block is decompressed (the sorts of the compress phase find the SMs free of coder CTAs)."""
+        def __init__(self, task, comp, decomp):
+            self.flow, self.comp, self.decomp = Pipeline(nb, workers, task), Pipeline(nb, workers, phase(comp)), Pipeline(nb, workers, phase(decomp))
+
+        def run(self, steps):
+            if args.mode == "pipeline":
+                self.flow.run(steps)
+            else:
+                for _ in range(steps):
+                    self.comp.run(1); self.decomp.run(1)
+
+    pipe = Steps(dev_task, dev_compress, dev_decompress)
     pipe.run(args.warmup)
     for c in ctxs:
         c.set_profile(True)
@@ -444,7 +461,15 @@ def run_b200(args, rank, local_rank, world):
                 hsize[i] = r
                 r = L.bsc_decompress(h_cmp[i].data_ptr(), hsize[i], h_back[i].data_ptr(), bb, 3)
                 assert r == 0, "bsc_decompress failed: %d" % r
-            hp = Pipeline(nb, workers, host_task)
+            def host_comp(w, i):
+                r = L.bsc_compress(h_in[i].data_ptr(), h_cmp[i].data_ptr(), bb, 0, 0, args.sorter, 1, 3)
+                assert r > 0, "bsc_compress failed: %d" % r
+                hsize[i] = r
+
+            def host_decomp(w, i):
+                r = L.bsc_decompress(h_cmp[i].data_ptr(), hsize[i], h_back[i].data_ptr(), bb, 3)
+                assert r == 0, "bsc_decompress failed: %d" % r
+            hp = Steps(host_task, host_comp, host_decomp)
             if warm:
                 hp.run(warm)
             l0 = int(L.bscb200_total_kernel_launches())
@@ -534,8 +559,8 @@ def run_b200(args, rank, local_rank, world):
 
     line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, {"blocks_in_flight_per_gpu": workers, "step": "every block compressed then decompressed; the K steps flow as one pipeline "
-                                                                                          "(no drain between steps), timed barrier to barrier",
+            "config": workload_config(args, {"blocks_in_flight_per_gpu": workers, "mode": args.mode, "step": "phased: all blocks compressed, then all blocks decompressed; pipeline: compress -> decompress per block, "
+                                                                                          "steps flow into each other; timed barrier to barrier",
                                              "parallelism": "blocks round-robin over %d GPU(s), no collective" % world}),
             "compress_MBps": total_mb / (ms_c / 1e3), "decompress_MBps": total_mb / (ms_d / 1e3), "phase_note": "each direction alone, one drained pass over the batch",
             "compressed_bytes_rank0": comp_bytes, "ratio": comp_bytes / float(nb * bb),

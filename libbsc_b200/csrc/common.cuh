@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <vector>
 #include <mutex>
+#include <condition_variable>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -155,6 +156,26 @@ struct Ctx {
     }
 };
 
+// Optional cap on the coder CTAs in flight per device (BSCB200_CODER_SLOTS, default: none).  A coder CTA pins half an SM's shared memory for
+// 0.1 - 2 s; the sort kernels of other blocks need shared memory too and can only run where a half is free.  With every half taken by
+// coders the sorts starve (compress fell from 1.4 to 0.35 GB/s in a saturated pipeline, profiles/r2e_call_e.log), so a caller that keeps
+// both directions in flight can leave a share of the SMs to the sorts.  Host-side counting semaphore; a launch waits for its CTAs' worth.
+struct CoderSlots {
+    static int limit() { static const int v = [] { const char *e = getenv("BSCB200_CODER_SLOTS"); int k = e ? atoi(e) : 0; return k >= 8 ? k : 0; }(); return v; }
+    struct State { std::mutex m; std::condition_variable cv; int used = 0; };
+    static State &state(int device) { static State s[16]; return s[device & 15]; }
+    struct Lease {
+        int device, n;
+        Lease(int dev, int ctas) : device(dev), n(limit() ? (ctas < limit() ? ctas : limit()) : 0) {
+            if (!n) return;
+            State &S = state(device); std::unique_lock<std::mutex> lk(S.m);
+            S.cv.wait(lk, [&] { return S.used + n <= limit(); });
+            S.used += n;
+        }
+        ~Lease() { if (!n) return; State &S = state(device); { std::lock_guard<std::mutex> lk(S.m); S.used -= n; } S.cv.notify_all(); }
+    };
+};
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the call is not free and
 // must not sit in front of every launch of a kernel that other streams are running.
 template <typename F> static inline void ensure_dyn_smem(F *kernel, int device, size_t bytes)
@@ -179,6 +200,7 @@ template <typename F> static inline void ensure_dyn_smem(F *kernel, int device, 
 // LAST parameter and calls signal_done once per CTA; the closing profile event is recorded after the wait, not behind the kernel.
 #define LAUNCH_LONG(ctx, kernel, grid, block, smem, ...) do { \
         Ctx *c_ = (ctx); cudaEvent_t ea_ = nullptr, eb_ = nullptr; const bool p_ = c_->profile; const double nb_ = c_->next_bytes; \
+        CoderSlots::Lease lease_(c_->device, (int)(grid)); \
         if (p_) { ea_ = c_->ev(); eb_ = c_->ev(); CUDA_TRY(cudaEventRecord(ea_, c_->stream)); } \
         const Ctx::DoneSignalArgs sg_ = c_->next_signal(); \
         kernel<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__, DoneSignal{sg_.ctr, sg_.host_flag, sg_.seq}); KERNEL_CHECK(); \

@@ -362,8 +362,12 @@ rs_onesweep_tma(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
 }
 
 // ---- host driver ---------------------------------------------------------------------------
-// BSCB200_SORT_TMA=0: every pass through rs_onesweep (A/B of the TMA-staged kernel, tools/sort_ab.sh)
-static inline bool rs_use_tma() { static const bool on = [] { const char *e = getenv("BSCB200_SORT_TMA"); return !(e && e[0] == '0'); }(); return on; }
+// BSCB200_SORT_TMA=1: passes over materialised keys through rs_onesweep_tma.  A/B on the B200 (profiles/r2e_call_e.log, r2e_ncu_sort_stalls.txt):
+// the TMA-staged persistent kernel runs at 1757 GB/s against 2490 GB/s for rs_onesweep -- a persistent CTA holds the id of its PREFETCHED
+// tile while it still works on the current one, so that tile's aggregate reaches the look-back a whole tile time later and the chain of
+// waits grows (long_scoreboard + branch_resolving 12.4 of 24.5 cycles per instruction); it also takes 109 KB of shared memory per CTA, which
+// no SM half next to a coder CTA can give.  So it is not the default; it stays selectable and parity-tested.
+static inline bool rs_use_tma() { static const bool on = [] { const char *e = getenv("BSCB200_SORT_TMA"); return e && e[0] == '1'; }(); return on; }
 
 // Scratch needed by one sort (histograms, tile counters, look-back descriptors).
 static inline size_t rs_scratch_bytes(u32 n, int npasses)
