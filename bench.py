@@ -55,7 +55,7 @@ def parse_args():
                                                          "streams keep the 296 coder slots of a B200 (two per SM) full while the others sort")
     ap.add_argument("--sorter", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="phased", choices=["phased", "pipeline"], help="order of the work inside the timed steps (see class Steps)")
+    ap.add_argument("--mode", default="pipeline", choices=["phased", "pipeline"], help="order of the work inside the timed steps (see class Steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the extra keys for BASELINE configs C2 / C3-strong / C4 / C5")
     return ap.parse_args()

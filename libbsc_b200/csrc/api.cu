@@ -62,6 +62,9 @@ void ctx_delete(Ctx *c)
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->qlfc_tables) cudaFree(c->qlfc_tables);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->stream_hi) cudaStreamDestroy(c->stream_hi);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

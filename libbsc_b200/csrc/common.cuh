@@ -122,6 +122,18 @@ struct Ctx {
     // (profiles/r2c_call_c.log).  Polling cudaStreamQuery from 48 threads instead made the launch-heavy sort stages of the other
     // blocks four times slower (driver lock; profiles/r2d_call_d.log).  So the kernel itself reports: its last CTA writes a sequence
     // number into this context's pinned mailbox (signal_done below) and the host thread sleeps on that word.
+    // Side stream of the highest priority for the LONG streams of a coder launch (qlfc.cu: split launches): when SM halves free up, the
+    // CTA scheduler places pending CTAs of higher-priority streams first, whichever block launched first -- longest-stream-first
+    // ACROSS blocks without any coordination between the host threads.
+    cudaStream_t stream_hi = nullptr;
+    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
+    void ensure_hi() {
+        if (stream_hi) return;
+        int lo = 0, hi = 0; CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&stream_hi, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
     u32 done_seq = 0;
     struct DoneSignalArgs { u32 *ctr; u32 *host_flag; u32 seq; };
     DoneSignalArgs next_signal() { ++done_seq; return DoneSignalArgs{d_mail + 128, h_mail + 250, done_seq}; }
@@ -203,7 +215,7 @@ template <typename F> static inline void ensure_dyn_smem(F *kernel, int device, 
         CoderSlots::Lease lease_(c_->device, (int)(grid)); \
         if (p_) { ea_ = c_->ev(); eb_ = c_->ev(); CUDA_TRY(cudaEventRecord(ea_, c_->stream)); } \
         const Ctx::DoneSignalArgs sg_ = c_->next_signal(); \
-        kernel<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__, DoneSignal{sg_.ctr, sg_.host_flag, sg_.seq}); KERNEL_CHECK(); \
+        kernel<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__, DoneSignal{sg_.ctr, sg_.host_flag, sg_.seq, (u32)(grid)}); KERNEL_CHECK(); \
         c_->next_bytes = 0; c_->kernels_launched++; \
         c_->wait_signal(); \
         if (p_) { CUDA_TRY(cudaEventRecord(eb_, c_->stream)); c_->prof.push_back(ProfRec{#kernel, ea_, eb_, nb_}); } } while (0)
@@ -213,11 +225,11 @@ __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 
 // Completion report of a long kernel (LAUNCH_LONG): ONE thread per CTA calls it after the CTA's results are in global memory; the
 // last CTA of the grid re-arms the counter and writes `seq` into the context's pinned host mailbox.
-struct DoneSignal { u32 *ctr; u32 *host_flag; u32 seq; };
+struct DoneSignal { u32 *ctr; u32 *host_flag; u32 seq; u32 total; };   // total = CTAs that report (one launch, or the two launches of a split)
 __device__ __forceinline__ void signal_done(const DoneSignal &s)
 {
     __threadfence();
-    if (atomicAdd(s.ctr, 1u) == gridDim.x * gridDim.y - 1u) {
+    if (atomicAdd(s.ctr, 1u) == s.total - 1u) {
         *s.ctr = 0;
         __threadfence_system();
         *(volatile u32 *)s.host_flag = s.seq;

@@ -249,6 +249,32 @@ static void init_models(Ctx *ctx, short *models, int count)
     LAUNCH(ctx, q_model_init, ceil_div(total, 256 * 8), 256, 0, models, total);
 }
 
+// Split launch of a static-coder kernel: the streams of `order[0 .. n_hi)` (the long ones; `order` is sorted longest first) go to the
+// context's high-priority side stream, the rest to its main stream; both halves report to ONE completion signal.  See Ctx::stream_hi.
+// BSCB200_CODER_SPLIT=0 turns it off (A/B).
+static bool coder_split_enabled() { static const bool on = [] { const char *e = getenv("BSCB200_CODER_SPLIT"); return !(e && e[0] == '0'); }(); return on; }
+static int coder_split_point(const u32 *weight, const u32 *order, int n)
+{
+    if (!coder_split_enabled() || n < 3) return 0;
+    int k = 0;
+    while (k < n && (u64)weight[order[k]] * 20 >= (u64)weight[order[0]] * 11) ++k;      // >= 55 % of the longest
+    return (k == n) ? 0 : k;
+}
+struct SplitLaunch {
+    Ctx *c; cudaEvent_t ea = nullptr, eb = nullptr; bool prof; double bytes; Ctx::DoneSignalArgs sg; CoderSlots::Lease lease; int n_hi;
+    SplitLaunch(Ctx *ctx, int total, int hi) : c(ctx), prof(ctx->profile), bytes(ctx->next_bytes), lease(ctx->device, total), n_hi(hi) {
+        if (prof) { ea = c->ev(); eb = c->ev(); CUDA_TRY(cudaEventRecord(ea, c->stream)); }
+        sg = c->next_signal();
+        if (n_hi > 0) { c->ensure_hi(); CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream)); CUDA_TRY(cudaStreamWaitEvent(c->stream_hi, c->ev_fork, 0)); }
+    }
+    void finish(const char *name, int launches) {
+        c->next_bytes = 0; c->kernels_launched += launches;
+        c->wait_signal();
+        if (n_hi > 0) { CUDA_TRY(cudaEventRecord(c->ev_join, c->stream_hi)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); }   // both kernels have reported: nothing waits here
+        if (prof) { CUDA_TRY(cudaEventRecord(eb, c->stream)); c->prof.push_back(ProfRec{name, ea, eb, bytes}); }
+    }
+};
+
 int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder, int features, int bare_out_size)
 {
     { const int g = coder_gate(coder); if (g != LIBBSC_NO_ERROR) return g; }
@@ -337,7 +363,13 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         init_models(ctx, models, nBlocks);
         PROF_BYTES(ctx, (double)n);                      // + c written; the launch is latency-, not bandwidth-bound
         ensure_dyn_smem(q_encode5<LayoutEncDiet>, ctx->device, enc_smem);
-        LAUNCH_LONG(ctx, (q_encode5<LayoutEncDiet>), nBlocks, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order);
+        u32 runs[Q_MAX_SUB]; for (int b = 0; b < nBlocks; ++b) runs[b] = h_sb[b].run_end - h_sb[b].run_begin;
+        const int n_hi = coder_split_point(runs, enc_order, nBlocks);
+        SplitLaunch sl(ctx, nBlocks, n_hi);
+        const DoneSignal done{sl.sg.ctr, sl.sg.host_flag, sl.sg.seq, (u32)nBlocks};
+        if (n_hi > 0) { q_encode5<LayoutEncDiet><<<n_hi, QE_THREADS, enc_smem, ctx->stream_hi>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order, done); KERNEL_CHECK(); }
+        q_encode5<LayoutEncDiet><<<nBlocks - n_hi, QE_THREADS, enc_smem, ctx->stream>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)(d_order + n_hi), done); KERNEL_CHECK();
+        sl.finish("q_encode5", n_hi > 0 ? 2 : 1);
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();                                         // short: the encoder (0.01 - 0.7 s) was waited for by LAUNCH_LONG
@@ -482,8 +514,16 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             static_assert(LayoutDiet::BYTES <= 232448 / 2 - 1024, "two decoder streams must fit one SM");
             if (prof) { ensure_dyn_smem(q_decode6<LayoutDiet, true>, ctx->device, LayoutDiet::BYTES);
                         LAUNCH_LONG(ctx, (q_decode6<LayoutDiet, true>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
-            else      { ensure_dyn_smem(q_decode6<LayoutDiet, false>, ctx->device, LayoutDiet::BYTES);
-                        LAUNCH_LONG(ctx, (q_decode6<LayoutDiet, false>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
+            else {
+                ensure_dyn_smem(q_decode6<LayoutDiet, false>, ctx->device, LayoutDiet::BYTES);
+                u32 packed[Q_MAX_SUB]; for (int b = 0; b < Q_MAX_SUB; ++b) packed[b] = h_sb[b].out_cap;
+                const int n_hi = coder_split_point(packed, list, nlist);
+                SplitLaunch sl(ctx, nlist, n_hi);
+                const DoneSignal done{sl.sg.ctr, sl.sg.host_flag, sl.sg.seq, (u32)nlist};
+                if (n_hi > 0) { q_decode6<LayoutDiet, false><<<n_hi, 32, LayoutDiet::BYTES, ctx->stream_hi>>>(d_in, d_sb, models, tables, d_out, (const u32 *)d_list, done); KERNEL_CHECK(); }
+                q_decode6<LayoutDiet, false><<<nlist - n_hi, 32, LayoutDiet::BYTES, ctx->stream>>>(d_in, d_sb, models + (size_t)n_hi * MODEL_SHORTS_PAD, tables, d_out, (const u32 *)(d_list + n_hi), done); KERNEL_CHECK();
+                sl.finish("q_decode6", n_hi > 0 ? 2 : 1);
+            }
         }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));
     }
