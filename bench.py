@@ -17,9 +17,9 @@ context / stream, so the HBM-bound sorts of some blocks overlap the latency-boun
   cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref) driven like its CLI
           (oracle/ref_driver.c) on the box's host cores.
 
-Workload (BASELINE.json config C3, per GPU): G_text(seed 2 + rank), 48 blocks of 64 MiB per step, sorter BWT,
-coder QLFC static, LZP off.  48 blocks = 384 coder streams for the 296 coder slots of a B200 (two CTAs per SM).
-Weak scaling: every rank processes its own 3 GiB per step.
+Workload (BASELINE.json config C3, per GPU): G_text(seed 2 + rank), 64 blocks of 64 MiB per step, sorter BWT,
+coder QLFC static, LZP off.  64 blocks = 512 coder streams for the 296 coder slots of a B200 (two CTAs per SM).
+Weak scaling: every rank processes its own 4 GiB per step.
 """
 import argparse
 import ctypes
@@ -49,9 +49,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--blocks", type=int, default=48, help="blocks per GPU and step")
+    ap.add_argument("--blocks", type=int, default=64, help="blocks per GPU and step")
     ap.add_argument("--block-mib", type=int, default=64)
-    ap.add_argument("--workers", type=int, default=0, help="blocks in flight per GPU = contexts = worker threads (0 = all blocks of the step); 48 x 8 coder "
+    ap.add_argument("--workers", type=int, default=0, help="blocks in flight per GPU = contexts = worker threads (0 = all blocks of the step); 64 x 8 coder "
                                                          "streams keep the 296 coder slots of a B200 (two per SM) full while the others sort")
     ap.add_argument("--sorter", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -12,8 +12,8 @@
 //                warp match-any multisplit ranks the bytes, per-symbol decoupled look-back gives
 //                the tile's global offsets in the same pass              (reads n, writes 4n)
 //   unbwt_walk   K ~ n/64 start rows (one per 64-row window, jittered); one thread per segment chases LF until it
-//                reaches another start row -- ONCE: the bytes it meets are staged in 64-byte slabs (node k = segment k's first
-//                slab; a segment longer than 64 bytes takes further nodes from an atomic counter and links them), so the
+//                reaches another start row -- ONCE: the bytes it meets are staged in 128-byte slabs (node k = segment k's first
+//                slab; a segment longer than 128 bytes takes further nodes from an atomic counter and links them), so the
 //                pointer chase, which is sector/latency bound (one dependent 4-byte gather per output byte), is never repeated
 //                (round 1 walked twice: 1.2 + 2.3 ms per 64 MiB; the reference stages too, libcubwt.cu:2744-2906)
 //   lr_jump      device-side pointer-jumping list ranking over the nodes (list_rank.cuh; no host round trip, cf.
@@ -38,7 +38,7 @@ __device__ __forceinline__ u32 mark_row(u32 w, u32 n)
 }
 __device__ __forceinline__ bool is_mark(u32 row, u32 n) { return mark_row(row >> 6, n) == row; }
 
-#define UW_SLAB 64u                                     // bytes per node
+#define UW_SLAB 128u                                    // bytes per node: a segment (mean 64 bytes, geometric) needs a second node in 13 % of the cases
 
 // One thread per segment k (start row mark_row(k)); node ids: k for the first slab, K + (atomic counter) for the others.
 // pair[node] = (next node | bytes in this node << 32) for lr_jump; the node whose walk reaches row `index` ends the text's list.
@@ -68,16 +68,23 @@ __global__ void __launch_bounds__(256) unbwt_walk(const u32 *__restrict__ LF, co
 }
 
 // Byte j (walk order) of node i is text position D(i) - 1 - j, D(i) = bytes from the start of node i to the end of the walk.
-__global__ void __launch_bounds__(256) unbwt_place(const u64 *__restrict__ pair, const u8 *__restrict__ node_len, const u8 *__restrict__ stage, const u32 *__restrict__ node_counter,
+// One thread per 4 staged bytes: a warp reads 128 contiguous bytes and writes 128 contiguous bytes (reversed).
+__global__ void __launch_bounds__(256) unbwt_place(const u64 *__restrict__ pair, const u8 *__restrict__ node_len, const u32 *__restrict__ stage, const u32 *__restrict__ node_counter,
                                                    u32 K, u32 n, u8 *__restrict__ out)
 {
-    const u64 t = (u64)blockIdx.x * 256 + threadIdx.x;
-    const u32 node = (u32)(t / UW_SLAB), j = (u32)(t % UW_SLAB);
+    const u64 t = (u64)blockIdx.x * 256 + threadIdx.x;     // word index into the slabs
+    const u32 node = (u32)(t / (UW_SLAB / 4)), j0 = (u32)(t % (UW_SLAB / 4)) * 4u;
     if (node >= K + min(*node_counter, n / UW_SLAB + 1u)) return;
-    if (j >= node_len[node]) return;
+    const u32 len = node_len[node];
+    if (j0 >= len) return;
     const u32 D = (u32)(pair[node] >> 32) & ~LR_DONE;
-    const u64 pos = (u64)D - 1 - j;
-    if (D > j && pos < n) out[pos] = stage[t];
+    const u32 w = stage[t];
+#pragma unroll
+    for (u32 b = 0; b < 4; ++b) {
+        const u32 j = j0 + b;
+        const u64 pos = (u64)D - 1 - j;
+        if (j < len && D > j && pos < n) out[pos] = (u8)(w >> (8 * b));
+    }
 }
 
 }  // namespace
@@ -117,7 +124,7 @@ int stage_bwt_decode(Ctx *ctx, u8 *d_T, int n_, int index_)
     LAUNCH(ctx, unbwt_walk, ceil_div(K, 256), 256, 0, LF, Lp, n, index, K, max_nodes, hist + 320, pair, nlen, stage);
     lr_rank(ctx, pair, max_nodes, max_nodes, hist + 321);
     PROF_BYTES(ctx, 2.0 * n);
-    LAUNCH(ctx, unbwt_place, ceil_div((u64)max_nodes * UW_SLAB, 256), 256, 0, pair, nlen, (const u8 *)stage, hist + 320, K, n, d_T);
+    LAUNCH(ctx, unbwt_place, ceil_div((u64)max_nodes * (UW_SLAB / 4), 256), 256, 0, pair, nlen, (const u32 *)stage, hist + 320, K, n, d_T);
     A.release(mark);
     return LIBBSC_NO_ERROR;
 }

@@ -99,8 +99,10 @@ template <typename K> __device__ __forceinline__ K rs_all_ones();
 template <> __device__ __forceinline__ u64 rs_all_ones<u64>() { return ~0ull; }
 template <> __device__ __forceinline__ u32 rs_all_ones<u32>() { return ~0u; }
 
+// 55 KB for (u64, u32) pairs: with the 1 KB the system reserves per CTA, TWO sort CTAs fit the half SM that a coder CTA (<= 113 KB) leaves
+// free -- in the compress / decompress pipeline the sorts run in those halves, and at 59 KB (u32 warp histograms) only one fitted.
 template <typename K, bool HAS_VAL> struct RsSmem {
-    u32 whist[RS_WARPS][256];
+    u16 whist[RS_WARPS][256];                            // per-warp digit counts (<= 512), then exclusive prefixes over the warps (< 4096)
     u32 dstart[256];
     u32 gbase[256];
     u32 nexthist[256];
@@ -138,7 +140,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
     const u32 dmask = (1u << bits) - 1u;
 
     if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&S.whist[0][0])[i] = 0;
+    for (int i = tid; i < RS_WARPS * 256 / 2; i += RS_THREADS) ((u32 *)&S.whist[0][0])[i] = 0;
     S.nexthist[tid] = 0;
     // global digit bases = exclusive scan of this digit's histogram (complete: the previous kernel ended)
     const u32 gdigit_base = rs_block_excl_scan(hist_in[tid], S.scan_tmp, lane, warp);   // contains __syncthreads
@@ -162,7 +164,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
         u32 m = __match_any_sync(0xffffffffu, d);
         u32 leader = __ffs(m) - 1;
         u32 pre = 0;
-        if (lane == leader) { pre = S.whist[warp][d]; S.whist[warp][d] = pre + __popc(m); }
+        if (lane == leader) { pre = S.whist[warp][d]; S.whist[warp][d] = (u16)(pre + __popc(m)); }
         pre = __shfl_sync(0xffffffffu, pre, leader);
         pos[i] = pre + __popc(m & lanemask_lt());
         __syncwarp();
@@ -174,7 +176,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
         const u32 d = tid;                               // RS_THREADS == 256 digits
         u32 run = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) { u32 t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
+        for (int w = 0; w < RS_WARPS; ++w) { u32 t = S.whist[w][d]; S.whist[w][d] = (u16)run; run += t; }
         const u32 count = run;
         const u32 excl = rs_block_excl_scan(count, S.scan_tmp, lane, warp);
         S.dstart[d] = excl;

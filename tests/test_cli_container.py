@@ -136,3 +136,24 @@ def test_product_cli_round_trip_on_gpu(gen, tmp_path):
         theirs = str(tmp_path / "t.bsc")
         _run(REFCLI, "e", path, theirs, "-b8", "-p", "-t")
         assert open(arch, "rb").read() == open(theirs, "rb").read()
+
+
+@pytest.mark.gpu
+def test_reference_cli_with_our_stage_library_on_gpu(gen, tmp_path):
+    """INTEGRATION.md option 1, executed: oracle/_ref/bsc_dropin = the reference's own bsc.cpp + libbsc.cpp + host stages linked against
+    libbsc_b200.so for the stage entry points.  Its archives must equal the stock reference binary's, each must decode the other's, for
+    BWT and ST blocks, with the reference's default LZP stage on and off."""
+    dropin = os.path.join(REFDIR, "bsc_dropin")
+    if not (os.path.exists(dropin) and os.path.exists(REFCLI)):
+        pytest.skip("oracle/_ref/bsc_dropin not built (needs /root/reference at build time)")
+    path = str(tmp_path / "in.bin")
+    np.concatenate([gen.text(2, 5 << 20), np.tile(gen.text(3, 700), 900), gen.skew(3, 1 << 20)]).tofile(path)
+    for opts in (["-b2", "-p"], ["-b2"], ["-b3", "-m5", "-p"], ["-b2", "-e2", "-p"]):
+        ours, theirs, back = str(tmp_path / "o.bsc"), str(tmp_path / "t.bsc"), str(tmp_path / "b.bin")
+        _run(dropin, "e", path, ours, *opts, "-t")
+        _run(REFCLI, "e", path, theirs, *opts, "-t")
+        assert open(ours, "rb").read() == open(theirs, "rb").read(), opts
+        _run(dropin, "d", theirs, back)
+        assert open(back, "rb").read() == open(path, "rb").read(), opts
+        _run(REFCLI, "d", ours, back)
+        assert open(back, "rb").read() == open(path, "rb").read(), opts
