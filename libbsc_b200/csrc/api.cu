@@ -60,7 +60,6 @@ void ctx_delete(Ctx *c)
     if (c->h_mail) cudaFreeHost(c->h_mail);
     if (c->d_mail) cudaFree(c->d_mail);
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->qlfc_tables) cudaFree(c->qlfc_tables);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream_hi) cudaStreamDestroy(c->stream_hi);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -186,7 +185,7 @@ template <class F> int guarded(Ctx *c, F body)
 
 // arena sizes (bytes) generous enough for each stage at block length n
 size_t need_bwt_encode(size_t n) { return 58 * n + (64u << 20); }
-size_t need_bwt_decode(size_t n) { return 8 * n + (16u << 20); }
+size_t need_bwt_decode(size_t n) { return 10 * n + (16u << 20); }   // L n, LF 4n, look-back n/2, nodes + 128-byte slabs 3.3 n
 size_t need_st_encode(size_t n)  { return 30 * n + (16u << 20); }
 size_t need_st_decode(size_t n)  { return 41 * n + (16u << 20); }
 size_t need_coder(size_t n)      { return 12 * n + (64u << 20); }

@@ -102,7 +102,6 @@ struct Ctx {
     u32         *d_mail = nullptr;      // device mailbox (64 words)
     u8          *h_stage = nullptr;     // pinned staging for host<->device block copies
     size_t       h_stage_cap = 0;
-    void        *qlfc_tables = nullptr; // device copy of the QLFC state tables (lazily uploaded)
     u64          kernels_launched = 0;  // our own kernel launches enqueued through this ctx
     bool         profile = false;       // bracket every launch with CUDA events (bench.py roofline leg)
     double       next_bytes = 0;        // algorithmic bytes of the next launch (PROF_BYTES)

@@ -216,27 +216,30 @@ static int coder_num_blocks(int n)                        // coder.cpp:52-59
     return 8;
 }
 
+// ONE copy of the constant tables per device (never freed: 58 KB), shared by every context: the coders that read the state tables
+// through L1 (LayoutDietTG) then share their cache lines between the CTAs of different blocks on an SM.
 static const QTables *get_tables(Ctx *ctx)
 {
-    if (!ctx->qlfc_tables) {
-        QTables *d = nullptr;
-        // multipliers of the hot counter moves (qlfc_decoder6.cuh), stored right after the tables; filled once (thread-safe static init)
-        struct Moves { int v[QD6_MOVES]; };
-        static const Moves h_moves_ = [] { Moves m; qd6_fill_moves(m.v); return m; }();
-        const int (&h_moves)[QD6_MOVES] = h_moves_.v;
+    static std::mutex m; static QTables *per_device[16] = {};
+    std::lock_guard<std::mutex> lk(m);
+    QTables *&d = per_device[ctx->device & 15];
+    if (!d) {
+        // multipliers of the hot counter moves (qlfc_decoder6.cuh), stored right after the tables
+        int h_moves[QD6_MOVES]; qd6_fill_moves(h_moves);
         // device image: QTables | moves (padded to 128 B) | stretch | squash (the adaptive coder's tables, qlfc_adaptive.cuh)
         static_assert(sizeof(h_moves) <= 128, "moves table slot");
-        CUDA_TRY(cudaMalloc((void **)&d, sizeof(QTables) + 128 + 2 * QA_TAB_BYTES));
-        CUDA_TRY(cudaMemcpyAsync(d->rank_state, bscb_rank_state_tab, 32768, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(d->run_state, bscb_run_state_tab, 8192, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(d + 1, h_moves, sizeof(h_moves), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync((u8 *)(d + 1) + 128, bscb_stretch_le16, 2 * 4097, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync((u8 *)(d + 1) + 128 + QA_TAB_BYTES, bscb_squash_le16, 2 * 4097, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyToSymbolAsync(c_params, bscb_static_params, sizeof(c_params), 0, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->sync();
-        ctx->qlfc_tables = d;
+        QTables *t = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&t, sizeof(QTables) + 128 + 2 * QA_TAB_BYTES));
+        CUDA_TRY(cudaMemcpy(t->rank_state, bscb_rank_state_tab, 32768, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(t->run_state, bscb_run_state_tab, 8192, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(t + 1, h_moves, sizeof(h_moves), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy((u8 *)(t + 1) + 128, bscb_stretch_le16, 2 * 4097, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy((u8 *)(t + 1) + 128 + QA_TAB_BYTES, bscb_squash_le16, 2 * 4097, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpyToSymbol(c_params, bscb_static_params, sizeof(c_params), 0, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaDeviceSynchronize());
+        d = t;
     }
-    return (const QTables *)ctx->qlfc_tables;
+    return d;
 }
 
 // Coder ids (libbsc.h:60-62): 1 static, 2 adaptive, 3 fast -- all three run on the device (parity on the B200: profiles/r2a_call_a.log).
@@ -348,7 +351,11 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     // 110 KB for the decoder), so that TWO coder CTAs share an SM: a coder CTA keeps one scheduler a third busy (ncu: 0.27-0.35
     // issue slots per cycle, profiles/r2a_ncu_coder_kernels_4MiB.txt), and a second stream on the SM costs the first one ~15 %.
     static_assert(((sizeof(CoderSmemT<LayoutEncDiet>) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448 / 2 - 1024, "two encoders must fit one SM");
-    const size_t enc_smem = ((sizeof(CoderSmemT<LayoutEncDiet>) + 15) & ~(size_t)15) + sizeof(EncPipe);
+    static_assert(3 * (((sizeof(CoderSmemT<LayoutEncDietTG>) + 15) & ~(size_t)15) + sizeof(EncPipe) + 1024) <= 232448, "three encoders without resident state tables must fit one SM");
+    // BSCB200_ENC_TG=0: state tables resident (LayoutEncDiet, two encoder CTAs per SM); default: tables through L1, three per SM
+    static const bool enc_tg = [] { const char *e = getenv("BSCB200_ENC_TG"); return !(e && e[0] == '0'); }();
+    const size_t enc_smem = (((enc_tg ? sizeof(CoderSmemT<LayoutEncDietTG>) : sizeof(CoderSmemT<LayoutEncDiet>)) + 15) & ~(size_t)15) + sizeof(EncPipe);
+    auto *const enc_kernel = enc_tg ? q_encode5<LayoutEncDietTG> : q_encode5<LayoutEncDiet>;
     if (fast) {
         LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
         ensure_dyn_smem(q_fast_encode, ctx->device, sizeof(FastSmem));
@@ -362,13 +369,13 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     } else {
         init_models(ctx, models, nBlocks);
         PROF_BYTES(ctx, (double)n);                      // + c written; the launch is latency-, not bandwidth-bound
-        ensure_dyn_smem(q_encode5<LayoutEncDiet>, ctx->device, enc_smem);
+        ensure_dyn_smem(enc_kernel, ctx->device, enc_smem);
         u32 runs[Q_MAX_SUB]; for (int b = 0; b < nBlocks; ++b) runs[b] = h_sb[b].run_end - h_sb[b].run_begin;
         const int n_hi = coder_split_point(runs, enc_order, nBlocks);
         SplitLaunch sl(ctx, nBlocks, n_hi);
         const DoneSignal done{sl.sg.ctr, sl.sg.host_flag, sl.sg.seq, (u32)nBlocks};
-        if (n_hi > 0) { q_encode5<LayoutEncDiet><<<n_hi, QE_THREADS, enc_smem, ctx->stream_hi>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order, done); KERNEL_CHECK(); }
-        q_encode5<LayoutEncDiet><<<nBlocks - n_hi, QE_THREADS, enc_smem, ctx->stream>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)(d_order + n_hi), done); KERNEL_CHECK();
+        if (n_hi > 0) { enc_kernel<<<n_hi, QE_THREADS, enc_smem, ctx->stream_hi>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order, done); KERNEL_CHECK(); }
+        enc_kernel<<<nBlocks - n_hi, QE_THREADS, enc_smem, ctx->stream>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)(d_order + n_hi), done); KERNEL_CHECK();
         sl.finish("q_encode5", n_hi > 0 ? 2 : 1);
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
@@ -422,7 +429,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
                     LAUNCH_LONG(ctx, q_adaptive_encode, 1, 32, QA_BYTES, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 } else {
                     init_models(ctx, models + (size_t)b * MODEL_SHORTS_PAD, 1);
-                    LAUNCH_LONG(ctx, (q_encode5<LayoutEncDiet>), 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
+                    LAUNCH_LONG(ctx, enc_kernel, 1, QE_THREADS, enc_smem, run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_list);
                 }
                 CUDA_TRY(cudaMemcpyAsync(&h_sb[b], d_sb + b, sizeof(SubBlock), cudaMemcpyDeviceToHost, ctx->stream));
                 ctx->sync();
@@ -515,14 +522,26 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
             if (prof) { ensure_dyn_smem(q_decode6<LayoutDiet, true>, ctx->device, LayoutDiet::BYTES);
                         LAUNCH_LONG(ctx, (q_decode6<LayoutDiet, true>), nlist, 32, LayoutDiet::BYTES, d_in, d_sb, models, tables, d_out, d_list); }
             else {
-                ensure_dyn_smem(q_decode6<LayoutDiet, false>, ctx->device, LayoutDiet::BYTES);
                 u32 packed[Q_MAX_SUB]; for (int b = 0; b < Q_MAX_SUB; ++b) packed[b] = h_sb[b].out_cap;
                 const int n_hi = coder_split_point(packed, list, nlist);
-                SplitLaunch sl(ctx, nlist, n_hi);
-                const DoneSignal done{sl.sg.ctr, sl.sg.host_flag, sl.sg.seq, (u32)nlist};
-                if (n_hi > 0) { q_decode6<LayoutDiet, false><<<n_hi, 32, LayoutDiet::BYTES, ctx->stream_hi>>>(d_in, d_sb, models, tables, d_out, (const u32 *)d_list, done); KERNEL_CHECK(); }
-                q_decode6<LayoutDiet, false><<<nlist - n_hi, 32, LayoutDiet::BYTES, ctx->stream>>>(d_in, d_sb, models + (size_t)n_hi * MODEL_SHORTS_PAD, tables, d_out, (const u32 *)(d_list + n_hi), done); KERNEL_CHECK();
-                sl.finish("q_decode6", n_hi > 0 ? 2 : 1);
+                // Streams per SM = how much of the counter file is resident (qlfc_decoder6.cuh).  BSCB200_DEC_PER_SM = 2: LayoutDiet (state
+                // tables resident, 110 KB); 3: LayoutDietTG (tables through L1, 71 KB); 4: LayoutDiet4 (55 KB, rank exponent 4 row-wise);
+                // 5: LayoutDiet5 (39 KB).  A/B on the B200 in profiles/r2i_*.
+                static const int per_sm = [] { const char *e = getenv("BSCB200_DEC_PER_SM"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 5) ? v : QD6_DEFAULT_PER_SM; }();
+                auto launch = [&](auto kernel, size_t smem) {
+                    ensure_dyn_smem(kernel, ctx->device, smem);
+                    SplitLaunch sl(ctx, nlist, n_hi);
+                    const DoneSignal done{sl.sg.ctr, sl.sg.host_flag, sl.sg.seq, (u32)nlist};
+                    if (n_hi > 0) { kernel<<<n_hi, 32, smem, ctx->stream_hi>>>(d_in, d_sb, models, tables, d_out, (const u32 *)d_list, done); KERNEL_CHECK(); }
+                    kernel<<<nlist - n_hi, 32, smem, ctx->stream>>>(d_in, d_sb, models + (size_t)n_hi * MODEL_SHORTS_PAD, tables, d_out, (const u32 *)(d_list + n_hi), done); KERNEL_CHECK();
+                    sl.finish("q_decode6", n_hi > 0 ? 2 : 1);
+                };
+                switch (per_sm) {
+                case 2:  launch(q_decode6<LayoutDiet, false>, LayoutDiet::BYTES); break;
+                case 3:  launch(q_decode6<LayoutDietTG, false>, LayoutDietTG::BYTES); break;
+                case 4:  launch(q_decode6<LayoutDiet4, false>, LayoutDiet4::BYTES); break;
+                default: launch(q_decode6<LayoutDiet5, false>, LayoutDiet5::BYTES); break;
+                }
             }
         }
         CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * Q_MAX_SUB, cudaMemcpyDeviceToHost, ctx->stream));

@@ -21,6 +21,8 @@
 template <u32 MAXE_R_, u32 MAXE_U_, int CLOG_> struct QLayout {
     static constexpr u32 MAXE_R = MAXE_R_, MAXE_U = MAXE_U_;                 // resident mantissa exponents (rank, run length)
     static constexpr bool BR = false;                                        // renormalisation of the range decoder as a rarely taken branch (q_decode8)
+    static constexpr bool TG = false;                                        // state tables resident in shared memory (TablesInGlobal: read through L1)
+    static constexpr u32  SHIFT = 0;                                         // bytes cut off the front of the shared-memory image
     static constexpr u32 ROW_R = (2u << MAXE_R_) - 2u, ROW_U = (2u << MAXE_U_) - 2u;   // compact row: exponent e at offsets 2^e-2 .. 2^(e+1)-3
     // counter file, indices in u16 units (same order as qlfc_coder.cuh)
     static constexpr u32 R_RT_SHARED = 0, R_RT_STATE = 2, R_RT_CHAR = R_RT_STATE + 256;
@@ -50,8 +52,8 @@ template <u32 MAXE_R_, u32 MAXE_U_, int CLOG_> struct QLayout {
 };
 // the same image as a struct (what the encoder uses); for QLayout<5, 5, 12> it is CoderSmem, member for member
 template <class LY> struct CoderSmemT {
-    u8    rank_state[32768];
-    u8    run_state[8192];
+    u8    rank_state[LY::TG ? 16 : 32768];                   // TablesInGlobal: not resident (16-byte placeholders keep the alignment)
+    u8    run_state[LY::TG ? 16 : 8192];
     u16   s16[LY::S16_COUNT];
     u16   tag_state[LY::SLOTS];
     u16   tag_char[LY::SLOTS];
@@ -60,10 +62,23 @@ template <class LY> struct CoderSmemT {
     alignas(16) u8 inwin[256];
 };
 template <class LY_> struct WithBranchRenorm : LY_ { static constexpr bool BR = true; };   // same image, other range-decoder step (qd6_step)
+// The same image WITHOUT its first 40 KB (the two state tables): they are read-only and identical for every stream, so they are read
+// through L1 from the ONE copy per device in global memory (4 one-byte look-ups per run, two of them issued a decision ahead of
+// their use).  All offsets stay as they are: the accessor's base is moved back by SHIFT instead (SM3::b = image - SHIFT; offsets
+// below SHIFT are never used).  70 KB per decoder stream instead of 110: THREE streams per SM.
+template <class LY_> struct TablesInGlobal : LY_ {
+    static constexpr bool TG = true;
+    static constexpr u32  SHIFT = LY_::O_S16;
+    static constexpr u32  BYTES = LY_::BYTES - LY_::O_S16;
+};
 typedef QLayout<5, 5, 12> LayoutFull;     // = qlfc_coder.cuh: 205 KB, one stream per SM
 typedef QLayout<4, 3, 2> LayoutDiet;      // 110 KB, two DEcoder streams per SM: q_decode6 uses no caches (rows instead, see qd6_rows_in), so
                                           // their 8 KB hold the run-mantissa exponent 3 (run lengths 8..15) instead
+typedef TablesInGlobal<LayoutDiet> LayoutDietTG;   // 70.7 KB: three decoder streams per SM
+typedef TablesInGlobal<QLayout<3, 3, 2> > LayoutDiet4;   // 54.7 KB: FOUR per SM; the rank mantissa of exponent 4 (ranks 16..31) goes row-wise too
+typedef TablesInGlobal<QLayout<2, 2, 2> > LayoutDiet5;   // 38.7 KB: five per SM (rank exponents 3, 4 and run exponent 3 row-wise)
 typedef QLayout<4, 1, 10> LayoutEncDiet;  // 106 KB + the encoder's pipe state (5.6 KB): two six-warp encoders per SM
+typedef TablesInGlobal<LayoutEncDiet> LayoutEncDietTG;   // 66 KB + 5.6 KB: three per SM (the model warps gather their states through L1, a batch of 32 runs at a time)
 static_assert(LayoutFull::R_END == R_END && LayoutFull::S16_COUNT == S16_COUNT && LayoutFull::O_S16 == O3_S16, "LayoutFull must reproduce qlfc_coder.cuh");
 static_assert(LayoutFull::R_RM_STATE == R_RM_STATE && LayoutFull::R_UM_CHAR == R_UM_CHAR && LayoutFull::C_CHAR_VAL == C_CHAR_VAL, "LayoutFull must reproduce qlfc_coder.cuh");
 static_assert(sizeof(CoderSmemT<LayoutFull>) == sizeof(CoderSmem) && offsetof(CoderSmemT<LayoutFull>, tag_state) == offsetof(CoderSmem, tag_state) &&
@@ -73,6 +88,40 @@ static_assert(LayoutDiet::BYTES <= 113 * 1024, "two diet decoders must fit one S
 static_assert(LayoutDiet::O_S16 == O3_S16 && (LayoutDiet::O_WIN & 15u) == 0 && (LayoutDiet::O_MTF & 3u) == 0, "alignment of the shared-memory image");
 static_assert((LayoutDiet::O_ROWS & 15u) == 0 && (LayoutFull::O_ROWS & 15u) == 0 && (LayoutDiet::O_TAG_STATE & 3u) == 0, "staged rows are moved 16 bytes at a time");
 static_assert(LayoutFull::BYTES <= 232448, "one full decoder per SM");
+static_assert(3 * (LayoutDietTG::BYTES + 1024) <= 232448, "three decoders without resident state tables must fit one SM");
+#define QD6_DEFAULT_PER_SM 3                             // decoder streams per SM the product launches (qlfc.cu; BSCB200_DEC_PER_SM overrides)
+static_assert(4 * (LayoutDiet4::BYTES + 1024) <= 232448 && 5 * (LayoutDiet5::BYTES + 1024) <= 232448, "four / five decoders per SM");
+static_assert((LayoutDiet4::O_ROWS & 15u) == 0 && (LayoutDiet5::O_ROWS & 15u) == 0 && (LayoutDiet4::O_WIN & 15u) == 0 && (LayoutDiet5::O_WIN & 15u) == 0 &&
+              (LayoutDiet4::O_MTF & 3u) == 0 && (LayoutDiet5::O_MTF & 3u) == 0 && (LayoutDiet4::O_TAG_STATE & 3u) == 0 && (LayoutDiet5::O_TAG_STATE & 3u) == 0, "alignment of the smaller images");
+
+// state-table look-ups: resident image, or the per-device copy in global memory through L1 (LY::TG)
+#ifndef QD6_TABSIM_TOUCH
+#define QD6_TABSIM_TOUCH(i) do { } while (0)     // tools/qdec3_host.cpp -DQD6_TABSIM: LRU model of the L1 lines these look-ups touch
+#endif
+template <class LY> QD3_FN u32 qd6_rank_state(const SM3 &sm, const u8 *__restrict__ tab, u32 idx)
+{
+    if (LY::TG) {
+#ifdef QD3_HOST
+        QD6_TABSIM_TOUCH(idx);
+        return tab[idx];
+#else
+        return (u32)__ldg(tab + idx);
+#endif
+    }
+    return sm.ld8(LY::O_RANK_STATE + idx);
+}
+template <class LY> QD3_FN u32 qd6_run_state(const SM3 &sm, const u8 *__restrict__ tab, u32 idx)
+{
+    if (LY::TG) {
+#ifdef QD3_HOST
+        QD6_TABSIM_TOUCH(32768u + idx);
+        return tab[32768u + idx];
+#else
+        return (u32)__ldg(tab + 32768u + idx);
+#endif
+    }
+    return sm.ld8(LY::O_RUN_STATE + idx);
+}
 
 // Index (into the counter file) of rare counter `idx` through the direct-mapped write-back cache (uniform).
 template <class LY> QD3_FN u32 qd6_cache_get(const SM3 &sm, u32 val_base, u32 tags_off, short *__restrict__ cold, u32 idx, u32 &misses)
@@ -328,8 +377,10 @@ template <class LY> QD3_FN int qd6_prologue(const SM3 &sm, Rc3 &rc, QD3_LREGS_PA
 template <class LY> __device__ __forceinline__ void coder_smem_init_t(CoderSmemT<LY> &S, const QTables *__restrict__ g)
 {
     const u32 lane = threadIdx.x & 31;
-    const uint4 *src = (const uint4 *)g; uint4 *dst = (uint4 *)S.rank_state;      // rank_state and run_state are contiguous
-    for (u32 i = lane; i < sizeof(QTables) / 16; i += 32) dst[i] = src[i];
+    if (!LY::TG) {
+        const uint4 *src = (const uint4 *)g; uint4 *dst = (uint4 *)S.rank_state;  // rank_state and run_state are contiguous
+        for (u32 i = lane; i < sizeof(QTables) / 16; i += 32) dst[i] = src[i];
+    }
     u32 *w = (u32 *)S.s16;
     for (u32 i = lane; i < LY::S16_COUNT / 2; i += 32) w[i] = 0x08000800u;        // every counter starts at 2048
     u32 *t = (u32 *)S.tag_state;
@@ -340,12 +391,14 @@ template <class LY> __device__ __forceinline__ void coder_smem_init_t(CoderSmemT
 template <class LY> __device__ __forceinline__ void qd6_smem_init(u8 *raw, const QTables *__restrict__ g)
 {
     const u32 lane = threadIdx.x & 31;
-    const uint4 *src = (const uint4 *)g; uint4 *dst = (uint4 *)raw;                                   // rank_state and run_state are contiguous
-    for (u32 i = lane; i < sizeof(QTables) / 16; i += 32) dst[i] = src[i];
-    u32 *w = (u32 *)(raw + LY::O_S16);
+    if (!LY::TG) {
+        const uint4 *src = (const uint4 *)g; uint4 *dst = (uint4 *)raw;                               // rank_state and run_state are contiguous
+        for (u32 i = lane; i < sizeof(QTables) / 16; i += 32) dst[i] = src[i];
+    }
+    u32 *w = (u32 *)(raw + (LY::O_S16 - LY::SHIFT));
     for (u32 i = lane; i < LY::S16_COUNT / 2; i += 32) w[i] = 0x08000800u;                            // every counter starts at 2048
-    u32 *t = (u32 *)(raw + LY::O_TAG_STATE);
-    for (u32 i = lane; i < (LY::BYTES - LY::O_TAG_STATE) / 4; i += 32) t[i] = 0;                      // tags, histories, mtf, window
+    u32 *t = (u32 *)(raw + (LY::O_TAG_STATE - LY::SHIFT));
+    for (u32 i = lane; i < (LY::BYTES + LY::SHIFT - LY::O_TAG_STATE) / 4; i += 32) t[i] = 0;          // tags, histories, mtf, window
     __syncwarp();
 }
 
@@ -354,13 +407,13 @@ template <class LY, bool PROF> __global__ void __launch_bounds__(32) q_decode6(c
 {
     extern __shared__ __align__(16) u8 q_smem_raw[];
     qd6_smem_init<LY>(q_smem_raw, tables);
-    SM3 sm; sm.b = (u32)__cvta_generic_to_shared(q_smem_raw);
+    SM3 sm; sm.b = (u32)__cvta_generic_to_shared(q_smem_raw) - LY::SHIFT;        // u32 wrap-around is intended: every offset used is >= SHIFT
     asm volatile("" : "+r"(sm.b) :: "memory");
     const u32 sid = sb_list[blockIdx.x];
     SubBlock &sb = sbs[sid];
     short *cold_s = cold_all + (size_t)blockIdx.x * 2 * COLD_PAD, *cold_c = cold_s + COLD_PAD;
     u32 st_cached = 0, st_miss = 0;
-    const int r = qd6_decode_stream<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), st_cached, st_miss);
+    const int r = qd6_decode_stream<LY, PROF>(sm, in_all + sb.out_off, sb.out_cap, out_all + sb.in_start, sb.in_size, cold_s, cold_c, (const int *)(tables + 1), (const u8 *)tables, st_cached, st_miss);
     __syncwarp();                                        // every lane's output stores precede lane 0's report
     if (threadIdx.x == 0) { sb.result = r; sb.stat_cached = st_cached; sb.stat_miss = st_miss; signal_done(done); }
 }

@@ -430,7 +430,7 @@ template <class LY> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(c
         if (rank_side) {
             const u32 er_prev = __shfl_sync(0xffffffffu, er, prevl);
             const u32 rh = below ? er_prev : (u32)my_hist[sym & 255u];             // rankHistory = exponent of the previous rank (0 for rank 1)
-            my_st = S.rank_state[(ctxRun << 11) | (ctxRank4 << 3) | rh];
+            { const u32 ti = (ctxRun << 11) | (ctxRank4 << 3) | rh; my_st = LY::TG ? (u32)__ldg(tables->rank_state + ti) : (u32)S.rank_state[LY::TG ? 0 : ti]; }
             __syncwarp();
             if (last_of_sym) my_hist[sym] = (u8)er;
         } else {
@@ -440,7 +440,7 @@ template <class LY> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(c
                 const u32 t = __shfl_sync(0xffffffffu, vout, prevl);
                 if (occ == round) { if (round) vin = t; vout = (len == 1) ? (vin + 2u) >> 2 : (vin + 3u * eu + 3u) >> 2; }
             }
-            my_st = S.run_state[(ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7 ? rank0 : 7u) << 3) | (vin < 7 ? vin : 7u)];
+            { const u32 ti = (ctxRank0 << 10) | (ctxRun << 6) | ((rank0 < 7 ? rank0 : 7u) << 3) | (vin < 7 ? vin : 7u); my_st = LY::TG ? (u32)__ldg(tables->run_state + ti) : (u32)S.run_state[LY::TG ? 0 : ti]; }
             __syncwarp();
             if (last_of_sym) my_hist[sym] = (u8)vout;
         }

@@ -65,7 +65,7 @@ def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
             r, s = enc.encode_block(a)
             if r <= 0:
                 continue                                              # not compressible: the container stores it raw
-            for mode in (1, 0):                                       # the product's diet layout, the full layout
+            for mode in (2, 1, 0):                                    # the product layout (tables in global memory), diet, full
                 n, out, stats = qdec3(s, a.size, mode)
                 assert n == a.size, (name, mode, n)
                 assert np.array_equal(out, a), (name, mode)
@@ -159,13 +159,14 @@ def test_layout_templated_decoder_host_emulation(gen, checker, port):
         r, s = checker.encode_block(a)
         if r <= 0:
             continue
-        for layout in (0, 1):
+        for layout in (0, 1, 2):
             out = np.full(a.size + 64, 0xAA, dtype=np.uint8)
             stats = (ctypes.c_uint * 2)()
             s_ = np.ascontiguousarray(s)
             n = lib.qdec6_host_decode(s_.ctypes.data, s_.size, out.ctypes.data, a.size, stats, layout)
             assert n == a.size and np.array_equal(out[:a.size], a) and np.all(out[a.size:] == 0xAA), (name, layout)
-            rare[layout & 1] += stats[0]
+            if layout < 2:
+                rare[layout] += stats[0]
         covered += 1
     assert covered >= 8
     assert rare[1] > rare[0]                                                      # the diet layout really has more row events (stats[0] = 2 per event)
@@ -184,7 +185,7 @@ def test_escape_mode_rows_instead_of_cache_misses(gen, checker):
     assert r > 0
     s_ = np.ascontiguousarray(s)
     runs = int((np.diff(a.astype(np.int16)) != 0).sum() + 1)
-    for layout in (0, 1):
+    for layout in (0, 1, 2):
         out = np.full(a.size + 64, 0xAA, dtype=np.uint8)
         stats = (ctypes.c_uint * 2)()
         n = lib.qdec6_host_decode(s_.ctypes.data, s_.size, out.ctypes.data, a.size, stats, layout)

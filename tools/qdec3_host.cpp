@@ -31,6 +31,33 @@ static inline void __syncwarp() {}
 #include "../libbsc_b200/csrc/qlfc_tables.inc"
 #include "../libbsc_b200/csrc/qlfc_tables2.inc"
 
+#ifdef QD6_TABSIM
+// LRU model of the L1 behind the state-table look-ups of a TablesInGlobal layout: fully associative, 128-byte lines, three capacities.
+// (diagnostic build only: g++ -DQD6_TABSIM; results in DESIGN.md 4.5)
+static const int TS_CAP[3] = {64, 128, 224};
+static struct { unsigned line[224]; int n; unsigned long long hit, miss; } ts_lru[3];
+static unsigned long long ts_touch = 0; static unsigned char ts_seen[41 * 1024 / 128 + 1];
+static void tabsim_touch(unsigned idx)
+{
+    const unsigned ln = idx >> 7; ++ts_touch; ts_seen[ln] = 1;
+    for (int c = 0; c < 3; ++c) {
+        auto &L = ts_lru[c]; int k = 0;
+        while (k < L.n && L.line[k] != ln) ++k;
+        if (k < L.n) ++L.hit; else { ++L.miss; if (L.n < TS_CAP[c]) k = L.n++; else k = L.n - 1; }
+        for (; k > 0; --k) L.line[k] = L.line[k - 1];
+        L.line[0] = ln;
+    }
+}
+#define QD6_TABSIM_TOUCH(i) tabsim_touch(i)
+extern "C" void qdec6_tabsim_report(unsigned long long *out)       // touches, distinct lines, then (hits, misses) x 3 capacities; resets
+{
+    unsigned d = 0; for (unsigned i = 0; i < sizeof(ts_seen); ++i) d += ts_seen[i];
+    out[0] = ts_touch; out[1] = d;
+    for (int c = 0; c < 3; ++c) { out[2 + 2 * c] = ts_lru[c].hit; out[3 + 2 * c] = ts_lru[c].miss; }
+    memset(ts_lru, 0, sizeof(ts_lru)); memset(ts_seen, 0, sizeof(ts_seen)); ts_touch = 0;
+}
+#endif
+
 namespace {
 enum { K_RANK_T, K_RANK_E, K_RANK_M, K_RANK_P, K_RUN_T, K_RUN_E, K_RUN_M };
 struct SubBlock { u32 in_start, in_size, run_begin, run_end, out_off, out_cap; int result; u32 nsym, tile_base, tiles, stat_cached, stat_miss; };
@@ -84,9 +111,15 @@ extern "C" int qfast_host_encode(const unsigned *run_pos, const unsigned char *r
 }
 
 // ---- layout-templated serial decoder (libbsc_b200/csrc/qlfc_decoder6.cuh): layout 0 = full (205 KB), 1 = diet (101 KB) ------------
+static const QTables *host_tables()
+{
+    static QTables t; static bool ready = false;
+    if (!ready) { memcpy(t.rank_state, bscb_rank_state_tab, 32768); memcpy(t.run_state, bscb_run_state_tab, 8192); ready = true; }
+    return &t;
+}
 template <class LY> static int qdec6_run(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats)
 {
-    u8 *smem = (u8 *)calloc(1, LY::BYTES);
+    u8 *smem = (u8 *)calloc(1, LY::BYTES + LY::SHIFT);       // the host keeps the whole image; a TG layout just never reads its first SHIFT bytes
     short *cold = (short *)malloc(sizeof(short) * 2 * (size_t)COLD_PAD);
     if (!smem || !cold) { free(smem); free(cold); return LIBBSC_NOT_ENOUGH_MEMORY; }
     memcpy(smem + LY::O_RANK_STATE, bscb_rank_state_tab, 32768);
@@ -96,7 +129,7 @@ template <class LY> static int qdec6_run(const unsigned char *in, unsigned in_si
     SM3 sm; sm.b = smem;
     u32 st_cached = 0, st_miss = 0;
     int moves[QD6_MOVES]; qd6_fill_moves(moves);
-    const int r = qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, st_cached, st_miss);
+    const int r = qd6_decode_stream<LY, false>(sm, in, in_size, out, out_cap, cold, cold + COLD_PAD, moves, (const u8 *)host_tables(), st_cached, st_miss);
     if (stats) { stats[0] = st_cached; stats[1] = st_miss; }
     free(smem); free(cold);
     return r;
@@ -104,9 +137,12 @@ template <class LY> static int qdec6_run(const unsigned char *in, unsigned in_si
 extern "C" int qdec6_host_decode(const unsigned char *in, unsigned in_size, unsigned char *out, unsigned out_cap, unsigned *stats, int layout)
 {
     return layout == 0 ? qdec6_run<LayoutFull>(in, in_size, out, out_cap, stats)         // 0: the full layout (what the adaptive coder derives from)
-                       : qdec6_run<LayoutDiet>(in, in_size, out, out_cap, stats);        // 1: the product's layout
+         : layout == 1 ? qdec6_run<LayoutDiet>(in, in_size, out, out_cap, stats)         // 1: two streams per SM
+         : layout == 2 ? qdec6_run<LayoutDietTG>(in, in_size, out, out_cap, stats)       // 2: state tables in global memory, three per SM
+         : layout == 3 ? qdec6_run<LayoutDiet4>(in, in_size, out, out_cap, stats)        // 3: four per SM
+                       : qdec6_run<LayoutDiet5>(in, in_size, out, out_cap, stats);       // 4: five per SM
 }
-extern "C" unsigned qdec6_smem_bytes(int layout) { return layout == 0 ? LayoutFull::BYTES : LayoutDiet::BYTES; }
+extern "C" unsigned qdec6_smem_bytes(int layout) { return layout == 0 ? LayoutFull::BYTES : layout == 1 ? LayoutDiet::BYTES : layout == 2 ? LayoutDietTG::BYTES : layout == 3 ? LayoutDiet4::BYTES : LayoutDiet5::BYTES; }
 
 // ---- adaptive coder (coder id 2), libbsc_b200/csrc/qlfc_adaptive.cuh ---------------------------------------------------
 static u8 *adaptive_smem_new(short **cold_out)
