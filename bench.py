@@ -55,8 +55,9 @@ def parse_args():
                                                          "streams keep the 296 coder slots of a B200 (two per SM) full while the others sort")
     ap.add_argument("--sorter", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="pipeline", choices=["phased", "pipeline"], help="order of the work inside the timed steps (see class Steps)")
+    ap.add_argument("--mode", default="pipeline", choices=["phased", "pipeline"], help="order of the work inside the timed steps of the device-resident leg (see class Steps); the e2e leg always flows as a pipeline")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=6, help="the end-to-end (host buffer) leg times min(--steps, this) steps, so that a long --steps run still ends within minutes")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the extra keys for BASELINE configs C2 / C3-strong / C4 / C5")
     return ap.parse_args()
 
@@ -193,13 +194,15 @@ def workload_config(args, extra=None):
 
 # ------------------------------------------------------------------------------------------------
 class Pipeline:
-    """K steps of the batch as ONE continuous flow: W worker threads (one context / one stream each) take (step, block) tasks in order
-    and run compress -> decompress on each.  Blocks are at different stages at any moment, so the HBM-bound sorts of some overlap the
-    latency-bound coder kernels of others, and the SMs a short coder stream frees are taken by the next block's streams."""
+    """K steps of the batch as ONE continuous flow: W worker threads (one context / one stream / one pair of output buffers each) take
+    (step, block) tasks in order and run task(worker, block) on each.  Blocks are at different stages at any moment, so the HBM-bound
+    sorts of some overlap the latency-bound coder kernels of others, and the SM slots a short coder stream frees are taken by the
+    next block's streams.  W (blocks in flight) is independent of the number of blocks per step."""
 
-    def __init__(self, nb, workers, task):
+    def __init__(self, nb, workers, task, block_buffers=False):
         self.nb, self.workers, self.task = nb, workers, task
-        self.block_lock = [threading.Lock() for _ in range(nb)]     # a block's buffers belong to one task at a time (step s+1 may catch up with step s)
+        # block_buffers: the task writes per-BLOCK buffers (extra_configs), so a block belongs to one task at a time (step s+1 may catch up with step s)
+        self.block_lock = [threading.Lock() for _ in range(nb)] if block_buffers else None
 
     def run(self, steps):
         lock, nxt, errs = threading.Lock(), [0], []
@@ -212,12 +215,14 @@ class Pipeline:
                         t = nxt[0]; nxt[0] += 1
                     if t >= total or errs:
                         return
-                    i = t % self.nb
-                    with self.block_lock[i]:
-                        self.task(w, i)
+                    if self.block_lock:
+                        with self.block_lock[t % self.nb]:
+                            self.task(w, t % self.nb)
+                    else:
+                        self.task(w, t % self.nb)
             except BaseException as ex:                              # surface the first failure, stop the others
                 errs.append(ex)
-        ths = [threading.Thread(target=loop, args=(w,)) for w in range(self.workers)]
+        ths = [threading.Thread(target=loop, args=(w,)) for w in range(min(self.workers, total))]
         for t in ths:
             t.start()
         for t in ths:
@@ -245,7 +250,7 @@ def extra_configs(args, rank, local_rank, world, L, gen, torch, dist, dev):
             barrier(); barrier()
             ms = 0.0
         else:
-            pipe = Pipeline(nb, nb, task)
+            pipe = Pipeline(nb, nb, task, block_buffers=True)
             pipe.run(1)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -336,31 +341,46 @@ def run_b200(args, rank, local_rank, world):
     gen = pyoracle.Gen()
     nb, bb = args.blocks, args.block_mib << 20
     host_blocks = make_blocks(gen, 2 + rank, nb, bb)
-    workers = min(args.workers or nb, nb)
+    workers = args.workers or nb                         # blocks in flight = contexts = worker threads; independent of the blocks per step
 
     # ---- device-resident leg ------------------------------------------------------------------
+    # inputs per block; compressed / restored buffers per WORKER (a task = compress block i, then decompress it, on one context),
+    # plus one compressed buffer per block for the passes that run each direction alone
     d_in = [torch.from_numpy(b).to(dev) for b in host_blocks]
-    d_cmp = [torch.empty(bb + 28 + 64, dtype=torch.uint8, device=dev) for _ in range(nb)]
-    d_back = [torch.empty(bb + 64, dtype=torch.uint8, device=dev) for _ in range(nb)]
+    d_cmp = [torch.empty(bb + 28 + 64, dtype=torch.uint8, device=dev) for _ in range(workers)]
+    d_back = [torch.empty(bb + 64, dtype=torch.uint8, device=dev) for _ in range(workers)]
+    d_cmp_blk = [torch.empty(bb + 28 + 64, dtype=torch.uint8, device=dev) for _ in range(nb)]
     ctxs = [libbsc_b200.DeviceCtx(local_rank) for _ in range(workers)]
     ws = int(L.bscb200_workspace_bytes(bb, args.sorter))
     for c in ctxs:
         assert c.reserve(ws) == 0, "workspace allocation failed"
     csize = [0] * nb
+    last = [-1] * workers                                # block whose restored bytes sit in d_back[w]
 
-    def dev_compress(w, i):
+    def dev_compress(w, i, dst=None):
         # +4: payload (offset 28) 16-byte aligned for the vectorised device adler32
-        r = ctxs[w].compress(d_in[i].data_ptr(), d_cmp[i].data_ptr() + 4, bb, args.sorter, 1, 3)
+        r = ctxs[w].compress(d_in[i].data_ptr(), (d_cmp[w] if dst is None else dst).data_ptr() + 4, bb, args.sorter, 1, 3)
         assert r > 0, "compress failed: %d" % r
         csize[i] = r
 
-    def dev_decompress(w, i):
-        r = ctxs[w].decompress(d_cmp[i].data_ptr() + 4, csize[i], d_back[i].data_ptr(), bb, 3)
+    def dev_decompress(w, i, src=None):
+        r = ctxs[w].decompress((d_cmp[w] if src is None else src).data_ptr() + 4, csize[i], d_back[w].data_ptr(), bb, 3)
         assert r == 0, "decompress failed: %d" % r
+        last[w] = i
 
     def dev_task(w, i):
         torch.cuda.set_device(local_rank)
         dev_compress(w, i); dev_decompress(w, i)
+
+    def dev_compress_blk(w, i):
+        dev_compress(w, i, d_cmp_blk[i])
+
+    def dev_decompress_blk(w, i):
+        dev_decompress(w, i, d_cmp_blk[i])
+
+    def dev_verify_blk(w, i):                            # every block restored once more and compared (outside every timed region)
+        dev_decompress(w, i, d_cmp_blk[i])
+        assert torch.equal(d_back[w][:bb], d_in[i]), "round trip mismatch in block %d" % i
 
     def barrier():
         torch.cuda.synchronize()
@@ -394,7 +414,7 @@ def run_b200(args, rank, local_rank, world):
                 for _ in range(steps):
                     self.comp.run(1); self.decomp.run(1)
 
-    pipe = Steps(dev_task, dev_compress, dev_decompress)
+    pipe = Steps(dev_task, dev_compress_blk, dev_decompress_blk)
     pipe.run(args.warmup)
     for c in ctxs:
         c.set_profile(True)
@@ -405,8 +425,8 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     clocks = sampler.stop()
     launches = sum(c.launches() for c in ctxs) - launches0
-    for i in range(nb):
-        assert torch.equal(d_back[i][:bb], d_in[i]), "round trip mismatch in block %d" % i
+    for w in range(workers):                             # what the timed steps left behind: each worker's last block
+        assert last[w] < 0 or torch.equal(d_back[w][:bb], d_in[last[w]]), "round trip mismatch in block %d" % last[w]
     # per-kernel CUDA-event timings gathered during the timed steps
     kern = {}
     for c in ctxs:
@@ -415,17 +435,18 @@ def run_b200(args, rank, local_rank, world):
         c.set_profile(False)
 
     # phase-separated pass (extra keys): all blocks compressed, drain, all blocks decompressed -- what each direction does alone
-    ms_c = timed(lambda: Pipeline(nb, workers, lambda w, i: (torch.cuda.set_device(local_rank), dev_compress(w, i))).run(1))
-    ms_d = timed(lambda: Pipeline(nb, workers, lambda w, i: (torch.cuda.set_device(local_rank), dev_decompress(w, i))).run(1))
+    ms_c = timed(lambda: Pipeline(nb, workers, phase(dev_compress_blk)).run(1))
+    ms_d = timed(lambda: Pipeline(nb, workers, phase(dev_decompress_blk)).run(1))
+    Pipeline(nb, workers, phase(dev_verify_blk)).run(1)
 
     # standalone pass: ONE block at a time on one stream, so that the per-launch durations of the
     # bandwidth-bound kernels are not stretched by the other blocks sharing HBM (roofline leg)
     alone = {}
     ctxs[0].set_profile(True)
     for i in range(min(2, nb)):
-        csz_i = ctxs[0].compress(d_in[i].data_ptr(), d_cmp[i].data_ptr() + 4, bb, args.sorter, 1, 3)
+        csz_i = ctxs[0].compress(d_in[i].data_ptr(), d_cmp[0].data_ptr() + 4, bb, args.sorter, 1, 3)
         assert csz_i == csize[i]
-        assert ctxs[0].decompress(d_cmp[i].data_ptr() + 4, csz_i, d_back[i].data_ptr(), bb, 3) == 0
+        assert ctxs[0].decompress(d_cmp[0].data_ptr() + 4, csz_i, d_back[0].data_ptr(), bb, 3) == 0
     for name, (cnt, ms, by) in ctxs[0].profile_report().items():
         alone[name] = [cnt, ms, by]
     ctxs[0].set_profile(False)
@@ -444,32 +465,25 @@ def run_b200(args, rank, local_rank, world):
     if not args.no_e2e:
         for c in ctxs:
             c.close()
-        del d_cmp, d_back, d_in
+        del d_cmp, d_back, d_in, d_cmp_blk
         torch.cuda.empty_cache()
 
         def host_leg(pinned, steps, warm):
             mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
             h_in = [mk(torch.from_numpy(b)) for b in host_blocks]
-            h_cmp = [mk(torch.empty(bb + 28 + 64, dtype=torch.uint8)) for _ in range(nb)]
-            h_back = [mk(torch.zeros(bb + 64, dtype=torch.uint8)) for _ in range(nb)]
-            hsize = [0] * nb
+            h_cmp = [mk(torch.empty(bb + 28 + 64, dtype=torch.uint8)) for _ in range(workers)]      # per worker, as in the device leg
+            h_back = [mk(torch.zeros(bb + 64, dtype=torch.uint8)) for _ in range(workers)]
+            hsize, hlast = [0] * nb, [-1] * workers
 
             def host_task(w, i):
                 torch.cuda.set_device(local_rank)
-                r = L.bsc_compress(h_in[i].data_ptr(), h_cmp[i].data_ptr(), bb, 0, 0, args.sorter, 1, 3)
+                r = L.bsc_compress(h_in[i].data_ptr(), h_cmp[w].data_ptr(), bb, 0, 0, args.sorter, 1, 3)
                 assert r > 0, "bsc_compress failed: %d" % r
                 hsize[i] = r
-                r = L.bsc_decompress(h_cmp[i].data_ptr(), hsize[i], h_back[i].data_ptr(), bb, 3)
+                r = L.bsc_decompress(h_cmp[w].data_ptr(), hsize[i], h_back[w].data_ptr(), bb, 3)
                 assert r == 0, "bsc_decompress failed: %d" % r
-            def host_comp(w, i):
-                r = L.bsc_compress(h_in[i].data_ptr(), h_cmp[i].data_ptr(), bb, 0, 0, args.sorter, 1, 3)
-                assert r > 0, "bsc_compress failed: %d" % r
-                hsize[i] = r
-
-            def host_decomp(w, i):
-                r = L.bsc_decompress(h_cmp[i].data_ptr(), hsize[i], h_back[i].data_ptr(), bb, 3)
-                assert r == 0, "bsc_decompress failed: %d" % r
-            hp = Steps(host_task, host_comp, host_decomp)
+                hlast[w] = i
+            hp = Pipeline(nb, workers, host_task)
             if warm:
                 hp.run(warm)
             l0 = int(L.bscb200_total_kernel_launches())
@@ -477,11 +491,12 @@ def run_b200(args, rank, local_rank, world):
             ms = timed(lambda: hp.run(steps)) / steps
             barrier()
             nl = int(L.bscb200_total_kernel_launches()) - l0
-            for i in range(nb):
-                assert torch.equal(h_back[i][:bb], h_in[i]), "e2e round trip mismatch in block %d" % i
+            for w in range(workers):
+                assert hlast[w] < 0 or torch.equal(h_back[w][:bb], h_in[hlast[w]]), "e2e round trip mismatch in block %d" % hlast[w]
             return ms, nl, int(sum(hsize))
 
-        ms_e, nl, hbytes = host_leg(True, args.steps, max(1, args.warmup - 1))
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        ms_e, nl, hbytes = host_leg(True, e2e_steps, max(1, min(args.warmup, 3) - 1))
         launches += nl
         ms_p, _, _ = host_leg(False, 1, 1)               # the C API takes any host pointer: the same call from PAGEABLE memory, one step
         if dist is not None:
@@ -489,7 +504,7 @@ def run_b200(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e, ms_p = float(t[0]), float(t[1])
         e2e = {"value": total_mb / (ms_e / 1e3), "unit": "MB/s", "h2d_bytes_per_step": nb * bb + hbytes, "d2h_bytes_per_step": hbytes + nb * bb,
-               "ms_per_step": ms_e, "host_memory": "pinned", "pageable": {"value": total_mb / (ms_p / 1e3), "unit": "MB/s", "steps": 1}}
+               "ms_per_step": ms_e, "steps": e2e_steps, "host_memory": "pinned", "pageable": {"value": total_mb / (ms_p / 1e3), "unit": "MB/s", "steps": 1}}
 
     extras = None
     if args.extras:

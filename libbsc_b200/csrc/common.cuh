@@ -138,10 +138,12 @@ struct Ctx {
     DoneSignalArgs next_signal() { ++done_seq; return DoneSignalArgs{d_mail + 128, h_mail + 250, done_seq}; }
     void wait_signal() {
         volatile u32 *flag = (volatile u32 *)(h_mail + 250);
-        unsigned us = 20, slept = 0;
+        // 20 us steps growing to 0.4 ms, and to 2 ms once the kernel has run for 50 ms (a coder launch takes 0.1 - 2 s; with 8 ranks x 64+
+        // waiting threads per host the wake-ups themselves must stay cheap)
+        unsigned us = 20, slept = 0, total = 0;
         while (*flag != done_seq) {
             struct timespec ts = {0, (long)us * 1000L}; nanosleep(&ts, nullptr);
-            slept += us; if (us < 400) us += us / 2;
+            slept += us; total += us; if (us < (total > 50000 ? 2000u : 400u)) us += us / 2;
             if (slept > 200000) {                            // every 0.2 s: has the stream died (launch failure, kernel fault)?
                 slept = 0;
                 cudaError_t e = cudaStreamQuery(stream);
@@ -200,11 +202,13 @@ template <typename F> static inline void ensure_dyn_smem(F *kernel, int device, 
 }
 
 #define PROF_BYTES(ctx, b) do { (ctx)->next_bytes = (double)(b); } while (0)
-#define LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
+#define LAUNCH(ctx, kernel, grid, block, smem, ...) LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
+// the same for a kernel chosen at run time (a function pointer): `name` is what the profile reports
+#define LAUNCH_NAMED(ctx, name, kernel, grid, block, smem, ...) do { \
         Ctx *c_ = (ctx); cudaEvent_t ea_ = nullptr, eb_ = nullptr; const bool p_ = c_->profile; \
         if (p_) { ea_ = c_->ev(); eb_ = c_->ev(); CUDA_TRY(cudaEventRecord(ea_, c_->stream)); } \
         kernel<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__); KERNEL_CHECK(); \
-        if (p_) { CUDA_TRY(cudaEventRecord(eb_, c_->stream)); c_->prof.push_back(ProfRec{#kernel, ea_, eb_, c_->next_bytes}); } \
+        if (p_) { CUDA_TRY(cudaEventRecord(eb_, c_->stream)); c_->prof.push_back(ProfRec{name, ea_, eb_, c_->next_bytes}); } \
         c_->next_bytes = 0; c_->kernels_launched++; } while (0)
 
 // A launch that the host waits for before anything else goes onto the stream (Ctx::wait_signal): the kernel takes a DoneSignal as its

@@ -103,7 +103,7 @@ template <> __device__ __forceinline__ u32 rs_all_ones<u32>() { return ~0u; }
 // free -- in the compress / decompress pipeline the sorts run in those halves, and at 59 KB (u32 warp histograms) only one fitted.
 template <typename K, bool HAS_VAL> struct RsSmem {
     u16 whist[RS_WARPS][256];                            // per-warp digit counts (<= 512), then exclusive prefixes over the warps (< 4096)
-    u32 dstart[256];
+    u32 dstart[256];                                     // (folding dstart into whist saves a load per item but made ptxas spill 40 - 100 bytes: kept apart)
     u32 gbase[256];
     u32 nexthist[256];
     u32 scan_tmp[RS_WARPS];
@@ -127,8 +127,10 @@ __device__ __forceinline__ u32 rs_block_excl_scan(u32 v, u32 *tmp, u32 lane, u32
     return woff + incl - v;
 }
 
-template <typename K, bool HAS_VAL, class Src>
-__global__ void __launch_bounds__(RS_THREADS, 3)
+// MINB = CTAs per SM the register budget is cut for: 3 -> 80 registers (37 % occupancy), 4 -> 64 registers without spills (50 %); four
+// 56 KB CTAs fill the 228 KB of an SM.  A/B on the B200: profiles/r2j_*.
+template <typename K, bool HAS_VAL, class Src, int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB)
 rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int shift, int bits,
             const u32 *__restrict__ hist_in, u32 *__restrict__ hist_next, int shift2, int bits2,
             u32 *tile_counter, u64 *lookback)
@@ -175,6 +177,7 @@ rs_onesweep(Src src, K *__restrict__ kout, u32 *__restrict__ vout, u32 n, int sh
     {
         const u32 d = tid;                               // RS_THREADS == 256 digits
         u32 run = 0;
+#pragma unroll
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { u32 t = S.whist[w][d]; S.whist[w][d] = (u16)run; run += t; }
         const u32 count = run;
@@ -369,6 +372,7 @@ rs_onesweep_tma(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
 // tile while it still works on the current one, so that tile's aggregate reaches the look-back a whole tile time later and the chain of
 // waits grows (long_scoreboard + branch_resolving 12.4 of 24.5 cycles per instruction); it also takes 109 KB of shared memory per CTA, which
 // no SM half next to a coder CTA can give.  So it is not the default; it stays selectable and parity-tested.
+static inline int rs_min_blocks() { static const int v = [] { const char *e = getenv("BSCB200_SORT_OCC"); return (e && e[0] == '3') ? 3 : 4; }(); return v; }
 static inline bool rs_use_tma() { static const bool on = [] { const char *e = getenv("BSCB200_SORT_TMA"); return e && e[0] == '1'; }(); return on; }
 
 // Scratch needed by one sort (histograms, tile counters, look-back descriptors).
@@ -397,8 +401,11 @@ static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32
     LAUNCH(ctx, (rs_hist1<FirstSrc>), hgrid, RS_THREADS, 0, first, n, (int)passes.shift[0], (int)passes.bits[0], ghist);
 
     const size_t smem = sizeof(RsSmem<K, HAS_VAL>);
-    ensure_dyn_smem(rs_onesweep<K, HAS_VAL, FirstSrc>, ctx->device, smem);
-    ensure_dyn_smem(rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>, ctx->device, smem);
+    const bool occ4 = rs_min_blocks() == 4;
+    auto *const k_first = occ4 ? rs_onesweep<K, HAS_VAL, FirstSrc, 4> : rs_onesweep<K, HAS_VAL, FirstSrc, 3>;
+    auto *const k_next  = occ4 ? rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>, 4> : rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>, 3>;
+    ensure_dyn_smem(k_first, ctx->device, smem);
+    ensure_dyn_smem(k_next, ctx->device, smem);
     const size_t smem_tma = sizeof(RsSmemTma<K, HAS_VAL>);
     ensure_dyn_smem(rs_onesweep_tma<K, HAS_VAL>, ctx->device, smem_tma);
 
@@ -410,11 +417,11 @@ static int rs_sort(Ctx *ctx, FirstSrc first, K *const k[2], u32 *const v[2], u32
         const int s2 = more ? (int)passes.shift[p + 1] : 0, b2 = more ? (int)passes.bits[p + 1] : 1;
         PROF_BYTES(ctx, pass_bytes);
         if (p == 0) {
-            LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, FirstSrc>), tiles, RS_THREADS, smem,
+            LAUNCH_NAMED(ctx, "rs_onesweep", k_first, tiles, RS_THREADS, smem,
                    first, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, hnext, s2, b2, counters + p, lb);
         } else if (!rs_use_tma()) {
             SrcArray<K, HAS_VAL> src{k[dst ^ 1], v[dst ^ 1]};
-            LAUNCH(ctx, (rs_onesweep<K, HAS_VAL, SrcArray<K, HAS_VAL>>), tiles, RS_THREADS, smem,
+            LAUNCH_NAMED(ctx, "rs_onesweep", k_next, tiles, RS_THREADS, smem,
                    src, k[dst], v[dst], n, (int)passes.shift[p], (int)passes.bits[p], ghist + 256 * p, hnext, s2, b2, counters + p, lb);
         } else {
             const u32 grid = min(tiles, (u32)(B200_SMS * 2));                // persistent: two CTAs per SM, each loops over tiles

@@ -1,10 +1,10 @@
 #!/bin/bash
-# tools/r2_call_i.sh -- round 2, ninth GPU call: state tables through L1 (3 / 4 / 5 decoder streams per SM, 3 encoders per SM): parity, one block
+# tools/r2_call_i.sh -- round 2, ninth GPU call: state tables through L1 (3 / 4 / 5 decoder streams per SM, 3 encoders per SM; sort at 4 CTAs per SM = 64 registers): parity, one block
 # alone, pipeline A/B; then the full default bench with the winner and the reference arm at N = 1.
 mkdir -p gpurun_out
 run() { name=$1; shift; envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
   env "${envs[@]}" timeout 500 python bench.py "$@" --no-cpu-baseline --no-e2e --no-extras --steps 3 --warmup 1 > gpurun_out/r2i_$name.json 2> gpurun_out/r2i_$name.err
-  python -c "import json;d=json.load(open('gpurun_out/r2i_$name.json'));print('$name: value', round(d['value'],1), 'compress', round(d['compress_MBps'],1), 'decompress', round(d['decompress_MBps'],1), 'ms/step', round(d['ms_per_step']))" || tail -5 gpurun_out/r2i_$name.err
+  python -c "import json;d=json.load(open('gpurun_out/r2i_$name.json'));print('$name: value', round(d['value'],1), 'compress', round(d['compress_MBps'],1), 'decompress', round(d['decompress_MBps'],1), 'ms/step', round(d['ms_per_step']), 'rs_onesweep alone GB/s', (d.get('roofline_hbm_kernel') or {}).get('achieved'))" || tail -5 gpurun_out/r2i_$name.err
 }
 {
 echo "== 1. parity at the new defaults (3 decoder / 3 encoder streams per SM, state tables through L1)"
@@ -15,7 +15,8 @@ BSCB200_DEC_PER_SM=5 timeout 600 python -m pytest tests/test_gpu_parity.py -m gp
 echo "== 2. one 64 MiB block alone: coder kernel times by layout"
 for p in 2 3 4 5; do echo "-- DEC_PER_SM=$p ENC_TG=$([ $p = 2 ] && echo 0 || echo 1)"; BSCB200_DEC_PER_SM=$p BSCB200_ENC_TG=$([ $p = 2 ] && echo 0 || echo 1) timeout 300 python tools/dec_ab.py 64 2>&1 | tail -2; done
 echo "== 3. pipeline A/B"
-run base_2_64   BSCB200_DEC_PER_SM=2 BSCB200_ENC_TG=0 -- --blocks 64
+run base_2_64   BSCB200_DEC_PER_SM=2 BSCB200_ENC_TG=0 BSCB200_SORT_OCC=3 -- --blocks 64
+run base_2_64_sortocc4 BSCB200_DEC_PER_SM=2 BSCB200_ENC_TG=0 -- --blocks 64
 run dec3_enc2_64 BSCB200_DEC_PER_SM=3 BSCB200_ENC_TG=0 -- --blocks 64
 run dec3_enc3_64 BSCB200_DEC_PER_SM=3 BSCB200_ENC_TG=1 -- --blocks 64
 run dec3_enc3_96 BSCB200_DEC_PER_SM=3 BSCB200_ENC_TG=1 -- --blocks 96
