@@ -55,6 +55,7 @@ def parse_args():
                                                          "streams keep the 296 coder slots of a B200 (two per SM) full while the others sort")
     ap.add_argument("--sorter", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-blocks", type=int, default=16, help="blocks per step of the reference arm / cpu_baseline leg (see reference_sample_blocks)")
     ap.add_argument("--mode", default="pipeline", choices=["phased", "pipeline"], help="order of the work inside the timed steps of the device-resident leg (see class Steps); the e2e leg always flows as a pipeline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=6, help="the end-to-end (host buffer) leg times min(--steps, this) steps, so that a long --steps run still ends within minutes")
@@ -111,10 +112,7 @@ def run_reference(args, rank, world):
     from oracle import pyoracle
     if rank != 0:
         return
-    # Same workload as the GPU arm (world x blocks-per-GPU blocks of the same size), bounded to ONE block per host thread:
-    # the reference's throughput saturates there (one block per OpenMP thread, bsc.cpp:184-199), more blocks only lengthen the step.
-    threads = len(os.sched_getaffinity(0))
-    sample = max(1, min(world * args.blocks, threads))
+    sample = reference_sample_blocks(args, world)
     info = reference_timing(args, steps=args.steps, warmup=args.warmup, sample_blocks=sample)
     line = {"metric": METRIC, "value": info["value"], "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -124,6 +122,16 @@ def run_reference(args, rank, world):
             "e2e": {"value": info["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "compress_MBps": info["compress_MBps"], "decompress_MBps": info["decompress_MBps"]}
     print(json.dumps(line), flush=True)
+
+
+def reference_sample_blocks(args, world=1):
+    """Blocks per step of the reference arm: a BOUNDED sample of the GPU arm's workload (same generator, block size, sorter, coder).
+    16 blocks of 64 MiB = BASELINE C3's 1 GiB, one block per OpenMP thread as the reference CLI does (bsc.cpp:184-199).  Measured on the
+    B200 box's host (128 hardware threads): 16 blocks / 16 threads 145.6 MB/s, 18 / 18 144-159 MB/s, 64 / 64 109-117 MB/s at 39 s per step
+    (profiles/r1g, r1h, r2i) -- more blocks at once make the reference SLOWER (memory-bound suffix sorting), so the sample is also its
+    best configuration, and a --steps 20 --warmup 5 run ends in ~3.5 minutes instead of 16."""
+    threads = len(os.sched_getaffinity(0))
+    return max(1, min(world * args.blocks, threads, args.ref_blocks))
 
 
 def reference_timing(args, steps, warmup, sample_blocks=None):
@@ -565,8 +573,7 @@ def run_b200(args, rank, local_rank, world):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            threads = len(os.sched_getaffinity(0))
-            info = reference_timing(args, steps=1, warmup=0, sample_blocks=max(1, min(nb, threads)))
+            info = reference_timing(args, steps=1, warmup=0, sample_blocks=reference_sample_blocks(args))
             cpu = {"value": info["value"], "unit": "MB/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
                    "compress_MBps": info["compress_MBps"], "decompress_MBps": info["decompress_MBps"]}
         except Exception as ex:      # never lose the GPU line because the baseline leg failed

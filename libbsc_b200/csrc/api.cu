@@ -64,6 +64,7 @@ void ctx_delete(Ctx *c)
     if (c->stream_hi) cudaStreamDestroy(c->stream_hi);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

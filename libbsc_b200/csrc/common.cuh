@@ -113,7 +113,18 @@ struct Ctx {
         return ev_pool[ev_used++];
     }
 
-    void sync() { CUDA_TRY(cudaStreamSynchronize(stream)); }
+    // Host wait for this context's stream.  cudaStreamSynchronize spins (cudaDeviceScheduleAuto), and in a full pipeline the sort kernels a
+    // thread waits for are queued behind other blocks' coder CTAs for tens of milliseconds: dozens of threads per GPU (x 8 ranks per host)
+    // would burn a core each.  So the wait BLOCKS on an event created with cudaEventBlockingSync (the thread sleeps until the driver's
+    // interrupt; ~30 us later than a spin would see it, ~1 ms per block).  BSCB200_SYNC=spin restores the spinning wait (A/B).
+    cudaEvent_t ev_sync = nullptr;
+    void sync() {
+        static const bool spin = [] { const char *e = getenv("BSCB200_SYNC"); return e && e[0] == 's'; }();
+        if (spin) { CUDA_TRY(cudaStreamSynchronize(stream)); return; }
+        if (!ev_sync) CUDA_TRY(cudaEventCreateWithFlags(&ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ev_sync, stream));
+        CUDA_TRY(cudaEventSynchronize(ev_sync));
+    }
     // Wait for a kernel that runs for 0.01 - 2 s (the coder kernels) WITHOUT putting anything behind it on the stream and without
     // driver calls.  A process has at most 32 hardware work queues per GPU (CUDA_DEVICE_MAX_CONNECTIONS), so with 40+ blocks in
     // flight two streams share a queue; an event record or a copy enqueued behind the 2 s kernel of one of them holds the queue's head

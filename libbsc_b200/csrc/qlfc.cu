@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "stages.cuh"
 #include <algorithm>
+#include <atomic>
 #include "qlfc_tables.inc"
 #include "qlfc_tables2.inc"
 
@@ -263,6 +264,13 @@ static int coder_split_point(const u32 *weight, const u32 *order, int n)
     while (k < n && (u64)weight[order[k]] * 20 >= (u64)weight[order[0]] * 11) ++k;      // >= 55 % of the longest
     return (k == n) ? 0 : k;
 }
+// decoder launches in progress per device (a launch = one block's streams): the decoder layout is chosen by load
+struct DecodersInFlight {
+    static std::atomic<int> &ctr(int device) { static std::atomic<int> c[16]; return c[device & 15]; }
+    int device, count;
+    explicit DecodersInFlight(int dev) : device(dev), count(++ctr(dev)) {}
+    ~DecodersInFlight() { --ctr(device); }
+};
 struct SplitLaunch {
     Ctx *c; cudaEvent_t ea = nullptr, eb = nullptr; bool prof; double bytes; Ctx::DoneSignalArgs sg; CoderSlots::Lease lease; int n_hi;
     SplitLaunch(Ctx *ctx, int total, int hi) : c(ctx), prof(ctx->profile), bytes(ctx->next_bytes), lease(ctx->device, total), n_hi(hi) {
@@ -352,10 +360,14 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     // issue slots per cycle, profiles/r2a_ncu_coder_kernels_4MiB.txt), and a second stream on the SM costs the first one ~15 %.
     static_assert(((sizeof(CoderSmemT<LayoutEncDiet>) + 15) & ~(size_t)15) + sizeof(EncPipe) <= 232448 / 2 - 1024, "two encoders must fit one SM");
     static_assert(3 * (((sizeof(CoderSmemT<LayoutEncDietTG>) + 15) & ~(size_t)15) + sizeof(EncPipe) + 1024) <= 232448, "three encoders without resident state tables must fit one SM");
-    // BSCB200_ENC_TG=0: state tables resident (LayoutEncDiet, two encoder CTAs per SM); default: tables through L1, three per SM
-    static const bool enc_tg = [] { const char *e = getenv("BSCB200_ENC_TG"); return !(e && e[0] == '0'); }();
-    const size_t enc_smem = (((enc_tg ? sizeof(CoderSmemT<LayoutEncDietTG>) : sizeof(CoderSmemT<LayoutEncDiet>)) + 15) & ~(size_t)15) + sizeof(EncPipe);
-    auto *const enc_kernel = enc_tg ? q_encode5<LayoutEncDietTG> : q_encode5<LayoutEncDiet>;
+    static_assert(4 * (((sizeof(CoderSmemT<LayoutEncDiet4>) + 15) & ~(size_t)15) + sizeof(EncPipe) + 1024) <= 232448, "four encoders per SM");
+    // Encoder streams per SM: BSCB200_ENC_PER_SM = 2 (state tables resident, LayoutEncDiet), 3 (tables through L1, LayoutEncDietTG; default),
+    // 4 (LayoutEncDiet4).  BSCB200_ENC_TG=0 is the old spelling of 2.
+    static const int enc_per_sm = [] { const char *t = getenv("BSCB200_ENC_TG"); if (t && t[0] == '0') return 2;
+                                       const char *e = getenv("BSCB200_ENC_PER_SM"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 4) ? v : 3; }();
+    const size_t enc_image = enc_per_sm == 2 ? sizeof(CoderSmemT<LayoutEncDiet>) : enc_per_sm == 3 ? sizeof(CoderSmemT<LayoutEncDietTG>) : sizeof(CoderSmemT<LayoutEncDiet4>);
+    const size_t enc_smem = ((enc_image + 15) & ~(size_t)15) + sizeof(EncPipe);
+    auto *const enc_kernel = enc_per_sm == 2 ? q_encode5<LayoutEncDiet, 2> : enc_per_sm == 3 ? q_encode5<LayoutEncDietTG, 3> : q_encode5<LayoutEncDiet4, 4>;
     if (fast) {
         LAUNCH(ctx, q_fast_model_init, 256, 256, 0, models, (u32)nBlocks);
         ensure_dyn_smem(q_fast_encode, ctx->device, sizeof(FastSmem));
@@ -526,8 +538,11 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
                 const int n_hi = coder_split_point(packed, list, nlist);
                 // Streams per SM = how much of the counter file is resident (qlfc_decoder6.cuh).  BSCB200_DEC_PER_SM = 2: LayoutDiet (state
                 // tables resident, 110 KB); 3: LayoutDietTG (tables through L1, 71 KB); 4: LayoutDiet4 (55 KB, rank exponent 4 row-wise);
-                // 5: LayoutDiet5 (39 KB).  A/B on the B200 in profiles/r2i_*.
-                static const int per_sm = [] { const char *e = getenv("BSCB200_DEC_PER_SM"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 5) ? v : QD6_DEFAULT_PER_SM; }();
+                // 5: LayoutDiet5 (39 KB, 11 % slower per stream when alone).  Default: by load -- 4 per SM while the decoders in flight on
+                // this device fit 592 slots (74 blocks), 5 per SM beyond.  A/B on the B200: profiles/r2i_call_i.log.
+                static const int forced = [] { const char *e = getenv("BSCB200_DEC_PER_SM"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 5) ? v : 0; }();
+                DecodersInFlight in_flight(ctx->device);
+                const int per_sm = forced ? forced : (in_flight.count * Q_MAX_SUB > 4 * B200_SMS ? 5 : 4);
                 auto launch = [&](auto kernel, size_t smem) {
                     ensure_dyn_smem(kernel, ctx->device, smem);
                     SplitLaunch sl(ctx, nlist, n_hi);

@@ -78,6 +78,7 @@ typedef TablesInGlobal<LayoutDiet> LayoutDietTG;   // 70.7 KB: three decoder str
 typedef TablesInGlobal<QLayout<3, 3, 2> > LayoutDiet4;   // 54.7 KB: FOUR per SM; the rank mantissa of exponent 4 (ranks 16..31) goes row-wise too
 typedef TablesInGlobal<QLayout<2, 2, 2> > LayoutDiet5;   // 38.7 KB: five per SM (rank exponents 3, 4 and run exponent 3 row-wise)
 typedef QLayout<4, 1, 10> LayoutEncDiet;  // 106 KB + the encoder's pipe state (5.6 KB): two six-warp encoders per SM
+typedef TablesInGlobal<QLayout<3, 1, 10> > LayoutEncDiet4;   // 50 KB + 5.6 KB: four per SM (rank exponent 4 through the write-back cache)
 typedef TablesInGlobal<LayoutEncDiet> LayoutEncDietTG;   // 66 KB + 5.6 KB: three per SM (the model warps gather their states through L1, a batch of 32 runs at a time)
 static_assert(LayoutFull::R_END == R_END && LayoutFull::S16_COUNT == S16_COUNT && LayoutFull::O_S16 == O3_S16, "LayoutFull must reproduce qlfc_coder.cuh");
 static_assert(LayoutFull::R_RM_STATE == R_RM_STATE && LayoutFull::R_UM_CHAR == R_UM_CHAR && LayoutFull::C_CHAR_VAL == C_CHAR_VAL, "LayoutFull must reproduce qlfc_coder.cuh");
@@ -89,7 +90,6 @@ static_assert(LayoutDiet::O_S16 == O3_S16 && (LayoutDiet::O_WIN & 15u) == 0 && (
 static_assert((LayoutDiet::O_ROWS & 15u) == 0 && (LayoutFull::O_ROWS & 15u) == 0 && (LayoutDiet::O_TAG_STATE & 3u) == 0, "staged rows are moved 16 bytes at a time");
 static_assert(LayoutFull::BYTES <= 232448, "one full decoder per SM");
 static_assert(3 * (LayoutDietTG::BYTES + 1024) <= 232448, "three decoders without resident state tables must fit one SM");
-#define QD6_DEFAULT_PER_SM 3                             // decoder streams per SM the product launches (qlfc.cu; BSCB200_DEC_PER_SM overrides)
 static_assert(4 * (LayoutDiet4::BYTES + 1024) <= 232448 && 5 * (LayoutDiet5::BYTES + 1024) <= 232448, "four / five decoders per SM");
 static_assert((LayoutDiet4::O_ROWS & 15u) == 0 && (LayoutDiet5::O_ROWS & 15u) == 0 && (LayoutDiet4::O_WIN & 15u) == 0 && (LayoutDiet5::O_WIN & 15u) == 0 &&
               (LayoutDiet4::O_MTF & 3u) == 0 && (LayoutDiet5::O_MTF & 3u) == 0 && (LayoutDiet4::O_TAG_STATE & 3u) == 0 && (LayoutDiet5::O_TAG_STATE & 3u) == 0, "alignment of the smaller images");

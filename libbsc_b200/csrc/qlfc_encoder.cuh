@@ -148,7 +148,8 @@ __device__ __forceinline__ u32 enc_window(u32 prev_rev, u32 cur_rev, u32 lane) {
 // LY: layout of the counter file (qlfc_decoder6.cuh).  The product instantiates LayoutEncDiet: fewer mantissa rows resident, 106 KB
 // + 5.6 KB of pipe state, so that two six-warp encoders share an SM (same time per stream as the 205 KB layout when alone: 682 ms
 // per 64 MiB block, profiles/r2a_call_a.log).  (A one-multiply-add form of the range recurrence was tried in round 2: 707 vs 682 ms.)
-template <class LY> __global__ void __launch_bounds__(QE_THREADS, 1) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
+// MINB: encoder CTAs per SM the REGISTER budget must allow (192 threads: 122 registers fit two CTAs, <= 112 three, <= 80 four)
+template <class LY, int MINB> __global__ void __launch_bounds__(QE_THREADS, MINB) q_encode5(const u32 *__restrict__ run_pos, const u8 *__restrict__ run_sym, const u8 *__restrict__ run_rank,
                                                     SubBlock *__restrict__ sbs, const u8 *__restrict__ mtf_all, short *__restrict__ cold_all,
                                                     const QTables *__restrict__ tables, u8 *__restrict__ out_all, const u32 *__restrict__ sb_list, DoneSignal done)
 {
