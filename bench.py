@@ -51,8 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=64, help="blocks per GPU and step")
     ap.add_argument("--block-mib", type=int, default=64)
-    ap.add_argument("--workers", type=int, default=0, help="blocks in flight per GPU = contexts = worker threads (0 = all blocks of the step); 64 x 8 coder "
-                                                         "streams keep the 296 coder slots of a B200 (two per SM) full while the others sort")
+    ap.add_argument("--workers", type=int, default=0, help="blocks in flight per GPU = contexts = worker threads (0 = 96, or all blocks of a step of fewer than 64 blocks)")
     ap.add_argument("--sorter", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-blocks", type=int, default=16, help="blocks per step of the reference arm / cpu_baseline leg (see reference_sample_blocks)")
@@ -349,7 +348,9 @@ def run_b200(args, rank, local_rank, world):
     gen = pyoracle.Gen()
     nb, bb = args.blocks, args.block_mib << 20
     host_blocks = make_blocks(gen, 2 + rank, nb, bb)
-    workers = args.workers or nb                         # blocks in flight = contexts = worker threads; independent of the blocks per step
+    # blocks in flight = contexts = worker threads, independent of the blocks per step.  96 keep the 740 decoder slots of a B200 (five per SM)
+    # and six sort slabs busy (A/B: 64 / 96 / 128 in flight -> 768 / 836 / 815 MB/s, profiles/r2i_call_i.log, r2j_call_j.log)
+    workers = args.workers if args.workers > 0 else (96 if nb >= 64 else nb)
 
     # ---- device-resident leg ------------------------------------------------------------------
     # inputs per block; compressed / restored buffers per WORKER (a task = compress block i, then decompress it, on one context),

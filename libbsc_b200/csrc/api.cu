@@ -90,43 +90,61 @@ void ctx_release(Ctx *c)
 }
 
 // ---- scratch pool: a few large slabs per device for the sort stages, shared by every context of that device -----------------
-// BSCB200_SORT_SLABS (default 3) bounds how many exist; a sort waits (host side) for a free one.  Handing a slab from one stream to
+// BSCB200_SORT_SLABS (default 6) bounds how many exist; a sort waits (host side) for a free one.  Handing a slab from one stream to
 // another is ordered by an event recorded at release and waited for at acquisition, so no host synchronisation is needed.
-struct ScratchPool { std::mutex m; std::condition_variable cv; std::vector<Scratch *> free_list; int created = 0; };
+// Slabs are made on demand.  With the coder at five streams per SM the pipeline turns over 12+ blocks a second while a forward BWT that
+// shares the SMs with coder CTAs holds its slab for ~0.3 s: three slabs (round 2's first setting) made the sorts queue for memory.
+// A slab that cannot be allocated any more (the caller filled the HBM) lowers the bound to what exists instead of failing the block.
+struct ScratchPool { std::mutex m; std::condition_variable cv; std::vector<Scratch *> free_list; int created = 0, cap = -1; };
 ScratchPool g_scratch[MAX_DEVICES];
 int scratch_limit()
 {
-    static const int v = [] { const char *e = getenv("BSCB200_SORT_SLABS"); int k = e ? atoi(e) : 0; return k >= 1 && k <= 64 ? k : 3; }();
+    static const int v = [] { const char *e = getenv("BSCB200_SORT_SLABS"); int k = e ? atoi(e) : 0; return k >= 1 && k <= 64 ? k : 6; }();
     return v;
 }
 
 Scratch *scratch_acquire(Ctx *c, size_t bytes)
 {
     ScratchPool &P = g_scratch[c->device];
-    Scratch *s = nullptr;
-    {
-        std::unique_lock<std::mutex> lk(P.m);
-        for (;;) {
-            if (!P.free_list.empty()) { s = P.free_list.back(); P.free_list.pop_back(); break; }
-            if (P.created < scratch_limit()) { P.created++; break; }         // make a new one outside the lock
-            P.cv.wait(lk);
+    for (;;) {
+        Scratch *s = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(P.m);
+            for (;;) {
+                if (!P.free_list.empty()) { s = P.free_list.back(); P.free_list.pop_back(); break; }
+                if (P.created < (P.cap >= 0 ? P.cap : scratch_limit())) { P.created++; break; }      // make a new one outside the lock
+                P.cv.wait(lk);
+            }
         }
-    }
-    try {
-        if (!s) { s = new Scratch(); CUDA_TRY(cudaEventCreateWithFlags(&s->idle, cudaEventDisableTiming)); }
-        if (s->idle_valid) CUDA_TRY(cudaStreamWaitEvent(c->stream, s->idle, 0));
-        if (s->arena.cap < bytes) {
-            if (s->idle_valid) CUDA_TRY(cudaEventSynchronize(s->idle));         // the slab is about to be freed: its last user must be done
-            s->arena.reset(); s->arena.reserve(bytes);
+        const bool fresh = (s == nullptr);
+        try {
+            if (!s) { s = new Scratch(); CUDA_TRY(cudaEventCreateWithFlags(&s->idle, cudaEventDisableTiming)); }
+            if (s->idle_valid) CUDA_TRY(cudaStreamWaitEvent(c->stream, s->idle, 0));
+            if (s->arena.cap < bytes) {
+                if (s->idle_valid) CUDA_TRY(cudaEventSynchronize(s->idle));         // the slab is about to be freed: its last user must be done
+                s->arena.reset(); s->arena.reserve(bytes);
+            }
+        } catch (const CudaFail &f) {
+            std::unique_lock<std::mutex> lk(P.m);
+            if (fresh && f.err == cudaErrorMemoryAllocation && P.created > 1) {       // no room for one more slab: live with the ones there are
+                cudaGetLastError();
+                if (s) { if (s->idle) cudaEventDestroy(s->idle); s->arena.destroy(); delete s; }
+                P.created--; P.cap = P.created;
+                P.cv.notify_all();
+                continue;
+            }
+            if (s && !fresh) { P.free_list.push_back(s); } else { if (s) { if (s->idle) cudaEventDestroy(s->idle); s->arena.destroy(); delete s; } P.created--; }
+            P.cv.notify_one();
+            throw;
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(P.m);
+            if (s && !fresh) { P.free_list.push_back(s); } else { P.created--; }
+            P.cv.notify_one();
+            throw;
         }
-    } catch (...) {
-        std::lock_guard<std::mutex> lk(P.m);
-        if (s) { P.free_list.push_back(s); } else { P.created--; }
-        P.cv.notify_one();
-        throw;
+        s->arena.reset();
+        return s;
     }
-    s->arena.reset();
-    return s;
 }
 
 void scratch_release(Ctx *c, Scratch *s)
@@ -716,7 +734,7 @@ void bscb200_release_pools(void)
     for (int d = 0; d < MAX_DEVICES; ++d) {
         std::vector<Ctx *> ctxs; std::vector<Scratch *> slabs;
         { std::lock_guard<std::mutex> lk(g_pool_mutex); ctxs.swap(g_pool[d]); for (Ctx *c : ctxs) g_launches_retired += c->kernels_launched; }
-        { std::lock_guard<std::mutex> lk(g_scratch[d].m); slabs.swap(g_scratch[d].free_list); g_scratch[d].created -= (int)slabs.size(); }
+        { std::lock_guard<std::mutex> lk(g_scratch[d].m); slabs.swap(g_scratch[d].free_list); g_scratch[d].created -= (int)slabs.size(); g_scratch[d].cap = -1; }
         for (Ctx *c : ctxs) ctx_delete(c);
         if (!slabs.empty()) cudaSetDevice(d);
         for (Scratch *s : slabs) { if (s->idle_valid) cudaEventSynchronize(s->idle); s->arena.destroy(); if (s->idle) cudaEventDestroy(s->idle); delete s; }

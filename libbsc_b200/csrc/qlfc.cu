@@ -264,12 +264,13 @@ static int coder_split_point(const u32 *weight, const u32 *order, int n)
     while (k < n && (u64)weight[order[k]] * 20 >= (u64)weight[order[0]] * 11) ++k;      // >= 55 % of the longest
     return (k == n) ? 0 : k;
 }
-// decoder launches in progress per device (a launch = one block's streams): the decoder layout is chosen by load
-struct DecodersInFlight {
+// blocks inside a coder stage (either direction) per device: the decoder layout is chosen by this load
+struct CodersInFlight {
     static std::atomic<int> &ctr(int device) { static std::atomic<int> c[16]; return c[device & 15]; }
     int device, count;
-    explicit DecodersInFlight(int dev) : device(dev), count(++ctr(dev)) {}
-    ~DecodersInFlight() { --ctr(device); }
+    explicit CodersInFlight(int dev) : device(dev), count(++ctr(dev)) {}
+    ~CodersInFlight() { --ctr(device); }
+    static int now(int device) { return ctr(device).load(); }
 };
 struct SplitLaunch {
     Ctx *c; cudaEvent_t ea = nullptr, eb = nullptr; bool prof; double bytes; Ctx::DoneSignalArgs sg; CoderSlots::Lease lease; int n_hi;
@@ -291,6 +292,7 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
     { const int g = coder_gate(coder); if (g != LIBBSC_NO_ERROR) return g; }
     const bool fast = coder == 3;
     if (n_ <= 0) return LIBBSC_BAD_PARAMETER;
+    CodersInFlight load_(ctx->device);
     const u32 n = (u32)n_;
     // bare_out_size >= 0: ONE stream without the container byte, output capacity as given (bsc_qlfc_*_encode_block, qlfc.h:55-77)
     const bool bare = bare_out_size >= 0;
@@ -478,6 +480,7 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
     (void)features;
     { const int g = coder_gate(coder); if (g != LIBBSC_NO_ERROR) return g; }
     if (in_size < 1) return LIBBSC_UNEXPECTED_EOB;
+    CodersInFlight load_(ctx->device);
     const QTables *tables = get_tables(ctx);
     Arena &A = ctx->arena;
     const size_t mark = A.mark();
@@ -538,11 +541,11 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
                 const int n_hi = coder_split_point(packed, list, nlist);
                 // Streams per SM = how much of the counter file is resident (qlfc_decoder6.cuh).  BSCB200_DEC_PER_SM = 2: LayoutDiet (state
                 // tables resident, 110 KB); 3: LayoutDietTG (tables through L1, 71 KB); 4: LayoutDiet4 (55 KB, rank exponent 4 row-wise);
-                // 5: LayoutDiet5 (39 KB, 11 % slower per stream when alone).  Default: by load -- 4 per SM while the decoders in flight on
-                // this device fit 592 slots (74 blocks), 5 per SM beyond.  A/B on the B200: profiles/r2i_call_i.log.
+                // 5: LayoutDiet5 (39 KB; 11 % slower per stream when alone, 836 against 807 MB/s in a full pipeline, profiles/r2j_call_j.log).
+                // Default: by load -- 4 per SM while the blocks in coder stages on this device fit the 296 slots of two streams per SM
+                // (37 blocks: a caller with a handful of blocks wants the short latency), 5 per SM beyond.
                 static const int forced = [] { const char *e = getenv("BSCB200_DEC_PER_SM"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 5) ? v : 0; }();
-                DecodersInFlight in_flight(ctx->device);
-                const int per_sm = forced ? forced : (in_flight.count * Q_MAX_SUB > 4 * B200_SMS ? 5 : 4);
+                const int per_sm = forced ? forced : (CodersInFlight::now(ctx->device) * Q_MAX_SUB > 2 * B200_SMS ? 5 : 4);
                 auto launch = [&](auto kernel, size_t smem) {
                     ensure_dyn_smem(kernel, ctx->device, smem);
                     SplitLaunch sl(ctx, nlist, n_hi);
