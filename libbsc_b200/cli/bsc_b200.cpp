@@ -61,7 +61,7 @@ const unsigned char kSign[4] = {'b', 's', 'c', 0x31};
 enum { kFeatures = 1 | 2, kContextsFollowing = 1, kContextsPreceding = 2, kRecordBytes = 10 };
 
 struct Options {
-    int block_bytes = 25 << 20, sorter = 1, coder = 1, slots = 40;
+    int block_bytes = 25 << 20, sorter = 1, coder = 1, slots = 96;
     int lzp_hash = 0, lzp_min = 0;                                       // -l: the reference's LZP stage (host side of the library), off by default
     std::vector<int> devices;
 };
@@ -104,8 +104,8 @@ void put_record(unsigned char *rec, long long offset, int recordSize, int contex
     rec[8] = (unsigned char)recordSize; rec[9] = (unsigned char)contexts;
 }
 
-// Blocks in flight per GPU, bounded by its free memory: a context holds the staged block + the coder stage (~15 n + 64 MB); three sort
-// slabs (~58 n each for BWT) are shared by all of them.  At -b1024 that is one or two blocks, at -b25 the full -j.
+// Blocks in flight per GPU, bounded by its free memory: a context holds the staged block + the coder stage (~15 n + 64 MB); the sort
+// slabs (~58 n each for BWT; three are reserved here, the library makes up to six while memory lasts) are shared by all of them.  At -b1024 that is one or two blocks, at -b25 the full -j.
 int fit_slots(const Options &opt, int want)
 {
     int slots = want;
@@ -278,7 +278,7 @@ void usage()
             "  -e<algo>  entropy coder: -e1 static QLFC (default), -e0 fast, -e2 adaptive (experimental, see DESIGN.md)\n"
             "  -l        LZP preprocessing on (host stage; -H<10..28> hash bits, -M<4..255> minimum match; bsc's defaults 15 / 128)\n"
             "  -g<list>  GPUs to use, e.g. -g0,1,2,3 (default: all visible)\n"
-            "  -j<n>     blocks in flight per GPU, default -j40, fewer when HBM is short (8 coder streams per block, two per SM)\n"
+            "  -j<n>     blocks in flight per GPU, default -j96, fewer when HBM is short (8 coder streams per block, up to five per SM)\n"
             "Writes what `bsc e in out -p` writes; reads `bsc` archives made without -r / -c (LZP is undone on the host).\n");
     exit(0);
 }

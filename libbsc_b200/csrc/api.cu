@@ -42,7 +42,10 @@ Ctx *ctx_new(int device, cudaStream_t stream, bool own)
     c->device = device;
     try {
         CUDA_TRY(cudaSetDevice(device));
-        if (own) { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->owns_stream = true; }
+        if (own) {                                   // the context's own stream carries the short kernels: highest priority (Ctx::stream_hi)
+            int lo = 0, hi = 0; CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, Ctx::priorities_on() ? hi : lo)); c->owns_stream = true;
+        }
         else c->stream = stream;
         CUDA_TRY(cudaMallocHost((void **)&c->h_mail, 1024));
         CUDA_TRY(cudaMalloc((void **)&c->d_mail, 1024));
@@ -62,6 +65,8 @@ void ctx_delete(Ctx *c)
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream_hi) cudaStreamDestroy(c->stream_hi);
+    if (c->stream_lo) cudaStreamDestroy(c->stream_lo);
+    if (c->ev_join_lo) cudaEventDestroy(c->ev_join_lo);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);

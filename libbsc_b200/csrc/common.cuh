@@ -132,18 +132,29 @@ struct Ctx {
     // (profiles/r2c_call_c.log).  Polling cudaStreamQuery from 48 threads instead made the launch-heavy sort stages of the other
     // blocks four times slower (driver lock; profiles/r2d_call_d.log).  So the kernel itself reports: its last CTA writes a sequence
     // number into this context's pinned mailbox (signal_done below) and the host thread sleeps on that word.
-    // Side stream of the highest priority for the LONG streams of a coder launch (qlfc.cu: split launches): when SM halves free up, the
-    // CTA scheduler places pending CTAs of higher-priority streams first, whichever block launched first -- longest-stream-first
-    // ACROSS blocks without any coordination between the host threads.
-    cudaStream_t stream_hi = nullptr;
-    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
+    // Stream priorities (BSCB200_PRIO=0 turns them off).  When SM slots free up, the CTA scheduler places pending CTAs of higher-priority
+    // streams first, whichever block launched first.  Three levels per context:
+    //   stream     (highest)  everything that is short: the sort / scan / rank kernels.  A coder CTA holds its slot for 0.1 - 4 s, a sort
+    //                         CTA for microseconds; at equal priority the sort launches of a full pipeline ran 12 - 15 times longer than
+    //                         alone (rs_onesweep 3.8 - 5.2 ms against 0.33 ms per launch, profiles/r2i, r2j), each block spent ~2 s of its
+    //                         7.7 s round trip in sort stages and the coder slots stood half empty meanwhile;
+    //   stream_hi  (middle)   the LONG streams of a coder launch (qlfc.cu: split launches): longest-stream-first ACROSS blocks without any
+    //                         coordination between the host threads;
+    //   stream_lo  (lowest)   the other coder streams.
+    cudaStream_t stream_hi = nullptr, stream_lo = nullptr;
+    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr, ev_join_lo = nullptr;
+    static bool priorities_on() { static const bool on = [] { const char *e = getenv("BSCB200_PRIO"); return !(e && e[0] == '0'); }(); return on; }
     void ensure_hi() {
         if (stream_hi) return;
-        int lo = 0, hi = 0; CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&stream_hi, cudaStreamNonBlocking, hi));
+        int lo = 0, hi = 0; CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = least (numerically greatest), hi = greatest priority
+        const bool on = priorities_on();
+        CUDA_TRY(cudaStreamCreateWithPriority(&stream_hi, cudaStreamNonBlocking, on ? (lo + hi) / 2 : hi));
+        if (on) { CUDA_TRY(cudaStreamCreateWithPriority(&stream_lo, cudaStreamNonBlocking, lo)); CUDA_TRY(cudaEventCreateWithFlags(&ev_join_lo, cudaEventDisableTiming)); }
         CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     }
+    // the stream the SHORT streams of a coder launch go to (the main stream when priorities are off)
+    cudaStream_t coder_stream() { ensure_hi(); return stream_lo ? stream_lo : stream; }
     u32 done_seq = 0;
     struct DoneSignalArgs { u32 *ctr; u32 *host_flag; u32 seq; };
     DoneSignalArgs next_signal() { ++done_seq; return DoneSignalArgs{d_mail + 128, h_mail + 250, done_seq}; }

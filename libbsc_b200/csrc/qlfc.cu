@@ -254,7 +254,7 @@ static void init_models(Ctx *ctx, short *models, int count)
 }
 
 // Split launch of a static-coder kernel: the streams of `order[0 .. n_hi)` (the long ones; `order` is sorted longest first) go to the
-// context's high-priority side stream, the rest to its main stream; both halves report to ONE completion signal.  See Ctx::stream_hi.
+// context's middle-priority side stream, the rest to its lowest-priority one; both halves report to ONE completion signal.  See Ctx::stream_hi.
 // BSCB200_CODER_SPLIT=0 turns it off (A/B).
 static bool coder_split_enabled() { static const bool on = [] { const char *e = getenv("BSCB200_CODER_SPLIT"); return !(e && e[0] == '0'); }(); return on; }
 static int coder_split_point(const u32 *weight, const u32 *order, int n)
@@ -274,15 +274,23 @@ struct CodersInFlight {
 };
 struct SplitLaunch {
     Ctx *c; cudaEvent_t ea = nullptr, eb = nullptr; bool prof; double bytes; Ctx::DoneSignalArgs sg; CoderSlots::Lease lease; int n_hi;
+    cudaStream_t s_long, s_short;                      // where the long / the other streams of the launch go (Ctx::stream_hi)
     SplitLaunch(Ctx *ctx, int total, int hi) : c(ctx), prof(ctx->profile), bytes(ctx->next_bytes), lease(ctx->device, total), n_hi(hi) {
         if (prof) { ea = c->ev(); eb = c->ev(); CUDA_TRY(cudaEventRecord(ea, c->stream)); }
         sg = c->next_signal();
-        if (n_hi > 0) { c->ensure_hi(); CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream)); CUDA_TRY(cudaStreamWaitEvent(c->stream_hi, c->ev_fork, 0)); }
+        s_short = c->coder_stream(); s_long = c->stream_hi;
+        if (n_hi > 0 || s_short != c->stream) {
+            CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+            if (n_hi > 0) CUDA_TRY(cudaStreamWaitEvent(s_long, c->ev_fork, 0));
+            if (s_short != c->stream) CUDA_TRY(cudaStreamWaitEvent(s_short, c->ev_fork, 0));
+        }
     }
     void finish(const char *name, int launches) {
         c->next_bytes = 0; c->kernels_launched += launches;
         c->wait_signal();
-        if (n_hi > 0) { CUDA_TRY(cudaEventRecord(c->ev_join, c->stream_hi)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); }   // both kernels have reported: nothing waits here
+        // every kernel of the launch has reported: the joins below never make anything wait
+        if (n_hi > 0) { CUDA_TRY(cudaEventRecord(c->ev_join, s_long)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); }
+        if (s_short != c->stream) { CUDA_TRY(cudaEventRecord(c->ev_join_lo, s_short)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join_lo, 0)); }
         if (prof) { CUDA_TRY(cudaEventRecord(eb, c->stream)); c->prof.push_back(ProfRec{name, ea, eb, bytes}); }
     }
 };
@@ -388,8 +396,8 @@ int stage_coder_compress(Ctx *ctx, const u8 *d_in, u8 *d_out, int n_, int coder,
         const int n_hi = coder_split_point(runs, enc_order, nBlocks);
         SplitLaunch sl(ctx, nBlocks, n_hi);
         const DoneSignal done{sl.sg.ctr, sl.sg.host_flag, sl.sg.seq, (u32)nBlocks};
-        if (n_hi > 0) { enc_kernel<<<n_hi, QE_THREADS, enc_smem, ctx->stream_hi>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order, done); KERNEL_CHECK(); }
-        enc_kernel<<<nBlocks - n_hi, QE_THREADS, enc_smem, ctx->stream>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)(d_order + n_hi), done); KERNEL_CHECK();
+        if (n_hi > 0) { enc_kernel<<<n_hi, QE_THREADS, enc_smem, sl.s_long>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)d_order, done); KERNEL_CHECK(); }
+        enc_kernel<<<nBlocks - n_hi, QE_THREADS, enc_smem, sl.s_short>>>(run_pos, run_sym, run_rank, d_sb, mtf, models, tables, tmp, (const u32 *)(d_order + n_hi), done); KERNEL_CHECK();
         sl.finish("q_encode5", n_hi > 0 ? 2 : 1);
     }
     CUDA_TRY(cudaMemcpyAsync(h_sb, d_sb, sizeof(SubBlock) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
@@ -550,8 +558,8 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
                     ensure_dyn_smem(kernel, ctx->device, smem);
                     SplitLaunch sl(ctx, nlist, n_hi);
                     const DoneSignal done{sl.sg.ctr, sl.sg.host_flag, sl.sg.seq, (u32)nlist};
-                    if (n_hi > 0) { kernel<<<n_hi, 32, smem, ctx->stream_hi>>>(d_in, d_sb, models, tables, d_out, (const u32 *)d_list, done); KERNEL_CHECK(); }
-                    kernel<<<nlist - n_hi, 32, smem, ctx->stream>>>(d_in, d_sb, models + (size_t)n_hi * MODEL_SHORTS_PAD, tables, d_out, (const u32 *)(d_list + n_hi), done); KERNEL_CHECK();
+                    if (n_hi > 0) { kernel<<<n_hi, 32, smem, sl.s_long>>>(d_in, d_sb, models, tables, d_out, (const u32 *)d_list, done); KERNEL_CHECK(); }
+                    kernel<<<nlist - n_hi, 32, smem, sl.s_short>>>(d_in, d_sb, models + (size_t)n_hi * MODEL_SHORTS_PAD, tables, d_out, (const u32 *)(d_list + n_hi), done); KERNEL_CHECK();
                     sl.finish("q_decode6", n_hi > 0 ? 2 : 1);
                 };
                 switch (per_sm) {
