@@ -272,6 +272,17 @@ struct CodersInFlight {
     ~CodersInFlight() { --ctr(device); }
     static int now(int device) { return ctr(device).load(); }
 };
+// decoder streams per SM chosen by load (see stage_coder_decompress); sticky per device so that the layouts do not alternate
+static int decoder_layout_by_load(int device)
+{
+    static std::atomic<int> mode[16];
+    const int load = CodersInFlight::now(device);
+    std::atomic<int> &m = mode[device & 15];
+    if (load * Q_MAX_SUB > B200_SMS) m.store(5);
+    else if (load <= 4) m.store(4);
+    const int v = m.load();
+    return v ? v : 4;
+}
 struct SplitLaunch {
     Ctx *c; cudaEvent_t ea = nullptr, eb = nullptr; bool prof; double bytes; Ctx::DoneSignalArgs sg; CoderSlots::Lease lease; int n_hi;
     cudaStream_t s_long, s_short;                      // where the long / the other streams of the launch go (Ctx::stream_hi)
@@ -550,10 +561,13 @@ int stage_coder_decompress(Ctx *ctx, const u8 *d_in, int in_size, u8 *d_out, int
                 // Streams per SM = how much of the counter file is resident (qlfc_decoder6.cuh).  BSCB200_DEC_PER_SM = 2: LayoutDiet (state
                 // tables resident, 110 KB); 3: LayoutDietTG (tables through L1, 71 KB); 4: LayoutDiet4 (55 KB, rank exponent 4 row-wise);
                 // 5: LayoutDiet5 (39 KB; 11 % slower per stream when alone, 836 against 807 MB/s in a full pipeline, profiles/r2j_call_j.log).
-                // Default: by load -- 4 per SM while the blocks in coder stages on this device fit the 296 slots of two streams per SM
-                // (37 blocks: a caller with a handful of blocks wants the short latency), 5 per SM beyond.
+                // Default: by load, with hysteresis -- 4 per SM while every stream of the blocks in coder stages on this device can have an SM
+                // share of its own choosing (<= 18 blocks = 144 streams: a caller with a handful of blocks wants the short latency); 5 per SM
+                // once streams have to share SMs anyway, and then until the device has drained to 4 blocks: a MIX of 55 KB and 39 KB CTAs packs
+                // an SM badly (a load hovering around the old threshold of 37 blocks gave 786 MB/s against 807 / 836 for all-4 / all-5,
+                // profiles/r2j_call_j.log).
                 static const int forced = [] { const char *e = getenv("BSCB200_DEC_PER_SM"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 5) ? v : 0; }();
-                const int per_sm = forced ? forced : (CodersInFlight::now(ctx->device) * Q_MAX_SUB > 2 * B200_SMS ? 5 : 4);
+                const int per_sm = forced ? forced : decoder_layout_by_load(ctx->device);
                 auto launch = [&](auto kernel, size_t smem) {
                     ensure_dyn_smem(kernel, ctx->device, smem);
                     SplitLaunch sl(ctx, nlist, n_hi);

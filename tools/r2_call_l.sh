@@ -1,5 +1,6 @@
 #!/bin/bash
-# tools/r2_call_l.sh -- round 2, twelfth GPU call: stream priorities (sorts highest, long coder streams middle, other coder streams lowest) A/B
+# tools/r2_call_l.sh -- round 2, twelfth GPU call: stream priorities (sorts highest, long coder streams middle, other coder streams lowest) A/B;
+# decoder layout by load with hysteresis (no mix of 55 KB and 39 KB CTAs)
 mkdir -p gpurun_out
 run() { name=$1; shift; envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
   env "${envs[@]}" timeout 500 python bench.py "$@" --blocks 64 --no-cpu-baseline --no-e2e --no-extras --steps 3 --warmup 1 > gpurun_out/r2l_$name.json 2> gpurun_out/r2l_$name.err
