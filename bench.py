@@ -116,7 +116,7 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": info["value"], "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, extra={"host_threads": info["cores"]}),
+            "config": workload_config(args), "arm": {"host_threads": info["cores"], "blocks_per_step": sample},
             "cpu_baseline": {"value": info["value"], "unit": "MB/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
             "e2e": {"value": info["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "compress_MBps": info["compress_MBps"], "decompress_MBps": info["decompress_MBps"]}
@@ -582,9 +582,11 @@ def run_b200(args, rank, local_rank, world):
 
     line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, {"blocks_in_flight_per_gpu": workers, "mode": args.mode, "step": "phased: all blocks compressed, then all blocks decompressed; pipeline: compress -> decompress per block, "
-                                                                                          "steps flow into each other; timed barrier to barrier",
-                                             "parallelism": "blocks round-robin over %d GPU(s), no collective" % world}),
+            # `config` is the workload and identical in both arms; what is specific to this arm sits in `arm`
+            "config": workload_config(args),
+            "arm": {"blocks_in_flight_per_gpu": workers, "mode": args.mode, "step": "phased: all blocks compressed, then all blocks decompressed; pipeline: compress -> decompress per block, "
+                                                                                   "steps flow into each other; timed barrier to barrier",
+                    "parallelism": "blocks round-robin over %d GPU(s), no collective" % world},
             "compress_MBps": total_mb / (ms_c / 1e3), "decompress_MBps": total_mb / (ms_d / 1e3), "phase_note": "each direction alone, one drained pass over the batch",
             "compressed_bytes_rank0": comp_bytes, "ratio": comp_bytes / float(nb * bb),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue, "roofline_hbm_kernel": roofline_hbm,

@@ -158,7 +158,9 @@ struct Ctx {
     u32 done_seq = 0;
     struct DoneSignalArgs { u32 *ctr; u32 *host_flag; u32 seq; };
     DoneSignalArgs next_signal() { ++done_seq; return DoneSignalArgs{d_mail + 128, h_mail + 250, done_seq}; }
-    void wait_signal() {
+    // `a`, `b`: the streams the reporting kernels were launched on (default: the context's own stream)
+    void wait_signal(cudaStream_t a = nullptr, cudaStream_t b = nullptr) {
+        if (!a) a = stream;
         volatile u32 *flag = (volatile u32 *)(h_mail + 250);
         // 20 us steps growing to 0.4 ms, and to 2 ms once the kernel has run for 50 ms (a coder launch takes 0.1 - 2 s; with 8 ranks x 64+
         // waiting threads per host the wake-ups themselves must stay cheap)
@@ -168,7 +170,8 @@ struct Ctx {
             slept += us; total += us; if (us < (total > 50000 ? 2000u : 400u)) us += us / 2;
             if (slept > 200000) {                            // every 0.2 s: has the stream died (launch failure, kernel fault)?
                 slept = 0;
-                cudaError_t e = cudaStreamQuery(stream);
+                cudaError_t e = cudaStreamQuery(a);
+                if (e == cudaSuccess && b) e = cudaStreamQuery(b);
                 if (e == cudaSuccess) { if (*flag != done_seq) { cudaGetLastError(); throw CudaFail{cudaErrorUnknown, __FILE__, __LINE__}; } break; }
                 if (e != cudaErrorNotReady) { cudaGetLastError(); throw CudaFail{e, __FILE__, __LINE__}; }
             }

@@ -298,7 +298,7 @@ struct SplitLaunch {
     }
     void finish(const char *name, int launches) {
         c->next_bytes = 0; c->kernels_launched += launches;
-        c->wait_signal();
+        c->wait_signal(s_short, n_hi > 0 ? s_long : nullptr);
         // every kernel of the launch has reported: the joins below never make anything wait
         if (n_hi > 0) { CUDA_TRY(cudaEventRecord(c->ev_join, s_long)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); }
         if (s_short != c->stream) { CUDA_TRY(cudaEventRecord(c->ev_join_lo, s_short)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join_lo, 0)); }

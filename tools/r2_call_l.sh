@@ -9,7 +9,7 @@ import json
 d=json.load(open('gpurun_out/r2l_$name.json'))
 k={x['kernel']:x for x in d['kernels']}
 def per(n): return round(k[n]['ms_total']/k[n]['launches'],2) if n in k else None
-print('$name: value', round(d['value'],1), 'compress', round(d['compress_MBps'],1), 'decompress', round(d['decompress_MBps'],1), 'ms/step', round(d['ms_per_step']), 'in flight', d['config']['blocks_in_flight_per_gpu'],
+print('$name: value', round(d['value'],1), 'compress', round(d['compress_MBps'],1), 'decompress', round(d['decompress_MBps'],1), 'ms/step', round(d['ms_per_step']), 'in flight', d['arm']['blocks_in_flight_per_gpu'],
       '| per launch ms: decode', per('q_decode6'), 'encode', per('q_encode5'), 'onesweep', per('rs_onesweep'), 'lr_jump', per('lr_jump'))
 PY
 }
@@ -20,5 +20,8 @@ echo "== 2. pipeline A/B: priorities on / off, 96 and 128 in flight"
 run prio_on_w96   X=1 -- --workers 96
 run prio_off_w96  BSCB200_PRIO=0 -- --workers 96
 run prio_on_w128  X=1 -- --workers 128
-run prio_on_w64   X=1 -- --workers 64
-} 2>&1 | tee gpurun_out/r2_call_l.log
+run prio_on_w96_dec4 BSCB200_DEC_PER_SM=4 -- --workers 96
+run prio_on_w96_nosplit BSCB200_CODER_SPLIT=0 -- --workers 96
+run prio_off_w96_again BSCB200_PRIO=0 -- --workers 96
+run prio_on_w96_again X=1 -- --workers 96
+} 2>&1 | tee gpurun_out/r2_call_l2.log
