@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--ref-blocks", type=int, default=16, help="blocks per step of the reference arm / cpu_baseline leg (see reference_sample_blocks)")
     ap.add_argument("--mode", default="pipeline", choices=["phased", "pipeline"], help="order of the work inside the timed steps of the device-resident leg (see class Steps); the e2e leg always flows as a pipeline")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=6, help="the end-to-end (host buffer) leg times min(--steps, this) steps, so that a long --steps run still ends within minutes")
+    ap.add_argument("--e2e-steps", type=int, default=12, help="the end-to-end (host buffer) leg times min(--steps, this) steps, so that a long --steps run still ends within minutes")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the extra keys for BASELINE configs C2 / C3-strong / C4 / C5")
     return ap.parse_args()
 
