@@ -251,3 +251,60 @@ def test_host_only_entry_points_need_no_gpu():
     hdr = np.zeros(28, dtype=np.uint8)
     assert L.bsc_block_info(hdr.ctypes.data, 10, None, None, 0) == -5          # UNEXPECTED_EOB
     assert L.bsc_block_info(hdr.ctypes.data, 28, None, None, 0) == -6          # bad header adler
+
+
+# ---- seeded sweep: many small inputs of random size / alphabet / structure, port vs reference, every stage -------------------
+def _sweep_inputs(count, seed):
+    rng = np.random.default_rng(seed)
+    for i in range(count):
+        n = int(rng.integers(1, 6000)) if i % 7 else int(rng.integers(1, 40))
+        sigma = int(rng.choice([1, 2, 3, 4, 16, 64, 256]))
+        kind = i % 5
+        if kind == 0:                                       # i.i.d. symbols
+            a = rng.integers(0, sigma, n, dtype=np.uint8)
+        elif kind == 1:                                     # long runs
+            a = np.repeat(rng.integers(0, sigma, n, dtype=np.uint8), rng.integers(1, 40, n))[:n].astype(np.uint8)
+        elif kind == 2:                                     # periodic with a defect
+            p = rng.integers(0, sigma, int(rng.integers(1, 12)), dtype=np.uint8)
+            a = np.tile(p, n // p.size + 1)[:n].copy(); a[int(rng.integers(0, n))] ^= 1
+        elif kind == 3:                                     # repeats of earlier material (LZ-like)
+            a = rng.integers(0, sigma, n, dtype=np.uint8)
+            for _ in range(4):
+                if n > 8:
+                    s, d, l = (int(x) for x in (rng.integers(0, n - 4), rng.integers(0, n - 4), rng.integers(1, n // 2)))
+                    l = min(l, n - s, n - d); a[d:d + l] = a[s:s + l].copy()
+        else:                                               # high bytes, zeros mixed in
+            a = rng.integers(200, 256, n, dtype=np.uint8); a[rng.integers(0, n, max(1, n // 9))] = 0
+        yield "sweep%d(n=%d,sigma=%d,kind=%d)" % (i, n, sigma, kind), np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def test_port_matches_reference_on_a_seeded_sweep(port, ref):
+    for name, a in _sweep_inputs(160, 20260924):
+        aux = a.size >= 16                                   # secondary indexes need n >= 16 (test_small_n_bwt_conventions)
+        r1, L1, i1 = port.bwt_encode(a, aux)
+        r2, L2, i2 = ref.bwt_encode(a, aux)
+        assert r1 == r2 and i1 == i2 and np.array_equal(L1, L2), name
+        if a.size > 1:
+            d, T = port.bwt_decode(L2, r2)
+            assert d == 0 and np.array_equal(T, a), name
+        for coder in (1, 2, 3):
+            c1, s1 = port.coder_compress(L2, coder, 3)
+            c2, s2 = ref.coder_compress(L2, coder, 3)
+            assert c1 == c2, (name, coder)
+            if c2 > 0:
+                assert np.array_equal(s1, s2), (name, coder)
+                n1, o1 = port.coder_decompress(s2, a.size, coder)
+                assert n1 == a.size and np.array_equal(o1, L2), (name, coder)
+        k = 3 + (a.size % 4)
+        x1, y1 = port.st_encode(a, k)
+        x2, y2 = ref.st_encode(a, k)
+        assert x1 == x2 and np.array_equal(y1, y2), (name, k)
+        if x2 >= 0:
+            d1, t1 = port.st_decode(y2, k, x2)
+            assert d1 == 0 and np.array_equal(t1, a), (name, k)
+        sorter = (1, 3, 4, 5, 6)[a.size % 5]
+        z1, b1 = port.compress(a, sorter, 1, 3)
+        z2, b2 = ref.compress(a, sorter, 1, 3)
+        assert z1 == z2 and np.array_equal(b1, b2), (name, sorter)
+        q, u = port.decompress(b2)
+        assert q == 0 and np.array_equal(u, a), (name, sorter)

@@ -65,7 +65,7 @@ def test_host_emulation_matches_oracle(qdec3, gen, checker, port):
             r, s = enc.encode_block(a)
             if r <= 0:
                 continue                                              # not compressible: the container stores it raw
-            for mode in (2, 1, 0):                                    # the product layout (tables in global memory), diet, full
+            for mode in (4, 3, 2, 1, 0):                              # the product layouts (five / four streams per SM; tables in global memory), three per SM, diet, full
                 n, out, stats = qdec3(s, a.size, mode)
                 assert n == a.size, (name, mode, n)
                 assert np.array_equal(out, a), (name, mode)
@@ -154,12 +154,14 @@ def test_layout_templated_decoder_host_emulation(gen, checker, port):
     lib.qdec6_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int]
     lib.qdec6_smem_bytes.restype = ctypes.c_uint
     assert lib.qdec6_smem_bytes(1) <= 113 * 1024 < lib.qdec6_smem_bytes(0)       # diet: two CTAs per SM; full: one
+    for layout, per_sm in ((2, 3), (3, 4), (4, 5)):                              # 228 KB per SM, 1 KB reserved per CTA
+        assert lib.qdec6_smem_bytes(layout) + 1024 <= 228 * 1024 // per_sm, (layout, per_sm)
     covered, rare = 0, [0, 0]
     for name, a in inputs(gen, checker):
         r, s = checker.encode_block(a)
         if r <= 0:
             continue
-        for layout in (0, 1, 2):
+        for layout in (0, 1, 2, 3, 4):
             out = np.full(a.size + 64, 0xAA, dtype=np.uint8)
             stats = (ctypes.c_uint * 2)()
             s_ = np.ascontiguousarray(s)
