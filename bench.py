@@ -565,6 +565,19 @@ def run_b200(args, rank, local_rank, world):
                         "issue, not by HBM -- see roofline_issue; launch durations of concurrent streams overlap, shares are of summed kernel time"}
     # the bound that does apply to the coder kernels: issue slots (ncu capture committed under profiles/, keyed by kernel)
     roofline_issue = (prof.get("issue") or {}).get(dom["kernel"])
+    try:
+        # live cross-check of the committed ncu figure: the kernel's instruction count is a property of the stream bytes (ncu, same block
+        # generator and size), its duration alone on the GPU is measured here with CUDA events -> warp instructions per cycle, summed over
+        # the streams of a launch and per stream (a LOWER bound of the per-scheduler rate: the streams of a launch end at different times)
+        if roofline_issue and dom["kernel"] in alone and clocks.get("sm_mhz") and bb == (64 << 20) and args.sorter == 1:
+            cnt_a, ms_a, _ = alone[dom["kernel"]]
+            cyc = (ms_a / max(cnt_a, 1)) * 1e-3 * clocks["sm_mhz"] * 1e6
+            per_launch = roofline_issue["instructions_per_launch"] / cyc
+            roofline_issue = dict(roofline_issue, live={"launch_ms_alone": ms_a / max(cnt_a, 1), "sm_mhz": clocks["sm_mhz"],
+                                                         "warp_instructions_per_cycle_per_launch": round(per_launch, 3),
+                                                         "per_stream_lower_bound": round(per_launch / roofline_issue.get("streams_per_launch", 8), 3)})
+    except Exception:
+        pass
 
     # HBM-bound kernels, timed alone: achieved algorithmic GB/s against the measured copy peak
     alone_table = []
