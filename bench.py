@@ -120,6 +120,10 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": info["value"], "unit": "MB/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
             "e2e": {"value": info["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "compress_MBps": info["compress_MBps"], "decompress_MBps": info["decompress_MBps"]}
+    try:
+        line["cpu_baseline"]["stages"] = reference_stage_seconds(args)
+    except Exception as ex:                                  # the stage table is an extra: never lose the line over it
+        line["cpu_baseline"]["stages"] = {"failed": repr(ex)[:200]}
     print(json.dumps(line), flush=True)
 
 
@@ -188,6 +192,30 @@ def _reference_native(drv_path, blocks, steps, warmup, sorter):
     return {"value": mb / (c + dd), "ms_per_step": (c + dd) * 1e3, "cores": int(T), "kind": "reference",
             "sample": "%d blocks x %d MiB G_text, CLI block loop (bsc.cpp:184-199), %d OpenMP threads of %d host threads" % (nb, blocks[0].size >> 20, T, d.refdrv_max_threads()),
             "compress_MBps": mb / c, "decompress_MBps": mb / dd, "compressed_bytes": int(sum(outsz))}
+
+
+def reference_stage_seconds(args):
+    """Per-stage seconds of the reference on ONE block of the workload, one host thread (what each thread of its CLI block loop does when
+    there are at least as many blocks as threads, bsc.cpp:188): bsc_bwt_encode, bsc_coder_compress, bsc_coder_decompress, bsc_bwt_decode.
+    SURVEY 8(d) asks for them beside the MB/s.  Only with the compiled reference (oracle/_ref)."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or args.sorter != 1:
+        return None
+    ref = pyoracle.Ref()
+    ref.features = 1                                         # LIBBSC_FEATURE_FASTMODE, no intra-block OpenMP
+    a = pyoracle.Gen().text(2, args.block_mib << 20)
+    t0 = time.perf_counter()
+    idx, L, _ = ref.bwt_encode(a, aux=False)
+    t1 = time.perf_counter()
+    c, stream = ref.coder_compress(L, 1, 1)
+    t2 = time.perf_counter()
+    n, L2 = ref.coder_decompress(stream, a.size, 1, 1)
+    t3 = time.perf_counter()
+    r, back = ref.bwt_decode(L2, idx)
+    t4 = time.perf_counter()
+    assert idx > 0 and c > 0 and n == a.size and r == 0 and np.array_equal(back, a), "reference stage round trip failed"
+    return {"block": "1 x %d MiB G_text(2), one host thread" % args.block_mib, "bwt_encode_s": round(t1 - t0, 3), "coder_compress_s": round(t2 - t1, 3),
+            "coder_decompress_s": round(t3 - t2, 3), "bwt_decode_s": round(t4 - t3, 3), "compressed_bytes": int(c)}
 
 
 def workload_config(args, extra=None):
@@ -602,6 +630,10 @@ def run_b200(args, rank, local_rank, world):
                    "compress_MBps": info["compress_MBps"], "decompress_MBps": info["decompress_MBps"]}
         except Exception as ex:      # never lose the GPU line because the baseline leg failed
             cpu = {"value": None, "unit": "MB/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+        try:
+            cpu["stages"] = reference_stage_seconds(args)
+        except Exception as ex:
+            cpu["stages"] = {"failed": repr(ex)[:200]}
 
     line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",

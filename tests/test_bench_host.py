@@ -62,3 +62,6 @@ def test_reference_arm_line_on_a_tiny_workload():
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "MB/s" and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == min(2, len(os.sched_getaffinity(0)))
     assert line["e2e"] == {"value": line["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    st = line["cpu_baseline"]["stages"]                      # per-stage seconds of one block, one thread
+    assert all(st[k] > 0 for k in ("bwt_encode_s", "coder_compress_s", "coder_decompress_s", "bwt_decode_s")) and st["compressed_bytes"] > 0
+    assert line["config"]["blocks_per_gpu"] == 2 and "arm" in line
